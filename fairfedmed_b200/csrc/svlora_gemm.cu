@@ -1,0 +1,679 @@
+// Fused SVLoRA / FairLoRA linear on Blackwell tensor cores (sm_100a).
+//
+// Computes, for row-major bf16 operands,
+//
+//     H[T,RP]  = X[T,K] · Aside[RP,K]^T                                   (fp32, side output)
+//     OUT[T,N] = epi( X · Wmat[N,K]^T + bias + (H ⊙ s_rows[sample(t)]) · Bside[N,RP]^T )
+//
+// in ONE persistent kernel.  This single contraction serves both directions of the reference's
+// FairLoRALinear (trainers/GLP_OT_SVLoRA.py:450-482):
+//   forward : X=x,  Wmat=W  [out,in],  Aside=A^T (pad), Bside=B^T (pad), s_rows = scaling·s_eff
+//   backward: X=dy, Wmat=W^T[in,out],  Aside=B   (pad), Bside=A   (pad), s_rows = scaling·s_eff
+//             -> OUT = dx, H = dy·B^T (un-scaled dz)
+//
+// Structure (one CTA per SM, 256 threads, static round-robin tile scheduler):
+//   warp 0   : TMA producer  — X / Wmat / Aside k-slices into a 4-stage SW128 smem ring
+//   warp 1   : MMA issuer    — one tcgen05.mma (M=128, N=192+16, K=16) per k-step: the W tile and the
+//                              Aside tile are adjacent in smem, so a single UMMA accumulates both
+//                              D (192 cols) and H (16 cols) into TMEM; later one K=16 "fix-up" UMMA
+//                              D += Z · Bside^T with Z = bf16(H ⊙ s_rows) staged by the epilogue warps
+//   warp 2   : TMEM allocator (512 columns = 2 accumulator stages x 256)
+//   warps 4-7: epilogue      — tcgen05.ld H -> scale -> Z (SW32 smem) -> signal; then tcgen05.ld D
+//                              -> +bias / QuickGELU / QuickGELU' -> bf16 -> SW128 smem -> TMA store
+// TMEM accumulators are double buffered so tile i's epilogue overlaps tile i+1's mainloop; the
+// fix-up UMMA of tile i is slotted into tile i+1's k-loop as soon as Z(i) is ready.
+#include <stdarg.h>
+#include <string.h>
+
+#include <mutex>
+
+#include "../../include/ffm_b200.h"
+#include "ffm_common.cuh"
+
+namespace ffm {
+
+// ----------------------------------------------------------------------------------------------
+// error string + device info (shared by the whole library)
+// ----------------------------------------------------------------------------------------------
+static thread_local char g_last_error[512] = "";
+
+void set_last_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_last_error, sizeof(g_last_error), fmt, ap);
+  va_end(ap);
+}
+
+int num_sms() {
+  static int cached[64] = {0};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 148;
+  if (cached[dev] == 0) {
+    int n = 0;
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+    cached[dev] = n;
+  }
+  return cached[dev];
+}
+
+// ----------------------------------------------------------------------------------------------
+// tile configuration
+// ----------------------------------------------------------------------------------------------
+constexpr int BM = 128;             // rows of X per tile      (UMMA M, one TMEM lane per row)
+constexpr int BN = 192;             // rows of Wmat per tile   (output columns)
+constexpr int BK = 64;              // k-slice per stage = one 128-byte swizzle row of bf16
+constexpr int RP = 16;              // padded adapter rank
+constexpr int UMMA_K = 16;
+constexpr int UMMA_N_MAIN = BN + RP;  // 208: [D | H] in one instruction
+constexpr int STAGES = 4;
+constexpr int ACC_COLS = 256;       // TMEM columns per accumulator stage (208 used)
+constexpr int TMEM_COLS = 512;
+constexpr int OUT_CHUNK = 64;       // output columns per TMA-store unit (128 B of bf16)
+
+constexpr int X_TILE_BYTES = BM * BK * 2;   // 16384
+constexpr int W_TILE_BYTES = BN * BK * 2;   // 24576
+constexpr int A_TILE_BYTES = RP * BK * 2;   //  2048
+constexpr int STAGE_BYTES = X_TILE_BYTES + W_TILE_BYTES + A_TILE_BYTES;  // 43008 (1024-multiple)
+constexpr int OUT_TILE_BYTES = BM * OUT_CHUNK * 2;  // 16384
+constexpr int Z_TILE_BYTES = BM * RP * 2;           //  4096
+constexpr int BS_TILE_BYTES = BN * RP * 2;          //  6144
+constexpr int BIAS_TILE_BYTES = BN * 4;             //   768
+
+constexpr int OFF_STAGES = 0;
+constexpr int OFF_OUT = OFF_STAGES + STAGES * STAGE_BYTES;
+constexpr int OFF_Z = OFF_OUT + 2 * OUT_TILE_BYTES;
+constexpr int OFF_BS = OFF_Z + 2 * Z_TILE_BYTES;
+constexpr int OFF_BIAS = OFF_BS + 2 * BS_TILE_BYTES;
+constexpr int OFF_BAR = OFF_BIAS + 2 * BIAS_TILE_BYTES;
+constexpr int NUM_BARS = 2 * STAGES + 5 * 2;
+constexpr int SMEM_USED = OFF_BAR + NUM_BARS * 8 + 16;
+constexpr int SMEM_BYTES = SMEM_USED + 1024;  // slack for manual 1024-B alignment
+
+static_assert(STAGE_BYTES % 1024 == 0, "stage must keep 1024-B alignment of SW128 tiles");
+static_assert((X_TILE_BYTES + W_TILE_BYTES) % 1024 == 0, "Aside tile must start on a swizzle atom");
+static_assert(OFF_OUT % 1024 == 0 && OFF_Z % 1024 == 0 && OFF_BS % 1024 == 0, "tile alignment");
+static_assert(SMEM_BYTES <= 232448, "exceeds 227 KB of shared memory per CTA");
+static_assert(BN % OUT_CHUNK == 0, "epilogue chunks");
+
+constexpr int NUM_THREADS = 256;
+constexpr int EPI_THREADS = 128;
+constexpr int EPI_BAR_ID = 1;
+
+enum : int { ACT_NONE = 0, ACT_QUICKGELU = 1, ACT_QUICKGELU_GRAD = 2 };
+
+struct GemmParams {
+  const float* bias;            // [N] or nullptr
+  const float* s_rows;          // [n_samples, RP] fp32 (already multiplied by alpha/r)
+  float* h_out;                 // [T, RP] fp32 or nullptr
+  const __nv_bfloat16* aux;     // ACT_QUICKGELU_GRAD: pre-activation u [T, N]
+  int T, K, N;
+  int b_prime, num_slices;      // sample(t) = (t % b_prime) / num_slices
+  int act;
+  int has_pre;                  // ACT_QUICKGELU: also store the pre-activation through tm_y2
+  int m_tiles, n_tiles, k_blocks;
+};
+
+__device__ __forceinline__ float fast_sigmoid(float v) { return __frcp_rn(1.0f + __expf(-v)); }
+__device__ __forceinline__ float quick_gelu(float u) { return u * fast_sigmoid(1.702f * u); }
+__device__ __forceinline__ float quick_gelu_grad(float u) {
+  const float s = fast_sigmoid(1.702f * u);
+  return s * (1.0f + 1.702f * u * (1.0f - s));
+}
+
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+svlora_gemm_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_w,
+                   const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b,
+                   const __grid_constant__ CUtensorMap tm_y, const __grid_constant__ CUtensorMap tm_y2,
+                   const GemmParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + OFF_BAR);
+  uint64_t* full_bar = bars;                   // [STAGES] TMA -> MMA
+  uint64_t* empty_bar = bars + STAGES;         // [STAGES] MMA -> TMA
+  uint64_t* h_full = bars + 2 * STAGES;        // [2] mainloop done: H (and D partial) in TMEM
+  uint64_t* z_full = h_full + 2;               // [2] epilogue wrote Z tile
+  uint64_t* d_full = z_full + 2;               // [2] fix-up UMMA done: D final
+  uint64_t* tmem_empty = d_full + 2;           // [2] epilogue drained accumulator stage
+  uint64_t* bs_full = tmem_empty + 2;          // [2] Bside tile landed
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + NUM_BARS);
+
+  const uint32_t warp = threadIdx.x >> 5;
+  const uint32_t lane = threadIdx.x & 31u;
+  const int num_tiles = p.m_tiles * p.n_tiles;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tm_x);
+    tma_prefetch_desc(&tm_w);
+    tma_prefetch_desc(&tm_a);
+    tma_prefetch_desc(&tm_b);
+    tma_prefetch_desc(&tm_y);
+    if (p.has_pre) tma_prefetch_desc(&tm_y2);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < STAGES; ++i) {
+      mbar_init(&full_bar[i], 1);
+      mbar_init(&empty_bar[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&h_full[i], 1);
+      mbar_init(&z_full[i], EPI_THREADS);
+      mbar_init(&d_full[i], 1);
+      mbar_init(&tmem_empty[i], EPI_THREADS / 32);
+      mbar_init(&bs_full[i], 1);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 2) {
+    tmem_alloc(tmem_ptr, TMEM_COLS);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  if (warp == 0) {
+    // =========================== TMA producer ===========================
+    if (lane == 0) {
+      uint32_t stage = 0, phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int m_blk = tile / p.n_tiles;
+        const int n_blk = tile - m_blk * p.n_tiles;
+        for (int kb = 0; kb < p.k_blocks; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1u, 100 + stage);
+          uint8_t* st = smem + OFF_STAGES + stage * STAGE_BYTES;
+          mbar_arrive_expect_tx(&full_bar[stage], STAGE_BYTES);
+          tma_load_2d(st, &tm_x, &full_bar[stage], kb * BK, m_blk * BM);
+          tma_load_2d(st + X_TILE_BYTES, &tm_w, &full_bar[stage], kb * BK, n_blk * BN);
+          tma_load_2d(st + X_TILE_BYTES + W_TILE_BYTES, &tm_a, &full_bar[stage], kb * BK, 0);
+          if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // =========================== MMA issuer ===========================
+    if (lane == 0) {
+      constexpr uint32_t idesc_main = umma_idesc_bf16(BM, UMMA_N_MAIN);
+      constexpr uint32_t idesc_fix = umma_idesc_bf16(BM, BN);
+      uint32_t stage = 0, phase = 0;
+      int pend = -1;
+      uint32_t pend_phase = 0;
+
+      auto fixup = [&](int s, uint32_t ph) {
+        // D[s] += Z[s] (128 x 16) · Bside[s]^T (16 x 192)
+        mbar_wait(&bs_full[s], ph, 200 + s);
+        tc_fence_after();
+        const uint64_t zd = umma_desc_sw32(smem_u32(smem + OFF_Z + s * Z_TILE_BYTES));
+        const uint64_t bd = umma_desc_sw32(smem_u32(smem + OFF_BS + s * BS_TILE_BYTES));
+        umma_bf16(tmem_base + s * ACC_COLS, zd, bd, idesc_fix, 1u);
+        umma_commit(&d_full[s]);
+      };
+
+      int it = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+        const int m_blk = tile / p.n_tiles;
+        const int n_blk = tile - m_blk * p.n_tiles;
+        const int s = it & 1;
+        const uint32_t aph = (it >> 1) & 1u;
+        mbar_wait(&tmem_empty[s], aph ^ 1u, 300 + s);   // epilogue drained tile it-2 (=> Bside[s], Z[s] free)
+        tc_fence_after();
+        mbar_arrive_expect_tx(&bs_full[s], BS_TILE_BYTES);
+        tma_load_2d(smem + OFF_BS + s * BS_TILE_BYTES, &tm_b, &bs_full[s], 0, n_blk * BN);
+
+        const uint32_t d_tmem = tmem_base + s * ACC_COLS;
+        for (int kb = 0; kb < p.k_blocks; ++kb) {
+          if (pend >= 0 && mbar_test_wait(&z_full[pend], pend_phase)) {
+            fixup(pend, pend_phase);
+            pend = -1;
+          }
+          mbar_wait(&full_bar[stage], phase, 400 + stage);
+          tc_fence_after();
+          const uint32_t st = smem_u32(smem + OFF_STAGES + stage * STAGE_BYTES);
+          const uint64_t adesc = umma_desc_sw128(st);
+          const uint64_t bdesc = umma_desc_sw128(st + X_TILE_BYTES);
+#pragma unroll
+          for (int k = 0; k < BK / UMMA_K; ++k) {
+            // advance 32 B along K inside the 128-B swizzle row: +2 in the (>>4) address field
+            umma_bf16(d_tmem, adesc + 2u * k, bdesc + 2u * k, idesc_main, (kb | k) != 0 ? 1u : 0u);
+          }
+          umma_commit(&empty_bar[stage]);
+          if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+        }
+        umma_commit(&h_full[s]);
+        if (pend >= 0) {
+          mbar_wait(&z_full[pend], pend_phase, 500 + pend);
+          fixup(pend, pend_phase);
+        }
+        pend = s;
+        pend_phase = aph;
+        (void)m_blk;
+      }
+      if (pend >= 0) {
+        mbar_wait(&z_full[pend], pend_phase, 510 + pend);
+        fixup(pend, pend_phase);
+      }
+    }
+  } else if (warp >= 4) {
+    // =========================== epilogue ===========================
+    const uint32_t q = warp & 3u;              // TMEM lane quarter accessible by this warp
+    const uint32_t row = q * 32u + lane;       // row of the tile owned by this thread
+    const uint32_t et = threadIdx.x - 128u;    // 0..127
+    const uint32_t lane_addr = (q * 32u) << 16;
+    uint32_t store_unit = 0;                   // running count of TMA-store units (buffer = unit & 1)
+    int it = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+      const int m_blk = tile / p.n_tiles;
+      const int n_blk = tile - m_blk * p.n_tiles;
+      const int s = it & 1;
+      const uint32_t aph = (it >> 1) & 1u;
+      const int grow = m_blk * BM + static_cast<int>(row);   // global row
+      const int n0 = n_blk * BN;
+      const uint32_t acc = tmem_base + lane_addr + s * ACC_COLS;
+
+      // ---- H -> Z ----
+      mbar_wait(&h_full[s], aph, 600 + s);
+      tc_fence_after();
+      uint32_t hv[16];
+      tmem_ld16(acc + BN, hv);
+      tmem_ld_wait();
+      {
+        const int grow_c = grow < p.T ? grow : (p.T - 1);
+        const int sample = (grow_c % p.b_prime) / p.num_slices;
+        const float4* sr = reinterpret_cast<const float4*>(p.s_rows + static_cast<size_t>(sample) * RP);
+        float zf[16];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float4 sv = __ldg(sr + j);
+          zf[4 * j + 0] = __uint_as_float(hv[4 * j + 0]) * sv.x;
+          zf[4 * j + 1] = __uint_as_float(hv[4 * j + 1]) * sv.y;
+          zf[4 * j + 2] = __uint_as_float(hv[4 * j + 2]) * sv.z;
+          zf[4 * j + 3] = __uint_as_float(hv[4 * j + 3]) * sv.w;
+        }
+        if (p.h_out != nullptr && n_blk == 0 && grow < p.T) {
+          float4* ho = reinterpret_cast<float4*>(p.h_out + static_cast<size_t>(grow) * RP);
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            ho[j] = make_float4(__uint_as_float(hv[4 * j]), __uint_as_float(hv[4 * j + 1]),
+                                __uint_as_float(hv[4 * j + 2]), __uint_as_float(hv[4 * j + 3]));
+        }
+        // SW32 K-major tile: row r at r*32 B, 16-B chunk c stored at chunk (c ^ ((r>>2)&1))
+        uint8_t* zrow = smem + OFF_Z + s * Z_TILE_BYTES + row * 32u;
+        const uint32_t sw = (row >> 2) & 1u;
+        uint4 c0, c1;
+        c0.x = pack_bf16x2(zf[0], zf[1]);   c0.y = pack_bf16x2(zf[2], zf[3]);
+        c0.z = pack_bf16x2(zf[4], zf[5]);   c0.w = pack_bf16x2(zf[6], zf[7]);
+        c1.x = pack_bf16x2(zf[8], zf[9]);   c1.y = pack_bf16x2(zf[10], zf[11]);
+        c1.z = pack_bf16x2(zf[12], zf[13]); c1.w = pack_bf16x2(zf[14], zf[15]);
+        *reinterpret_cast<uint4*>(zrow + ((0u ^ sw) << 4)) = c0;
+        *reinterpret_cast<uint4*>(zrow + ((1u ^ sw) << 4)) = c1;
+      }
+      // bias slice for this n block (visible to the other epilogue threads after the named barrier below)
+      float* bias_s = reinterpret_cast<float*>(smem + OFF_BIAS + s * BIAS_TILE_BYTES);
+      for (int j = et; j < BN; j += EPI_THREADS) {
+        const int col = n0 + j;
+        bias_s[j] = (p.bias != nullptr && col < p.N) ? __ldg(p.bias + col) : 0.0f;
+      }
+      fence_proxy_async_smem();
+      mbar_arrive(&z_full[s]);
+      named_bar_sync(EPI_BAR_ID, EPI_THREADS);   // bias_s visible to all epilogue threads
+
+      // ---- D -> OUT ----
+      mbar_wait(&d_full[s], aph, 700 + s);
+      tc_fence_after();
+#pragma unroll 1
+      for (int c = 0; c < BN / OUT_CHUNK; ++c) {
+        uint32_t v0[32], v1[32];
+        tmem_ld32(acc + c * OUT_CHUNK, v0);
+        tmem_ld32(acc + c * OUT_CHUNK + 32, v1);
+        tmem_ld_wait();
+        if (c == BN / OUT_CHUNK - 1) {
+          // accumulator stage fully read: hand it back to the MMA warp
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&tmem_empty[s]);
+        }
+        float f[64];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          f[j] = __uint_as_float(v0[j]) + bias_s[c * OUT_CHUNK + j];
+          f[32 + j] = __uint_as_float(v1[j]) + bias_s[c * OUT_CHUNK + 32 + j];
+        }
+        const int col0 = n0 + c * OUT_CHUNK;
+        const int n_pass = (p.act == ACT_QUICKGELU && p.has_pre) ? 2 : 1;
+        if (p.act == ACT_QUICKGELU_GRAD) {
+          // f <- f * gelu'(u), u = pre-activation saved by the forward pass
+          if (grow < p.T) {
+            const __nv_bfloat16* up = p.aux + static_cast<size_t>(grow) * p.N + col0;
+            if (col0 + OUT_CHUNK <= p.N) {
+#pragma unroll
+              for (int j8 = 0; j8 < 8; ++j8) {
+                const uint4 raw = __ldg(reinterpret_cast<const uint4*>(up) + j8);
+                const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&raw);
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                  const float2 uu = __bfloat1622float2(h2[e]);
+                  f[j8 * 8 + 2 * e] *= quick_gelu_grad(uu.x);
+                  f[j8 * 8 + 2 * e + 1] *= quick_gelu_grad(uu.y);
+                }
+              }
+            } else {
+              for (int j = 0; j < OUT_CHUNK; ++j)
+                if (col0 + j < p.N) f[j] *= quick_gelu_grad(__bfloat162float(up[j]));
+            }
+          }
+        }
+#pragma unroll 1
+        for (int pass = 0; pass < n_pass; ++pass) {
+          // pass 0 of a dual store writes the pre-activation (tm_y2), the last pass the activated value
+          const bool apply_act = (p.act == ACT_QUICKGELU) && (pass == n_pass - 1);
+          const uint32_t buf = store_unit & 1u;
+          uint8_t* ob = smem + OFF_OUT + buf * OUT_TILE_BYTES;
+          // the TMA store that last read this buffer (2 units ago) must have finished reading smem
+          if (et == 0) tma_store_wait_read<1>();
+          named_bar_sync(EPI_BAR_ID, EPI_THREADS);
+          uint8_t* orow = ob + row * 128u;
+          if (apply_act) {   // warp-uniform branch: keep the MUFU work out of the plain-store path
+#pragma unroll
+            for (int j = 0; j < OUT_CHUNK; ++j) f[j] = quick_gelu(f[j]);
+          }
+#pragma unroll
+          for (int j8 = 0; j8 < 8; ++j8) {
+            uint4 pk;
+            pk.x = pack_bf16x2(f[j8 * 8 + 0], f[j8 * 8 + 1]);
+            pk.y = pack_bf16x2(f[j8 * 8 + 2], f[j8 * 8 + 3]);
+            pk.z = pack_bf16x2(f[j8 * 8 + 4], f[j8 * 8 + 5]);
+            pk.w = pack_bf16x2(f[j8 * 8 + 6], f[j8 * 8 + 7]);
+            // SW128: 16-B chunk j8 of row r lives at chunk (j8 ^ (r & 7))
+            *reinterpret_cast<uint4*>(orow + ((static_cast<uint32_t>(j8) ^ (row & 7u)) << 4)) = pk;
+          }
+          fence_proxy_async_smem();
+          named_bar_sync(EPI_BAR_ID, EPI_THREADS);
+          if (et == 0) {
+            const CUtensorMap* tm = (n_pass == 2 && pass == 0) ? &tm_y2 : &tm_y;
+            tma_store_2d(tm, ob, col0, m_blk * BM);
+            tma_store_commit();
+          }
+          ++store_unit;
+        }
+      }
+    }
+    if (et == 0) tma_store_wait_all<0>();
+  }
+
+  __syncwarp();
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) tmem_dealloc(tmem_base, TMEM_COLS);
+}
+
+// ----------------------------------------------------------------------------------------------
+// Prep kernel: fp32 master adapter parameters -> bf16 padded side tiles + scaled singular values.
+//   a_side[RP, Kdim]  (row j = column j of the [Kdim, r] matrix, or row j of an [r, Kdim] matrix)
+//   b_side[Ndim, RP]  (row n = column n of the [r, Ndim] matrix, or row n of an [Ndim, r] matrix)
+//   s_rows[nS, RP]    = scaling * s_eff[nS, r], zero padded
+// ----------------------------------------------------------------------------------------------
+__global__ void svlora_prep_kernel(const float* __restrict__ a_src, int a_transposed,  // a_transposed: src is [Kdim, r]
+                                   const float* __restrict__ b_src, int b_transposed,  // b_transposed: src is [r, Ndim]
+                                   const float* __restrict__ s_eff, __nv_bfloat16* __restrict__ a_side,
+                                   __nv_bfloat16* __restrict__ b_side, float* __restrict__ s_rows, int Kdim,
+                                   int Ndim, int r, int nS, float scaling) {
+  const int tid = blockIdx.x * blockDim.x + threadIdx.x;
+  const int nthreads = gridDim.x * blockDim.x;
+  for (int i = tid; i < RP * Kdim; i += nthreads) {
+    const int j = i / Kdim, k = i - j * Kdim;
+    float v = 0.f;
+    if (j < r) v = a_transposed ? a_src[static_cast<size_t>(k) * r + j] : a_src[static_cast<size_t>(j) * Kdim + k];
+    a_side[i] = __float2bfloat16(v);
+  }
+  for (int i = tid; i < Ndim * RP; i += nthreads) {
+    const int n = i / RP, j = i - n * RP;
+    float v = 0.f;
+    if (j < r) v = b_transposed ? b_src[static_cast<size_t>(j) * Ndim + n] : b_src[static_cast<size_t>(n) * r + j];
+    b_side[i] = __float2bfloat16(v);
+  }
+  for (int i = tid; i < nS * RP; i += nthreads) {
+    const int b = i / RP, j = i - b * RP;
+    s_rows[i] = (j < r) ? scaling * s_eff[static_cast<size_t>(b) * r + j] : 0.f;
+  }
+}
+
+// ----------------------------------------------------------------------------------------------
+// host side: tensor maps + launch
+// ----------------------------------------------------------------------------------------------
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,
+                                    CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
+                                    CUtensorMapFloatOOBfill);
+
+static PFN_encodeTiled get_encode_fn() {
+  static PFN_encodeTiled fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<PFN_encodeTiled>(p);
+  });
+  return fn;
+}
+
+// row-major bf16 matrix [rows, cols] (cols contiguous) -> 2-D tiled map with box [box_rows, box_cols]
+static int make_map_bf16(CUtensorMap* out, const void* ptr, uint64_t rows, uint64_t cols, uint32_t box_rows,
+                         uint32_t box_cols, CUtensorMapSwizzle swz, bool promote) {
+  PFN_encodeTiled enc = get_encode_fn();
+  if (enc == nullptr) {
+    set_last_error("cuTensorMapEncodeTiled driver entry point not available");
+    return FFM_ERR_CUDA;
+  }
+  cuuint64_t dims[2] = {cols, rows};
+  cuuint64_t strides[1] = {cols * 2};
+  cuuint32_t box[2] = {box_cols, box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, swz,
+                   promote ? CU_TENSOR_MAP_L2_PROMOTION_L2_256B : CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_last_error("cuTensorMapEncodeTiled failed (%d) for [%llu x %llu] box [%u x %u]", (int)r,
+                   (unsigned long long)rows, (unsigned long long)cols, box_rows, box_cols);
+    return FFM_ERR_CUDA;
+  }
+  return FFM_OK;
+}
+
+struct GemmOperands {
+  const void* x;        // [T, K] bf16
+  const void* wmat;     // [N, K] bf16
+  const void* a_side;   // [RP, K] bf16
+  const void* b_side;   // [N, RP] bf16
+  const float* s_rows;  // [nS, RP]
+  const float* bias;    // [N] or null
+  void* out;            // [T, N] bf16
+  void* out_pre;        // [T, N] bf16 or null (ACT_QUICKGELU only)
+  float* h_out;         // [T, RP] or null
+  const void* aux;      // [T, N] bf16 (ACT_QUICKGELU_GRAD)
+  int T, K, N, b_prime, num_slices, act;
+};
+
+static int launch_svlora_gemm(const GemmOperands& o, cudaStream_t stream) {
+  FFM_CHECK_ARG(o.T > 0 && o.K > 0 && o.N > 0, "svlora gemm: empty problem T=%d K=%d N=%d", o.T, o.K, o.N);
+  FFM_CHECK_ARG(o.K % 8 == 0 && o.N % 8 == 0, "svlora gemm: K (%d) and N (%d) must be multiples of 8 (TMA 16-B strides)",
+                o.K, o.N);
+  FFM_CHECK_ARG(o.b_prime > 0 && o.num_slices > 0, "svlora gemm: b_prime/num_slices must be positive");
+  FFM_CHECK_ARG(o.act != ACT_QUICKGELU_GRAD || o.aux != nullptr, "svlora gemm: ACT_QUICKGELU_GRAD needs aux");
+  const uintptr_t align_or = reinterpret_cast<uintptr_t>(o.x) | reinterpret_cast<uintptr_t>(o.wmat) |
+                             reinterpret_cast<uintptr_t>(o.a_side) | reinterpret_cast<uintptr_t>(o.b_side) |
+                             reinterpret_cast<uintptr_t>(o.out) | reinterpret_cast<uintptr_t>(o.out_pre) |
+                             reinterpret_cast<uintptr_t>(o.s_rows) | reinterpret_cast<uintptr_t>(o.h_out) |
+                             reinterpret_cast<uintptr_t>(o.aux);
+  FFM_CHECK_ARG((align_or & 15u) == 0, "svlora gemm: all device pointers must be 16-byte aligned");
+
+  CUtensorMap tm_x, tm_w, tm_a, tm_b, tm_y, tm_y2;
+  int rc;
+  if ((rc = make_map_bf16(&tm_x, o.x, o.T, o.K, BM, BK, CU_TENSOR_MAP_SWIZZLE_128B, true))) return rc;
+  if ((rc = make_map_bf16(&tm_w, o.wmat, o.N, o.K, BN, BK, CU_TENSOR_MAP_SWIZZLE_128B, true))) return rc;
+  if ((rc = make_map_bf16(&tm_a, o.a_side, RP, o.K, RP, BK, CU_TENSOR_MAP_SWIZZLE_128B, true))) return rc;
+  if ((rc = make_map_bf16(&tm_b, o.b_side, o.N, RP, BN, RP, CU_TENSOR_MAP_SWIZZLE_32B, false))) return rc;
+  if ((rc = make_map_bf16(&tm_y, o.out, o.T, o.N, BM, OUT_CHUNK, CU_TENSOR_MAP_SWIZZLE_128B, false))) return rc;
+  const bool has_pre = (o.act == ACT_QUICKGELU && o.out_pre != nullptr);
+  if ((rc = make_map_bf16(&tm_y2, has_pre ? o.out_pre : o.out, o.T, o.N, BM, OUT_CHUNK, CU_TENSOR_MAP_SWIZZLE_128B,
+                          false)))
+    return rc;
+
+  GemmParams p;
+  p.bias = o.bias;
+  p.s_rows = o.s_rows;
+  p.h_out = o.h_out;
+  p.aux = reinterpret_cast<const __nv_bfloat16*>(o.aux);
+  p.T = o.T; p.K = o.K; p.N = o.N;
+  p.b_prime = o.b_prime; p.num_slices = o.num_slices;
+  p.act = o.act;
+  p.has_pre = has_pre ? 1 : 0;
+  p.m_tiles = (o.T + BM - 1) / BM;
+  p.n_tiles = (o.N + BN - 1) / BN;
+  p.k_blocks = (o.K + BK - 1) / BK;
+
+  static std::once_flag attr_once;
+  static cudaError_t attr_err = cudaSuccess;
+  std::call_once(attr_once, [] {
+    attr_err = cudaFuncSetAttribute(svlora_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+  });
+  // the attribute is per-device; re-apply cheaply when several devices are used from one process
+  if (attr_err == cudaSuccess) {
+    static thread_local int attr_dev = -1;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev != attr_dev) {
+      attr_err = cudaFuncSetAttribute(svlora_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+      attr_dev = dev;
+    }
+  }
+  FFM_CHECK_CUDA(attr_err);
+
+  const int tiles = p.m_tiles * p.n_tiles;
+  const int grid = tiles < num_sms() ? tiles : num_sms();
+  svlora_gemm_kernel<<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(tm_x, tm_w, tm_a, tm_b, tm_y, tm_y2, p);
+  FFM_CHECK_CUDA(cudaGetLastError());
+  return FFM_OK;
+}
+
+// workspace carve-up shared by fwd and bwd (all offsets 256-B aligned)
+struct SvloraWorkspace {
+  __nv_bfloat16* a_side;  // [RP, Kdim]
+  __nv_bfloat16* b_side;  // [Ndim, RP]
+  float* s_rows;          // [nS, RP]
+  uint8_t* rest;          // remaining bytes (bwd partials)
+  size_t rest_bytes;
+};
+
+static size_t align256(size_t v) { return (v + 255) & ~size_t(255); }
+
+static size_t svlora_ws_prefix(int Kdim, int Ndim, int nS) {
+  return align256(static_cast<size_t>(RP) * Kdim * 2) + align256(static_cast<size_t>(Ndim) * RP * 2) +
+         align256(static_cast<size_t>(nS) * RP * 4);
+}
+
+static void carve(SvloraWorkspace* w, void* ws, size_t ws_bytes, int Kdim, int Ndim, int nS) {
+  uint8_t* p = static_cast<uint8_t*>(ws);
+  w->a_side = reinterpret_cast<__nv_bfloat16*>(p);
+  p += align256(static_cast<size_t>(RP) * Kdim * 2);
+  w->b_side = reinterpret_cast<__nv_bfloat16*>(p);
+  p += align256(static_cast<size_t>(Ndim) * RP * 2);
+  w->s_rows = reinterpret_cast<float*>(p);
+  p += align256(static_cast<size_t>(nS) * RP * 4);
+  w->rest = p;
+  w->rest_bytes = ws_bytes - static_cast<size_t>(p - static_cast<uint8_t*>(ws));
+}
+
+// implemented in svlora_small.cu
+int launch_svlora_bwd_small(const __nv_bfloat16* x, const __nv_bfloat16* dy, const float* h, const float* dzu,
+                            const float* s_rows, float* dA, float* dB, float* ds_eff, void* scratch,
+                            size_t scratch_bytes, int T, int K, int N, int r, int nS, int b_prime, int num_slices,
+                            float scaling, cudaStream_t stream);
+size_t svlora_bwd_small_scratch_bytes(int T, int K, int N);
+
+}  // namespace ffm
+
+using namespace ffm;
+
+extern "C" {
+
+const char* ffm_last_error(void) { return g_last_error; }
+
+int ffm_version(void) { return 100; }
+
+int ffm_svlora_max_rank(void) { return RP; }
+
+size_t ffm_svlora_fwd_workspace_bytes(int T, int K, int N, int n_samples) {
+  (void)T;
+  return svlora_ws_prefix(K, N, n_samples);
+}
+
+size_t ffm_svlora_bwd_workspace_bytes(int T, int K, int N, int n_samples) {
+  // backward GEMM contracts over N and produces K columns
+  return svlora_ws_prefix(N, K, n_samples) + align256(static_cast<size_t>(T) * RP * 4) +
+         svlora_bwd_small_scratch_bytes(T, K, N);
+}
+
+int ffm_svlora_fwd(const void* x, const void* w, const float* bias, const float* lora_a, const float* lora_b,
+                   const float* s_eff, void* y, void* y_pre, float* h_out, void* workspace, size_t workspace_bytes,
+                   int T, int K, int N, int r, int n_samples, int b_prime, int num_slices, float scaling, int act,
+                   cudaStream_t stream) {
+  FFM_CHECK_ARG(x && w && lora_a && lora_b && s_eff && y && workspace, "ffm_svlora_fwd: null pointer argument");
+  FFM_CHECK_ARG(r >= 1 && r <= RP, "ffm_svlora_fwd: rank %d not in [1, %d]", r, RP);
+  FFM_CHECK_ARG(n_samples >= 1, "ffm_svlora_fwd: n_samples must be >= 1");
+  FFM_CHECK_ARG(b_prime >= 1 && num_slices >= 1 && (b_prime - 1) / num_slices < n_samples,
+                "ffm_svlora_fwd: sample mapping (b_prime=%d, num_slices=%d) exceeds n_samples=%d", b_prime,
+                num_slices, n_samples);
+  FFM_CHECK_ARG(act == ACT_NONE || act == ACT_QUICKGELU, "ffm_svlora_fwd: act must be 0 or 1");
+  FFM_CHECK_ARG(workspace_bytes >= ffm_svlora_fwd_workspace_bytes(T, K, N, n_samples),
+                "ffm_svlora_fwd: workspace too small");
+  SvloraWorkspace ws;
+  carve(&ws, workspace, workspace_bytes, K, N, n_samples);
+  // forward: Aside = A^T (A is [K, r]), Bside = B^T (B is [r, N])
+  svlora_prep_kernel<<<64, 256, 0, stream>>>(lora_a, 1, lora_b, 1, s_eff, ws.a_side, ws.b_side, ws.s_rows, K, N, r,
+                                             n_samples, scaling);
+  FFM_CHECK_CUDA(cudaGetLastError());
+  GemmOperands o;
+  o.x = x; o.wmat = w; o.a_side = ws.a_side; o.b_side = ws.b_side; o.s_rows = ws.s_rows; o.bias = bias;
+  o.out = y; o.out_pre = y_pre; o.h_out = h_out; o.aux = nullptr;
+  o.T = T; o.K = K; o.N = N; o.b_prime = b_prime; o.num_slices = num_slices; o.act = act;
+  return launch_svlora_gemm(o, stream);
+}
+
+int ffm_svlora_bwd(const void* dy, const void* x, const void* w_t, const float* lora_a, const float* lora_b,
+                   const float* s_eff, const float* h, const void* gelu_pre, void* dx, float* d_lora_a,
+                   float* d_lora_b, float* d_s_eff, void* workspace, size_t workspace_bytes, int T, int K, int N,
+                   int r, int n_samples, int b_prime, int num_slices, float scaling, cudaStream_t stream) {
+  FFM_CHECK_ARG(dy && x && w_t && lora_a && lora_b && s_eff && h && dx && d_lora_a && d_lora_b && d_s_eff &&
+                    workspace,
+                "ffm_svlora_bwd: null pointer argument");
+  FFM_CHECK_ARG(r >= 1 && r <= RP, "ffm_svlora_bwd: rank %d not in [1, %d]", r, RP);
+  FFM_CHECK_ARG(b_prime >= 1 && num_slices >= 1 && (b_prime - 1) / num_slices < n_samples,
+                "ffm_svlora_bwd: sample mapping exceeds n_samples");
+  FFM_CHECK_ARG(workspace_bytes >= ffm_svlora_bwd_workspace_bytes(T, K, N, n_samples),
+                "ffm_svlora_bwd: workspace too small");
+  SvloraWorkspace ws;
+  carve(&ws, workspace, workspace_bytes, N, K, n_samples);
+  float* dzu = reinterpret_cast<float*>(ws.rest);
+  uint8_t* scratch = ws.rest + align256(static_cast<size_t>(T) * RP * 4);
+  const size_t scratch_bytes = ws.rest_bytes - align256(static_cast<size_t>(T) * RP * 4);
+  // backward: contraction over N.  Aside = B (already [r, N]), Bside = A (already [K, r]).
+  svlora_prep_kernel<<<64, 256, 0, stream>>>(lora_b, 0, lora_a, 0, s_eff, ws.a_side, ws.b_side, ws.s_rows, N, K, r,
+                                             n_samples, scaling);
+  FFM_CHECK_CUDA(cudaGetLastError());
+  GemmOperands o;
+  o.x = dy; o.wmat = w_t; o.a_side = ws.a_side; o.b_side = ws.b_side; o.s_rows = ws.s_rows; o.bias = nullptr;
+  o.out = dx; o.out_pre = nullptr; o.h_out = dzu; o.aux = gelu_pre;
+  o.T = T; o.K = N; o.N = K; o.b_prime = b_prime; o.num_slices = num_slices;
+  o.act = gelu_pre != nullptr ? ACT_QUICKGELU_GRAD : ACT_NONE;
+  int rc = launch_svlora_gemm(o, stream);
+  if (rc != FFM_OK) return rc;
+  return launch_svlora_bwd_small(reinterpret_cast<const __nv_bfloat16*>(x), reinterpret_cast<const __nv_bfloat16*>(dy),
+                                 h, dzu, ws.s_rows, d_lora_a, d_lora_b, d_s_eff, scratch, scratch_bytes, T, K, N, r,
+                                 n_samples, b_prime, num_slices, scaling, stream);
+}
+
+}  // extern "C"

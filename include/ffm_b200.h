@@ -1,0 +1,203 @@
+/*
+ * ffm_b200.h — C ABI of libffm_b200.so: the sm_100a (B200) kernels behind the FairLoRA training
+ * hot path of Harvard-AI-and-Robotics-Lab/FairFedMed.
+ *
+ * The reference is pure Python/PyTorch and has no FFI of its own; each entry point below therefore
+ * cites the reference *Python call site* it replaces (paths relative to the reference repo root).
+ * A maintainer binds these with ctypes (see INTEGRATION.md and fairfedmed_b200/_cabi.py).
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless its name ends in `_host`;
+ *   - every function is asynchronous on `stream` (a cudaStream_t passed as void*), allocates nothing
+ *     and never throws: it returns 0 on success or a negative errno-style code
+ *     (-22 invalid argument, -5 CUDA error, -38 not supported); ffm_last_error() gives the text;
+ *   - matrices are dense row-major; "bf16" means __nv_bfloat16 storage, "f32" IEEE binary32;
+ *   - callers own all workspaces (sizes from the *_workspace_bytes helpers).
+ */
+#ifndef FFM_B200_H_
+#define FFM_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#ifndef FFM_STREAM_T
+#define FFM_STREAM_T
+#ifdef __CUDACC__
+#include <cuda_runtime.h>
+typedef cudaStream_t ffm_stream_t;
+#else
+typedef void* ffm_stream_t;
+#endif
+#endif
+
+/* ---------------------------------------------------------------- library ------------------ */
+const char* ffm_last_error(void);
+int ffm_version(void);
+
+/* ------------------------------------------------- FairLoRA / SVLoRA linear ------------------ */
+/* Maximum adapter rank the fused GEMM was built for (r is zero-padded to this). */
+int ffm_svlora_max_rank(void);
+
+size_t ffm_svlora_fwd_workspace_bytes(int T, int K, int N, int n_samples);
+size_t ffm_svlora_bwd_workspace_bytes(int T, int K, int N, int n_samples);
+
+/*
+ * Forward of FairLoRALinear / SVLoRALinear / LoRALinear
+ *   replaces trainers/GLP_OT_SVLoRA.py:450-482 (FairLoRALinear.forward), :308-312, :241-242.
+ *
+ *   h[t,:]  = x[t,:] · A                                      (f32 [T,16], columns >= r are 0)
+ *   u[t,:]  = x[t,:] · W^T + bias + scaling · (h[t,:] ⊙ s_eff[sample(t),:]) · B
+ *   y       = act ? QuickGELU(u) : u          (clip/model.py:313-315 fused when act = 1)
+ *   y_pre   = u   (only when act = 1 and y_pre != NULL; needed by the backward pass)
+ *
+ *   sample(t) = (t mod b_prime) / num_slices   — activations are sequence-first [L, B', C]
+ *               (clip/model.py:438-440); OCT volumes fold num_slices slice-images per sample into B'
+ *               (trainers/GLP_OT_SVLoRA.py:473-475).
+ *
+ *   x [T,K] bf16, W [N,K] bf16 (frozen nn.Linear weight), bias [N] f32 or NULL,
+ *   lora_a [K,r] f32, lora_b [r,N] f32, s_eff [n_samples,r] f32 (from ffm_seff), y / y_pre [T,N] bf16.
+ *   Requirements: K % 8 == 0, N % 8 == 0, 1 <= r <= ffm_svlora_max_rank(), 16-byte aligned pointers.
+ */
+int ffm_svlora_fwd(const void* x, const void* w, const float* bias, const float* lora_a, const float* lora_b,
+                   const float* s_eff, void* y, void* y_pre, float* h_out, void* workspace, size_t workspace_bytes,
+                   int T, int K, int N, int r, int n_samples, int b_prime, int num_slices, float scaling, int act,
+                   ffm_stream_t stream);
+
+/*
+ * Backward of the same module (autograd of trainers/GLP_OT_SVLoRA.py:450-482; W and bias frozen :375-376).
+ *
+ *   dy' = gelu_pre ? dy  (then dx is multiplied by QuickGELU'(gelu_pre), see below) : dy
+ *   dzu = dy · B^T                         dz = scaling·dzu       dh = dz ⊙ s_eff[sample]
+ *   dx  = dy · W + dh · A^T               (bf16 [T,K]); if gelu_pre != NULL (bf16 [T,K], the
+ *         pre-activation of the *preceding* QuickGELU) dx is multiplied element-wise by QuickGELU'(gelu_pre)
+ *   d_lora_a [K,r] = x^T · dh             d_lora_b [r,N] = scaling · (h ⊙ s_eff[sample])^T · dy
+ *   d_s_eff [n_samples,r] = scaling · sum_{t in sample} dzu ⊙ h
+ *
+ *   w_t is W transposed, [K,N] bf16 (the frozen weight is transposed once at module construction).
+ *   h is the f32 [T,16] side output of ffm_svlora_fwd.
+ */
+int ffm_svlora_bwd(const void* dy, const void* x, const void* w_t, const float* lora_a, const float* lora_b,
+                   const float* s_eff, const float* h, const void* gelu_pre, void* dx, float* d_lora_a,
+                   float* d_lora_b, float* d_s_eff, void* workspace, size_t workspace_bytes, int T, int K, int N,
+                   int r, int n_samples, int b_prime, int num_slices, float scaling, ffm_stream_t stream);
+
+/*
+ * Group mixing of singular values — trainers/GLP_OT_SVLoRA.py:453-467.
+ *   attr != NULL: pi[b,g] = lambda (0.7 in the reference) if attr[b]==g else (1-lambda)/(G-1)
+ *   attr == NULL: n_samples must be 1 and pi = 1/G
+ *   s_eff[b,:] = sum_g pi[b,g] S[g,:] (+ S_global when not NULL)
+ * attr is int64 [n_samples] ON THE DEVICE (the host mirror copies the reference's CPU tensor once per step).
+ */
+int ffm_seff(const long long* attr, const float* S, const float* S_global, float* s_eff, int n_samples, int G, int r,
+             float lambda, ffm_stream_t stream);
+
+/* Transpose of ffm_seff: dS[g,:] = sum_b pi[b,g] ds_eff[b,:]; dS_global = sum_b ds_eff[b,:] (optional). */
+int ffm_ds(const long long* attr, const float* ds_eff, float* dS, float* dS_global, int n_samples, int G, int r,
+           float lambda, ffm_stream_t stream);
+
+/* ------------------------------------------------------ GLP_OT head -------------------------- */
+#define FFM_OT_NONE 0
+#define FFM_OT_SINKHORN 1
+#define FFM_OT_COT 2
+
+size_t ffm_ot_head_workspace_bytes(int M, int Bp, int D, int n_prompts, int n_cls);
+
+/*
+ * Forward of the GLP_OT head — trainers/GLP_OT_SVLoRA.py:713-757 with Sinkhorn :615-634 and
+ * entropic_COT_fast :636-675.
+ *
+ *   img  [M+1, Bp, D] bf16 or f32 (row 0 = pooled token, skipped like :696-697), txt [n_prompts, n_cls, D] f32
+ *   sim[b*n_cls+c, m, n] = <img_n[m+1,b,:], txt_n[n,c,:]>      (both L2-normalised, F.normalize eps 1e-12)
+ *   K = exp(-(1-sim)/eps);  T = Sinkhorn(K, 1/M, 1/n_prompts) | COT(...) | 1
+ *   sim_op[b*n_cls+c] = sum(T*sim) (mean for OT=None);  logits[b,c] = exp(logit_scale) * mean_slices(sim_op)
+ *
+ *   Outputs: logits [Bp/num_slices, n_cls] f32; T_out [Bp*n_cls, M, n_prompts] f32 (may be NULL when mode = NONE);
+ *   status_out int32[2] = {iterations run, 1 if T contains NaN (reference returns None :738-743)}.
+ *   img_is_bf16 selects the storage type of img.
+ */
+int ffm_ot_head_fwd(const void* img, int img_is_bf16, const float* txt, const float* logit_scale, float* logits,
+                    float* T_out, float* sim_out, float* inv_norm_out, int32_t* status_out, void* workspace,
+                    size_t workspace_bytes, int M, int Bp, int D, int n_prompts, int n_cls, int num_slices, int mode,
+                    float eps, float thresh, int max_iter, float top_percent, ffm_stream_t stream);
+
+/*
+ * Backward of the head. The transport plan is a constant (computed under no_grad, :734), so gradients flow
+ * through sim only:  d_sim = T * d_sim_op (or 1/(M*n_prompts) for OT=None), then through both normalisations.
+ *   d_img [M+1, Bp, D] (same storage type as img; row 0 receives zeros), d_txt [n_prompts, n_cls, D] f32,
+ *   d_logit_scale f32[1].
+ */
+int ffm_ot_head_bwd(const void* img, int img_is_bf16, const float* txt, const float* logit_scale,
+                    const float* d_logits, const float* T_plan, const float* sim, const float* inv_norm, void* d_img,
+                    float* d_txt, float* d_logit_scale, void* workspace, size_t workspace_bytes, int M, int Bp, int D,
+                    int n_prompts, int n_cls, int num_slices, int mode, ffm_stream_t stream);
+
+/*
+ * Stand-alone Sinkhorn / COT on a pre-built kernel matrix K [P, M, N] f32 (u = 1/M, v = v_mass/N rows):
+ * the persistent kernel used by the head, exposed for parity tests and the bandwidth stress shape.
+ * status_out as above.
+ */
+size_t ffm_sinkhorn_workspace_bytes(int P, int M, int N);
+int ffm_sinkhorn(const float* Kmat, float* T_out, int32_t* status_out, void* workspace, size_t workspace_bytes, int P,
+                 int M, int N, int mode, float v_mass, float thresh, int max_iter, ffm_stream_t stream);
+
+/* ------------------------------------------------- federated aggregation --------------------- */
+/*
+ * Server aggregation — utils/fed_utils.py:42-100 (average_weights_EMA) and :6-40 (average_weights).
+ * Clients are sharded one per rank; each rank scales its flat f32 parameter buffer locally, the host mirror
+ * all-reduces (NCCL sum) the result, and the epilogue applies shared-half-S and the EMA with the previous global.
+ *
+ *   seg_kind[i] / seg_off[i] / seg_len[i] describe contiguous segments of the flat buffer:
+ *     kind 0: ordinary tensor, weight = w_scalar (= n_k / sum n_k, 0 for unselected clients)
+ *     kind 1: lora_S tensor [G, r] with shape[0]==G: row g weighted by w_group[g] (= n_{k,g} / sum_k n_{k,g})
+ */
+int ffm_fedavg_scale(const float* flat_in, float* flat_out, const int32_t* seg_kind, const int64_t* seg_off,
+                     const int64_t* seg_len, int n_seg, int64_t n_elem, float w_scalar, const float* w_group, int G,
+                     int r, ffm_stream_t stream);
+
+/*
+ * out = (1-beta_decay) * shared_half(avg) + beta_decay * prev_global; shared_half replaces the first r/2
+ * columns of every kind-1 segment by their mean over the G rows (utils/fed_utils.py:90-98) when enabled.
+ */
+int ffm_fedavg_epilogue(const float* avg, const float* prev_global, float* out, const int32_t* seg_kind,
+                        const int64_t* seg_off, const int64_t* seg_len, int n_seg, int64_t n_elem, float beta_decay,
+                        int shared_half_s, int G, int r, ffm_stream_t stream);
+
+/* --------------------------------------------------- fairness metrics ------------------------ */
+/*
+ * Group-wise rank statistics — evaluation/metrics.py:340-356 (compute_auc), :513-547 (equity_scaled_AUC),
+ * :486-511 (equity_scaled_accuracy), :248-292 (DPD / EOD / AOD inputs).
+ *
+ *   prob [N, 2] f32 (softmax), label int32 [N] in {0,1}, attrs int32 [n_attr, N] (-1 = unknown).
+ *   For every attribute a and group id g in [-1, max_groups) plus the "overall" slot, computes per probability
+ *   column c in {0,1} the tie-aware Mann–Whitney counts of the one-vs-rest problem (positives = label==c):
+ *       gt[c]  = #{(i,j): label_i==c, label_j!=c, prob[i,c] >  prob[j,c]}
+ *       eq[c]  = #{(i,j): label_i==c, label_j!=c, prob[i,c] == prob[j,c]}
+ *   (AUC_c = (gt + eq/2)/(P*Nn), exactly sklearn's roc_auc_score on stored f32 values) and the confusion
+ *   counts of pred = argmax(prob): tp, fp, tn, fn.
+ *
+ *   counts_out: uint64 [n_slots, 8] = {gt0, eq0, gt1, eq1, tp, fp, tn, fn}, n_slots = 1 + n_attr*(max_groups+1);
+ *   slot 0 = overall, slot 1 + a*(max_groups+1) + (g+1) = (attribute a, group g).
+ */
+size_t ffm_group_auc_workspace_bytes(int N, int n_attr, int max_groups);
+int ffm_group_auc(const float* prob, const int32_t* label, const int32_t* attrs, uint64_t* counts_out,
+                  void* workspace, size_t workspace_bytes, int N, int n_attr, int max_groups, ffm_stream_t stream);
+
+/* ------------------------------------------------------ training utils ----------------------- */
+/*
+ * Fused SGD over a flat f32 parameter buffer (torch.optim.SGD semantics, momentum/weight decay/no nesterov),
+ * applied `n_steps` times with the SAME gradient: the reference registers one optimizer under two model names,
+ * so optimizer.step() runs twice per iteration (trainers/GLP_OT_SVLoRA.py:864-871,
+ * Dassl/dassl/engine/trainer.py:333-342).  first_step != 0 initialises the momentum buffer with the gradient.
+ */
+int ffm_sgd_step(float* param, const float* grad, float* momentum_buf, int64_t n, float lr, float momentum,
+                 float weight_decay, int n_steps, int first_step, ffm_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+
+#endif /* FFM_B200_H_ */
