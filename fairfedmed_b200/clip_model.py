@@ -1,0 +1,308 @@
+"""CLIP ViT image encoder, text encoder, prompt learner and CustomCLIP with the reference's module interfaces.
+
+Class names, attribute names, call signatures (`MLP.forward(x, attr)`, `ResidualAttentionBlock.forward(x, attr)`,
+`ModifiedVisionTransformer.forward(x, attr)` returning ALL tokens sequence-first, `CustomCLIP.forward(image, attr)`)
+and state-dict keys follow clip/model.py:304-449 and trainers/GLP_OT_SVLoRA.py:46-200,575-763 of the reference, so
+checkpoints and the federated key conventions carry over.  What differs is how it runs:
+
+  * the adapted MLP (c_fc -> QuickGELU -> c_proj) is two fused tcgen05 kernels forward and two backward
+    (ops.svlora_mlp), QuickGELU and its derivative living in the GEMM epilogues;
+  * the GLP_OT head (normalise, similarities, Sinkhorn / COT, logits) is the fused head op (ops.ot_head);
+  * frozen weights are consumed from cached bf16 copies (fp32 masters stay in the state dict); activations are
+    bf16, sequence-first [L, B', C] like the reference so the row -> sample mapping of the adapters holds.
+Frozen attention / LayerNorm / patch embedding use PyTorch library kernels (bf16 cuBLAS, SDPA) — they are the
+"next" row of the scope table, not the hot path built here.
+"""
+from __future__ import annotations
+
+import math
+from typing import Optional, Sequence
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from . import ops
+from .modules import FairLoRALinear, LoRALinear, SVLoRALinear, _AdapterBase, _attr_on
+
+PIXEL_MEAN = (0.48145466, 0.4578275, 0.40821073)
+PIXEL_STD = (0.26862954, 0.26130258, 0.27577711)
+
+
+class _Bf16Cache:
+    """bf16 compute copies of frozen fp32 parameters, refreshed when the master changes (load_state_dict, .to())."""
+
+    def _bf(self, name: str, tensor: Optional[torch.Tensor], dtype=torch.bfloat16):
+        if tensor is None:
+            return None
+        store = self.__dict__.setdefault("_bf_store", {})
+        key = (tensor.data_ptr(), tensor._version, tensor.device, dtype)
+        hit = store.get(name)
+        if hit is None or hit[0] != key:
+            store[name] = (key, tensor.detach().to(dtype).contiguous())
+            hit = store[name]
+        return hit[1]
+
+
+class LayerNorm(nn.LayerNorm, _Bf16Cache):
+    """fp32 statistics on bf16 activations (clip/model.py:304-310 computes in fp32 and casts back)."""
+
+    def forward(self, x: torch.Tensor):
+        if x.dtype == torch.float32:
+            return super().forward(x)
+        return F.layer_norm(x, self.normalized_shape, self._bf("w", self.weight, x.dtype),
+                            self._bf("b", self.bias, x.dtype), self.eps)
+
+
+class QuickGELU(nn.Module):
+    def forward(self, x: torch.Tensor):
+        return x * torch.sigmoid(1.702 * x)
+
+
+class MLP(nn.Module, _Bf16Cache):
+    def __init__(self, d_model: int):
+        super().__init__()
+        self.c_fc = nn.Linear(d_model, d_model * 4)
+        self.gelu = QuickGELU()
+        self.c_proj = nn.Linear(d_model * 4, d_model)
+
+    def _adapter_operands(self, layer: _AdapterBase, attr, device):
+        w, w_t, bias = layer._operands()
+        if isinstance(layer, FairLoRALinear):
+            s_eff = layer._s_eff(attr, device)
+        elif isinstance(layer, SVLoRALinear):
+            s_eff = layer.lora_S.weight.reshape(1, -1)
+            if layer.global_s:
+                s_eff = s_eff + layer.lora_S_global.weight.reshape(1, -1)
+            s_eff = s_eff.contiguous()
+        else:
+            s_eff = torch.ones((1, layer.rank), device=device, dtype=torch.float32)
+        return (w, w_t, bias, layer.lora_A.weight, layer.lora_B.weight, s_eff)
+
+    def forward(self, x: torch.Tensor, attr: Optional[torch.Tensor] = None):
+        fused = isinstance(self.c_fc, _AdapterBase) and isinstance(self.c_proj, _AdapterBase) and x.is_cuda \
+            and x.dim() == 3 and self.c_fc.scaling == self.c_proj.scaling
+        if fused:
+            L, bp, c = x.shape
+            fc = self._adapter_operands(self.c_fc, attr, x.device)
+            pj = self._adapter_operands(self.c_proj, attr, x.device)
+            n_samples = fc[5].shape[0]
+            x2d = x.reshape(L * bp, c)
+            if x2d.dtype != torch.bfloat16:
+                x2d = x2d.to(torch.bfloat16)
+            y = ops.svlora_mlp(x2d.contiguous(), fc, pj, self.c_fc.scaling, bp, bp // n_samples)
+            return y.reshape(L, bp, -1).to(x.dtype)
+        if isinstance(self.c_fc, _AdapterBase):
+            return self.c_proj(self.gelu(self.c_fc(x, attr)), attr)
+        # un-adapted (text tower): plain frozen linears on bf16 copies
+        h = F.linear(x, self._bf("fc_w", self.c_fc.weight, x.dtype), self._bf("fc_b", self.c_fc.bias, x.dtype))
+        h = self.gelu(h)
+        return F.linear(h, self._bf("pj_w", self.c_proj.weight, x.dtype), self._bf("pj_b", self.c_proj.bias, x.dtype))
+
+
+class ResidualAttentionBlock(nn.Module, _Bf16Cache):
+    def __init__(self, d_model: int, n_head: int, attn_mask: Optional[torch.Tensor] = None):
+        super().__init__()
+        self.attn = nn.MultiheadAttention(d_model, n_head)   # parameter container (same state-dict keys)
+        self.ln_1 = LayerNorm(d_model)
+        self.mlp = MLP(d_model)
+        self.ln_2 = LayerNorm(d_model)
+        self.attn_mask = attn_mask
+        self.n_head = n_head
+
+    def attention(self, x: torch.Tensor):
+        """Self-attention, sequence-first in/out (nn.MultiheadAttention semantics, clip/model.py:350-352)."""
+        L, bn, c = x.shape
+        hd = c // self.n_head
+        a = self.attn
+        qkv = F.linear(x, self._bf("in_w", a.in_proj_weight, x.dtype), self._bf("in_b", a.in_proj_bias, x.dtype))
+        qkv = qkv.view(L, bn, 3, self.n_head, hd).permute(2, 1, 3, 0, 4)          # [3, B, H, L, hd]
+        causal = self.attn_mask is not None
+        out = F.scaled_dot_product_attention(qkv[0], qkv[1], qkv[2], is_causal=causal)   # [B, H, L, hd]
+        out = out.permute(2, 0, 1, 3).reshape(L, bn, c)
+        return F.linear(out, self._bf("out_w", a.out_proj.weight, x.dtype), self._bf("out_b", a.out_proj.bias, x.dtype))
+
+    def forward(self, x: torch.Tensor, attr: Optional[torch.Tensor] = None):
+        x = x + self.attention(self.ln_1(x))
+        x = x + self.mlp(self.ln_2(x), attr=attr)
+        return x
+
+
+class Transformer(nn.Module):
+    def __init__(self, width: int, layers: int, heads: int, attn_mask: Optional[torch.Tensor] = None,
+                 text_layer=False, design_details=None):
+        super().__init__()
+        self.width, self.layers = width, layers
+        self.resblocks = nn.ModuleList([ResidualAttentionBlock(width, heads, attn_mask) for _ in range(layers)])
+
+    def forward(self, x: torch.Tensor, attr=None):
+        for block in self.resblocks:
+            x = block(x, attr)
+        return x
+
+
+class ModifiedVisionTransformer(nn.Module, _Bf16Cache):
+    """Returns all 197 tokens, sequence-first [L, B', output_dim] (clip/model.py:413-449)."""
+
+    def __init__(self, input_resolution: int, patch_size: int, width: int, layers: int, heads: int, output_dim: int,
+                 design_details=None):
+        super().__init__()
+        self.input_resolution, self.output_dim, self.patch_size = input_resolution, output_dim, patch_size
+        self.conv1 = nn.Conv2d(3, width, kernel_size=patch_size, stride=patch_size, bias=False)
+        scale = width ** -0.5
+        self.class_embedding = nn.Parameter(scale * torch.randn(width))
+        self.positional_embedding = nn.Parameter(scale * torch.randn((input_resolution // patch_size) ** 2 + 1, width))
+        self.ln_pre = LayerNorm(width)
+        self.transformer = Transformer(width, layers, heads, design_details=design_details)
+        self.ln_post = LayerNorm(width)
+        self.proj = nn.Parameter(scale * torch.randn(width, output_dim))
+
+    def forward(self, x: torch.Tensor, attr: Optional[torch.Tensor] = None):
+        dt = x.dtype
+        x = F.conv2d(x, self._bf("conv1", self.conv1.weight, dt), stride=self.patch_size)      # [B', width, g, g]
+        x = x.flatten(2).permute(2, 0, 1)                                                      # [g*g, B', width]
+        cls = self._bf("cls", self.class_embedding, dt).expand(1, x.shape[1], -1)
+        x = torch.cat([cls, x], dim=0) + self._bf("pos", self.positional_embedding, dt).unsqueeze(1)
+        x = self.ln_pre(x)
+        x = self.transformer(x, attr=attr)
+        x = self.ln_post(x)
+        return x @ self._bf("proj", self.proj, dt)                                             # [L, B', output_dim]
+
+
+class TextEncoder(nn.Module, _Bf16Cache):
+    """trainers/GLP_OT_SVLoRA.py:46-66."""
+
+    def __init__(self, width=512, layers=12, heads=8, context_length=77, embed_dim=512):
+        super().__init__()
+        mask = torch.full((context_length, context_length), float("-inf")).triu_(1)
+        self.transformer = Transformer(width, layers, heads, attn_mask=mask)
+        self.positional_embedding = nn.Parameter(torch.empty(context_length, width))
+        self.ln_final = LayerNorm(width)
+        self.text_projection = nn.Parameter(torch.empty(width, embed_dim))
+        self.compute_dtype = torch.bfloat16
+
+    def forward(self, prompts: torch.Tensor, eot_index: torch.Tensor):
+        dt = self.compute_dtype if prompts.is_cuda else prompts.dtype
+        x = prompts.to(dt) + self._bf("pos", self.positional_embedding, dt)
+        x = self.transformer(x.permute(1, 0, 2)).permute(1, 0, 2)
+        x = self.ln_final(x)
+        x = x[torch.arange(x.shape[0], device=x.device), eot_index]
+        return x.float() @ self.text_projection
+
+
+class PromptLearner(nn.Module):
+    """Generic learnable context, class token at the end (trainers/GLP_OT_SVLoRA.py:68-152).
+
+    The tokenizer / token-embedding lookup that produces `token_prefix` / `token_suffix` and the EOT positions is
+    host-side glue outside the hot path: pass them in (from the reference's PromptLearner — see INTEGRATION.md — or
+    `synthetic_prompt_buffers` for offline runs with random-init weights)."""
+
+    def __init__(self, n_prompts: int, n_ctx: int, ctx_dim: int, n_cls: int, token_prefix: torch.Tensor,
+                 token_suffix: torch.Tensor, eot_index: torch.Tensor):
+        super().__init__()
+        ctx = torch.empty(n_prompts, n_ctx, ctx_dim)
+        nn.init.normal_(ctx, std=0.02)
+        self.ctx = nn.Parameter(ctx)
+        self.register_buffer("token_prefix", token_prefix.clone())      # [N*n_cls, 1, D]
+        self.register_buffer("token_suffix", token_suffix.clone())      # [N*n_cls, 77-1-n_ctx, D]
+        self.register_buffer("eot_index", eot_index.clone().long(), persistent=False)
+        self.N, self.n_cls, self.n_ctx = n_prompts, n_cls, n_ctx
+
+    def forward(self):
+        ctx = self.ctx.unsqueeze(0).expand(self.n_cls, -1, -1, -1).permute(1, 0, 2, 3)
+        ctx = ctx.reshape(self.N * self.n_cls, self.n_ctx, -1)
+        return torch.cat([self.token_prefix, ctx.to(self.token_prefix.dtype), self.token_suffix], dim=1)
+
+
+def synthetic_prompt_buffers(n_prompts: int, n_cls: int, n_ctx: int, ctx_dim: int, context_length: int = 77,
+                             name_lens: Sequence[int] = (3, 2), seed: int = 1):
+    """Random stand-ins for the frozen token embeddings of "X X X X <classname>." (std 0.02 like
+    CLIP.initialize_parameters) and the matching EOT positions: SOS + n_ctx + name tokens + '.' then EOT."""
+    g = torch.Generator().manual_seed(seed)
+    n = n_prompts * n_cls
+    prefix = 0.02 * torch.randn(n_cls, 1, ctx_dim, generator=g)
+    suffix = 0.02 * torch.randn(n_cls, context_length - 1 - n_ctx, ctx_dim, generator=g)
+    eot = torch.tensor([1 + n_ctx + name_lens[c % len(name_lens)] + 1 for c in range(n_cls)])
+    return prefix.repeat(n_prompts, 1, 1), suffix.repeat(n_prompts, 1, 1), eot.repeat(n_prompts)[:n]
+
+
+class CustomCLIP(nn.Module):
+    """FairLoRA model: image encoder (adapted), text encoder, prompt learner and the GLP_OT head (:575-763)."""
+
+    def __init__(self, *, classnames: Sequence[str] = ("NOT Glaucoma", "Glaucoma"), n_prompts: int = 2, n_ctx: int = 4,
+                 ot: str = "None", eps: float = 0.1, thresh: float = 1e-3, max_iter: int = 100,
+                 top_percent: float = 0.8, image_resolution: int = 224, vision_layers: int = 12,
+                 vision_width: int = 768, vision_patch_size: int = 16, embed_dim: int = 512, text_width: int = 512,
+                 text_layers: int = 12, text_heads: int = 8, context_length: int = 77,
+                 dim_per_3d_slice: Optional[int] = None, prompt_buffers=None, dataset: str = "FairFedMed",
+                 seed: int = 1):
+        super().__init__()
+        self.n_cls = len(classnames)
+        self.N = n_prompts
+        self.OT, self.eps, self.thresh, self.max_iter, self.top_percent = ot, eps, thresh, max_iter, top_percent
+        self.dataset = dataset
+        self.is_3d_input = dim_per_3d_slice is not None
+        self.dim_per_3d_slice = dim_per_3d_slice
+        if self.is_3d_input:
+            self.proj_per_3d_slice = nn.Conv2d(dim_per_3d_slice, 3, kernel_size=5, padding=2)
+            nn.init.normal_(self.proj_per_3d_slice.weight, std=dim_per_3d_slice ** -0.5)
+            nn.init.zeros_(self.proj_per_3d_slice.bias)
+        if prompt_buffers is None:
+            prompt_buffers = synthetic_prompt_buffers(n_prompts, self.n_cls, n_ctx, text_width, context_length,
+                                                      seed=seed)
+        self.prompt_learner = PromptLearner(n_prompts, n_ctx, text_width, self.n_cls, *prompt_buffers)
+        self.image_encoder = ModifiedVisionTransformer(image_resolution, vision_patch_size, vision_width,
+                                                       vision_layers, vision_width // 64, embed_dim)
+        self.text_encoder = TextEncoder(text_width, text_layers, text_heads, context_length, embed_dim)
+        self.logit_scale = nn.Parameter(torch.ones([]) * math.log(1 / 0.07))
+        self.compute_dtype = torch.bfloat16
+        self.register_buffer("pixel_mean", torch.tensor(PIXEL_MEAN).reshape(1, -1, 1, 1), persistent=False)
+        self.register_buffer("pixel_std", torch.tensor(PIXEL_STD).reshape(1, -1, 1, 1), persistent=False)
+        self.last_status = None
+        self.initialize_parameters()
+
+    def initialize_parameters(self):
+        """Random init in the spirit of CLIP.initialize_parameters (clip/model.py:533-560); no checkpoints offline."""
+        te, ve = self.text_encoder, self.image_encoder
+        nn.init.normal_(te.positional_embedding, std=0.01)
+        for tower in (te.transformer, ve.transformer):
+            proj_std = (tower.width ** -0.5) * ((2 * tower.layers) ** -0.5)
+            attn_std = tower.width ** -0.5
+            fc_std = (2 * tower.width) ** -0.5
+            for block in tower.resblocks:
+                nn.init.normal_(block.attn.in_proj_weight, std=attn_std)
+                nn.init.normal_(block.attn.out_proj.weight, std=proj_std)
+                nn.init.normal_(block.mlp.c_fc.weight, std=fc_std)
+                nn.init.normal_(block.mlp.c_proj.weight, std=proj_std)
+        nn.init.normal_(te.text_projection, std=te.transformer.width ** -0.5)
+
+    def preprocess(self, image: torch.Tensor):
+        """/255, OCT slice projection + per-item min-max, mean/std normalisation (:679-693)."""
+        b, c, h, w = image.shape
+        image = image / 255.0
+        if self.is_3d_input:
+            image = image.reshape(-1, self.dim_per_3d_slice, h, w)
+            image = self.proj_per_3d_slice(image)
+            lo = image.amin(dim=(1, 2, 3), keepdim=True)
+            hi = image.amax(dim=(1, 2, 3), keepdim=True)
+            image = (image - lo) / (hi - lo + 1e-5)
+        return (image - self.pixel_mean) / self.pixel_std
+
+    def forward(self, image: torch.Tensor, attr: Optional[torch.Tensor] = None):
+        b = image.shape[0]
+        x = self.preprocess(image.float())
+        dt = self.compute_dtype if x.is_cuda else x.dtype
+        attr_dev = _attr_on(x.device, attr)
+        feats = self.image_encoder(x.to(dt), attr=attr_dev)                        # [M+1, B', D]
+        prompts = self.prompt_learner()
+        txt = self.text_encoder(prompts, self.prompt_learner.eot_index)           # [N*n_cls, D] fp32
+        num_slices = feats.shape[1] // b
+        logits, status, _ = ops.ot_head(feats, txt, self.logit_scale, n_cls=self.n_cls, num_slices=num_slices,
+                                        ot=self.OT, eps=self.eps, thresh=self.thresh, max_iter=self.max_iter,
+                                        top_percent=self.top_percent)
+        self.last_status = status
+        if self.OT != "None" and self.check_nan and int(status[1].item()) != 0:
+            return None                                                            # reference :738-743
+        return logits
+
+    check_nan = True

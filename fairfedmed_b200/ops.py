@@ -1,0 +1,354 @@
+"""torch custom ops over the C ABI (libffm_b200.so) + their autograd wiring.
+
+Every op passes raw device pointers, sizes and the current CUDA stream to the shared library through ctypes
+(`_cabi`).  PyTorch only provides memory, streams and autograd bookkeeping here; there is no eager fallback:
+a CPU tensor or a missing library raises.
+"""
+from __future__ import annotations
+
+from typing import Optional, Tuple
+
+import torch
+from torch import Tensor
+
+from . import _cabi
+
+RP = 16  # padded adapter rank of the fused GEMM (ffm_svlora_max_rank)
+
+OT_MODES = {"None": 0, "Sinkhorn": 1, "COT": 2}
+
+
+def _ptr(t: Optional[Tensor]) -> int:
+    return 0 if t is None else t.data_ptr()
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _need_cuda(*tensors):
+    for t in tensors:
+        if t is not None and not t.is_cuda:
+            raise _cabi.FfmError("fairfedmed_b200 ops run on CUDA tensors only (no CPU fallback)")
+
+
+# =====================================================================================================
+# raw ops
+# =====================================================================================================
+@torch.library.custom_op("ffm::svlora_fwd", mutates_args=())
+def svlora_fwd(x: Tensor, w: Tensor, bias: Optional[Tensor], lora_a: Tensor, lora_b: Tensor, s_eff: Tensor,
+               scaling: float, b_prime: int, num_slices: int, act: int) -> Tuple[Tensor, Tensor, Tensor]:
+    """y, y_pre, h = fused FairLoRA linear.  x [T,K] bf16, w [N,K] bf16, lora_a [K,r], lora_b [r,N], s_eff [nS,r]."""
+    _need_cuda(x, w, lora_a, lora_b, s_eff)
+    T, K = x.shape
+    N = w.shape[0]
+    r = lora_a.shape[1]
+    nS = s_eff.shape[0]
+    y = torch.empty((T, N), device=x.device, dtype=torch.bfloat16)
+    y_pre = torch.empty((T, N), device=x.device, dtype=torch.bfloat16) if act else y.new_empty((0,))
+    h = torch.empty((T, RP), device=x.device, dtype=torch.float32)
+    lib = _cabi.load()
+    ws_bytes = lib.ffm_svlora_fwd_workspace_bytes(T, K, N, nS)
+    ws = torch.empty((ws_bytes,), device=x.device, dtype=torch.uint8)
+    _cabi.call("ffm_svlora_fwd", _ptr(x), _ptr(w), _ptr(bias), _ptr(lora_a), _ptr(lora_b), _ptr(s_eff), _ptr(y),
+               _ptr(y_pre) if act else 0, _ptr(h), _ptr(ws), ws_bytes, T, K, N, r, nS, b_prime, num_slices,
+               float(scaling), int(act), _stream())
+    return y, y_pre, h
+
+
+@svlora_fwd.register_fake
+def _(x, w, bias, lora_a, lora_b, s_eff, scaling, b_prime, num_slices, act):
+    T, N = x.shape[0], w.shape[0]
+    y = x.new_empty((T, N))
+    return y, (x.new_empty((T, N)) if act else x.new_empty((0,))), x.new_empty((T, RP), dtype=torch.float32)
+
+
+@torch.library.custom_op("ffm::svlora_bwd", mutates_args=())
+def svlora_bwd(dy: Tensor, x: Tensor, w_t: Tensor, lora_a: Tensor, lora_b: Tensor, s_eff: Tensor, h: Tensor,
+               gelu_pre: Optional[Tensor], scaling: float, b_prime: int,
+               num_slices: int) -> Tuple[Tensor, Tensor, Tensor, Tensor]:
+    """dx, d_lora_a, d_lora_b, d_s_eff.  dy [T,N] bf16, x [T,K] bf16, w_t [K,N] bf16 (transposed frozen weight)."""
+    _need_cuda(dy, x, w_t)
+    T, N = dy.shape
+    K = x.shape[1]
+    r = lora_a.shape[1]
+    nS = s_eff.shape[0]
+    dx = torch.empty((T, K), device=x.device, dtype=torch.bfloat16)
+    dA = torch.empty((K, r), device=x.device, dtype=torch.float32)
+    dB = torch.empty((r, N), device=x.device, dtype=torch.float32)
+    dse = torch.empty((nS, r), device=x.device, dtype=torch.float32)
+    lib = _cabi.load()
+    ws_bytes = lib.ffm_svlora_bwd_workspace_bytes(T, K, N, nS)
+    ws = torch.empty((ws_bytes,), device=x.device, dtype=torch.uint8)
+    _cabi.call("ffm_svlora_bwd", _ptr(dy), _ptr(x), _ptr(w_t), _ptr(lora_a), _ptr(lora_b), _ptr(s_eff), _ptr(h),
+               _ptr(gelu_pre), _ptr(dx), _ptr(dA), _ptr(dB), _ptr(dse), _ptr(ws), ws_bytes, T, K, N, r, nS, b_prime,
+               num_slices, float(scaling), _stream())
+    return dx, dA, dB, dse
+
+
+@svlora_bwd.register_fake
+def _(dy, x, w_t, lora_a, lora_b, s_eff, h, gelu_pre, scaling, b_prime, num_slices):
+    return (x.new_empty(x.shape), lora_a.new_empty(lora_a.shape), lora_b.new_empty(lora_b.shape),
+            s_eff.new_empty(s_eff.shape))
+
+
+@torch.library.custom_op("ffm::seff", mutates_args=())
+def seff_op(attr: Optional[Tensor], S: Tensor, S_global: Optional[Tensor], lam: float) -> Tensor:
+    """s_eff [nS, r] = pi(attr) @ S (+ S_global);  attr int64 [nS] on the device or None (=> nS = 1, pi = 1/G)."""
+    _need_cuda(S, attr, S_global)
+    G, r = S.shape
+    nS = 1 if attr is None else attr.shape[0]
+    out = torch.empty((nS, r), device=S.device, dtype=torch.float32)
+    _cabi.call("ffm_seff", _ptr(attr), _ptr(S), _ptr(S_global), _ptr(out), nS, G, r, float(lam), _stream())
+    return out
+
+
+@seff_op.register_fake
+def _(attr, S, S_global, lam):
+    return S.new_empty((1 if attr is None else attr.shape[0], S.shape[1]))
+
+
+@torch.library.custom_op("ffm::ds", mutates_args=())
+def ds_op(attr: Optional[Tensor], ds_eff: Tensor, G: int, lam: float, want_global: bool) -> Tuple[Tensor, Tensor]:
+    nS, r = ds_eff.shape
+    dS = torch.empty((G, r), device=ds_eff.device, dtype=torch.float32)
+    dSg = torch.empty((r,), device=ds_eff.device, dtype=torch.float32) if want_global else dS.new_empty((0,))
+    _cabi.call("ffm_ds", _ptr(attr), _ptr(ds_eff), _ptr(dS), _ptr(dSg) if want_global else 0, nS, G, r, float(lam),
+               _stream())
+    return dS, dSg
+
+
+@ds_op.register_fake
+def _(attr, ds_eff, G, lam, want_global):
+    r = ds_eff.shape[1]
+    return ds_eff.new_empty((G, r)), ds_eff.new_empty((r,) if want_global else (0,))
+
+
+# =====================================================================================================
+# autograd wiring
+# =====================================================================================================
+class _SEff(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, attr, S, S_global, lam):
+        ctx.attr, ctx.lam, ctx.G = attr, lam, S.shape[0]
+        ctx.has_global = S_global is not None
+        ctx.sg_shape = None if S_global is None else S_global.shape
+        sg = None if S_global is None else S_global.reshape(-1).contiguous()
+        return seff_op(attr, S.contiguous(), sg, lam)
+
+    @staticmethod
+    def backward(ctx, ds_eff):
+        dS, dSg = ds_op(ctx.attr, ds_eff.contiguous(), ctx.G, ctx.lam, ctx.has_global)
+        return None, dS, (dSg.reshape(ctx.sg_shape) if ctx.has_global else None), None
+
+
+def effective_singular_values(attr: Optional[Tensor], S: Tensor, S_global: Optional[Tensor] = None,
+                              lam: float = 0.7) -> Tensor:
+    """Differentiable s_eff (trainers/GLP_OT_SVLoRA.py:453-467)."""
+    return _SEff.apply(attr, S, S_global, lam)
+
+
+class _SVLoRALinear(torch.autograd.Function):
+    """y = x W^T + b + scaling ((x A) ⊙ s_eff[sample]) B — one fused kernel each way."""
+
+    @staticmethod
+    def forward(ctx, x2d, w, w_t, bias, lora_a, lora_b, s_eff, scaling, b_prime, num_slices):
+        y, _, h = svlora_fwd(x2d, w, bias, lora_a, lora_b, s_eff, scaling, b_prime, num_slices, 0)
+        ctx.save_for_backward(x2d, w_t, lora_a, lora_b, s_eff, h)
+        ctx.cfg = (scaling, b_prime, num_slices)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x2d, w_t, lora_a, lora_b, s_eff, h = ctx.saved_tensors
+        scaling, b_prime, num_slices = ctx.cfg
+        dx, dA, dB, dse = svlora_bwd(dy.contiguous(), x2d, w_t, lora_a, lora_b, s_eff, h, None, scaling, b_prime,
+                                     num_slices)
+        return dx, None, None, None, dA, dB, dse, None, None, None
+
+
+def svlora_linear(x2d: Tensor, w: Tensor, w_t: Tensor, bias: Optional[Tensor], lora_a: Tensor, lora_b: Tensor,
+                  s_eff: Tensor, scaling: float, b_prime: int, num_slices: int) -> Tensor:
+    return _SVLoRALinear.apply(x2d, w, w_t, bias, lora_a, lora_b, s_eff, scaling, b_prime, num_slices)
+
+
+class _SVLoRAMLP(torch.autograd.Function):
+    """c_proj(QuickGELU(c_fc(x))) with both adapters (clip/model.py:325-332): QuickGELU is fused into the c_fc
+    epilogue (dual store of pre-activation and activation) and QuickGELU' into the c_proj backward epilogue."""
+
+    @staticmethod
+    def forward(ctx, x2d, w1, w1_t, b1, a1, bb1, s1, w2, w2_t, b2, a2, bb2, s2, scaling, b_prime, num_slices):
+        g, u, h1 = svlora_fwd(x2d, w1, b1, a1, bb1, s1, scaling, b_prime, num_slices, 1)
+        y, _, h2 = svlora_fwd(g, w2, b2, a2, bb2, s2, scaling, b_prime, num_slices, 0)
+        ctx.save_for_backward(x2d, g, u, h1, h2, w1_t, a1, bb1, s1, w2_t, a2, bb2, s2)
+        ctx.cfg = (scaling, b_prime, num_slices)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x2d, g, u, h1, h2, w1_t, a1, bb1, s1, w2_t, a2, bb2, s2 = ctx.saved_tensors
+        scaling, b_prime, num_slices = ctx.cfg
+        du, dA2, dB2, ds2 = svlora_bwd(dy.contiguous(), g, w2_t, a2, bb2, s2, h2, u, scaling, b_prime, num_slices)
+        dx, dA1, dB1, ds1 = svlora_bwd(du, x2d, w1_t, a1, bb1, s1, h1, None, scaling, b_prime, num_slices)
+        return dx, None, None, None, dA1, dB1, ds1, None, None, None, dA2, dB2, ds2, None, None, None
+
+
+def svlora_mlp(x2d, fc, proj, scaling: float, b_prime: int, num_slices: int) -> Tensor:
+    """fc / proj = (w, w_t, bias, lora_a, lora_b, s_eff) tuples."""
+    return _SVLoRAMLP.apply(x2d, *fc, *proj, scaling, b_prime, num_slices)
+
+
+# =====================================================================================================
+# GLP_OT head
+# =====================================================================================================
+@torch.library.custom_op("ffm::ot_head_fwd", mutates_args=())
+def ot_head_fwd(img: Tensor, txt: Tensor, logit_scale: Tensor, num_slices: int, mode: int, eps: float, thresh: float,
+                max_iter: int, top_percent: float) -> Tuple[Tensor, Tensor, Tensor, Tensor, Tensor, Tensor]:
+    """logits, T, sim, inv_norm, status, workspace.  img [M+1, Bp, D] (bf16/f32), txt [N, n_cls, D] f32."""
+    _need_cuda(img, txt, logit_scale)
+    Mp1, Bp, D = img.shape
+    M = Mp1 - 1
+    N, n_cls, _ = txt.shape
+    P = Bp * n_cls
+    dev = img.device
+    logits = torch.empty((Bp // num_slices, n_cls), device=dev, dtype=torch.float32)
+    T = torch.empty((P, M, N), device=dev, dtype=torch.float32) if mode else logits.new_empty((0,))
+    sim = torch.empty((P, M, N), device=dev, dtype=torch.float32)
+    inv_norm = torch.empty((M, Bp), device=dev, dtype=torch.float32)
+    status = torch.empty((2,), device=dev, dtype=torch.int32)
+    lib = _cabi.load()
+    ws_bytes = lib.ffm_ot_head_workspace_bytes(M, Bp, D, N, n_cls)
+    ws = torch.empty((ws_bytes,), device=dev, dtype=torch.uint8)
+    _cabi.call("ffm_ot_head_fwd", _ptr(img), int(img.dtype == torch.bfloat16), _ptr(txt), _ptr(logit_scale),
+               _ptr(logits), _ptr(T) if mode else 0, _ptr(sim), _ptr(inv_norm), _ptr(status), _ptr(ws), ws_bytes, M,
+               Bp, D, N, n_cls, num_slices, mode, float(eps), float(thresh), int(max_iter), float(top_percent),
+               _stream())
+    return logits, T, sim, inv_norm, status, ws
+
+
+@ot_head_fwd.register_fake
+def _(img, txt, logit_scale, num_slices, mode, eps, thresh, max_iter, top_percent):
+    Mp1, Bp, D = img.shape
+    N, n_cls, _ = txt.shape
+    f = dict(device=img.device, dtype=torch.float32)
+    P = Bp * n_cls
+    return (torch.empty((Bp // num_slices, n_cls), **f), torch.empty((P, Mp1 - 1, N) if mode else (0,), **f),
+            torch.empty((P, Mp1 - 1, N), **f), torch.empty((Mp1 - 1, Bp), **f),
+            torch.empty((2,), device=img.device, dtype=torch.int32),
+            torch.empty((1,), device=img.device, dtype=torch.uint8))
+
+
+@torch.library.custom_op("ffm::ot_head_bwd", mutates_args=())
+def ot_head_bwd(img: Tensor, txt: Tensor, logit_scale: Tensor, d_logits: Tensor, T: Tensor, sim: Tensor,
+                inv_norm: Tensor, ws: Tensor, num_slices: int, mode: int) -> Tuple[Tensor, Tensor, Tensor]:
+    Mp1, Bp, D = img.shape
+    N, n_cls, _ = txt.shape
+    d_img = torch.empty_like(img)
+    d_txt = torch.empty_like(txt)
+    d_ls = torch.empty((), device=img.device, dtype=torch.float32)
+    _cabi.call("ffm_ot_head_bwd", _ptr(img), int(img.dtype == torch.bfloat16), _ptr(txt), _ptr(logit_scale),
+               _ptr(d_logits), _ptr(T) if mode else 0, _ptr(sim), _ptr(inv_norm), _ptr(d_img), _ptr(d_txt), _ptr(d_ls),
+               _ptr(ws), ws.numel(), Mp1 - 1, Bp, D, N, n_cls, num_slices, mode, _stream())
+    return d_img, d_txt, d_ls
+
+
+@ot_head_bwd.register_fake
+def _(img, txt, logit_scale, d_logits, T, sim, inv_norm, ws, num_slices, mode):
+    return torch.empty_like(img), torch.empty_like(txt), logit_scale.new_empty(())
+
+
+class _OTHead(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, img, txt, logit_scale, num_slices, mode, eps, thresh, max_iter, top_percent):
+        logits, T, sim, inv_norm, status, ws = ot_head_fwd(img, txt, logit_scale, num_slices, mode, eps, thresh,
+                                                           max_iter, top_percent)
+        ctx.save_for_backward(img, txt, logit_scale, T, sim, inv_norm, ws)
+        ctx.cfg = (num_slices, mode)
+        ctx.mark_non_differentiable(status, T)
+        return logits, status, T
+
+    @staticmethod
+    def backward(ctx, d_logits, _d_status, _d_T):
+        img, txt, logit_scale, T, sim, inv_norm, ws = ctx.saved_tensors
+        num_slices, mode = ctx.cfg
+        d_img, d_txt, d_ls = ot_head_bwd(img, txt, logit_scale, d_logits.contiguous().float(), T, sim, inv_norm, ws,
+                                         num_slices, mode)
+        return d_img, d_txt, d_ls.reshape(logit_scale.shape), None, None, None, None, None, None
+
+
+def ot_head(image_features: Tensor, text_features: Tensor, logit_scale: Tensor, *, n_cls: int, num_slices: int = 1,
+            ot: str = "Sinkhorn", eps: float = 0.1, thresh: float = 1e-3, max_iter: int = 100,
+            top_percent: float = 0.8):
+    """Head of CustomCLIP.forward (trainers/GLP_OT_SVLoRA.py:696-757).
+
+    image_features [M+1, Bp, D] (bf16 or f32), text_features [N*n_cls, D] prompt-major. Returns
+    (logits [Bp/num_slices, n_cls] f32, status int32[2] = {iterations, nan flag}, T)."""
+    img = image_features.contiguous()
+    if img.dtype not in (torch.bfloat16, torch.float32):
+        img = img.float()
+    D = img.shape[-1]
+    txt = text_features.float().contiguous().view(-1, n_cls, D)
+    ls = logit_scale.float().reshape(1) if logit_scale.dim() == 0 else logit_scale.float()
+    return _OTHead.apply(img, txt, ls, num_slices, OT_MODES[ot], eps, thresh, max_iter, top_percent)
+
+
+def sinkhorn(K: Tensor, *, mode: str = "Sinkhorn", v_mass: float = 1.0, thresh: float = 1e-3, max_iter: int = 100):
+    """Stand-alone persistent Sinkhorn / COT on K [P, M, N] f32 with u = 1/M, v = v_mass/N. Returns (T, status)."""
+    _need_cuda(K)
+    K = K.float().contiguous()
+    P, M, N = K.shape
+    T = torch.empty_like(K)
+    status = torch.empty((2,), device=K.device, dtype=torch.int32)
+    lib = _cabi.load()
+    ws_bytes = lib.ffm_sinkhorn_workspace_bytes(P, M, N)
+    ws = torch.empty((ws_bytes,), device=K.device, dtype=torch.uint8)
+    _cabi.call("ffm_sinkhorn", _ptr(K), _ptr(T), _ptr(status), _ptr(ws), ws_bytes, P, M, N, OT_MODES[mode],
+               float(v_mass), float(thresh), int(max_iter), _stream())
+    return T, status
+
+
+# =====================================================================================================
+# flat-buffer utilities (aggregation / SGD) and metrics
+# =====================================================================================================
+def fedavg_scale(flat_in: Tensor, seg_kind: Tensor, seg_off: Tensor, seg_len: Tensor, w_scalar: float,
+                 w_group: Tensor, G: int, r: int, out: Optional[Tensor] = None) -> Tensor:
+    _need_cuda(flat_in, seg_kind, seg_off, seg_len, w_group)
+    out = torch.empty_like(flat_in) if out is None else out
+    _cabi.call("ffm_fedavg_scale", _ptr(flat_in), _ptr(out), _ptr(seg_kind), _ptr(seg_off), _ptr(seg_len),
+               seg_kind.numel(), flat_in.numel(), float(w_scalar), _ptr(w_group), G, r, _stream())
+    return out
+
+
+def fedavg_epilogue(avg: Tensor, prev_global: Tensor, seg_kind: Tensor, seg_off: Tensor, seg_len: Tensor,
+                    beta_decay: float, shared_half_s: bool, G: int, r: int) -> Tensor:
+    _need_cuda(avg, prev_global)
+    out = torch.empty_like(avg)
+    _cabi.call("ffm_fedavg_epilogue", _ptr(avg), _ptr(prev_global), _ptr(out), _ptr(seg_kind), _ptr(seg_off),
+               _ptr(seg_len), seg_kind.numel(), avg.numel(), float(beta_decay), int(bool(shared_half_s)), G, r,
+               _stream())
+    return out
+
+
+def sgd_step_(param: Tensor, grad: Tensor, momentum_buf: Tensor, lr: float, momentum: float, weight_decay: float,
+              n_steps: int, first_step: bool) -> None:
+    _need_cuda(param, grad, momentum_buf)
+    _cabi.call("ffm_sgd_step", _ptr(param), _ptr(grad), _ptr(momentum_buf), param.numel(), float(lr), float(momentum),
+               float(weight_decay), int(n_steps), int(bool(first_step)), _stream())
+
+
+def group_auc_counts(prob: Tensor, label: Tensor, attrs: Optional[Tensor], max_groups: int) -> Tensor:
+    """uint64-as-int64 counts [n_slots, 8] = {gt0, eq0, gt1, eq1, tp, fp, tn, fn}; see include/ffm_b200.h."""
+    _need_cuda(prob, label, attrs)
+    prob = prob.float().contiguous()
+    label = label.to(torch.int32).contiguous()
+    N = prob.shape[0]
+    n_attr = 0 if attrs is None else attrs.shape[0]
+    attrs_i = None if attrs is None else attrs.to(torch.int32).contiguous()
+    n_slots = 1 + n_attr * (max_groups + 1)
+    counts = torch.empty((n_slots, 8), device=prob.device, dtype=torch.int64)
+    lib = _cabi.load()
+    ws_bytes = lib.ffm_group_auc_workspace_bytes(N, n_attr, max_groups)
+    ws = torch.empty((ws_bytes,), device=prob.device, dtype=torch.uint8)
+    _cabi.call("ffm_group_auc", _ptr(prob), _ptr(label), _ptr(attrs_i), _ptr(counts), _ptr(ws), ws_bytes, N, n_attr,
+               max_groups, _stream())
+    return counts

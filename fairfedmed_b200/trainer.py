@@ -1,0 +1,254 @@
+"""GLP_OT_SVLoRA trainer — the plug-in boundary of the reference (trainers/GLP_OT_SVLoRA.py:767-1053 on top of
+Dassl's TrainerX, Dassl/dassl/engine/trainer.py:345-741), registered under the same TRAINER_REGISTRY name.
+
+What federated_main.py touches is kept: ctor `(cfg)`, `.model` (+ state_dict / load_state_dict), `.dm.dataset.
+classnames`, `.fed_train_loader_x_dict[i].dataset` (`len`, `count_by_attribute`), `.fed_before_train()`,
+`.train(idx=, global_epoch=, is_fed=, is_last_client=)`, `.test(idx=, current_epoch=)` -> list whose [0..3] are
+acc / err / macro-F1 / AUC, `.fed_after_train()`.
+
+B200-first differences (documented in DESIGN.md):
+  * all trainable tensors (prompt ctx, lora_A / lora_S / lora_B, OCT slice projection) are VIEWS into one flat fp32
+    buffer; gradients likewise.  The optimizer is ONE fused kernel over that buffer which also reproduces the
+    reference's double optimizer.step() per iteration (same SGD object registered under two model names,
+    :864-871) and the doubly-stepped StepLR; federated aggregation all-reduces the very same buffer;
+  * batches arrive in pinned memory and are copied asynchronously; loss / accuracy stay on the device and are
+    only synchronised when a caller asks for python floats;
+  * evaluation accumulates probabilities on the device and computes every fairness metric from one
+    segmented-sort kernel pass (fairfedmed_b200/metrics.py).
+"""
+from __future__ import annotations
+
+import time
+from collections import OrderedDict
+from typing import Optional
+
+import numpy as np
+import torch
+import torch.nn.functional as F
+
+from . import metrics as M
+from . import ops
+from .clip_model import CustomCLIP
+from .config import ATTRIBUTE_GROUPS
+from .data import SyntheticDataManager
+from .fed_utils import FlatSpec, build_spec
+from .modules import apply_lora_to_model
+from .registry import TRAINER_REGISTRY
+
+
+@TRAINER_REGISTRY.register()
+class GLP_OT_SVLoRA:
+    def __init__(self, cfg, device: Optional[torch.device] = None, data_manager=None):
+        if not torch.cuda.is_available():
+            raise RuntimeError("GLP_OT_SVLoRA (fairfedmed_b200) needs a CUDA device: the training path is made of "
+                               "sm_100a kernels and has no CPU fallback")
+        self.check_cfg(cfg)
+        self.cfg = cfg
+        self.device = device or torch.device("cuda", torch.cuda.current_device())
+        self.dm = data_manager or SyntheticDataManager(cfg)
+        self.fed_train_loader_x_dict = self.dm.fed_train_loader_x_dict
+        self.fed_test_loader_x_dict = self.dm.fed_test_loader_x_dict
+        self.max_epoch = cfg.OPTIM.MAX_EPOCH
+        self.sync_metrics = True          # python floats in loss summaries (reference behaviour)
+        self.step_auc = True              # per-step training AUC like the reference (:964-970)
+        self.sched_steps = 0              # StepLR.step() calls so far
+        self.first_step = True
+        self.build_model()
+
+    # ------------------------------------------------------------------ configuration
+    def check_cfg(self, cfg):
+        assert cfg.TRAINER.GLP_OT.PREC in ["bf16", "fp16", "fp32", "amp"]
+
+    def retrieval_attributes(self, attr_name):
+        try:
+            return ATTRIBUTE_GROUPS[self.cfg.DATASET.NAME][attr_name]
+        except KeyError as e:
+            raise NotImplementedError(f"{self.cfg.DATASET.NAME}/{attr_name}") from e
+
+    @property
+    def num_groups(self) -> int:
+        if self.cfg.TRAINER.GLP_OT_LORA.DISABLE_ATTR:
+            return 1
+        return len(self.retrieval_attributes(self.cfg.DATASET.ATTRIBUTE_TYPE))
+
+    # ------------------------------------------------------------------ model / optimizer
+    def build_model(self):
+        cfg = self.cfg
+        arch = cfg.MODEL_ARCH
+        ot = cfg.TRAINER.GLP_OT
+        torch.manual_seed(cfg.SEED)
+        is_3d = cfg.DATASET.MODALITY_TYPE in {"oct_bscans", "oct_bscans_3d", "mac_onh", "onh_mac"}
+        self.model = CustomCLIP(
+            classnames=self.dm.dataset.classnames, n_prompts=ot.N, n_ctx=ot.N_CTX, ot=ot.OT, eps=ot.EPS,
+            thresh=ot.THRESH, max_iter=ot.MAX_ITER, top_percent=ot.TOP_PERCENT, image_resolution=cfg.INPUT.SIZE[0],
+            vision_layers=arch.VISION_LAYERS, vision_width=arch.VISION_WIDTH, vision_patch_size=arch.PATCH,
+            embed_dim=arch.EMBED, text_width=arch.TEXT_WIDTH, text_layers=arch.TEXT_LAYERS,
+            text_heads=arch.TEXT_HEADS, context_length=arch.CONTEXT,
+            dim_per_3d_slice=cfg.DATASET.DIM_PER_3D_SLICE if is_3d else None, dataset=cfg.DATASET.NAME, seed=cfg.SEED)
+        # freeze everything but the prompt learner / OCT projection (:822-829), then wrap the MLP linears (:834-842)
+        for name, p in self.model.named_parameters():
+            p.requires_grad_("prompt_learner" in name or "proj_per_3d_slice" in name)
+        lora = cfg.TRAINER.GLP_OT_LORA
+        apply_lora_to_model(self.model, lora.UNFREEZE_IMAGE_ENCODER, rank=lora.RANK, alpha=lora.ALPHA,
+                            lora_type=lora.TYPE, global_s=lora.GLOBAL_S, num_attrs=self.num_groups)
+        self.model.to(self.device)
+        if cfg.TRAINER.GLP_OT.PREC == "fp32":
+            raise NotImplementedError("the B200 path computes in bf16 with fp32 accumulation; use the oracle for fp32")
+        self._flatten_trainables()
+        self.base_lr = cfg.OPTIM.LR
+
+    def _flatten_trainables(self):
+        named = [(n, p) for n, p in self.model.named_parameters() if p.requires_grad]
+        total = sum(p.numel() for _, p in named)
+        self.flat_params = torch.empty(total, device=self.device, dtype=torch.float32)
+        self.flat_grads = torch.zeros(total, device=self.device, dtype=torch.float32)
+        self.flat_mom = torch.zeros(total, device=self.device, dtype=torch.float32)
+        off = 0
+        for _, p in named:
+            n = p.numel()
+            self.flat_params[off:off + n].copy_(p.data.reshape(-1))
+            p.data = self.flat_params[off:off + n].view(p.shape)
+            p.grad = self.flat_grads[off:off + n].view(p.shape)
+            off += n
+        sd = {n: p for n, p in named}
+        self.flat_spec: FlatSpec = build_spec(sd, keys=[n for n, _ in named],
+                                              num_groups=None if self.num_groups == 1 else self.num_groups)
+        self.trainable_names = [n for n, _ in named]
+
+    def current_lr(self) -> float:
+        """StepLR(step_size, gamma) after `sched_steps` calls of .step() (Dassl/dassl/optim/lr_scheduler.py:83+)."""
+        step = self.cfg.OPTIM.STEPSIZE[0] if isinstance(self.cfg.OPTIM.STEPSIZE, (tuple, list)) else self.cfg.OPTIM.STEPSIZE
+        if step <= 0:
+            step = self.max_epoch
+        return self.base_lr * (self.cfg.OPTIM.GAMMA ** (self.sched_steps // max(step, 1)))
+
+    def model_backward_and_update(self, loss):
+        """zero_grad x2, backward, optimizer.step() x2 (engine/trainer.py:333-342 with the shared optimizer, F6)."""
+        self.flat_grads.zero_()
+        if self.sync_metrics and not bool(torch.isfinite(loss.detach())):   # detect_anomaly (engine/trainer.py:260-262)
+            raise FloatingPointError("Loss is infinite or NaN!")
+        loss.backward()
+        n_steps = 2 if self.cfg.TRAINER.GLP_OT_LORA.UNFREEZE_IMAGE_ENCODER else 1
+        o = self.cfg.OPTIM
+        ops.sgd_step_(self.flat_params, self.flat_grads, self.flat_mom, self.current_lr(), o.MOMENTUM, o.WEIGHT_DECAY,
+                      n_steps, self.first_step)
+        self.first_step = False
+
+    def update_lr(self):
+        self.sched_steps += 2 if self.cfg.TRAINER.GLP_OT_LORA.UNFREEZE_IMAGE_ENCODER else 1
+
+    # ------------------------------------------------------------------ batches
+    def _parse(self, batch):
+        image = batch["img"].to(self.device, non_blocking=True)
+        label = batch["label"].to(self.device, non_blocking=True)
+        attrs = batch["attrs"].t()
+        idx = self.cfg.DATASET.ATTRIBUTES.index(self.cfg.DATASET.ATTRIBUTE_TYPE)
+        tgt = None if self.cfg.TRAINER.GLP_OT_LORA.DISABLE_ATTR else attrs[idx].contiguous()
+        return image, label, attrs, tgt
+
+    parse_batch_train = _parse
+    parse_batch_test = _parse
+
+    # ------------------------------------------------------------------ one SGD step (HOT LOOP body)
+    def forward_backward(self, batch, is_last_client=False):
+        image, label, _, attr = self.parse_batch_train(batch)
+        output = self.model(image, attr)
+        if output is None:
+            raise FloatingPointError("transport plan contains NaN (CustomCLIP.forward returned None)")
+        cls_loss = F.cross_entropy(output, label)
+        loss = cls_loss
+        lam = self.cfg.TRAINER.LAMBDA_FAIRNESS
+        if attr is not None and lam != 0.0:
+            # detached confidence-gap regulariser: contributes to the VALUE of the loss only (:930-948)
+            with torch.no_grad():
+                probs = F.softmax(output, dim=1)
+                correct = probs[torch.arange(len(label), device=label.device), label]
+                a = attr.to(self.device)
+                conf = torch.stack([1 - correct[a == g].mean() for g in torch.unique(a)])
+                fairness = (conf - conf.mean()).abs().mean()
+            loss = cls_loss + lam * fairness
+        self.model_backward_and_update(loss)
+        with torch.no_grad():
+            acc = (output.argmax(dim=1) == label).float().mean() * 100.0
+        summary = {"loss": loss.detach(), "acc": acc}
+        if self.step_auc:
+            prob = output.detach().softmax(-1)
+            summary["auc"] = M.compute_auc(prob, label)
+        if self.sync_metrics:
+            summary = {k: (v.item() if torch.is_tensor(v) else float(v)) for k, v in summary.items()}
+        if (self.batch_idx + 1) == self.num_batches:
+            self.update_lr()
+        return summary
+
+    # ------------------------------------------------------------------ epoch / federated hooks
+    def fed_before_train(self):
+        self.time_start = time.time()
+
+    def fed_after_train(self):
+        pass
+
+    def run_epoch(self, idx=-1, global_epoch=0, is_fed=True, is_last_client=False):
+        self.model.train()
+        loader = self.fed_train_loader_x_dict[idx]
+        self.num_batches = len(loader)
+        last = None
+        for self.batch_idx, batch in enumerate(loader):
+            last = self.forward_backward(batch, is_last_client)
+        return last
+
+    def train(self, idx=-1, global_epoch=0, is_fed=False, is_last_client=False):
+        last = None
+        for self.epoch in range(self.max_epoch):
+            last = self.run_epoch(idx, global_epoch, is_fed, is_last_client)
+        if not self.cfg.TEST.NO_TEST and not is_fed:
+            self.test(idx, global_epoch)
+        return last
+
+    @torch.no_grad()
+    def model_inference(self, image, attr=None):
+        return self.model(image, attr)
+
+    @torch.no_grad()
+    def test(self, idx=-1, current_epoch=0, split=None):
+        """Classification_oph.process / evaluate (evaluation/evaluator_oph.py:37-151) with device-side accumulation."""
+        self.model.eval()
+        probs, labels, attrs_all = [], [], []
+        correct = torch.zeros((), device=self.device)
+        total = 0
+        for batch in self.fed_test_loader_x_dict[idx]:
+            image, label, attrs, tgt = self.parse_batch_test(batch)
+            out = self.model_inference(image, tgt).float()
+            probs.append(out.softmax(-1))
+            labels.append(label)
+            attrs_all.append(attrs.to(self.device, non_blocking=True))
+            correct += (out.argmax(1) == label).sum()
+            total += label.shape[0]
+        prob = torch.cat(probs)
+        gt = torch.cat(labels)
+        attr = torch.cat(attrs_all, dim=1)
+        res = M.evalute_comprehensive_perf_scores(prob, gt, attr)
+        counts = M.group_counts(prob, gt).slot()
+        tp, fp, tn, fn = (float(counts[i]) for i in (M.TP, M.FP, M.TN, M.FN))
+        f1s = []
+        if tp + fn > 0:
+            f1s.append(2 * tp / max(2 * tp + fp + fn, 1e-30) if (2 * tp + fp + fn) else 0.0)
+        if tn + fp > 0:
+            f1s.append(2 * tn / max(2 * tn + fn + fp, 1e-30) if (2 * tn + fn + fp) else 0.0)
+        acc = 100.0 * float(correct.item()) / total
+        results = OrderedDict()
+        results["accuracy"] = acc
+        results["error_rate"] = 100.0 - acc
+        results["macro_f1"] = 100.0 * float(np.mean(f1s))
+        results["auc"] = 100.0 * res[2]
+        (results["overall_acc"], results["esaccs_by_attrs"], results["overall_auc"], results["esaucs_by_attrs"],
+         results["aucs_by_attrs"], results["dpds"], results["eods"], results["aods"],
+         results["between_group_disparity"]) = res
+        self.last_results = results
+        return list(results.values())
+
+    # ------------------------------------------------------------------ flat-buffer access for aggregation
+    def get_flat(self) -> torch.Tensor:
+        return self.flat_params
+
+    def set_flat(self, flat: torch.Tensor) -> None:
+        self.flat_params.copy_(flat)

@@ -1,0 +1,60 @@
+"""The C-ABI library loads on a CPU-only box and exports exactly what include/ffm_b200.h declares."""
+import ctypes
+
+import pytest
+
+from fairfedmed_b200 import _cabi
+from fairfedmed_b200.build import build
+
+
+@pytest.fixture(scope="module")
+def lib():
+    build()   # no-op when the in-tree .so is up to date; nvcc cross-compiles without a GPU
+    return _cabi.load()
+
+
+def test_header_symbols_are_exported(lib):
+    raw = ctypes.CDLL(str(_cabi.LIB_PATH))
+    declared = _cabi.declared_symbols()
+    assert len(declared) >= 19
+    missing = [s for s in declared if not hasattr(raw, s)]
+    assert not missing, f"declared in include/ffm_b200.h but not exported: {missing}"
+
+
+def test_binding_covers_header():
+    declared = set(_cabi.declared_symbols())
+    bound = set(_cabi.SIGNATURES)
+    assert declared == bound, (declared - bound, bound - declared)
+
+
+def test_no_compute_metadata_calls(lib):
+    assert lib.ffm_version() >= 100
+    assert lib.ffm_svlora_max_rank() == 16
+    assert lib.ffm_svlora_fwd_workspace_bytes(1576, 768, 3072, 8) > 0
+    assert lib.ffm_svlora_bwd_workspace_bytes(1576, 768, 3072, 8) > lib.ffm_svlora_fwd_workspace_bytes(1576, 768, 3072, 8)
+    assert lib.ffm_ot_head_workspace_bytes(196, 64, 512, 2, 2) > 0
+    assert lib.ffm_sinkhorn_workspace_bytes(128, 196, 2) > 0
+    assert lib.ffm_group_auc_workspace_bytes(5000, 6, 3) > 0
+
+
+def test_argument_validation_without_gpu(lib):
+    # null pointers are rejected before any CUDA call is made
+    rc = lib.ffm_seff(0, 0, 0, 0, 1, 3, 12, 0.7, 0)
+    assert rc == -22
+    assert b"null pointer" in lib.ffm_last_error()
+
+
+def test_product_fails_loudly_without_cuda():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("CUDA present")
+    from fairfedmed_b200.config import get_cfg_default
+    from fairfedmed_b200.registry import build_trainer
+    import fairfedmed_b200.trainer  # noqa: F401  (registers GLP_OT_SVLoRA)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        build_trainer(get_cfg_default())
+    from fairfedmed_b200.modules import FairLoRALinear
+    import torch.nn as nn
+    layer = FairLoRALinear(nn.Linear(64, 64), rank=12, alpha=2.0, num_attrs=3)
+    with pytest.raises(Exception):
+        layer(torch.randn(4, 2, 64), torch.tensor([0, 1]))
