@@ -118,6 +118,7 @@ int ffm_fedavg_scale(const float* flat_in, float* flat_out, const int32_t* seg_k
   fedavg_scale_kernel<<<grid_for(n_elem), FA_THREADS, n_seg * sizeof(int64_t), stream>>>(flat_in, flat_out, st,
                                                                                           n_elem, w_scalar, w_group, r);
   FFM_CHECK_CUDA(cudaGetLastError());
+  count_launch();
   return FFM_OK;
 }
 
@@ -132,6 +133,7 @@ int ffm_fedavg_epilogue(const float* avg, const float* prev_global, float* out, 
   fedavg_epilogue_kernel<<<grid_for(n_elem), FA_THREADS, n_seg * sizeof(int64_t), stream>>>(
       avg, prev_global, out, st, n_elem, beta_decay, shared_half_s, G, r);
   FFM_CHECK_CUDA(cudaGetLastError());
+  count_launch();
   return FFM_OK;
 }
 
@@ -142,6 +144,7 @@ int ffm_sgd_step(float* param, const float* grad, float* momentum_buf, int64_t n
   sgd_kernel<<<grid_for(n), FA_THREADS, 0, stream>>>(param, grad, momentum_buf, n, lr, momentum, weight_decay,
                                                      n_steps, first_step);
   FFM_CHECK_CUDA(cudaGetLastError());
+  count_launch();
   return FFM_OK;
 }
 

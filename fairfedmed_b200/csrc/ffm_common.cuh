@@ -48,6 +48,7 @@ void set_last_error(const char* fmt, ...);
   } while (0)
 
 int num_sms();  // SM count of the current device (cached)
+void count_launch(int n = 1);  // bump the host-side kernel-launch counter (ffm_launch_count)
 
 #ifdef __CUDACC__
 

@@ -341,6 +341,7 @@ int ffm_group_auc(const float* prob, const int32_t* label, const int32_t* attrs,
   confusion_kernel<<<cgrid, RS_THREADS, static_cast<size_t>(n_slots) * 32, stream>>>(
       prob, label, attrs, reinterpret_cast<unsigned long long*>(counts_out), N, n_attr, n_slots, max_groups);
   FFM_CHECK_CUDA(cudaGetLastError());
+  count_launch(1 + 3 * RS_PASSES + 5);
   return FFM_OK;
 }
 

@@ -25,7 +25,9 @@
 #include <stdarg.h>
 #include <string.h>
 
+#include <atomic>
 #include <mutex>
+#include <vector>
 
 #include "../../include/ffm_b200.h"
 #include "ffm_common.cuh"
@@ -43,6 +45,15 @@ void set_last_error(const char* fmt, ...) {
   vsnprintf(g_last_error, sizeof(g_last_error), fmt, ap);
   va_end(ap);
 }
+
+static std::atomic<long long> g_launches{0};
+void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+
+// event profiling of the dominant kernel (bench.py roofline): records are appended at launch time
+struct GemmRecord { cudaEvent_t start, stop; int T, K, N; };
+static std::mutex g_prof_mutex;
+static bool g_prof_enabled = false;
+static std::vector<GemmRecord> g_prof_records;
 
 int num_sms() {
   static int cached[64] = {0};
@@ -554,8 +565,26 @@ static int launch_svlora_gemm(const GemmOperands& o, cudaStream_t stream) {
 
   const int tiles = p.m_tiles * p.n_tiles;
   const int grid = tiles < num_sms() ? tiles : num_sms();
+  GemmRecord rec{};
+  bool profiling = false;
+  {
+    std::lock_guard<std::mutex> lk(g_prof_mutex);
+    profiling = g_prof_enabled && g_prof_records.size() < 65536;
+  }
+  if (profiling) {
+    FFM_CHECK_CUDA(cudaEventCreate(&rec.start));
+    FFM_CHECK_CUDA(cudaEventCreate(&rec.stop));
+    rec.T = o.T; rec.K = o.K; rec.N = o.N;
+    FFM_CHECK_CUDA(cudaEventRecord(rec.start, stream));
+  }
   svlora_gemm_kernel<<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(tm_x, tm_w, tm_a, tm_b, tm_y, tm_y2, p);
   FFM_CHECK_CUDA(cudaGetLastError());
+  count_launch();
+  if (profiling) {
+    FFM_CHECK_CUDA(cudaEventRecord(rec.stop, stream));
+    std::lock_guard<std::mutex> lk(g_prof_mutex);
+    g_prof_records.push_back(rec);
+  }
   return FFM_OK;
 }
 
@@ -606,6 +635,42 @@ int ffm_version(void) { return 100; }
 
 int ffm_svlora_max_rank(void) { return RP; }
 
+long long ffm_launch_count(int reset) {
+  return reset ? g_launches.exchange(0) : g_launches.load();
+}
+
+int ffm_profile_enable(int enable) {
+  std::lock_guard<std::mutex> lk(g_prof_mutex);
+  g_prof_enabled = enable != 0;
+  return FFM_OK;
+}
+
+int ffm_profile_read(float* ms_host, int* tkn_host, int max_records) {
+  std::vector<GemmRecord> recs;
+  {
+    std::lock_guard<std::mutex> lk(g_prof_mutex);
+    recs.swap(g_prof_records);
+  }
+  int n = 0;
+  for (auto& r : recs) {
+    float ms = 0.f;
+    cudaError_t e = cudaEventSynchronize(r.stop);
+    if (e == cudaSuccess) e = cudaEventElapsedTime(&ms, r.start, r.stop);
+    cudaEventDestroy(r.start);
+    cudaEventDestroy(r.stop);
+    if (e != cudaSuccess) {
+      set_last_error("ffm_profile_read: %s", cudaGetErrorString(e));
+      return FFM_ERR_CUDA;
+    }
+    if (n < max_records && ms_host && tkn_host) {
+      ms_host[n] = ms;
+      tkn_host[3 * n] = r.T; tkn_host[3 * n + 1] = r.K; tkn_host[3 * n + 2] = r.N;
+      ++n;
+    }
+  }
+  return n;
+}
+
 size_t ffm_svlora_fwd_workspace_bytes(int T, int K, int N, int n_samples) {
   (void)T;
   return svlora_ws_prefix(K, N, n_samples);
@@ -636,6 +701,7 @@ int ffm_svlora_fwd(const void* x, const void* w, const float* bias, const float*
   svlora_prep_kernel<<<64, 256, 0, stream>>>(lora_a, 1, lora_b, 1, s_eff, ws.a_side, ws.b_side, ws.s_rows, K, N, r,
                                              n_samples, scaling);
   FFM_CHECK_CUDA(cudaGetLastError());
+  count_launch();
   GemmOperands o;
   o.x = x; o.wmat = w; o.a_side = ws.a_side; o.b_side = ws.b_side; o.s_rows = ws.s_rows; o.bias = bias;
   o.out = y; o.out_pre = y_pre; o.h_out = h_out; o.aux = nullptr;
@@ -664,6 +730,7 @@ int ffm_svlora_bwd(const void* dy, const void* x, const void* w_t, const float* 
   svlora_prep_kernel<<<64, 256, 0, stream>>>(lora_b, 0, lora_a, 0, s_eff, ws.a_side, ws.b_side, ws.s_rows, N, K, r,
                                              n_samples, scaling);
   FFM_CHECK_CUDA(cudaGetLastError());
+  count_launch();
   GemmOperands o;
   o.x = dy; o.wmat = w_t; o.a_side = ws.a_side; o.b_side = ws.b_side; o.s_rows = ws.s_rows; o.bias = nullptr;
   o.out = dx; o.out_pre = nullptr; o.h_out = dzu; o.aux = gelu_pre;

@@ -201,9 +201,11 @@ int launch_svlora_bwd_small(const __nv_bfloat16* x, const __nv_bfloat16* dy, con
                                                      num_slices);
     colsum_reduce_kernel<<<(N * RPS + 255) / 256, 256, 0, stream>>>(partial, dB, chunks, N, r, 1);
   }
+  count_launch(4);
   // ds_eff[nS, r]: one warp per sample
   dseff_kernel<<<(nS * 32 + 127) / 128, 128, 0, stream>>>(h, dzu, ds_eff, T, r, nS, b_prime, num_slices, scaling);
   FFM_CHECK_CUDA(cudaGetLastError());
+  count_launch();
   return FFM_OK;
 }
 
@@ -221,6 +223,7 @@ int ffm_seff(const long long* attr, const float* S, const float* S_global, float
   const int n = n_samples * r;
   seff_kernel<<<(n + 127) / 128, 128, 0, stream>>>(attr, S, S_global, s_eff, n_samples, G, r, lambda);
   FFM_CHECK_CUDA(cudaGetLastError());
+  count_launch();
   return FFM_OK;
 }
 
@@ -231,6 +234,7 @@ int ffm_ds(const long long* attr, const float* ds_eff, float* dS, float* dS_glob
   const int n = (G + 1) * r;
   ds_kernel<<<(n + 127) / 128, 128, 0, stream>>>(attr, ds_eff, dS, dS_global, n_samples, G, r, lambda);
   FFM_CHECK_CUDA(cudaGetLastError());
+  count_launch();
   return FFM_OK;
 }
 

@@ -38,6 +38,17 @@ typedef void* ffm_stream_t;
 const char* ffm_last_error(void);
 int ffm_version(void);
 
+/*
+ * Instrumentation used by bench.py (no reference counterpart).
+ *   ffm_launch_count : number of kernels this library has launched since the last reset (host-side counter).
+ *   ffm_profile_*    : when enabled, every launch of the fused SVLoRA GEMM kernel is bracketed by CUDA events on
+ *                      its own stream; ffm_profile_read synchronises them and returns per-launch milliseconds and
+ *                      (T, K, N) triples (host arrays), then clears the record list.
+ */
+long long ffm_launch_count(int reset);
+int ffm_profile_enable(int enable);
+int ffm_profile_read(float* ms_host, int* tkn_host, int max_records);
+
 /* ------------------------------------------------- FairLoRA / SVLoRA linear ------------------ */
 /* Maximum adapter rank the fused GEMM was built for (r is zero-padded to this). */
 int ffm_svlora_max_rank(void);

@@ -1,0 +1,159 @@
+"""GPU parity of the whole drop-in path: CustomCLIP forward/backward vs the reference goldens (same state-dict keys,
+same seeded weights), one trainer step vs the oracle's double-SGD step, and a 2-client federated round (config 1
+shape, shrunk towers) checked against a manual aggregation."""
+from __future__ import annotations
+
+from pathlib import Path
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from oracle import ref_port as rp
+from tests.golden import recipes
+
+pytestmark = pytest.mark.gpu
+GOLD = Path(__file__).resolve().parent / "golden"
+DEV = "cuda:0"
+
+
+def _build(rc, gold, name):
+    from fairfedmed_b200.clip_model import CustomCLIP
+    from fairfedmed_b200.modules import apply_lora_to_model
+    keys = [str(k) for k in gold[f"{name}.keys"]]
+    shapes = {k: tuple(int(v) for v in str(s).split(",") if v != "") for k, s in zip(keys, gold[f"{name}.shapes"])}
+    params = recipes.model_params(rc, shapes)
+    eot = torch.from_numpy(gold[f"{name}.eot"])
+    n_cls, N, n_ctx = 2, 2, 4
+    bufs = (params["prompt_learner.token_prefix"], params["prompt_learner.token_suffix"], eot)
+    is_oct = rc["modality"] == "oct_bscans"
+    m = CustomCLIP(n_prompts=N, n_ctx=n_ctx, ot=rc["ot"], image_resolution=rc["res"], vision_layers=rc["v_layers"],
+                   vision_width=rc["v_width"], embed_dim=rc["embed"], text_width=rc["t_width"],
+                   text_layers=rc["t_layers"], text_heads=rc["t_heads"],
+                   dim_per_3d_slice=rc.get("dim_per_3d_slice") if is_oct else None, prompt_buffers=bufs)
+    for n_, p_ in m.named_parameters():
+        p_.requires_grad_("prompt_learner" in n_ or "proj_per_3d_slice" in n_)
+    apply_lora_to_model(m, True, rank=rc["rank"], alpha=rc["alpha"], lora_type=rc["lora_type"],
+                        num_attrs=rc["groups"])
+    assert set(m.state_dict().keys()) == set(keys), "state-dict keys must equal the reference's"
+    m.load_state_dict(params, strict=True)
+    return m.to(DEV), params, eot
+
+
+@pytest.mark.parametrize("name", list(recipes.MODEL_CASES))
+def test_custom_clip_matches_reference_golden(name):
+    """bf16 activations vs the fp32 reference: logits within 3e-2 * max|logit| (+0.02), loss within 2e-2, adapter /
+    prompt gradients: cosine >= 0.99 and rel-to-max <= 6e-2 per tensor."""
+    rc = recipes.MODEL_CASES[name]
+    gold = np.load(GOLD / "model.npz")
+    m, params, _ = _build(rc, gold, name)
+    image, label, attr = recipes.model_batch(rc)
+    logits = m(image.to(DEV), attr)                       # attr stays on the CPU like the reference
+    assert logits is not None and logits.shape == (rc["batch"], 2)
+    ref = torch.from_numpy(gold[f"{name}.logits"])
+    assert float((logits.float().cpu() - ref).abs().max()) <= 3e-2 * float(ref.abs().max()) + 0.02
+    loss = F.cross_entropy(logits.float(), label.to(DEV))
+    assert abs(float(loss) - float(gold[f"{name}.loss"])) <= 2e-2
+    loss.backward()
+    checked = 0
+    for n_, p_ in m.named_parameters():
+        gk = f"{name}.grad.{n_}"
+        if gk not in gold.files or p_.grad is None:
+            continue
+        g, r = p_.grad.float().cpu().reshape(-1), torch.from_numpy(gold[gk]).reshape(-1)
+        if float(r.abs().max()) < 1e-7:
+            continue
+        cos = float(F.cosine_similarity(g, r, dim=0))
+        rel = float((g - r).abs().max() / r.abs().max())
+        assert cos >= 0.99 and rel <= 6e-2, f"{n_}: cos {cos:.4f} rel {rel:.3e}"
+        checked += 1
+    assert checked >= 7
+
+
+def _tiny_cfg(ot="None", users=2, batch=8, n_train=16):
+    from fairfedmed_b200.config import get_cfg_default
+    cfg = get_cfg_default()
+    cfg.MODEL_ARCH.merge_from_dict(dict(VISION_LAYERS=2, VISION_WIDTH=128, TEXT_LAYERS=2, TEXT_WIDTH=64, TEXT_HEADS=2,
+                                        EMBED=64))
+    cfg.INPUT.SIZE = (64, 64)
+    cfg.DATASET.merge_from_dict(dict(USERS=users, NUM_TRAIN_PER_CLIENT=n_train, NUM_TEST_PER_CLIENT=32))
+    cfg.DATALOADER.TRAIN_X.BATCH_SIZE = batch
+    cfg.TRAINER.GLP_OT.OT = ot
+    cfg.OPTIM.ROUND = 1
+    return cfg
+
+
+def test_trainer_step_matches_oracle_double_sgd():
+    """One forward_backward of the registered trainer vs the oracle: same weights, same batch, CE loss, SGD stepped
+    twice on one gradient.  bf16 compute => parameters after the step within 5e-2 of the update size."""
+    import fairfedmed_b200.trainer  # noqa: F401
+    from fairfedmed_b200.registry import build_trainer
+    cfg = _tiny_cfg(ot="Sinkhorn")
+    tr = build_trainer(cfg)
+    with torch.no_grad():                                   # lora_A = 0 at init gives dS = dB = 0: randomise (§8c)
+        for n_, p_ in tr.model.named_parameters():
+            if "lora_A" in n_:
+                p_.copy_(0.05 * torch.randn(p_.shape, generator=torch.Generator().manual_seed(1)).to(p_.device))
+    sd0 = {k: v.detach().float().cpu().clone() for k, v in tr.model.state_dict().items()}
+    batch = next(iter(tr.fed_train_loader_x_dict[0]))
+    tr.batch_idx, tr.num_batches = 0, 2
+    out = tr.forward_backward(batch)
+    assert np.isfinite(out["loss"]) and 0.0 <= out["acc"] <= 100.0 and 0.0 <= out["auc"] <= 1.0
+    # oracle step
+    names = tr.trainable_names
+    p = {k: v.clone() for k, v in sd0.items()}
+    for k in names:
+        p[k].requires_grad_(True)
+    eot = tr.model.prompt_learner.eot_index.cpu()
+    attr = batch["attrs"][:, 0]
+    logits = rp.custom_clip_forward(batch["img"].clone(), attr, p, eot, ot="Sinkhorn", vision_layers=2, vision_heads=2,
+                                    text_layers=2, text_heads=2, scaling=2.0 / 12)
+    loss = F.cross_entropy(logits, batch["label"])
+    assert abs(float(loss) - out["loss"]) <= 2e-2
+    grads = torch.autograd.grad(loss, [p[k] for k in names])
+    bufs = [None] * len(names)
+    rp.sgd_double_step([p[k] for k in names], grads, bufs, lr=cfg.OPTIM.LR)
+    sd1 = tr.model.state_dict()
+    for k in names:
+        upd = (p[k].detach() - sd0[k])
+        got = sd1[k].float().cpu() - sd0[k]
+        if float(upd.abs().max()) < 1e-9:
+            continue
+        assert float((got - upd).abs().max()) <= 6e-2 * float(upd.abs().max()) + 1e-7, k
+
+
+def test_two_client_round_and_evaluation():
+    """BASELINE config 1 shape (2 clients, batch 8, 1 local epoch, 1 round) on shrunken towers: the global weights
+    after the round equal the oracle's n_k / n_{k,g}-weighted average (+ shared half of S, EMA) of the two local
+    results obtained by driving an identical trainer by hand (same seeds, same shared optimizer state, F7)."""
+    import fairfedmed_b200.trainer  # noqa: F401
+    from fairfedmed_b200 import fed_utils
+    from fairfedmed_b200.federated import run_federated
+    from fairfedmed_b200.registry import build_trainer
+    cfg = _tiny_cfg(ot="None", users=2, batch=8, n_train=16)
+    manual = build_trainer(cfg)
+    manual.step_auc = False
+    start = manual.get_flat().clone()
+    locals_ = []
+    for k in range(2):
+        manual.set_flat(start)
+        manual.train(idx=k, global_epoch=0, is_fed=True)
+        locals_.append(manual.get_flat().clone())
+    fed = build_trainer(cfg)
+    fed.step_auc = False
+    torch.testing.assert_close(fed.get_flat(), start)                  # seeded construction is reproducible
+    _, global_flat, hist = run_federated(cfg, rounds=1, shared_half_s=True, trainer=fed)
+    spec = fed.flat_spec
+    n_k = [len(fed.fed_train_loader_x_dict[k].dataset) for k in range(2)]
+    n_kg = [fed.fed_train_loader_x_dict[k].dataset.count_by_attribute("race") for k in range(2)]
+    w = [{k2: v.cpu() for k2, v in fed_utils.unpack(spec, f).items()} for f in locals_]
+    w_g = {k2: v.cpu() for k2, v in fed_utils.unpack(spec, start).items()}
+    ref = rp.average_weights_ema(w_g, w, [0, 1], n_k, n_kg, 0, 1, shared_half_s=True)
+    got = fed_utils.unpack(spec, global_flat)
+    assert hist[0]["clients"] == [0, 1] and np.isfinite(hist[0]["auc"])
+    for k2 in spec.keys:
+        # identical kernels on identical inputs; the only run-to-run noise is atomics inside library attention bwd
+        torch.testing.assert_close(got[k2].cpu(), ref[k2], rtol=1e-3, atol=1e-5)
+    res = fed.test(idx=0, current_epoch=0)
+    assert len(res) == 13 and 0 <= res[0] <= 100 and 0 <= res[3] <= 100
