@@ -247,9 +247,11 @@ def run_ours(args):
         new = agg.aggregate(tr.get_flat(), prev, n_k, n_kg, True, epoch, 50, shared_half_s=True)
         tr.set_flat(new)
 
-    def timed(fn_step, steps, warmup, with_round=True):
+    def timed(fn_step, steps, warmup, with_round=True, finalize=None):
         for i in range(warmup):
             fn_step(i)
+        if finalize is not None:
+            finalize()
         if with_round:
             fed_round(0)
         barrier()
@@ -260,6 +262,8 @@ def run_ours(args):
             fn_step(i)
         if with_round:
             fed_round(1)
+        if finalize is not None:
+            finalize()
         e1.record()
         barrier()
         launches = lib.ffm_launch_count(0)
@@ -268,14 +272,36 @@ def run_ours(args):
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return float(ms.item()), int(launches)
 
+    # one eager step to count this library's launches per step, then capture the whole step into a CUDA graph
+    for i in range(2):
+        tr.forward_backward(devb[i % pool])
+    torch.cuda.synchronize()
+    lib.ffm_launch_count(1)
+    tr.forward_backward(devb[0])
+    torch.cuda.synchronize()
+    launches_per_step = int(lib.ffm_launch_count(0))
+    use_graph = not args.no_graph
+    graph_note = "eager launches"
+    if use_graph:
+        try:
+            tr.capture_step_graph(devb[0])
+            graph_note = "whole step (fwd+bwd+2xSGD) replayed from one CUDA graph"
+        except Exception as e:                       # capture is an optimisation, not a correctness requirement
+            use_graph = False
+            graph_note = f"eager launches (graph capture failed: {type(e).__name__}: {e})"[:300]
+            torch.cuda.synchronize()
+    run_step = tr.forward_backward_graphed if use_graph else tr.forward_backward
+
     # ---- value: inputs resident in HBM ----
     def step_device(i):
-        tr.forward_backward(devb[i % pool])
+        run_step(devb[i % pool])
 
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
     ms_total, launches = timed(step_device, args.steps, args.warmup)
+    if use_graph:       # replayed kernels do not pass through the library's launch counter: add them back
+        launches += launches_per_step * args.steps
     clocks = sampler.stop() if rank == 0 else None
     value = BATCH * world * args.steps / (ms_total / 1e3)
 
@@ -290,6 +316,14 @@ def run_ours(args):
             staged[i][1].record(copy_stream)
 
     losses = []
+    loss_ring = torch.zeros(8, dtype=torch.float32).pin_memory()
+    in_flight = []                                     # (slot, event) of losses whose D2H copy has been issued
+
+    def drain(keep):
+        while len(in_flight) > keep:
+            slot, ev = in_flight.pop(0)
+            ev.synchronize()
+            losses.append(float(loss_ring[slot]))      # the host reads EVERY step's loss inside the timed region
 
     def step_host(i):
         if i not in staged:
@@ -297,13 +331,18 @@ def run_ours(args):
         batch, ev = staged.pop(i)
         stage(i + 1)                                   # prefetch the next batch while this one computes
         torch.cuda.current_stream().wait_event(ev)
-        out = tr.forward_backward(batch)
-        losses.append(out["loss"].item())              # D2H read of the step's result, every step
+        out = run_step(batch)
+        slot = i % 8
+        loss_ring[slot:slot + 1].copy_(out["loss"].detach().reshape(1), non_blocking=True)   # D2H, every step
+        done = torch.cuda.Event()
+        done.record()
+        in_flight.append((slot, done))
+        drain(keep=1)                                  # read step i-1's loss while step i runs (no pipeline bubble)
         for v in batch.values():
             v.record_stream(torch.cuda.current_stream())
 
     staged.clear()
-    ms_e2e, _ = timed(step_host, args.steps, max(args.warmup, 3))
+    ms_e2e, _ = timed(step_host, args.steps, max(args.warmup, 3), finalize=lambda: drain(keep=0))
     staged.clear()
     e2e_value = BATCH * world * args.steps / (ms_e2e / 1e3)
 
@@ -366,7 +405,8 @@ def run_ours(args):
         "dtype": "bf16", "data": "synthetic", "config": workload_config(world, BATCH, args.ot), "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 4,
                 "ms_per_step": ms_e2e / args.steps},
-        "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu,
+        "gpu_launches": launches, "launches_per_step": launches_per_step, "step_submission": graph_note,
+        "roofline": roofline, "cpu_baseline": cpu,
         "final_loss": losses[-1] if losses else None, "plan_nan": status_nan,
     }
     print(json.dumps(line), flush=True)
@@ -385,6 +425,7 @@ def main():
     ap.add_argument("--cpu-batch", type=int, default=8)
     ap.add_argument("--cpu-budget", type=float, default=150.0, help="seconds of CPU work allowed for the oracle arm")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-graph", action="store_true", help="submit every kernel eagerly instead of replaying a CUDA graph")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3

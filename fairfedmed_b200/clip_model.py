@@ -60,11 +60,12 @@ class QuickGELU(nn.Module):
 
 
 class MLP(nn.Module, _Bf16Cache):
-    def __init__(self, d_model: int):
+    def __init__(self, d_model: int, batch_first: bool = False):
         super().__init__()
         self.c_fc = nn.Linear(d_model, d_model * 4)
         self.gelu = QuickGELU()
         self.c_proj = nn.Linear(d_model * 4, d_model)
+        self.batch_first = batch_first    # rows of x are [B', L, C] instead of the reference's [L, B', C]
 
     def _adapter_operands(self, layer: _AdapterBase, attr, device):
         w, w_t, bias = layer._operands()
@@ -83,16 +84,23 @@ class MLP(nn.Module, _Bf16Cache):
         fused = isinstance(self.c_fc, _AdapterBase) and isinstance(self.c_proj, _AdapterBase) and x.is_cuda \
             and x.dim() == 3 and self.c_fc.scaling == self.c_proj.scaling
         if fused:
-            L, bp, c = x.shape
+            if self.batch_first:
+                bp, L, c = x.shape
+                row_div = L          # row t = column * L + position: sample = (t // L) // num_slices
+            else:
+                L, bp, c = x.shape
+                row_div = 1          # row t = position * B' + column (reference layout)
             fc = self._adapter_operands(self.c_fc, attr, x.device)
             pj = self._adapter_operands(self.c_proj, attr, x.device)
             n_samples = fc[5].shape[0]
             x2d = x.reshape(L * bp, c)
             if x2d.dtype != torch.bfloat16:
                 x2d = x2d.to(torch.bfloat16)
-            y = ops.svlora_mlp(x2d.contiguous(), fc, pj, self.c_fc.scaling, bp, bp // n_samples)
-            return y.reshape(L, bp, -1).to(x.dtype)
+            y = ops.svlora_mlp(x2d.contiguous(), fc, pj, self.c_fc.scaling, bp, bp // n_samples, row_div)
+            return y.reshape(x.shape[0], x.shape[1], -1).to(x.dtype)
         if isinstance(self.c_fc, _AdapterBase):
+            if self.batch_first:     # the stand-alone adapter modules speak the reference's sequence-first layout
+                return self.c_proj(self.gelu(self.c_fc(x.transpose(0, 1), attr)), attr).transpose(0, 1)
             return self.c_proj(self.gelu(self.c_fc(x, attr)), attr)
         # un-adapted (text tower): plain frozen linears on bf16 copies
         h = F.linear(x, self._bf("fc_w", self.c_fc.weight, x.dtype), self._bf("fc_b", self.c_fc.bias, x.dtype))
@@ -101,25 +109,38 @@ class MLP(nn.Module, _Bf16Cache):
 
 
 class ResidualAttentionBlock(nn.Module, _Bf16Cache):
-    def __init__(self, d_model: int, n_head: int, attn_mask: Optional[torch.Tensor] = None):
+    def __init__(self, d_model: int, n_head: int, attn_mask: Optional[torch.Tensor] = None,
+                 batch_first: bool = False):
         super().__init__()
         self.attn = nn.MultiheadAttention(d_model, n_head)   # parameter container (same state-dict keys)
         self.ln_1 = LayerNorm(d_model)
-        self.mlp = MLP(d_model)
+        self.mlp = MLP(d_model, batch_first=batch_first)
         self.ln_2 = LayerNorm(d_model)
         self.attn_mask = attn_mask
         self.n_head = n_head
+        self.batch_first = batch_first
 
     def attention(self, x: torch.Tensor):
-        """Self-attention, sequence-first in/out (nn.MultiheadAttention semantics, clip/model.py:350-352)."""
-        L, bn, c = x.shape
-        hd = c // self.n_head
+        """Self-attention with nn.MultiheadAttention semantics (clip/model.py:350-352).
+
+        batch_first: x is [B, L, C]; q/k/v are strided views of the in_proj output in "bshd" memory order, which the
+        fused attention kernels consume without copies.  Otherwise x is the reference's [L, B, C]."""
         a = self.attn
-        qkv = F.linear(x, self._bf("in_w", a.in_proj_weight, x.dtype), self._bf("in_b", a.in_proj_bias, x.dtype))
-        qkv = qkv.view(L, bn, 3, self.n_head, hd).permute(2, 1, 3, 0, 4)          # [3, B, H, L, hd]
         causal = self.attn_mask is not None
-        out = F.scaled_dot_product_attention(qkv[0], qkv[1], qkv[2], is_causal=causal)   # [B, H, L, hd]
-        out = out.permute(2, 0, 1, 3).reshape(L, bn, c)
+        qkv = F.linear(x, self._bf("in_w", a.in_proj_weight, x.dtype), self._bf("in_b", a.in_proj_bias, x.dtype))
+        if self.batch_first:
+            bn, L, c = x.shape
+            hd = c // self.n_head
+            q, k, v = qkv.view(bn, L, 3, self.n_head, hd).unbind(2)                       # each [B, L, H, hd]
+            out = F.scaled_dot_product_attention(q.transpose(1, 2), k.transpose(1, 2), v.transpose(1, 2),
+                                                 is_causal=causal)                        # [B, H, L, hd]
+            out = out.transpose(1, 2).reshape(bn, L, c)
+        else:
+            L, bn, c = x.shape
+            hd = c // self.n_head
+            qkv = qkv.view(L, bn, 3, self.n_head, hd).permute(2, 1, 3, 0, 4)              # [3, B, H, L, hd]
+            out = F.scaled_dot_product_attention(qkv[0], qkv[1], qkv[2], is_causal=causal)
+            out = out.permute(2, 0, 1, 3).reshape(L, bn, c)
         return F.linear(out, self._bf("out_w", a.out_proj.weight, x.dtype), self._bf("out_b", a.out_proj.bias, x.dtype))
 
     def forward(self, x: torch.Tensor, attr: Optional[torch.Tensor] = None):
@@ -130,10 +151,11 @@ class ResidualAttentionBlock(nn.Module, _Bf16Cache):
 
 class Transformer(nn.Module):
     def __init__(self, width: int, layers: int, heads: int, attn_mask: Optional[torch.Tensor] = None,
-                 text_layer=False, design_details=None):
+                 text_layer=False, design_details=None, batch_first: bool = False):
         super().__init__()
         self.width, self.layers = width, layers
-        self.resblocks = nn.ModuleList([ResidualAttentionBlock(width, heads, attn_mask) for _ in range(layers)])
+        self.resblocks = nn.ModuleList([ResidualAttentionBlock(width, heads, attn_mask, batch_first)
+                                        for _ in range(layers)])
 
     def forward(self, x: torch.Tensor, attr=None):
         for block in self.resblocks:
@@ -153,20 +175,23 @@ class ModifiedVisionTransformer(nn.Module, _Bf16Cache):
         self.class_embedding = nn.Parameter(scale * torch.randn(width))
         self.positional_embedding = nn.Parameter(scale * torch.randn((input_resolution // patch_size) ** 2 + 1, width))
         self.ln_pre = LayerNorm(width)
-        self.transformer = Transformer(width, layers, heads, design_details=design_details)
+        # internal activations are batch-first [B', L, C] (no transposes around attention); the adapters are told
+        # through row_div, and the result is handed back sequence-first like the reference
+        self.transformer = Transformer(width, layers, heads, design_details=design_details, batch_first=True)
         self.ln_post = LayerNorm(width)
         self.proj = nn.Parameter(scale * torch.randn(width, output_dim))
 
     def forward(self, x: torch.Tensor, attr: Optional[torch.Tensor] = None):
         dt = x.dtype
         x = F.conv2d(x, self._bf("conv1", self.conv1.weight, dt), stride=self.patch_size)      # [B', width, g, g]
-        x = x.flatten(2).permute(2, 0, 1)                                                      # [g*g, B', width]
-        cls = self._bf("cls", self.class_embedding, dt).expand(1, x.shape[1], -1)
-        x = torch.cat([cls, x], dim=0) + self._bf("pos", self.positional_embedding, dt).unsqueeze(1)
+        x = x.flatten(2).transpose(1, 2)                                                       # [B', g*g, width]
+        cls = self._bf("cls", self.class_embedding, dt).expand(x.shape[0], 1, -1)
+        x = torch.cat([cls, x], dim=1) + self._bf("pos", self.positional_embedding, dt)
         x = self.ln_pre(x)
         x = self.transformer(x, attr=attr)
         x = self.ln_post(x)
-        return x @ self._bf("proj", self.proj, dt)                                             # [L, B', output_dim]
+        x = x @ self._bf("proj", self.proj, dt)                                                # [B', L, output_dim]
+        return x.transpose(0, 1)                                                               # [L, B', output_dim]
 
 
 class TextEncoder(nn.Module, _Bf16Cache):
@@ -175,7 +200,7 @@ class TextEncoder(nn.Module, _Bf16Cache):
     def __init__(self, width=512, layers=12, heads=8, context_length=77, embed_dim=512):
         super().__init__()
         mask = torch.full((context_length, context_length), float("-inf")).triu_(1)
-        self.transformer = Transformer(width, layers, heads, attn_mask=mask)
+        self.transformer = Transformer(width, layers, heads, attn_mask=mask, batch_first=True)
         self.positional_embedding = nn.Parameter(torch.empty(context_length, width))
         self.ln_final = LayerNorm(width)
         self.text_projection = nn.Parameter(torch.empty(width, embed_dim))
@@ -184,7 +209,7 @@ class TextEncoder(nn.Module, _Bf16Cache):
     def forward(self, prompts: torch.Tensor, eot_index: torch.Tensor):
         dt = self.compute_dtype if prompts.is_cuda else prompts.dtype
         x = prompts.to(dt) + self._bf("pos", self.positional_embedding, dt)
-        x = self.transformer(x.permute(1, 0, 2)).permute(1, 0, 2)
+        x = self.transformer(x)                      # prompts are already [n_prompts * n_cls, 77, width]
         x = self.ln_final(x)
         x = x[torch.arange(x.shape[0], device=x.device), eot_index]
         return x.float() @ self.text_projection

@@ -11,26 +11,31 @@
 //   backward: X=dy, Wmat=W^T[in,out],  Aside=B   (pad), Bside=A   (pad), s_rows = scaling·s_eff
 //             -> OUT = dx, H = dy·B^T (un-scaled dz)
 //
-// Structure (one CTA per SM, 256 threads, static round-robin tile scheduler):
+// Structure (one CTA per SM, 384 threads, static round-robin tile scheduler):
 //   warp 0   : TMA producer  — X / Wmat / Aside k-slices into a 4-stage SW128 smem ring
 //   warp 1   : MMA issuer    — one tcgen05.mma (M=128, N=192+16, K=16) per k-step: the W tile and the
 //                              Aside tile are adjacent in smem, so a single UMMA accumulates both
 //                              D (192 cols) and H (16 cols) into TMEM; later one K=16 "fix-up" UMMA
 //                              D += Z · Bside^T with Z = bf16(H ⊙ s_rows) staged by the epilogue warps
 //   warp 2   : TMEM allocator (512 columns = 2 accumulator stages x 256)
-//   warps 4-7: epilogue      — tcgen05.ld H -> scale -> Z (SW32 smem) -> signal; then tcgen05.ld D
+//   warps 4-11: epilogue     — tcgen05.ld H -> scale -> Z (SW32 smem) -> signal; then tcgen05.ld D
 //                              -> +bias / QuickGELU / QuickGELU' -> bf16 -> SW128 smem -> TMA store
 // TMEM accumulators are double buffered so tile i's epilogue overlaps tile i+1's mainloop; the
 // fix-up UMMA of tile i is slotted into tile i+1's k-loop as soon as Z(i) is ready.
 #include <stdarg.h>
+#include <stdlib.h>
 #include <string.h>
+
+#ifndef FFM_GEMM_PAIR_DEFAULT
+#define FFM_GEMM_PAIR_DEFAULT 0
+#endif
 
 #include <atomic>
 #include <mutex>
 #include <vector>
 
 #include "../../include/ffm_b200.h"
-#include "ffm_common.cuh"
+#include "svlora_gemm.cuh"
 
 namespace ffm {
 
@@ -55,6 +60,26 @@ static std::mutex g_prof_mutex;
 static bool g_prof_enabled = false;
 static std::vector<GemmRecord> g_prof_records;
 
+int gemm_profile_begin(GemmProfileScope* sc, cudaStream_t stream) {
+  {
+    std::lock_guard<std::mutex> lk(g_prof_mutex);
+    sc->active = g_prof_enabled && g_prof_records.size() < 65536;
+  }
+  if (!sc->active) return FFM_OK;
+  FFM_CHECK_CUDA(cudaEventCreate(&sc->start));
+  FFM_CHECK_CUDA(cudaEventCreate(&sc->stop));
+  FFM_CHECK_CUDA(cudaEventRecord(sc->start, stream));
+  return FFM_OK;
+}
+
+int gemm_profile_end(GemmProfileScope* sc, int T, int K, int N, cudaStream_t stream) {
+  if (!sc->active) return FFM_OK;
+  FFM_CHECK_CUDA(cudaEventRecord(sc->stop, stream));
+  std::lock_guard<std::mutex> lk(g_prof_mutex);
+  g_prof_records.push_back(GemmRecord{sc->start, sc->stop, T, K, N});
+  return FFM_OK;
+}
+
 int num_sms() {
   static int cached[64] = {0};
   int dev = 0;
@@ -73,7 +98,6 @@ int num_sms() {
 constexpr int BM = 128;             // rows of X per tile      (UMMA M, one TMEM lane per row)
 constexpr int BN = 192;             // rows of Wmat per tile   (output columns)
 constexpr int BK = 64;              // k-slice per stage = one 128-byte swizzle row of bf16
-constexpr int RP = 16;              // padded adapter rank
 constexpr int UMMA_K = 16;
 constexpr int UMMA_N_MAIN = BN + RP;  // 208: [D | H] in one instruction
 constexpr int STAGES = 4;
@@ -106,30 +130,11 @@ static_assert(OFF_OUT % 1024 == 0 && OFF_Z % 1024 == 0 && OFF_BS % 1024 == 0, "t
 static_assert(SMEM_BYTES <= 232448, "exceeds 227 KB of shared memory per CTA");
 static_assert(BN % OUT_CHUNK == 0, "epilogue chunks");
 
-constexpr int NUM_THREADS = 256;
-constexpr int EPI_THREADS = 128;
+constexpr int NUM_THREADS = 384;   // 4 control warps (TMA, MMA, TMEM alloc, spare) + 8 epilogue warps
+constexpr int EPI_THREADS = 256;
+constexpr int Z_THREADS = 128;     // epilogue threads that write the Z tile (one per tile row)
 constexpr int EPI_BAR_ID = 1;
 
-enum : int { ACT_NONE = 0, ACT_QUICKGELU = 1, ACT_QUICKGELU_GRAD = 2 };
-
-struct GemmParams {
-  const float* bias;            // [N] or nullptr
-  const float* s_rows;          // [n_samples, RP] fp32 (already multiplied by alpha/r)
-  float* h_out;                 // [T, RP] fp32 or nullptr
-  const __nv_bfloat16* aux;     // ACT_QUICKGELU_GRAD: pre-activation u [T, N]
-  int T, K, N;
-  int b_prime, num_slices;      // sample(t) = (t % b_prime) / num_slices
-  int act;
-  int has_pre;                  // ACT_QUICKGELU: also store the pre-activation through tm_y2
-  int m_tiles, n_tiles, k_blocks;
-};
-
-__device__ __forceinline__ float fast_sigmoid(float v) { return __frcp_rn(1.0f + __expf(-v)); }
-__device__ __forceinline__ float quick_gelu(float u) { return u * fast_sigmoid(1.702f * u); }
-__device__ __forceinline__ float quick_gelu_grad(float u) {
-  const float s = fast_sigmoid(1.702f * u);
-  return s * (1.0f + 1.702f * u * (1.0f - s));
-}
 
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 svlora_gemm_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_w,
@@ -168,7 +173,7 @@ svlora_gemm_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_consta
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&h_full[i], 1);
-      mbar_init(&z_full[i], EPI_THREADS);
+      mbar_init(&z_full[i], Z_THREADS);
       mbar_init(&d_full[i], 1);
       mbar_init(&tmem_empty[i], EPI_THREADS / 32);
       mbar_init(&bs_full[i], 1);
@@ -266,10 +271,13 @@ svlora_gemm_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_consta
       }
     }
   } else if (warp >= 4) {
-    // =========================== epilogue ===========================
-    const uint32_t q = warp & 3u;              // TMEM lane quarter accessible by this warp
-    const uint32_t row = q * 32u + lane;       // row of the tile owned by this thread
-    const uint32_t et = threadIdx.x - 128u;    // 0..127
+    // =========================== epilogue (8 warps) ===========================
+    // Two warps share each TMEM lane quarter (a warp may only touch lanes 32*(warpid%4)..+31): warp w handles
+    // columns [0,32) of every 64-column chunk, warp w+4 columns [32,64).  One tile row per thread.
+    const uint32_t q = warp & 3u;
+    const uint32_t half = (warp - 4u) >> 2;
+    const uint32_t row = q * 32u + lane;
+    const uint32_t et = threadIdx.x - 128u;    // 0..255
     const uint32_t lane_addr = (q * 32u) << 16;
     uint32_t store_unit = 0;                   // running count of TMA-store units (buffer = unit & 1)
     int it = 0;
@@ -281,16 +289,17 @@ svlora_gemm_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_consta
       const int grow = m_blk * BM + static_cast<int>(row);   // global row
       const int n0 = n_blk * BN;
       const uint32_t acc = tmem_base + lane_addr + s * ACC_COLS;
+      float* bias_s = reinterpret_cast<float*>(smem + OFF_BIAS + s * BIAS_TILE_BYTES);
 
-      // ---- H -> Z ----
-      mbar_wait(&h_full[s], aph, 600 + s);
-      tc_fence_after();
-      uint32_t hv[16];
-      tmem_ld16(acc + BN, hv);
-      tmem_ld_wait();
-      {
+      if (half == 0) {
+        // ---- H -> Z (SW32 K-major A operand of the fix-up UMMA) ----
+        mbar_wait(&h_full[s], aph, 600 + s);
+        tc_fence_after();
+        uint32_t hv[16];
+        tmem_ld16(acc + BN, hv);
+        tmem_ld_wait();
         const int grow_c = grow < p.T ? grow : (p.T - 1);
-        const int sample = (grow_c % p.b_prime) / p.num_slices;
+        const int sample = ((grow_c / p.row_div) % p.b_prime) / p.num_slices;
         const float4* sr = reinterpret_cast<const float4*>(p.s_rows + static_cast<size_t>(sample) * RP);
         float zf[16];
 #pragma unroll
@@ -308,7 +317,7 @@ svlora_gemm_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_consta
             ho[j] = make_float4(__uint_as_float(hv[4 * j]), __uint_as_float(hv[4 * j + 1]),
                                 __uint_as_float(hv[4 * j + 2]), __uint_as_float(hv[4 * j + 3]));
         }
-        // SW32 K-major tile: row r at r*32 B, 16-B chunk c stored at chunk (c ^ ((r>>2)&1))
+        // row r at r*32 B, 16-B chunk c stored at chunk (c ^ ((r>>2)&1))
         uint8_t* zrow = smem + OFF_Z + s * Z_TILE_BYTES + row * 32u;
         const uint32_t sw = (row >> 2) & 1u;
         uint4 c0, c1;
@@ -318,47 +327,45 @@ svlora_gemm_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_consta
         c1.z = pack_bf16x2(zf[12], zf[13]); c1.w = pack_bf16x2(zf[14], zf[15]);
         *reinterpret_cast<uint4*>(zrow + ((0u ^ sw) << 4)) = c0;
         *reinterpret_cast<uint4*>(zrow + ((1u ^ sw) << 4)) = c1;
+        fence_proxy_async_smem();
+        mbar_arrive(&z_full[s]);
+      } else {
+        // bias slice of this n block, staged by the other four warps meanwhile
+        for (int j = et - 128; j < BN; j += 128) {
+          const int col = n0 + j;
+          bias_s[j] = (p.bias != nullptr && col < p.N) ? __ldg(p.bias + col) : 0.0f;
+        }
       }
-      // bias slice for this n block (visible to the other epilogue threads after the named barrier below)
-      float* bias_s = reinterpret_cast<float*>(smem + OFF_BIAS + s * BIAS_TILE_BYTES);
-      for (int j = et; j < BN; j += EPI_THREADS) {
-        const int col = n0 + j;
-        bias_s[j] = (p.bias != nullptr && col < p.N) ? __ldg(p.bias + col) : 0.0f;
-      }
-      fence_proxy_async_smem();
-      mbar_arrive(&z_full[s]);
       named_bar_sync(EPI_BAR_ID, EPI_THREADS);   // bias_s visible to all epilogue threads
 
       // ---- D -> OUT ----
       mbar_wait(&d_full[s], aph, 700 + s);
       tc_fence_after();
+      const int n_pass = (p.act == ACT_QUICKGELU && p.has_pre) ? 2 : 1;
 #pragma unroll 1
       for (int c = 0; c < BN / OUT_CHUNK; ++c) {
-        uint32_t v0[32], v1[32];
-        tmem_ld32(acc + c * OUT_CHUNK, v0);
-        tmem_ld32(acc + c * OUT_CHUNK + 32, v1);
+        const int cc = c * OUT_CHUNK + static_cast<int>(half) * 32;   // first tile column of this thread's slice
+        uint32_t v[32];
+        tmem_ld32(acc + cc, v);
         tmem_ld_wait();
         if (c == BN / OUT_CHUNK - 1) {
-          // accumulator stage fully read: hand it back to the MMA warp
+          // accumulator stage fully read by this warp: hand it back to the MMA warp
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(&tmem_empty[s]);
         }
-        float f[64];
+        float f[32];
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          f[j] = __uint_as_float(v0[j]) + bias_s[c * OUT_CHUNK + j];
-          f[32 + j] = __uint_as_float(v1[j]) + bias_s[c * OUT_CHUNK + 32 + j];
-        }
-        const int col0 = n0 + c * OUT_CHUNK;
-        const int n_pass = (p.act == ACT_QUICKGELU && p.has_pre) ? 2 : 1;
+        for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]) + bias_s[cc + j];
+        const int col0 = n0 + c * OUT_CHUNK;     // first global column of the 64-wide store unit
         if (p.act == ACT_QUICKGELU_GRAD) {
-          // f <- f * gelu'(u), u = pre-activation saved by the forward pass
+          // f <- f * QuickGELU'(u), u = pre-activation saved by the forward pass
           if (grow < p.T) {
-            const __nv_bfloat16* up = p.aux + static_cast<size_t>(grow) * p.N + col0;
-            if (col0 + OUT_CHUNK <= p.N) {
+            const int gc = n0 + cc;
+            const __nv_bfloat16* up = p.aux + static_cast<size_t>(grow) * p.N + gc;
+            if (gc + 32 <= p.N) {
 #pragma unroll
-              for (int j8 = 0; j8 < 8; ++j8) {
+              for (int j8 = 0; j8 < 4; ++j8) {
                 const uint4 raw = __ldg(reinterpret_cast<const uint4*>(up) + j8);
                 const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&raw);
 #pragma unroll
@@ -369,8 +376,8 @@ svlora_gemm_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_consta
                 }
               }
             } else {
-              for (int j = 0; j < OUT_CHUNK; ++j)
-                if (col0 + j < p.N) f[j] *= quick_gelu_grad(__bfloat162float(up[j]));
+              for (int j = 0; j < 32; ++j)
+                if (gc + j < p.N) f[j] *= quick_gelu_grad(__bfloat162float(up[j]));
             }
           }
         }
@@ -386,17 +393,18 @@ svlora_gemm_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_consta
           uint8_t* orow = ob + row * 128u;
           if (apply_act) {   // warp-uniform branch: keep the MUFU work out of the plain-store path
 #pragma unroll
-            for (int j = 0; j < OUT_CHUNK; ++j) f[j] = quick_gelu(f[j]);
+            for (int j = 0; j < 32; ++j) f[j] = quick_gelu(f[j]);
           }
 #pragma unroll
-          for (int j8 = 0; j8 < 8; ++j8) {
+          for (int j8 = 0; j8 < 4; ++j8) {
             uint4 pk;
             pk.x = pack_bf16x2(f[j8 * 8 + 0], f[j8 * 8 + 1]);
             pk.y = pack_bf16x2(f[j8 * 8 + 2], f[j8 * 8 + 3]);
             pk.z = pack_bf16x2(f[j8 * 8 + 4], f[j8 * 8 + 5]);
             pk.w = pack_bf16x2(f[j8 * 8 + 6], f[j8 * 8 + 7]);
-            // SW128: 16-B chunk j8 of row r lives at chunk (j8 ^ (r & 7))
-            *reinterpret_cast<uint4*>(orow + ((static_cast<uint32_t>(j8) ^ (row & 7u)) << 4)) = pk;
+            // SW128: 16-B piece k of row r lives at piece (k ^ (r & 7)); this thread owns pieces half*4 .. +3
+            const uint32_t piece = half * 4u + static_cast<uint32_t>(j8);
+            *reinterpret_cast<uint4*>(orow + ((piece ^ (row & 7u)) << 4)) = pk;
           }
           fence_proxy_async_smem();
           named_bar_sync(EPI_BAR_ID, EPI_THREADS);
@@ -470,8 +478,7 @@ static PFN_encodeTiled get_encode_fn() {
   return fn;
 }
 
-// row-major bf16 matrix [rows, cols] (cols contiguous) -> 2-D tiled map with box [box_rows, box_cols]
-static int make_map_bf16(CUtensorMap* out, const void* ptr, uint64_t rows, uint64_t cols, uint32_t box_rows,
+int make_map_bf16(CUtensorMap* out, const void* ptr, uint64_t rows, uint64_t cols, uint32_t box_rows,
                          uint32_t box_cols, CUtensorMapSwizzle swz, bool promote) {
   PFN_encodeTiled enc = get_encode_fn();
   if (enc == nullptr) {
@@ -494,25 +501,22 @@ static int make_map_bf16(CUtensorMap* out, const void* ptr, uint64_t rows, uint6
   return FFM_OK;
 }
 
-struct GemmOperands {
-  const void* x;        // [T, K] bf16
-  const void* wmat;     // [N, K] bf16
-  const void* a_side;   // [RP, K] bf16
-  const void* b_side;   // [N, RP] bf16
-  const float* s_rows;  // [nS, RP]
-  const float* bias;    // [N] or null
-  void* out;            // [T, N] bf16
-  void* out_pre;        // [T, N] bf16 or null (ACT_QUICKGELU only)
-  float* h_out;         // [T, RP] or null
-  const void* aux;      // [T, N] bf16 (ACT_QUICKGELU_GRAD)
-  int T, K, N, b_prime, num_slices, act;
-};
+
+// FFM_GEMM_PAIR=0 selects the single-CTA build (kept for A/B measurements); default is the CTA-pair build
+static bool use_pair_kernel() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("FFM_GEMM_PAIR");
+    v = (e == nullptr) ? FFM_GEMM_PAIR_DEFAULT : (e[0] != '0');
+  }
+  return v != 0;
+}
 
 static int launch_svlora_gemm(const GemmOperands& o, cudaStream_t stream) {
   FFM_CHECK_ARG(o.T > 0 && o.K > 0 && o.N > 0, "svlora gemm: empty problem T=%d K=%d N=%d", o.T, o.K, o.N);
   FFM_CHECK_ARG(o.K % 8 == 0 && o.N % 8 == 0, "svlora gemm: K (%d) and N (%d) must be multiples of 8 (TMA 16-B strides)",
                 o.K, o.N);
-  FFM_CHECK_ARG(o.b_prime > 0 && o.num_slices > 0, "svlora gemm: b_prime/num_slices must be positive");
+  FFM_CHECK_ARG(o.b_prime > 0 && o.num_slices > 0 && o.row_div > 0, "svlora gemm: b_prime/num_slices/row_div must be positive");
   FFM_CHECK_ARG(o.act != ACT_QUICKGELU_GRAD || o.aux != nullptr, "svlora gemm: ACT_QUICKGELU_GRAD needs aux");
   const uintptr_t align_or = reinterpret_cast<uintptr_t>(o.x) | reinterpret_cast<uintptr_t>(o.wmat) |
                              reinterpret_cast<uintptr_t>(o.a_side) | reinterpret_cast<uintptr_t>(o.b_side) |
@@ -520,6 +524,7 @@ static int launch_svlora_gemm(const GemmOperands& o, cudaStream_t stream) {
                              reinterpret_cast<uintptr_t>(o.s_rows) | reinterpret_cast<uintptr_t>(o.h_out) |
                              reinterpret_cast<uintptr_t>(o.aux);
   FFM_CHECK_ARG((align_or & 15u) == 0, "svlora gemm: all device pointers must be 16-byte aligned");
+  if (use_pair_kernel()) return launch_svlora_gemm_pair(o, stream);
 
   CUtensorMap tm_x, tm_w, tm_a, tm_b, tm_y, tm_y2;
   int rc;
@@ -539,7 +544,7 @@ static int launch_svlora_gemm(const GemmOperands& o, cudaStream_t stream) {
   p.h_out = o.h_out;
   p.aux = reinterpret_cast<const __nv_bfloat16*>(o.aux);
   p.T = o.T; p.K = o.K; p.N = o.N;
-  p.b_prime = o.b_prime; p.num_slices = o.num_slices;
+  p.b_prime = o.b_prime; p.num_slices = o.num_slices; p.row_div = o.row_div;
   p.act = o.act;
   p.has_pre = has_pre ? 1 : 0;
   p.m_tiles = (o.T + BM - 1) / BM;
@@ -565,27 +570,12 @@ static int launch_svlora_gemm(const GemmOperands& o, cudaStream_t stream) {
 
   const int tiles = p.m_tiles * p.n_tiles;
   const int grid = tiles < num_sms() ? tiles : num_sms();
-  GemmRecord rec{};
-  bool profiling = false;
-  {
-    std::lock_guard<std::mutex> lk(g_prof_mutex);
-    profiling = g_prof_enabled && g_prof_records.size() < 65536;
-  }
-  if (profiling) {
-    FFM_CHECK_CUDA(cudaEventCreate(&rec.start));
-    FFM_CHECK_CUDA(cudaEventCreate(&rec.stop));
-    rec.T = o.T; rec.K = o.K; rec.N = o.N;
-    FFM_CHECK_CUDA(cudaEventRecord(rec.start, stream));
-  }
+  GemmProfileScope prof;
+  if ((rc = gemm_profile_begin(&prof, stream))) return rc;
   svlora_gemm_kernel<<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(tm_x, tm_w, tm_a, tm_b, tm_y, tm_y2, p);
   FFM_CHECK_CUDA(cudaGetLastError());
   count_launch();
-  if (profiling) {
-    FFM_CHECK_CUDA(cudaEventRecord(rec.stop, stream));
-    std::lock_guard<std::mutex> lk(g_prof_mutex);
-    g_prof_records.push_back(rec);
-  }
-  return FFM_OK;
+  return gemm_profile_end(&prof, o.T, o.K, o.N, stream);
 }
 
 // workspace carve-up shared by fwd and bwd (all offsets 256-B aligned)
@@ -620,7 +610,7 @@ static void carve(SvloraWorkspace* w, void* ws, size_t ws_bytes, int Kdim, int N
 int launch_svlora_bwd_small(const __nv_bfloat16* x, const __nv_bfloat16* dy, const float* h, const float* dzu,
                             const float* s_rows, float* dA, float* dB, float* ds_eff, void* scratch,
                             size_t scratch_bytes, int T, int K, int N, int r, int nS, int b_prime, int num_slices,
-                            float scaling, cudaStream_t stream);
+                            int row_div, float scaling, cudaStream_t stream);
 size_t svlora_bwd_small_scratch_bytes(int T, int K, int N);
 
 }  // namespace ffm
@@ -684,9 +674,10 @@ size_t ffm_svlora_bwd_workspace_bytes(int T, int K, int N, int n_samples) {
 
 int ffm_svlora_fwd(const void* x, const void* w, const float* bias, const float* lora_a, const float* lora_b,
                    const float* s_eff, void* y, void* y_pre, float* h_out, void* workspace, size_t workspace_bytes,
-                   int T, int K, int N, int r, int n_samples, int b_prime, int num_slices, float scaling, int act,
-                   cudaStream_t stream) {
+                   int T, int K, int N, int r, int n_samples, int b_prime, int num_slices, int row_div, float scaling,
+                   int act, cudaStream_t stream) {
   FFM_CHECK_ARG(x && w && lora_a && lora_b && s_eff && y && workspace, "ffm_svlora_fwd: null pointer argument");
+  FFM_CHECK_ARG(row_div >= 1, "ffm_svlora_fwd: row_div must be >= 1");
   FFM_CHECK_ARG(r >= 1 && r <= RP, "ffm_svlora_fwd: rank %d not in [1, %d]", r, RP);
   FFM_CHECK_ARG(n_samples >= 1, "ffm_svlora_fwd: n_samples must be >= 1");
   FFM_CHECK_ARG(b_prime >= 1 && num_slices >= 1 && (b_prime - 1) / num_slices < n_samples,
@@ -705,19 +696,20 @@ int ffm_svlora_fwd(const void* x, const void* w, const float* bias, const float*
   GemmOperands o;
   o.x = x; o.wmat = w; o.a_side = ws.a_side; o.b_side = ws.b_side; o.s_rows = ws.s_rows; o.bias = bias;
   o.out = y; o.out_pre = y_pre; o.h_out = h_out; o.aux = nullptr;
-  o.T = T; o.K = K; o.N = N; o.b_prime = b_prime; o.num_slices = num_slices; o.act = act;
+  o.T = T; o.K = K; o.N = N; o.b_prime = b_prime; o.num_slices = num_slices; o.row_div = row_div; o.act = act;
   return launch_svlora_gemm(o, stream);
 }
 
 int ffm_svlora_bwd(const void* dy, const void* x, const void* w_t, const float* lora_a, const float* lora_b,
                    const float* s_eff, const float* h, const void* gelu_pre, void* dx, float* d_lora_a,
                    float* d_lora_b, float* d_s_eff, void* workspace, size_t workspace_bytes, int T, int K, int N,
-                   int r, int n_samples, int b_prime, int num_slices, float scaling, cudaStream_t stream) {
+                   int r, int n_samples, int b_prime, int num_slices, int row_div, float scaling,
+                   cudaStream_t stream) {
   FFM_CHECK_ARG(dy && x && w_t && lora_a && lora_b && s_eff && h && dx && d_lora_a && d_lora_b && d_s_eff &&
                     workspace,
                 "ffm_svlora_bwd: null pointer argument");
   FFM_CHECK_ARG(r >= 1 && r <= RP, "ffm_svlora_bwd: rank %d not in [1, %d]", r, RP);
-  FFM_CHECK_ARG(b_prime >= 1 && num_slices >= 1 && (b_prime - 1) / num_slices < n_samples,
+  FFM_CHECK_ARG(b_prime >= 1 && num_slices >= 1 && row_div >= 1 && (b_prime - 1) / num_slices < n_samples,
                 "ffm_svlora_bwd: sample mapping exceeds n_samples");
   FFM_CHECK_ARG(workspace_bytes >= ffm_svlora_bwd_workspace_bytes(T, K, N, n_samples),
                 "ffm_svlora_bwd: workspace too small");
@@ -734,13 +726,13 @@ int ffm_svlora_bwd(const void* dy, const void* x, const void* w_t, const float* 
   GemmOperands o;
   o.x = dy; o.wmat = w_t; o.a_side = ws.a_side; o.b_side = ws.b_side; o.s_rows = ws.s_rows; o.bias = nullptr;
   o.out = dx; o.out_pre = nullptr; o.h_out = dzu; o.aux = gelu_pre;
-  o.T = T; o.K = N; o.N = K; o.b_prime = b_prime; o.num_slices = num_slices;
+  o.T = T; o.K = N; o.N = K; o.b_prime = b_prime; o.num_slices = num_slices; o.row_div = row_div;
   o.act = gelu_pre != nullptr ? ACT_QUICKGELU_GRAD : ACT_NONE;
   int rc = launch_svlora_gemm(o, stream);
   if (rc != FFM_OK) return rc;
   return launch_svlora_bwd_small(reinterpret_cast<const __nv_bfloat16*>(x), reinterpret_cast<const __nv_bfloat16*>(dy),
                                  h, dzu, ws.s_rows, d_lora_a, d_lora_b, d_s_eff, scratch, scratch_bytes, T, K, N, r,
-                                 n_samples, b_prime, num_slices, scaling, stream);
+                                 n_samples, b_prime, num_slices, row_div, scaling, stream);
 }
 
 }  // extern "C"

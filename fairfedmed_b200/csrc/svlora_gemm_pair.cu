@@ -1,0 +1,422 @@
+// CTA-pair build of the fused SVLoRA / FairLoRA GEMM: thread-block cluster of 2, tcgen05 cta_group::2.
+//
+// Same contraction and same epilogue as svlora_gemm.cu (see there), but two SMs of a TPC cooperate on a
+// 256 x 192 output tile (128 rows each).  Why: the single-CTA kernel is bound by SHARED-MEMORY bandwidth, not by
+// the tensor pipe (ncu: tensor pipe 53 % active, the MMA thread never waits for data): per k-step a CTA reads
+// A (128x16) + B (208x16) operands = 10.5 KB per 104 tensor cycles and TMA writes the same volume, ~204 B/clk
+// against ~128 B/clk of shared-memory bandwidth.  With cta_group::2 each CTA stages and reads only HALF of the
+// B operand (Wmat / Aside rows), so per-CTA smem traffic drops to ~142 B/clk and the L2 -> SM operand traffic by
+// the same 1.45x.
+//
+// B-operand split (N = 208 = 2 x 104 rows): CTA r stages [ Wmat rows n0+96r .. +95 | Aside rows 8r .. 8r+7 ],
+// so accumulator columns are  [0,96) out cols 0..95 | [96,104) H cols 0..7 | [104,200) out cols 96..191 |
+// [200,208) H cols 8..15 — identical box shapes for both CTAs, the epilogue un-permutes.
+// The K=16 fix-up UMMA uses the same N = 208 with Bside halves padded by 8 zero rows.
+//
+// Protocol (leader = cluster rank 0):
+//   * both producers wait their LOCAL empty barrier and issue cta_group::2 TMA loads that credit the LEADER's full
+//     barrier; the leader's producer arms it with the byte count of both CTAs;
+//   * only the leader's MMA thread issues tcgen05.mma.cta_group::2 (M = 256) and multicast-commits to the
+//     empty / h_full / d_full barriers of BOTH CTAs;
+//   * both epilogues read their own TMEM half; "Z written" and "accumulator drained" arrive on the LEADER's
+//     z_full / tmem_empty barriers (remote arrive through mapa for the peer).
+#include <mutex>
+
+#include "../../include/ffm_b200.h"
+#include "svlora_gemm.cuh"
+
+namespace ffm {
+namespace pair {
+
+constexpr int BM = 128;              // rows per CTA (UMMA M = 256 over the pair)
+constexpr int BN = 192;              // output columns per tile
+constexpr int HN = BN / 2;           // Wmat rows staged per CTA
+constexpr int HR = RP / 2;           // Aside rows staged per CTA
+constexpr int BH = HN + HR;          // 104 B-operand rows per CTA
+constexpr int BK = 64;
+constexpr int UMMA_K = 16;
+constexpr int UMMA_M = 2 * BM;       // 256
+constexpr int UMMA_N = 2 * BH;       // 208
+constexpr int STAGES = 6;
+constexpr int ACC_COLS = 256;
+constexpr int TMEM_COLS = 512;
+constexpr int OUT_CHUNK = 64;
+
+constexpr int X_TILE_BYTES = BM * BK * 2;     // 16384
+constexpr int W_TILE_BYTES = HN * BK * 2;     // 12288
+constexpr int A_TILE_BYTES = HR * BK * 2;     //  1024
+constexpr int STAGE_BYTES = X_TILE_BYTES + W_TILE_BYTES + A_TILE_BYTES;   // 29696 = 29 * 1024
+constexpr int OUT_TILE_BYTES = BM * OUT_CHUNK * 2;   // 16384
+constexpr int Z_TILE_BYTES = BM * RP * 2;            //  4096
+constexpr int BS_LOAD_BYTES = HN * RP * 2;           //  3072 (TMA box)
+constexpr int BS_TILE_BYTES = 4096;                  //  104 rows x 32 B = 3328, padded
+constexpr int BIAS_TILE_BYTES = BN * 4;              //   768
+
+constexpr int OFF_STAGES = 0;
+constexpr int OFF_OUT = OFF_STAGES + STAGES * STAGE_BYTES;
+constexpr int OFF_Z = OFF_OUT + 2 * OUT_TILE_BYTES;
+constexpr int OFF_BS = OFF_Z + 2 * Z_TILE_BYTES;
+constexpr int OFF_BIAS = OFF_BS + 2 * BS_TILE_BYTES;
+constexpr int OFF_BAR = OFF_BIAS + 2 * BIAS_TILE_BYTES;
+constexpr int NUM_BARS = 2 * STAGES + 5 * 2;
+constexpr int SMEM_USED = OFF_BAR + NUM_BARS * 8 + 16;
+constexpr int SMEM_BYTES = SMEM_USED + 1024;
+
+static_assert(STAGE_BYTES % 1024 == 0 && (X_TILE_BYTES + W_TILE_BYTES) % 1024 == 0, "SW128 tile alignment");
+static_assert(OFF_OUT % 1024 == 0 && OFF_Z % 1024 == 0 && OFF_BS % 1024 == 0, "tile alignment");
+static_assert(SMEM_BYTES <= 232448, "exceeds 227 KB of shared memory per CTA");
+static_assert(HN % 32 == 0, "a 32-column epilogue slice must not straddle the two accumulator halves");
+
+constexpr int NUM_THREADS = 384;
+constexpr int EPI_THREADS = 256;
+constexpr int Z_THREADS = 128;
+constexpr int EPI_BAR_ID = 1;
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
+svlora_gemm_pair_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_w,
+                        const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b,
+                        const __grid_constant__ CUtensorMap tm_y, const __grid_constant__ CUtensorMap tm_y2,
+                        const GemmParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + OFF_BAR);
+  uint64_t* full_bar = bars;                   // [STAGES] leader only: TMA (both CTAs) -> MMA
+  uint64_t* empty_bar = bars + STAGES;         // [STAGES] both: MMA (multicast commit) -> TMA
+  uint64_t* h_full = bars + 2 * STAGES;        // [2] both: mainloop of the tile done
+  uint64_t* z_full = h_full + 2;               // [2] leader only: Z tiles of both CTAs written
+  uint64_t* d_full = z_full + 2;               // [2] both: fix-up UMMA done
+  uint64_t* tmem_empty = d_full + 2;           // [2] leader only: both epilogues drained the stage
+  uint64_t* bs_full = tmem_empty + 2;          // [2] leader only: Bside halves landed
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + NUM_BARS);
+
+  const uint32_t warp = threadIdx.x >> 5;
+  const uint32_t lane = threadIdx.x & 31u;
+  const uint32_t rank = cluster_ctarank();
+  const bool leader = rank == 0;
+  const int cluster_id = blockIdx.x >> 1;
+  const int num_clusters = gridDim.x >> 1;
+  const int m_pairs = (p.m_tiles + 1) >> 1;
+  const int num_tiles = m_pairs * p.n_tiles;   // pair tiles
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tm_x);
+    tma_prefetch_desc(&tm_w);
+    tma_prefetch_desc(&tm_a);
+    tma_prefetch_desc(&tm_b);
+    tma_prefetch_desc(&tm_y);
+    if (p.has_pre) tma_prefetch_desc(&tm_y2);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < STAGES; ++i) {
+      mbar_init(&full_bar[i], 1);
+      mbar_init(&empty_bar[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&h_full[i], 1);
+      mbar_init(&z_full[i], 2 * Z_THREADS);
+      mbar_init(&d_full[i], 1);
+      mbar_init(&tmem_empty[i], 2 * (EPI_THREADS / 32));
+      mbar_init(&bs_full[i], 1);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 2) {
+    tmem_alloc_pair(tmem_ptr, TMEM_COLS);
+    tmem_relinquish_pair();
+  }
+  if (warp == 3) {
+    // zero rows 96..103 of both Bside buffers once: the fix-up UMMA reads 104 rows, TMA only ever writes 96
+    for (int b = 0; b < 2; ++b) {
+      uint8_t* base = smem + OFF_BS + b * BS_TILE_BYTES + HN * 32;
+      for (int i = lane; i < (HR * 32) / 4; i += 32) reinterpret_cast<uint32_t*>(base)[i] = 0u;
+    }
+    fence_proxy_async_smem();
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();          // peer barriers initialised / TMEM allocated before any cross-CTA traffic
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  if (warp == 0) {
+    // =========================== TMA producer (both CTAs) ===========================
+    if (lane == 0) {
+      uint32_t stage = 0, phase = 0;
+      int it = 0;
+      for (int tile = cluster_id; tile < num_tiles; tile += num_clusters, ++it) {
+        const int m_pair = tile / p.n_tiles;
+        const int n_blk = tile - m_pair * p.n_tiles;
+        const int m_blk = m_pair * 2 + static_cast<int>(rank);
+        const int s = it & 1;
+        // Bside half for this tile; buffer s is free once the fix-up UMMA of tile it-2 completed
+        if (it >= 2) mbar_wait(&d_full[s], ((it - 2) >> 1) & 1u, 150 + s);
+        if (leader) mbar_arrive_expect_tx(&bs_full[s], 2 * BS_LOAD_BYTES);
+        tma_load_2d_pair(smem + OFF_BS + s * BS_TILE_BYTES, &tm_b, &bs_full[s], 0,
+                         n_blk * BN + static_cast<int>(rank) * HN);
+        for (int kb = 0; kb < p.k_blocks; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1u, 100 + stage);
+          uint8_t* st = smem + OFF_STAGES + stage * STAGE_BYTES;
+          if (leader) mbar_arrive_expect_tx(&full_bar[stage], 2 * STAGE_BYTES);
+          tma_load_2d_pair(st, &tm_x, &full_bar[stage], kb * BK, m_blk * BM);
+          tma_load_2d_pair(st + X_TILE_BYTES, &tm_w, &full_bar[stage], kb * BK,
+                           n_blk * BN + static_cast<int>(rank) * HN);
+          tma_load_2d_pair(st + X_TILE_BYTES + W_TILE_BYTES, &tm_a, &full_bar[stage], kb * BK,
+                           static_cast<int>(rank) * HR);
+          if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // =========================== MMA issuer (leader CTA only) ===========================
+    if (lane == 0 && leader) {
+      constexpr uint32_t idesc = umma_idesc_bf16(UMMA_M, UMMA_N);
+      uint32_t stage = 0, phase = 0;
+      int pend = -1;
+      uint32_t pend_phase = 0;
+
+      auto fixup = [&](int s, uint32_t ph) {
+        // D[s] += Z[s] (256 x 16 over the pair) · [Bside | 0]^T (16 x 208)
+        mbar_wait(&bs_full[s], ph, 200 + s);
+        tc_fence_after();
+        const uint64_t zd = umma_desc_sw32(smem_u32(smem + OFF_Z + s * Z_TILE_BYTES));
+        const uint64_t bd = umma_desc_sw32(smem_u32(smem + OFF_BS + s * BS_TILE_BYTES));
+        umma_bf16_pair(tmem_base + s * ACC_COLS, zd, bd, idesc, 1u);
+        umma_commit_pair(&d_full[s]);
+      };
+
+      int it = 0;
+      for (int tile = cluster_id; tile < num_tiles; tile += num_clusters, ++it) {
+        const int s = it & 1;
+        const uint32_t aph = (it >> 1) & 1u;
+        mbar_wait_cluster(&tmem_empty[s], aph ^ 1u, 300 + s);   // both epilogues drained tile it-2
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + s * ACC_COLS;
+        for (int kb = 0; kb < p.k_blocks; ++kb) {
+          if (pend >= 0 && mbar_test_wait_cluster(&z_full[pend], pend_phase)) {
+            fixup(pend, pend_phase);
+            pend = -1;
+          }
+          mbar_wait(&full_bar[stage], phase, 400 + stage);
+          tc_fence_after();
+          const uint32_t st = smem_u32(smem + OFF_STAGES + stage * STAGE_BYTES);
+          const uint64_t adesc = umma_desc_sw128(st);
+          const uint64_t bdesc = umma_desc_sw128(st + X_TILE_BYTES);
+#pragma unroll
+          for (int k = 0; k < BK / UMMA_K; ++k)
+            umma_bf16_pair(d_tmem, adesc + 2u * k, bdesc + 2u * k, idesc, (kb | k) != 0 ? 1u : 0u);
+          umma_commit_pair(&empty_bar[stage]);
+          if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+        }
+        umma_commit_pair(&h_full[s]);
+        if (pend >= 0) {
+          mbar_wait_cluster(&z_full[pend], pend_phase, 500 + pend);
+          fixup(pend, pend_phase);
+        }
+        pend = s;
+        pend_phase = aph;
+      }
+      if (pend >= 0) {
+        mbar_wait_cluster(&z_full[pend], pend_phase, 510 + pend);
+        fixup(pend, pend_phase);
+      }
+    }
+  } else if (warp >= 4) {
+    // =========================== epilogue (8 warps, both CTAs) ===========================
+    const uint32_t q = warp & 3u;
+    const uint32_t half = (warp - 4u) >> 2;
+    const uint32_t row = q * 32u + lane;
+    const uint32_t et = threadIdx.x - 128u;
+    const uint32_t lane_addr = (q * 32u) << 16;
+    uint32_t store_unit = 0;
+    int it = 0;
+    for (int tile = cluster_id; tile < num_tiles; tile += num_clusters, ++it) {
+      const int m_pair = tile / p.n_tiles;
+      const int n_blk = tile - m_pair * p.n_tiles;
+      const int m_blk = m_pair * 2 + static_cast<int>(rank);
+      const int s = it & 1;
+      const uint32_t aph = (it >> 1) & 1u;
+      const int grow = m_blk * BM + static_cast<int>(row);
+      const int n0 = n_blk * BN;
+      const uint32_t acc = tmem_base + lane_addr + s * ACC_COLS;
+      float* bias_s = reinterpret_cast<float*>(smem + OFF_BIAS + s * BIAS_TILE_BYTES);
+
+      if (half == 0) {
+        // ---- H -> Z ----
+        mbar_wait(&h_full[s], aph, 600 + s);
+        tc_fence_after();
+        uint32_t h0[8], h1[8];
+        tmem_ld8(acc + HN, h0);            // H columns 0..7  (leader's Aside rows)
+        tmem_ld8(acc + BH + HN, h1);       // H columns 8..15 (peer's Aside rows)
+        tmem_ld_wait();
+        const int grow_c = grow < p.T ? grow : (p.T - 1);
+        const int sample = ((grow_c / p.row_div) % p.b_prime) / p.num_slices;
+        const float4* sr = reinterpret_cast<const float4*>(p.s_rows + static_cast<size_t>(sample) * RP);
+        const float4 s0 = __ldg(sr), s1 = __ldg(sr + 1), s2 = __ldg(sr + 2), s3 = __ldg(sr + 3);
+        float hf[16];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { hf[j] = __uint_as_float(h0[j]); hf[8 + j] = __uint_as_float(h1[j]); }
+        if (p.h_out != nullptr && n_blk == 0 && grow < p.T) {
+          float4* ho = reinterpret_cast<float4*>(p.h_out + static_cast<size_t>(grow) * RP);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) ho[j] = make_float4(hf[4 * j], hf[4 * j + 1], hf[4 * j + 2], hf[4 * j + 3]);
+        }
+        const float sv[16] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w,
+                              s2.x, s2.y, s2.z, s2.w, s3.x, s3.y, s3.z, s3.w};
+        float zf[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) zf[j] = hf[j] * sv[j];
+        uint8_t* zrow = smem + OFF_Z + s * Z_TILE_BYTES + row * 32u;
+        const uint32_t sw = (row >> 2) & 1u;
+        uint4 c0, c1;
+        c0.x = pack_bf16x2(zf[0], zf[1]);   c0.y = pack_bf16x2(zf[2], zf[3]);
+        c0.z = pack_bf16x2(zf[4], zf[5]);   c0.w = pack_bf16x2(zf[6], zf[7]);
+        c1.x = pack_bf16x2(zf[8], zf[9]);   c1.y = pack_bf16x2(zf[10], zf[11]);
+        c1.z = pack_bf16x2(zf[12], zf[13]); c1.w = pack_bf16x2(zf[14], zf[15]);
+        *reinterpret_cast<uint4*>(zrow + ((0u ^ sw) << 4)) = c0;
+        *reinterpret_cast<uint4*>(zrow + ((1u ^ sw) << 4)) = c1;
+        fence_proxy_async_smem();
+        mbar_arrive_cluster(mapa_u32(smem_u32(&z_full[s]), 0));       // leader's barrier (local when rank 0)
+      } else {
+        for (int j = et - 128; j < BN; j += 128) {
+          const int col = n0 + j;
+          bias_s[j] = (p.bias != nullptr && col < p.N) ? __ldg(p.bias + col) : 0.0f;
+        }
+      }
+      named_bar_sync(EPI_BAR_ID, EPI_THREADS);
+
+      // ---- D -> OUT ----
+      mbar_wait(&d_full[s], aph, 700 + s);
+      tc_fence_after();
+      const int n_pass = (p.act == ACT_QUICKGELU && p.has_pre) ? 2 : 1;
+#pragma unroll 1
+      for (int c = 0; c < BN / OUT_CHUNK; ++c) {
+        const int cc = c * OUT_CHUNK + static_cast<int>(half) * 32;   // tile column of this thread's 32-wide slice
+        const int tcol = cc < HN ? cc : cc + HR;                        // accumulator column (skip the H block)
+        uint32_t v[32];
+        tmem_ld32(acc + tcol, v);
+        tmem_ld_wait();
+        if (c == BN / OUT_CHUNK - 1) {
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive_cluster(mapa_u32(smem_u32(&tmem_empty[s]), 0));
+        }
+        float f[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]) + bias_s[cc + j];
+        const int col0 = n0 + c * OUT_CHUNK;
+        if (p.act == ACT_QUICKGELU_GRAD) {
+          if (grow < p.T) {
+            const int gc = n0 + cc;
+            const __nv_bfloat16* up = p.aux + static_cast<size_t>(grow) * p.N + gc;
+            if (gc + 32 <= p.N) {
+#pragma unroll
+              for (int j8 = 0; j8 < 4; ++j8) {
+                const uint4 raw = __ldg(reinterpret_cast<const uint4*>(up) + j8);
+                const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&raw);
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                  const float2 uu = __bfloat1622float2(h2[e]);
+                  f[j8 * 8 + 2 * e] *= quick_gelu_grad(uu.x);
+                  f[j8 * 8 + 2 * e + 1] *= quick_gelu_grad(uu.y);
+                }
+              }
+            } else {
+              for (int j = 0; j < 32; ++j)
+                if (gc + j < p.N) f[j] *= quick_gelu_grad(__bfloat162float(up[j]));
+            }
+          }
+        }
+#pragma unroll 1
+        for (int pass = 0; pass < n_pass; ++pass) {
+          const bool apply_act = (p.act == ACT_QUICKGELU) && (pass == n_pass - 1);
+          const uint32_t buf = store_unit & 1u;
+          uint8_t* ob = smem + OFF_OUT + buf * OUT_TILE_BYTES;
+          if (et == 0) tma_store_wait_read<1>();
+          named_bar_sync(EPI_BAR_ID, EPI_THREADS);
+          uint8_t* orow = ob + row * 128u;
+          if (apply_act) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) f[j] = quick_gelu(f[j]);
+          }
+#pragma unroll
+          for (int j8 = 0; j8 < 4; ++j8) {
+            uint4 pk;
+            pk.x = pack_bf16x2(f[j8 * 8 + 0], f[j8 * 8 + 1]);
+            pk.y = pack_bf16x2(f[j8 * 8 + 2], f[j8 * 8 + 3]);
+            pk.z = pack_bf16x2(f[j8 * 8 + 4], f[j8 * 8 + 5]);
+            pk.w = pack_bf16x2(f[j8 * 8 + 6], f[j8 * 8 + 7]);
+            const uint32_t piece = half * 4u + static_cast<uint32_t>(j8);
+            *reinterpret_cast<uint4*>(orow + ((piece ^ (row & 7u)) << 4)) = pk;
+          }
+          fence_proxy_async_smem();
+          named_bar_sync(EPI_BAR_ID, EPI_THREADS);
+          if (et == 0) {
+            const CUtensorMap* tm = (n_pass == 2 && pass == 0) ? &tm_y2 : &tm_y;
+            tma_store_2d(tm, ob, col0, m_blk * BM);
+            tma_store_commit();
+          }
+          ++store_unit;
+        }
+      }
+    }
+    if (et == 0) tma_store_wait_all<0>();
+  }
+
+  // teardown: nobody may leave while the peer can still address this CTA's barriers / TMEM
+  __syncwarp();
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  if (warp == 2) tmem_dealloc_pair(tmem_base, TMEM_COLS);
+}
+
+}  // namespace pair
+
+int launch_svlora_gemm_pair(const GemmOperands& o, cudaStream_t stream) {
+  using namespace pair;
+  CUtensorMap tm_x, tm_w, tm_a, tm_b, tm_y, tm_y2;
+  int rc;
+  if ((rc = make_map_bf16(&tm_x, o.x, o.T, o.K, BM, BK, CU_TENSOR_MAP_SWIZZLE_128B, true))) return rc;
+  if ((rc = make_map_bf16(&tm_w, o.wmat, o.N, o.K, HN, BK, CU_TENSOR_MAP_SWIZZLE_128B, true))) return rc;
+  if ((rc = make_map_bf16(&tm_a, o.a_side, RP, o.K, HR, BK, CU_TENSOR_MAP_SWIZZLE_128B, true))) return rc;
+  if ((rc = make_map_bf16(&tm_b, o.b_side, o.N, RP, HN, RP, CU_TENSOR_MAP_SWIZZLE_32B, false))) return rc;
+  if ((rc = make_map_bf16(&tm_y, o.out, o.T, o.N, BM, OUT_CHUNK, CU_TENSOR_MAP_SWIZZLE_128B, false))) return rc;
+  const bool has_pre = (o.act == ACT_QUICKGELU && o.out_pre != nullptr);
+  if ((rc = make_map_bf16(&tm_y2, has_pre ? o.out_pre : o.out, o.T, o.N, BM, OUT_CHUNK, CU_TENSOR_MAP_SWIZZLE_128B,
+                          false)))
+    return rc;
+
+  GemmParams p;
+  p.bias = o.bias;
+  p.s_rows = o.s_rows;
+  p.h_out = o.h_out;
+  p.aux = reinterpret_cast<const __nv_bfloat16*>(o.aux);
+  p.T = o.T; p.K = o.K; p.N = o.N;
+  p.b_prime = o.b_prime; p.num_slices = o.num_slices; p.row_div = o.row_div;
+  p.act = o.act;
+  p.has_pre = has_pre ? 1 : 0;
+  p.m_tiles = (o.T + BM - 1) / BM;
+  p.n_tiles = (o.N + BN - 1) / BN;
+  p.k_blocks = (o.K + BK - 1) / BK;
+
+  static thread_local int attr_dev = -1;
+  int dev = 0;
+  FFM_CHECK_CUDA(cudaGetDevice(&dev));
+  if (dev != attr_dev) {
+    FFM_CHECK_CUDA(cudaFuncSetAttribute(svlora_gemm_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        SMEM_BYTES));
+    attr_dev = dev;
+  }
+  const int pair_tiles = ((p.m_tiles + 1) / 2) * p.n_tiles;
+  const int max_clusters = num_sms() / 2;
+  const int clusters = pair_tiles < max_clusters ? pair_tiles : max_clusters;
+  GemmProfileScope prof;
+  if ((rc = gemm_profile_begin(&prof, stream))) return rc;
+  svlora_gemm_pair_kernel<<<2 * clusters, NUM_THREADS, SMEM_BYTES, stream>>>(tm_x, tm_w, tm_a, tm_b, tm_y, tm_y2, p);
+  FFM_CHECK_CUDA(cudaGetLastError());
+  count_launch();
+  return gemm_profile_end(&prof, o.T, o.K, o.N, stream);
+}
+
+}  // namespace ffm

@@ -58,64 +58,131 @@ __global__ void ds_kernel(const long long* __restrict__ attr, const float* __res
 }
 
 // ----------------------------------------------------------------------------------------------
-// out[c, j] = sum_t M[t, c] * v[t, j],  v[t, j] = src[t, j] * s_rows[sample(t), j]
-// bf16 M [T, C]; fp32 src [T, 16]; partial sums per row chunk, reduced by colsum_reduce_kernel.
+// out[c, j] = sum_t M[t, c] * v[t, j],  v[t, j] = bf16(src[t, j] * s_rows[sample(t), j])
+// bf16 M [T, C] (x or dy), fp32 src [T, 16] (dzu or h).  A skinny contraction over the T rows: M is read from HBM
+// exactly once (T*C*2 bytes) and that is the bound.  CUDA-core FMAs cannot keep up (16 FMA per 2 bytes), so the
+// products run on the legacy tensor path: mma.sync m16n8k16 with A = M^T and B = v, both fetched from shared memory
+// with ldmatrix.trans (the tiles sit in smem exactly as they sit in HBM: rows = t).
+//   CTA = 8 warps, tile = 128 columns x 64 rows per stage, 3-stage cp.async ring; warp w owns columns 16w..16w+15
+//   and all 16 ranks (two n-tiles).  Row chunks write fp32 partials; colsum_reduce_kernel folds them (deterministic).
 // ----------------------------------------------------------------------------------------------
-constexpr int CS_THREADS = 128;
-constexpr int CS_COLS = CS_THREADS * 2;  // columns per CTA (one bf16x2 per thread per row)
-constexpr int CS_ROWS = 32;              // rows staged per smem batch
+constexpr int CS_THREADS = 256;
+constexpr int CS_COLS = 128;             // columns per CTA
+constexpr int CS_ROWS = 64;              // rows per stage
+constexpr int CS_STAGES = 3;
+constexpr int CS_MSTRIDE = CS_COLS * 2 + 16;   // 272 B: rows 16 B apart mod 128 -> conflict-free ldmatrix
+constexpr int CS_VSTRIDE = 48;                 // 16 bf16 = 32 B padded to 48 B, same reason
+constexpr int CS_STAGE_BYTES = CS_ROWS * CS_MSTRIDE + CS_ROWS * CS_VSTRIDE;   // 20480
+constexpr int CS_SMEM_BYTES = CS_STAGES * CS_STAGE_BYTES;                      // 61440
+
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem_dst)), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+__device__ __forceinline__ void ldmatrix_x4_trans(uint32_t addr, uint32_t (&r)[4]) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0, %1, %2, %3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+               : "r"(addr));
+}
+__device__ __forceinline__ void mma_bf16_16816(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, "
+      "{%0, %1, %2, %3};"
+      : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
 
 __global__ void __launch_bounds__(CS_THREADS)
 colsum16_kernel(const __nv_bfloat16* __restrict__ M, const float* __restrict__ src,
                 const float* __restrict__ s_rows, float* __restrict__ partial, int T, int C, int rows_per_chunk,
-                int b_prime, int num_slices) {
-  __shared__ __align__(16) float v_s[CS_ROWS][RPS];
-  const int c0 = blockIdx.y * CS_COLS + threadIdx.x * 2;
+                int b_prime, int num_slices, int row_div) {
+  extern __shared__ __align__(16) uint8_t cs_smem[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int c_base = blockIdx.y * CS_COLS;
   const int t_begin = blockIdx.x * rows_per_chunk;
   const int t_end = min(T, t_begin + rows_per_chunk);
-  const bool col_ok = c0 < C;  // C is even (multiple of 8)
-  float acc0[RPS], acc1[RPS];
-#pragma unroll
-  for (int j = 0; j < RPS; ++j) { acc0[j] = 0.f; acc1[j] = 0.f; }
+  const int n_stages = (t_end - t_begin + CS_ROWS - 1) / CS_ROWS;
 
-  for (int tb = t_begin; tb < t_end; tb += CS_ROWS) {
-    const int nrows = min(CS_ROWS, t_end - tb);
-    __syncthreads();
-    for (int i = threadIdx.x; i < nrows * RPS; i += CS_THREADS) {
-      const int rr = i / RPS, j = i - rr * RPS;
-      const int t = tb + rr;
-      const int sample = (t % b_prime) / num_slices;
-      v_s[rr][j] = src[static_cast<size_t>(t) * RPS + j] * s_rows[sample * RPS + j];
-    }
-    __syncthreads();
-    if (col_ok) {
-#pragma unroll 4
-      for (int rr = 0; rr < nrows; ++rr) {
-        const __nv_bfloat162 m2 =
-            *reinterpret_cast<const __nv_bfloat162*>(M + static_cast<size_t>(tb + rr) * C + c0);
-        const float2 m = __bfloat1622float2(m2);
-        const float4* vp = reinterpret_cast<const float4*>(v_s[rr]);
+  // stage loader: M tile via cp.async (16 B = 8 columns per request), v tile computed and stored as bf16
+  auto load_stage = [&](int st_idx, int buf) {
+    uint8_t* mt = cs_smem + buf * CS_STAGE_BYTES;
+    uint8_t* vt = mt + CS_ROWS * CS_MSTRIDE;
+    const int t0 = t_begin + st_idx * CS_ROWS;
 #pragma unroll
-        for (int j4 = 0; j4 < 4; ++j4) {
-          const float4 v = vp[j4];
-          acc0[4 * j4 + 0] = fmaf(m.x, v.x, acc0[4 * j4 + 0]);
-          acc0[4 * j4 + 1] = fmaf(m.x, v.y, acc0[4 * j4 + 1]);
-          acc0[4 * j4 + 2] = fmaf(m.x, v.z, acc0[4 * j4 + 2]);
-          acc0[4 * j4 + 3] = fmaf(m.x, v.w, acc0[4 * j4 + 3]);
-          acc1[4 * j4 + 0] = fmaf(m.y, v.x, acc1[4 * j4 + 0]);
-          acc1[4 * j4 + 1] = fmaf(m.y, v.y, acc1[4 * j4 + 1]);
-          acc1[4 * j4 + 2] = fmaf(m.y, v.z, acc1[4 * j4 + 2]);
-          acc1[4 * j4 + 3] = fmaf(m.y, v.w, acc1[4 * j4 + 3]);
-        }
+    for (int k = 0; k < (CS_ROWS * (CS_COLS / 8)) / CS_THREADS; ++k) {     // 4 requests per thread
+      const int idx = k * CS_THREADS + threadIdx.x;
+      const int rr = idx / (CS_COLS / 8), ch = idx - rr * (CS_COLS / 8);
+      const int t = t0 + rr, c = c_base + ch * 8;
+      uint8_t* dst = mt + rr * CS_MSTRIDE + ch * 16;
+      if (t < t_end && c < C) cp_async16(dst, M + static_cast<size_t>(t) * C + c);
+      else *reinterpret_cast<uint4*>(dst) = make_uint4(0u, 0u, 0u, 0u);
+    }
+    {
+      // 64 rows x 16 ranks = 1024 values, 4 consecutive ranks per thread
+      const int rr = threadIdx.x >> 2, j0 = (threadIdx.x & 3) * 4;
+      const int t = t0 + rr;
+      uint2 packed = make_uint2(0u, 0u);
+      if (t < t_end) {
+        const int sample = ((t / row_div) % b_prime) / num_slices;
+        const float4 a = __ldg(reinterpret_cast<const float4*>(src + static_cast<size_t>(t) * RPS + j0));
+        const float4 sv = __ldg(reinterpret_cast<const float4*>(s_rows + sample * RPS + j0));
+        packed.x = pack_bf16x2(a.x * sv.x, a.y * sv.y);
+        packed.y = pack_bf16x2(a.z * sv.z, a.w * sv.w);
       }
+      *reinterpret_cast<uint2*>(vt + rr * CS_VSTRIDE + j0 * 2) = packed;
+    }
+  };
+
+  float acc[2][4];
+#pragma unroll
+  for (int n = 0; n < 2; ++n)
+#pragma unroll
+    for (int e = 0; e < 4; ++e) acc[n][e] = 0.f;
+
+  // prologue
+#pragma unroll
+  for (int s0 = 0; s0 < CS_STAGES - 1; ++s0) {
+    if (s0 < n_stages) load_stage(s0, s0);
+    cp_async_commit();
+  }
+  // ldmatrix lane roles (see header comment): matrix id = lane / 8, row inside the 8x8 block = lane % 8
+  const int mi = lane >> 3, r8 = lane & 7;
+  const uint32_t a_lane_off = (r8 + 8 * (mi >> 1)) * CS_MSTRIDE + (warp * 16 + 8 * (mi & 1)) * 2;
+  const uint32_t b_lane_off = (r8 + 8 * (mi & 1)) * CS_VSTRIDE + (8 * (mi >> 1)) * 2;
+
+  for (int st_idx = 0; st_idx < n_stages; ++st_idx) {
+    cp_async_wait<CS_STAGES - 2>();
+    __syncthreads();                       // stage st_idx landed (cp.async + plain stores); previous compute done
+    {
+      const int nxt = st_idx + CS_STAGES - 1;
+      if (nxt < n_stages) load_stage(nxt, nxt % CS_STAGES);
+      cp_async_commit();
+    }
+    const uint32_t mt = smem_u32(cs_smem + (st_idx % CS_STAGES) * CS_STAGE_BYTES);
+    const uint32_t vt = mt + CS_ROWS * CS_MSTRIDE;
+#pragma unroll
+    for (int ks = 0; ks < CS_ROWS / 16; ++ks) {
+      uint32_t a[4], b[4];
+      ldmatrix_x4_trans(mt + ks * 16 * CS_MSTRIDE + a_lane_off, a);   // A = M^T : 16 columns x 16 rows(t)
+      ldmatrix_x4_trans(vt + ks * 16 * CS_VSTRIDE + b_lane_off, b);   // B = v   : 16 rows(t) x 16 ranks
+      mma_bf16_16816(acc[0], a, b[0], b[1]);                           // ranks 0..7
+      mma_bf16_16816(acc[1], a, b[2], b[3]);                           // ranks 8..15
     }
   }
-  if (col_ok) {
-    float4* p0 = reinterpret_cast<float4*>(partial + (static_cast<size_t>(blockIdx.x) * C + c0) * RPS);
+  cp_async_wait<0>();
+
+  // D fragment: (row g, cols 2i,2i+1) and (row g+8, cols 2i,2i+1), g = lane/4, i = lane%4; row = column of M
+  const int g = lane >> 2, i2 = (lane & 3) * 2;
 #pragma unroll
-    for (int j4 = 0; j4 < 4; ++j4) {
-      p0[j4] = make_float4(acc0[4 * j4], acc0[4 * j4 + 1], acc0[4 * j4 + 2], acc0[4 * j4 + 3]);
-      p0[4 + j4] = make_float4(acc1[4 * j4], acc1[4 * j4 + 1], acc1[4 * j4 + 2], acc1[4 * j4 + 3]);
+  for (int hrow = 0; hrow < 2; ++hrow) {
+    const int c = c_base + warp * 16 + g + 8 * hrow;
+    if (c < C) {
+      float* p0 = partial + (static_cast<size_t>(blockIdx.x) * C + c) * RPS;
+      *reinterpret_cast<float2*>(p0 + i2) = make_float2(acc[0][2 * hrow], acc[0][2 * hrow + 1]);
+      *reinterpret_cast<float2*>(p0 + 8 + i2) = make_float2(acc[1][2 * hrow], acc[1][2 * hrow + 1]);
     }
   }
 }
@@ -126,45 +193,51 @@ __global__ void colsum_reduce_kernel(const float* __restrict__ partial, float* _
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= C * RPS) return;
   const int c = i / RPS, j = i - c * RPS;
-  if (j >= r) return;
   float acc = 0.f;
+#pragma unroll 8
   for (int k = 0; k < n_chunks; ++k) acc += partial[(static_cast<size_t>(k) * C + c) * RPS + j];
+  if (j >= r) return;
   if (transposed) out[static_cast<size_t>(j) * C + c] = acc;
   else out[static_cast<size_t>(c) * r + j] = acc;
 }
 
 // ----------------------------------------------------------------------------------------------
-// ds_eff[b, j] = sum_{t : sample(t) == b} dzu[t, j] * h[t, j] * scaling   (scaling folded by the caller
-// through s_rows? no: s_eff itself is the variable, so the factor is the bare alpha/r)
-// One warp per sample: lane = (row parity, component); the warp walks the sample's rows, which sit at
-// stride b_prime in the sequence-first [L, B', .] layout, then folds the two row-parity halves.
+// ds_eff[b, j] = scaling * sum_{t : sample(t) == b} dzu[t, j] * h[t, j]
+// The segmented reduction keyed by sample id: one CTA per sample; its rows sit at stride b_prime in the
+// sequence-first [L, B', .] layout (stride 1 inside a contiguous block for batch-first rows). 16 lanes cover the 16 components of a row, 16 rows per pass, then a fixed-order
+// shared-memory fold (deterministic).
 // ----------------------------------------------------------------------------------------------
-__global__ void dseff_kernel(const float* __restrict__ h, const float* __restrict__ dzu, float* __restrict__ ds_eff,
-                             int T, int r, int nS, int b_prime, int num_slices, float scaling) {
-  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const int lane = threadIdx.x & 31;
-  if (warp >= nS) return;
-  const int j = lane & 15, half = lane >> 4;
-  const int L = T / b_prime;              // sequence positions
-  const int rows = L * num_slices;        // rows belonging to this sample
+constexpr int DS_THREADS = 256;
+
+__global__ void __launch_bounds__(DS_THREADS)
+dseff_kernel(const float* __restrict__ h, const float* __restrict__ dzu, float* __restrict__ ds_eff, int T, int r,
+             int nS, int b_prime, int num_slices, int row_div, float scaling) {
+  __shared__ float red[DS_THREADS / RPS][RPS];
+  const int b = blockIdx.x;
+  const int j = threadIdx.x % RPS, lane_row = threadIdx.x / RPS;
+  const int L = T / b_prime;
+  const int rows = L * num_slices;
   float acc = 0.f;
-  for (int i = half; i < rows; i += 2) {
+  for (int i = lane_row; i < rows; i += DS_THREADS / RPS) {
     const int l = i / num_slices, sl = i - l * num_slices;
-    const size_t t = static_cast<size_t>(l) * b_prime + warp * num_slices + sl;
+    // sequence-first rows: t = l*B' + column; batch-first rows (row_div = L): t = column*L + l
+    const size_t col = static_cast<size_t>(b) * num_slices + sl;
+    const size_t t = (row_div == 1) ? static_cast<size_t>(l) * b_prime + col : col * row_div + l;
     acc = fmaf(dzu[t * RPS + j], h[t * RPS + j], acc);
   }
-  acc += __shfl_xor_sync(0xffffffffu, acc, 16);
-  if (half == 0 && j < r) ds_eff[warp * r + j] = acc * scaling;
+  red[lane_row][j] = acc;
+  __syncthreads();
+  if (lane_row == 0 && j < r) {
+    float tot = 0.f;
+#pragma unroll
+    for (int k = 0; k < DS_THREADS / RPS; ++k) tot += red[k][j];
+    ds_eff[b * r + j] = tot * scaling;
+  }
 }
 
-constexpr int CS_MAX_CHUNKS = 75;  // row chunks per column group (partials: chunks x C x 16 fp32)
+constexpr int CS_MAX_CHUNKS = 148;  // row chunks per column group (partials: chunks x C x 16 fp32)
 
-size_t svlora_bwd_small_scratch_bytes(int T, int K, int N) {
-  const int cmax = K > N ? K : N;
-  (void)T;
-  return static_cast<size_t>(CS_MAX_CHUNKS) * cmax * RPS * 4 + 256;
-}
-
+// about two CTAs per SM in total (61 KB of smem each, 3 fit): enough loads in flight without a ragged second wave
 static int pick_chunks(int T, int C) {
   const int col_groups = (C + CS_COLS - 1) / CS_COLS;
   int chunks = (2 * num_sms() + col_groups - 1) / col_groups;
@@ -175,10 +248,27 @@ static int pick_chunks(int T, int C) {
   return chunks;
 }
 
+size_t svlora_bwd_small_scratch_bytes(int T, int K, int N) {
+  const size_t a = static_cast<size_t>(pick_chunks(T, K)) * K;
+  const size_t b = static_cast<size_t>(pick_chunks(T, N)) * N;
+  return (a > b ? a : b) * RPS * 4 + 256;
+}
+
 int launch_svlora_bwd_small(const __nv_bfloat16* x, const __nv_bfloat16* dy, const float* h, const float* dzu,
                             const float* s_rows, float* dA, float* dB, float* ds_eff, void* scratch,
                             size_t scratch_bytes, int T, int K, int N, int r, int nS, int b_prime, int num_slices,
-                            float scaling, cudaStream_t stream) {
+                            int row_div, float scaling, cudaStream_t stream) {
+  FFM_CHECK_ARG(row_div == 1 || row_div * b_prime == T, "svlora bwd: batch-first rows need row_div * b_prime == T");
+  {
+    static thread_local int attr_dev = -1;
+    int dev = 0;
+    FFM_CHECK_CUDA(cudaGetDevice(&dev));
+    if (dev != attr_dev) {
+      FFM_CHECK_CUDA(cudaFuncSetAttribute(colsum16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          CS_SMEM_BYTES));
+      attr_dev = dev;
+    }
+  }
   FFM_CHECK_ARG(T % b_prime == 0, "svlora bwd: T (%d) must be a multiple of b_prime (%d)", T, b_prime);
   float* partial = static_cast<float*>(scratch);
   // dA[K, r] = x^T · (dzu ⊙ s_rows)
@@ -187,8 +277,8 @@ int launch_svlora_bwd_small(const __nv_bfloat16* x, const __nv_bfloat16* dy, con
     FFM_CHECK_ARG(static_cast<size_t>(chunks) * K * RPS * 4 <= scratch_bytes, "svlora bwd: scratch too small (dA)");
     const int rows_per_chunk = (T + chunks - 1) / chunks;
     dim3 grid(chunks, (K + CS_COLS - 1) / CS_COLS);
-    colsum16_kernel<<<grid, CS_THREADS, 0, stream>>>(x, dzu, s_rows, partial, T, K, rows_per_chunk, b_prime,
-                                                     num_slices);
+    colsum16_kernel<<<grid, CS_THREADS, CS_SMEM_BYTES, stream>>>(x, dzu, s_rows, partial, T, K, rows_per_chunk, b_prime,
+                                                     num_slices, row_div);
     colsum_reduce_kernel<<<(K * RPS + 255) / 256, 256, 0, stream>>>(partial, dA, chunks, K, r, 0);
   }
   // dB[r, N] = (h ⊙ s_rows)^T · dy
@@ -197,13 +287,13 @@ int launch_svlora_bwd_small(const __nv_bfloat16* x, const __nv_bfloat16* dy, con
     FFM_CHECK_ARG(static_cast<size_t>(chunks) * N * RPS * 4 <= scratch_bytes, "svlora bwd: scratch too small (dB)");
     const int rows_per_chunk = (T + chunks - 1) / chunks;
     dim3 grid(chunks, (N + CS_COLS - 1) / CS_COLS);
-    colsum16_kernel<<<grid, CS_THREADS, 0, stream>>>(dy, h, s_rows, partial, T, N, rows_per_chunk, b_prime,
-                                                     num_slices);
+    colsum16_kernel<<<grid, CS_THREADS, CS_SMEM_BYTES, stream>>>(dy, h, s_rows, partial, T, N, rows_per_chunk, b_prime,
+                                                     num_slices, row_div);
     colsum_reduce_kernel<<<(N * RPS + 255) / 256, 256, 0, stream>>>(partial, dB, chunks, N, r, 1);
   }
   count_launch(4);
   // ds_eff[nS, r]: one warp per sample
-  dseff_kernel<<<(nS * 32 + 127) / 128, 128, 0, stream>>>(h, dzu, ds_eff, T, r, nS, b_prime, num_slices, scaling);
+  dseff_kernel<<<nS, DS_THREADS, 0, stream>>>(h, dzu, ds_eff, T, r, nS, b_prime, num_slices, row_div, scaling);
   FFM_CHECK_CUDA(cudaGetLastError());
   count_launch();
   return FFM_OK;

@@ -37,8 +37,10 @@ def _need_cuda(*tensors):
 # =====================================================================================================
 @torch.library.custom_op("ffm::svlora_fwd", mutates_args=())
 def svlora_fwd(x: Tensor, w: Tensor, bias: Optional[Tensor], lora_a: Tensor, lora_b: Tensor, s_eff: Tensor,
-               scaling: float, b_prime: int, num_slices: int, act: int) -> Tuple[Tensor, Tensor, Tensor]:
-    """y, y_pre, h = fused FairLoRA linear.  x [T,K] bf16, w [N,K] bf16, lora_a [K,r], lora_b [r,N], s_eff [nS,r]."""
+               scaling: float, b_prime: int, num_slices: int, act: int,
+               row_div: int = 1) -> Tuple[Tensor, Tensor, Tensor]:
+    """y, y_pre, h = fused FairLoRA linear.  x [T,K] bf16, w [N,K] bf16, lora_a [K,r], lora_b [r,N], s_eff [nS,r].
+    Row t of x belongs to sample ((t // row_div) % b_prime) // num_slices (row_div = 1: sequence-first rows)."""
     _need_cuda(x, w, lora_a, lora_b, s_eff)
     T, K = x.shape
     N = w.shape[0]
@@ -52,12 +54,12 @@ def svlora_fwd(x: Tensor, w: Tensor, bias: Optional[Tensor], lora_a: Tensor, lor
     ws = torch.empty((ws_bytes,), device=x.device, dtype=torch.uint8)
     _cabi.call("ffm_svlora_fwd", _ptr(x), _ptr(w), _ptr(bias), _ptr(lora_a), _ptr(lora_b), _ptr(s_eff), _ptr(y),
                _ptr(y_pre) if act else 0, _ptr(h), _ptr(ws), ws_bytes, T, K, N, r, nS, b_prime, num_slices,
-               float(scaling), int(act), _stream())
+               int(row_div), float(scaling), int(act), _stream())
     return y, y_pre, h
 
 
 @svlora_fwd.register_fake
-def _(x, w, bias, lora_a, lora_b, s_eff, scaling, b_prime, num_slices, act):
+def _(x, w, bias, lora_a, lora_b, s_eff, scaling, b_prime, num_slices, act, row_div=1):
     T, N = x.shape[0], w.shape[0]
     y = x.new_empty((T, N))
     return y, (x.new_empty((T, N)) if act else x.new_empty((0,))), x.new_empty((T, RP), dtype=torch.float32)
@@ -65,8 +67,8 @@ def _(x, w, bias, lora_a, lora_b, s_eff, scaling, b_prime, num_slices, act):
 
 @torch.library.custom_op("ffm::svlora_bwd", mutates_args=())
 def svlora_bwd(dy: Tensor, x: Tensor, w_t: Tensor, lora_a: Tensor, lora_b: Tensor, s_eff: Tensor, h: Tensor,
-               gelu_pre: Optional[Tensor], scaling: float, b_prime: int,
-               num_slices: int) -> Tuple[Tensor, Tensor, Tensor, Tensor]:
+               gelu_pre: Optional[Tensor], scaling: float, b_prime: int, num_slices: int,
+               row_div: int = 1) -> Tuple[Tensor, Tensor, Tensor, Tensor]:
     """dx, d_lora_a, d_lora_b, d_s_eff.  dy [T,N] bf16, x [T,K] bf16, w_t [K,N] bf16 (transposed frozen weight)."""
     _need_cuda(dy, x, w_t)
     T, N = dy.shape
@@ -82,12 +84,12 @@ def svlora_bwd(dy: Tensor, x: Tensor, w_t: Tensor, lora_a: Tensor, lora_b: Tenso
     ws = torch.empty((ws_bytes,), device=x.device, dtype=torch.uint8)
     _cabi.call("ffm_svlora_bwd", _ptr(dy), _ptr(x), _ptr(w_t), _ptr(lora_a), _ptr(lora_b), _ptr(s_eff), _ptr(h),
                _ptr(gelu_pre), _ptr(dx), _ptr(dA), _ptr(dB), _ptr(dse), _ptr(ws), ws_bytes, T, K, N, r, nS, b_prime,
-               num_slices, float(scaling), _stream())
+               num_slices, int(row_div), float(scaling), _stream())
     return dx, dA, dB, dse
 
 
 @svlora_bwd.register_fake
-def _(dy, x, w_t, lora_a, lora_b, s_eff, h, gelu_pre, scaling, b_prime, num_slices):
+def _(dy, x, w_t, lora_a, lora_b, s_eff, h, gelu_pre, scaling, b_prime, num_slices, row_div=1):
     return (x.new_empty(x.shape), lora_a.new_empty(lora_a.shape), lora_b.new_empty(lora_b.shape),
             s_eff.new_empty(s_eff.shape))
 
@@ -152,24 +154,24 @@ class _SVLoRALinear(torch.autograd.Function):
     """y = x W^T + b + scaling ((x A) ⊙ s_eff[sample]) B — one fused kernel each way."""
 
     @staticmethod
-    def forward(ctx, x2d, w, w_t, bias, lora_a, lora_b, s_eff, scaling, b_prime, num_slices):
-        y, _, h = svlora_fwd(x2d, w, bias, lora_a, lora_b, s_eff, scaling, b_prime, num_slices, 0)
+    def forward(ctx, x2d, w, w_t, bias, lora_a, lora_b, s_eff, scaling, b_prime, num_slices, row_div):
+        y, _, h = svlora_fwd(x2d, w, bias, lora_a, lora_b, s_eff, scaling, b_prime, num_slices, 0, row_div)
         ctx.save_for_backward(x2d, w_t, lora_a, lora_b, s_eff, h)
-        ctx.cfg = (scaling, b_prime, num_slices)
+        ctx.cfg = (scaling, b_prime, num_slices, row_div)
         return y
 
     @staticmethod
     def backward(ctx, dy):
         x2d, w_t, lora_a, lora_b, s_eff, h = ctx.saved_tensors
-        scaling, b_prime, num_slices = ctx.cfg
+        scaling, b_prime, num_slices, row_div = ctx.cfg
         dx, dA, dB, dse = svlora_bwd(dy.contiguous(), x2d, w_t, lora_a, lora_b, s_eff, h, None, scaling, b_prime,
-                                     num_slices)
-        return dx, None, None, None, dA, dB, dse, None, None, None
+                                     num_slices, row_div)
+        return dx, None, None, None, dA, dB, dse, None, None, None, None
 
 
 def svlora_linear(x2d: Tensor, w: Tensor, w_t: Tensor, bias: Optional[Tensor], lora_a: Tensor, lora_b: Tensor,
-                  s_eff: Tensor, scaling: float, b_prime: int, num_slices: int) -> Tensor:
-    return _SVLoRALinear.apply(x2d, w, w_t, bias, lora_a, lora_b, s_eff, scaling, b_prime, num_slices)
+                  s_eff: Tensor, scaling: float, b_prime: int, num_slices: int, row_div: int = 1) -> Tensor:
+    return _SVLoRALinear.apply(x2d, w, w_t, bias, lora_a, lora_b, s_eff, scaling, b_prime, num_slices, row_div)
 
 
 class _SVLoRAMLP(torch.autograd.Function):
@@ -177,25 +179,27 @@ class _SVLoRAMLP(torch.autograd.Function):
     epilogue (dual store of pre-activation and activation) and QuickGELU' into the c_proj backward epilogue."""
 
     @staticmethod
-    def forward(ctx, x2d, w1, w1_t, b1, a1, bb1, s1, w2, w2_t, b2, a2, bb2, s2, scaling, b_prime, num_slices):
-        g, u, h1 = svlora_fwd(x2d, w1, b1, a1, bb1, s1, scaling, b_prime, num_slices, 1)
-        y, _, h2 = svlora_fwd(g, w2, b2, a2, bb2, s2, scaling, b_prime, num_slices, 0)
+    def forward(ctx, x2d, w1, w1_t, b1, a1, bb1, s1, w2, w2_t, b2, a2, bb2, s2, scaling, b_prime, num_slices,
+                row_div):
+        g, u, h1 = svlora_fwd(x2d, w1, b1, a1, bb1, s1, scaling, b_prime, num_slices, 1, row_div)
+        y, _, h2 = svlora_fwd(g, w2, b2, a2, bb2, s2, scaling, b_prime, num_slices, 0, row_div)
         ctx.save_for_backward(x2d, g, u, h1, h2, w1_t, a1, bb1, s1, w2_t, a2, bb2, s2)
-        ctx.cfg = (scaling, b_prime, num_slices)
+        ctx.cfg = (scaling, b_prime, num_slices, row_div)
         return y
 
     @staticmethod
     def backward(ctx, dy):
         x2d, g, u, h1, h2, w1_t, a1, bb1, s1, w2_t, a2, bb2, s2 = ctx.saved_tensors
-        scaling, b_prime, num_slices = ctx.cfg
-        du, dA2, dB2, ds2 = svlora_bwd(dy.contiguous(), g, w2_t, a2, bb2, s2, h2, u, scaling, b_prime, num_slices)
-        dx, dA1, dB1, ds1 = svlora_bwd(du, x2d, w1_t, a1, bb1, s1, h1, None, scaling, b_prime, num_slices)
-        return dx, None, None, None, dA1, dB1, ds1, None, None, None, dA2, dB2, ds2, None, None, None
+        scaling, b_prime, num_slices, row_div = ctx.cfg
+        du, dA2, dB2, ds2 = svlora_bwd(dy.contiguous(), g, w2_t, a2, bb2, s2, h2, u, scaling, b_prime, num_slices,
+                                       row_div)
+        dx, dA1, dB1, ds1 = svlora_bwd(du, x2d, w1_t, a1, bb1, s1, h1, None, scaling, b_prime, num_slices, row_div)
+        return dx, None, None, None, dA1, dB1, ds1, None, None, None, dA2, dB2, ds2, None, None, None, None
 
 
-def svlora_mlp(x2d, fc, proj, scaling: float, b_prime: int, num_slices: int) -> Tensor:
+def svlora_mlp(x2d, fc, proj, scaling: float, b_prime: int, num_slices: int, row_div: int = 1) -> Tensor:
     """fc / proj = (w, w_t, bias, lora_a, lora_b, s_eff) tuples."""
-    return _SVLoRAMLP.apply(x2d, *fc, *proj, scaling, b_prime, num_slices)
+    return _SVLoRAMLP.apply(x2d, *fc, *proj, scaling, b_prime, num_slices, row_div)
 
 
 # =====================================================================================================

@@ -180,6 +180,59 @@ class GLP_OT_SVLoRA:
             self.update_lr()
         return summary
 
+    # ------------------------------------------------------------------ CUDA-graph replay of the step
+    def capture_step_graph(self, example_batch, warmup: int = 3):
+        """Capture forward + backward + fused double-SGD of ONE step into a CUDA graph (launch-bound otherwise:
+        ~1000 kernel launches per step).  Inputs live in static device buffers; `forward_backward_graphed` copies a
+        batch in and replays.  The learning rate / first-step flag are baked in at capture time, so call this after
+        the first optimizer step and re-capture when the StepLR schedule changes the rate."""
+        assert not self.sync_metrics and not self.step_auc, "graph capture needs a sync-free step"
+        self.model.check_nan = False
+        image, label, _, attr = self.parse_batch_train(example_batch)
+        self._g_img = image.clone()
+        self._g_label = label.clone()
+        self._g_attr = None if attr is None else attr.to(self.device).clone()
+        static = {"img": self._g_img, "label": self._g_label}
+
+        def body():
+            output = self.model(self._g_img, self._g_attr)
+            loss = F.cross_entropy(output, self._g_label)
+            self.flat_grads.zero_()
+            loss.backward()
+            n_steps = 2 if self.cfg.TRAINER.GLP_OT_LORA.UNFREEZE_IMAGE_ENCODER else 1
+            o = self.cfg.OPTIM
+            ops.sgd_step_(self.flat_params, self.flat_grads, self.flat_mom, self._g_lr, o.MOMENTUM, o.WEIGHT_DECAY,
+                          n_steps, False)
+            with torch.no_grad():
+                acc = (output.argmax(dim=1) == self._g_label).float().mean() * 100.0
+            return loss.detach(), acc
+
+        self._g_lr = self.current_lr()
+        side = torch.cuda.Stream(device=self.device)
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(warmup):
+                body()
+        torch.cuda.current_stream().wait_stream(side)
+        self.first_step = False
+        self._graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self._graph):
+            self._g_loss, self._g_acc = body()
+        del static
+        return self._graph
+
+    def forward_backward_graphed(self, batch):
+        """Replay the captured step on `batch` (device or pinned-host tensors). Returns device tensors."""
+        if self.current_lr() != self._g_lr:
+            raise RuntimeError("learning rate changed since capture: call capture_step_graph again")
+        self._g_img.copy_(batch["img"], non_blocking=True)
+        self._g_label.copy_(batch["label"], non_blocking=True)
+        if self._g_attr is not None:
+            idx = self.cfg.DATASET.ATTRIBUTES.index(self.cfg.DATASET.ATTRIBUTE_TYPE)
+            self._g_attr.copy_(batch["attrs"][:, idx], non_blocking=True)
+        self._graph.replay()
+        return {"loss": self._g_loss, "acc": self._g_acc}
+
     # ------------------------------------------------------------------ epoch / federated hooks
     def fed_before_train(self):
         self.time_start = time.time()

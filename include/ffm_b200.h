@@ -65,9 +65,10 @@ size_t ffm_svlora_bwd_workspace_bytes(int T, int K, int N, int n_samples);
  *   y       = act ? QuickGELU(u) : u          (clip/model.py:313-315 fused when act = 1)
  *   y_pre   = u   (only when act = 1 and y_pre != NULL; needed by the backward pass)
  *
- *   sample(t) = (t mod b_prime) / num_slices   — activations are sequence-first [L, B', C]
- *               (clip/model.py:438-440); OCT volumes fold num_slices slice-images per sample into B'
- *               (trainers/GLP_OT_SVLoRA.py:473-475).
+ *   sample(t) = ((t / row_div) mod b_prime) / num_slices.  row_div = 1: rows are sequence-first [L, B', C] like the
+ *               reference's activations (clip/model.py:438-440); row_div = L: rows are batch-first [B', L, C]
+ *               (used by fairfedmed_b200.clip_model so attention needs no transposes).  OCT volumes fold
+ *               num_slices slice-images per sample into B' (trainers/GLP_OT_SVLoRA.py:473-475).
  *
  *   x [T,K] bf16, W [N,K] bf16 (frozen nn.Linear weight), bias [N] f32 or NULL,
  *   lora_a [K,r] f32, lora_b [r,N] f32, s_eff [n_samples,r] f32 (from ffm_seff), y / y_pre [T,N] bf16.
@@ -75,8 +76,8 @@ size_t ffm_svlora_bwd_workspace_bytes(int T, int K, int N, int n_samples);
  */
 int ffm_svlora_fwd(const void* x, const void* w, const float* bias, const float* lora_a, const float* lora_b,
                    const float* s_eff, void* y, void* y_pre, float* h_out, void* workspace, size_t workspace_bytes,
-                   int T, int K, int N, int r, int n_samples, int b_prime, int num_slices, float scaling, int act,
-                   ffm_stream_t stream);
+                   int T, int K, int N, int r, int n_samples, int b_prime, int num_slices, int row_div, float scaling,
+                   int act, ffm_stream_t stream);
 
 /*
  * Backward of the same module (autograd of trainers/GLP_OT_SVLoRA.py:450-482; W and bias frozen :375-376).
@@ -94,7 +95,8 @@ int ffm_svlora_fwd(const void* x, const void* w, const float* bias, const float*
 int ffm_svlora_bwd(const void* dy, const void* x, const void* w_t, const float* lora_a, const float* lora_b,
                    const float* s_eff, const float* h, const void* gelu_pre, void* dx, float* d_lora_a,
                    float* d_lora_b, float* d_s_eff, void* workspace, size_t workspace_bytes, int T, int K, int N,
-                   int r, int n_samples, int b_prime, int num_slices, float scaling, ffm_stream_t stream);
+                   int r, int n_samples, int b_prime, int num_slices, int row_div, float scaling,
+                   ffm_stream_t stream);
 
 /*
  * Group mixing of singular values — trainers/GLP_OT_SVLoRA.py:453-467.

@@ -188,6 +188,31 @@ def test_config2_full_size_properties():
     assert bool(torch.isfinite(y1[-64:].float()).all())
 
 
+def test_batch_first_rows_equal_sequence_first_rows():
+    """row_div = L (rows [B', L, C], used by clip_model) must give the same numbers as the reference's [L, B', C]."""
+    from fairfedmed_b200 import ops
+    dev = _dev()
+    L, Bp, K, N, r, slices = 197, 8, 768, 3072, 12, 2
+    g = torch.Generator().manual_seed(4)
+    x = (torch.randn(L, Bp, K, generator=g) * 0.5).bfloat16().to(dev)
+    dy = (torch.randn(L, Bp, N, generator=g) * 0.1).bfloat16().to(dev)
+    W = (torch.randn(N, K, generator=g) * K ** -0.5).bfloat16().to(dev)
+    A = (torch.randn(K, r, generator=g) * 0.05).to(dev)
+    Bm = torch.randn(r, N, generator=g).to(dev)
+    s = (torch.rand(Bp // slices, r, generator=g) + 0.1).to(dev)
+    Wt = W.t().contiguous()
+    y1, _, h1 = ops.svlora_fwd(x.reshape(L * Bp, K), W, None, A, Bm, s, 1 / 6, Bp, slices, 0, 1)
+    g1 = ops.svlora_bwd(dy.reshape(L * Bp, N), x.reshape(L * Bp, K), Wt, A, Bm, s, h1, None, 1 / 6, Bp, slices, 1)
+    xb = x.transpose(0, 1).contiguous()
+    dyb = dy.transpose(0, 1).contiguous()
+    y2, _, h2 = ops.svlora_fwd(xb.reshape(L * Bp, K), W, None, A, Bm, s, 1 / 6, Bp, slices, 0, L)
+    g2 = ops.svlora_bwd(dyb.reshape(L * Bp, N), xb.reshape(L * Bp, K), Wt, A, Bm, s, h2, None, 1 / 6, Bp, slices, L)
+    assert torch.equal(y2.view(Bp, L, N).transpose(0, 1), y1.view(L, Bp, N))
+    assert torch.equal(g2[0].view(Bp, L, K).transpose(0, 1), g1[0].view(L, Bp, K))
+    for a, b in zip(g1[1:], g2[1:]):          # dA, dB, ds_eff: same sums in a different row order
+        assert _rel_to_max(b, a) < 1e-4
+
+
 def test_invalid_arguments_raise():
     from fairfedmed_b200 import _cabi, ops
     dev = _dev()

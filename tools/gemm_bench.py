@@ -22,13 +22,13 @@ st = torch.cuda.current_stream().cuda_stream
 p = lambda t: 0 if t is None else t.data_ptr()
 def fwd():
     _cabi.call("ffm_svlora_fwd", p(x), p(W), p(bias), p(A), p(Bm), p(s_eff), p(y), p(ypre), p(h), p(ws), wsb,
-               T, K, N, r, B, B, 1, 1.0 / 6, a.act, st)
+               T, K, N, r, B, B, 1, 1, 1.0 / 6, a.act, st)
 dy = torch.randn(T, N, device=dev).bfloat16(); Wt = W.t().contiguous(); dx = torch.empty_like(x)
 dA = torch.zeros(K, r, device=dev); dB = torch.zeros(r, N, device=dev); dse = torch.zeros(B, r, device=dev)
 bwsb = lib.ffm_svlora_bwd_workspace_bytes(T, K, N, B); bws = torch.empty(bwsb, device=dev, dtype=torch.uint8)
 def bwd():
     _cabi.call("ffm_svlora_bwd", p(dy), p(x), p(Wt), p(A), p(Bm), p(s_eff), p(h), 0, p(dx), p(dA), p(dB), p(dse),
-               p(bws), bwsb, T, K, N, r, B, B, 1, 1.0 / 6, st)
+               p(bws), bwsb, T, K, N, r, B, B, 1, 1, 1.0 / 6, st)
 fn = bwd if a.bwd else fwd
 for _ in range(3): fn()
 torch.cuda.synchronize()

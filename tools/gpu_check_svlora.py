@@ -78,7 +78,7 @@ def run_case(T, K, N, r, b_prime, num_slices, act, seed=0, verbose=True, timing=
 
     def fwd():
         _cabi.call("ffm_svlora_fwd", ptr(x), ptr(W), ptr(bias), ptr(A), ptr(B), ptr(s_eff), ptr(y), ptr(y_pre),
-                   ptr(h), ptr(ws), ws_bytes, T, K, N, r, nS, b_prime, num_slices, scaling, act, stream())
+                   ptr(h), ptr(ws), ws_bytes, T, K, N, r, nS, b_prime, num_slices, 1, scaling, act, stream())
 
     fwd()
     torch.cuda.synchronize()
@@ -133,7 +133,7 @@ def run_case(T, K, N, r, b_prime, num_slices, act, seed=0, verbose=True, timing=
     def bwd():
         _cabi.call("ffm_svlora_bwd", ptr(dy), ptr(x), ptr(Wt), ptr(A), ptr(B), ptr(s_eff), ptr(h), ptr(gelu_pre),
                    ptr(dx), ptr(dA), ptr(dB), ptr(dse), ptr(bws), bws_bytes, T, K, N, r, nS, b_prime, num_slices,
-                   scaling, stream())
+                   1, scaling, stream())
 
     bwd()
     torch.cuda.synchronize()
@@ -218,6 +218,8 @@ def main():
         cases += [
             (12608, 768, 3072, 12, 64, 1, 0),
             (12608, 3072, 768, 12, 64, 1, 0),
+            (12608, 768, 3072, 12, 64, 1, 1),      # c_fc forward as used in the model (fused QuickGELU, dual store)
+            (12608, 3072, 768, 12, 64, 1, 1),      # c_proj backward as used in the model (QuickGELU' on dx)
         ]
     all_ok = True
     for c in cases:
