@@ -183,8 +183,12 @@ class ModifiedVisionTransformer(nn.Module, _Bf16Cache):
 
     def forward(self, x: torch.Tensor, attr: Optional[torch.Tensor] = None):
         dt = x.dtype
-        x = F.conv2d(x, self._bf("conv1", self.conv1.weight, dt), stride=self.patch_size)      # [B', width, g, g]
-        x = x.flatten(2).transpose(1, 2)                                                       # [B', g*g, width]
+        # stride = kernel = patch: the convolution is a GEMM over non-overlapping patches (clip/model.py:431-433)
+        bp, ch, hh, ww = x.shape
+        ps = self.patch_size
+        gh, gw = hh // ps, ww // ps
+        patches = x.view(bp, ch, gh, ps, gw, ps).permute(0, 2, 4, 1, 3, 5).reshape(bp, gh * gw, ch * ps * ps)
+        x = patches @ self._bf("conv1", self.conv1.weight, dt).flatten(1).t()                  # [B', g*g, width]
         cls = self._bf("cls", self.class_embedding, dt).expand(x.shape[0], 1, -1)
         x = torch.cat([cls, x], dim=1) + self._bf("pos", self.positional_embedding, dt)
         x = self.ln_pre(x)

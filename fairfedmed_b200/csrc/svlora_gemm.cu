@@ -354,7 +354,7 @@ svlora_gemm_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_consta
           __syncwarp();
           if (lane == 0) mbar_arrive(&tmem_empty[s]);
         }
-        float f[32];
+        float f[32], g2[32];
 #pragma unroll
         for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]) + bias_s[cc + j];
         const int col0 = n0 + c * OUT_CHUNK;     // first global column of the 64-wide store unit
@@ -371,29 +371,41 @@ svlora_gemm_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_consta
 #pragma unroll
                 for (int e = 0; e < 4; ++e) {
                   const float2 uu = __bfloat1622float2(h2[e]);
-                  f[j8 * 8 + 2 * e] *= quick_gelu_grad(uu.x);
-                  f[j8 * 8 + 2 * e + 1] *= quick_gelu_grad(uu.y);
+                  f[j8 * 8 + 2 * e] *= uu.x;
+                  f[j8 * 8 + 2 * e + 1] *= uu.y;
                 }
               }
             } else {
               for (int j = 0; j < 32; ++j)
-                if (gc + j < p.N) f[j] *= quick_gelu_grad(__bfloat162float(up[j]));
+                if (gc + j < p.N) f[j] *= __bfloat162float(up[j]);
             }
           }
         }
 #pragma unroll 1
         for (int pass = 0; pass < n_pass; ++pass) {
-          // pass 0 of a dual store writes the pre-activation (tm_y2), the last pass the activated value
-          const bool apply_act = (p.act == ACT_QUICKGELU) && (pass == n_pass - 1);
+          // pass 0 of a dual store writes QuickGELU'(u) (tm_y2), the last pass the activated value
           const uint32_t buf = store_unit & 1u;
           uint8_t* ob = smem + OFF_OUT + buf * OUT_TILE_BYTES;
           // the TMA store that last read this buffer (2 units ago) must have finished reading smem
           if (et == 0) tma_store_wait_read<1>();
           named_bar_sync(EPI_BAR_ID, EPI_THREADS);
           uint8_t* orow = ob + row * 128u;
-          if (apply_act) {   // warp-uniform branch: keep the MUFU work out of the plain-store path
+          if (p.act == ACT_QUICKGELU) {   // warp-uniform branch: keep the MUFU work out of the plain-store path
+            if (n_pass == 2 && pass == 0) {
+              // first store of the dual store: QuickGELU'(u), all the backward pass needs (u itself is not kept)
 #pragma unroll
-            for (int j = 0; j < 32; ++j) f[j] = quick_gelu(f[j]);
+              for (int j = 0; j < 32; ++j) {
+                const float sgm = fmaf(0.5f, tanh_approx(0.851f * f[j]), 0.5f);
+                g2[j] = f[j] * sgm;                                       // QuickGELU(u), stored by the next pass
+                f[j] = sgm * fmaf(1.702f * f[j], 1.0f - sgm, 1.0f);      // QuickGELU'(u)
+              }
+            } else if (n_pass == 2) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) f[j] = g2[j];
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) f[j] = quick_gelu(f[j]);
+            }
           }
 #pragma unroll
           for (int j8 = 0; j8 < 4; ++j8) {
@@ -673,7 +685,7 @@ size_t ffm_svlora_bwd_workspace_bytes(int T, int K, int N, int n_samples) {
 }
 
 int ffm_svlora_fwd(const void* x, const void* w, const float* bias, const float* lora_a, const float* lora_b,
-                   const float* s_eff, void* y, void* y_pre, float* h_out, void* workspace, size_t workspace_bytes,
+                   const float* s_eff, void* y, void* y_dact, float* h_out, void* workspace, size_t workspace_bytes,
                    int T, int K, int N, int r, int n_samples, int b_prime, int num_slices, int row_div, float scaling,
                    int act, cudaStream_t stream) {
   FFM_CHECK_ARG(x && w && lora_a && lora_b && s_eff && y && workspace, "ffm_svlora_fwd: null pointer argument");
@@ -695,13 +707,13 @@ int ffm_svlora_fwd(const void* x, const void* w, const float* bias, const float*
   count_launch();
   GemmOperands o;
   o.x = x; o.wmat = w; o.a_side = ws.a_side; o.b_side = ws.b_side; o.s_rows = ws.s_rows; o.bias = bias;
-  o.out = y; o.out_pre = y_pre; o.h_out = h_out; o.aux = nullptr;
+  o.out = y; o.out_pre = y_dact; o.h_out = h_out; o.aux = nullptr;
   o.T = T; o.K = K; o.N = N; o.b_prime = b_prime; o.num_slices = num_slices; o.row_div = row_div; o.act = act;
   return launch_svlora_gemm(o, stream);
 }
 
 int ffm_svlora_bwd(const void* dy, const void* x, const void* w_t, const float* lora_a, const float* lora_b,
-                   const float* s_eff, const float* h, const void* gelu_pre, void* dx, float* d_lora_a,
+                   const float* s_eff, const float* h, const void* gelu_dact, void* dx, float* d_lora_a,
                    float* d_lora_b, float* d_s_eff, void* workspace, size_t workspace_bytes, int T, int K, int N,
                    int r, int n_samples, int b_prime, int num_slices, int row_div, float scaling,
                    cudaStream_t stream) {
@@ -725,9 +737,9 @@ int ffm_svlora_bwd(const void* dy, const void* x, const void* w_t, const float* 
   count_launch();
   GemmOperands o;
   o.x = dy; o.wmat = w_t; o.a_side = ws.a_side; o.b_side = ws.b_side; o.s_rows = ws.s_rows; o.bias = nullptr;
-  o.out = dx; o.out_pre = nullptr; o.h_out = dzu; o.aux = gelu_pre;
+  o.out = dx; o.out_pre = nullptr; o.h_out = dzu; o.aux = gelu_dact;
   o.T = T; o.K = N; o.N = K; o.b_prime = b_prime; o.num_slices = num_slices; o.row_div = row_div;
-  o.act = gelu_pre != nullptr ? ACT_QUICKGELU_GRAD : ACT_NONE;
+  o.act = gelu_dact != nullptr ? ACT_QUICKGELU_GRAD : ACT_NONE;
   int rc = launch_svlora_gemm(o, stream);
   if (rc != FFM_OK) return rc;
   return launch_svlora_bwd_small(reinterpret_cast<const __nv_bfloat16*>(x), reinterpret_cast<const __nv_bfloat16*>(dy),

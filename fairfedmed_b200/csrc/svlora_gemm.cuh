@@ -12,12 +12,12 @@ struct GemmParams {
   const float* bias;            // [N] or nullptr
   const float* s_rows;          // [n_samples, RP] fp32 (already multiplied by alpha/r)
   float* h_out;                 // [T, RP] fp32 or nullptr
-  const __nv_bfloat16* aux;     // ACT_QUICKGELU_GRAD: pre-activation u [T, N]
+  const __nv_bfloat16* aux;     // ACT_QUICKGELU_GRAD: QuickGELU'(u) saved by the forward [T, N]
   int T, K, N;
   int b_prime, num_slices;      // sample(t) = ((t / row_div) % b_prime) / num_slices
   int row_div;                  // 1: sequence-first rows [L, B', C] (reference); L: batch-first rows [B', L, C]
   int act;
-  int has_pre;                  // ACT_QUICKGELU: also store the pre-activation through tm_y2
+  int has_pre;                  // ACT_QUICKGELU: also store QuickGELU'(u) through tm_y2
   int m_tiles, n_tiles, k_blocks;
 };
 
@@ -29,7 +29,7 @@ struct GemmOperands {
   const float* s_rows;  // [nS, RP]
   const float* bias;    // [N] or null
   void* out;            // [T, N] bf16
-  void* out_pre;        // [T, N] bf16 or null (ACT_QUICKGELU only)
+  void* out_pre;        // [T, N] bf16 or null (ACT_QUICKGELU only): receives QuickGELU'(u)
   float* h_out;         // [T, RP] or null
   const void* aux;      // [T, N] bf16 (ACT_QUICKGELU_GRAD)
   int T, K, N, b_prime, num_slices, row_div, act;

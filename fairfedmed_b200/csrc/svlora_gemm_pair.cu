@@ -301,7 +301,7 @@ svlora_gemm_pair_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_c
           __syncwarp();
           if (lane == 0) mbar_arrive_cluster(mapa_u32(smem_u32(&tmem_empty[s]), 0));
         }
-        float f[32];
+        float f[32], g2[32];
 #pragma unroll
         for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]) + bias_s[cc + j];
         const int col0 = n0 + c * OUT_CHUNK;
@@ -317,27 +317,39 @@ svlora_gemm_pair_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_c
 #pragma unroll
                 for (int e = 0; e < 4; ++e) {
                   const float2 uu = __bfloat1622float2(h2[e]);
-                  f[j8 * 8 + 2 * e] *= quick_gelu_grad(uu.x);
-                  f[j8 * 8 + 2 * e + 1] *= quick_gelu_grad(uu.y);
+                  f[j8 * 8 + 2 * e] *= uu.x;
+                  f[j8 * 8 + 2 * e + 1] *= uu.y;
                 }
               }
             } else {
               for (int j = 0; j < 32; ++j)
-                if (gc + j < p.N) f[j] *= quick_gelu_grad(__bfloat162float(up[j]));
+                if (gc + j < p.N) f[j] *= __bfloat162float(up[j]);
             }
           }
         }
 #pragma unroll 1
         for (int pass = 0; pass < n_pass; ++pass) {
-          const bool apply_act = (p.act == ACT_QUICKGELU) && (pass == n_pass - 1);
           const uint32_t buf = store_unit & 1u;
           uint8_t* ob = smem + OFF_OUT + buf * OUT_TILE_BYTES;
           if (et == 0) tma_store_wait_read<1>();
           named_bar_sync(EPI_BAR_ID, EPI_THREADS);
           uint8_t* orow = ob + row * 128u;
-          if (apply_act) {
+          if (p.act == ACT_QUICKGELU) {   // warp-uniform branch: keep the MUFU work out of the plain-store path
+            if (n_pass == 2 && pass == 0) {
+              // first store of the dual store: QuickGELU'(u), all the backward pass needs (u itself is not kept)
 #pragma unroll
-            for (int j = 0; j < 32; ++j) f[j] = quick_gelu(f[j]);
+              for (int j = 0; j < 32; ++j) {
+                const float sgm = fmaf(0.5f, tanh_approx(0.851f * f[j]), 0.5f);
+                g2[j] = f[j] * sgm;                                       // QuickGELU(u), stored by the next pass
+                f[j] = sgm * fmaf(1.702f * f[j], 1.0f - sgm, 1.0f);      // QuickGELU'(u)
+              }
+            } else if (n_pass == 2) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) f[j] = g2[j];
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) f[j] = quick_gelu(f[j]);
+            }
           }
 #pragma unroll
           for (int j8 = 0; j8 < 4; ++j8) {

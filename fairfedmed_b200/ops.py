@@ -39,7 +39,7 @@ def _need_cuda(*tensors):
 def svlora_fwd(x: Tensor, w: Tensor, bias: Optional[Tensor], lora_a: Tensor, lora_b: Tensor, s_eff: Tensor,
                scaling: float, b_prime: int, num_slices: int, act: int,
                row_div: int = 1) -> Tuple[Tensor, Tensor, Tensor]:
-    """y, y_pre, h = fused FairLoRA linear.  x [T,K] bf16, w [N,K] bf16, lora_a [K,r], lora_b [r,N], s_eff [nS,r].
+    """y, y_dact, h = fused FairLoRA linear (y_dact = QuickGELU'(u) when act = 1, else empty).  x [T,K] bf16, w [N,K] bf16, lora_a [K,r], lora_b [r,N], s_eff [nS,r].
     Row t of x belongs to sample ((t // row_div) % b_prime) // num_slices (row_div = 1: sequence-first rows)."""
     _need_cuda(x, w, lora_a, lora_b, s_eff)
     T, K = x.shape
@@ -176,7 +176,8 @@ def svlora_linear(x2d: Tensor, w: Tensor, w_t: Tensor, bias: Optional[Tensor], l
 
 class _SVLoRAMLP(torch.autograd.Function):
     """c_proj(QuickGELU(c_fc(x))) with both adapters (clip/model.py:325-332): QuickGELU is fused into the c_fc
-    epilogue (dual store of pre-activation and activation) and QuickGELU' into the c_proj backward epilogue."""
+    epilogue (dual store: the activation and its derivative) and the multiplication by that derivative into the
+    c_proj backward epilogue."""
 
     @staticmethod
     def forward(ctx, x2d, w1, w1_t, b1, a1, bb1, s1, w2, w2_t, b2, a2, bb2, s2, scaling, b_prime, num_slices,

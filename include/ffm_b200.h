@@ -63,7 +63,8 @@ size_t ffm_svlora_bwd_workspace_bytes(int T, int K, int N, int n_samples);
  *   h[t,:]  = x[t,:] · A                                      (f32 [T,16], columns >= r are 0)
  *   u[t,:]  = x[t,:] · W^T + bias + scaling · (h[t,:] ⊙ s_eff[sample(t),:]) · B
  *   y       = act ? QuickGELU(u) : u          (clip/model.py:313-315 fused when act = 1)
- *   y_pre   = u   (only when act = 1 and y_pre != NULL; needed by the backward pass)
+ *   y_dact  = QuickGELU'(u) (only when act = 1 and y_dact != NULL): the one thing the backward pass needs from the
+ *             activation, so u itself is never written.
  *
  *   sample(t) = ((t / row_div) mod b_prime) / num_slices.  row_div = 1: rows are sequence-first [L, B', C] like the
  *               reference's activations (clip/model.py:438-440); row_div = L: rows are batch-first [B', L, C]
@@ -75,17 +76,16 @@ size_t ffm_svlora_bwd_workspace_bytes(int T, int K, int N, int n_samples);
  *   Requirements: K % 8 == 0, N % 8 == 0, 1 <= r <= ffm_svlora_max_rank(), 16-byte aligned pointers.
  */
 int ffm_svlora_fwd(const void* x, const void* w, const float* bias, const float* lora_a, const float* lora_b,
-                   const float* s_eff, void* y, void* y_pre, float* h_out, void* workspace, size_t workspace_bytes,
+                   const float* s_eff, void* y, void* y_dact, float* h_out, void* workspace, size_t workspace_bytes,
                    int T, int K, int N, int r, int n_samples, int b_prime, int num_slices, int row_div, float scaling,
                    int act, ffm_stream_t stream);
 
 /*
  * Backward of the same module (autograd of trainers/GLP_OT_SVLoRA.py:450-482; W and bias frozen :375-376).
  *
- *   dy' = gelu_pre ? dy  (then dx is multiplied by QuickGELU'(gelu_pre), see below) : dy
  *   dzu = dy · B^T                         dz = scaling·dzu       dh = dz ⊙ s_eff[sample]
- *   dx  = dy · W + dh · A^T               (bf16 [T,K]); if gelu_pre != NULL (bf16 [T,K], the
- *         pre-activation of the *preceding* QuickGELU) dx is multiplied element-wise by QuickGELU'(gelu_pre)
+ *   dx  = dy · W + dh · A^T               (bf16 [T,K]); if gelu_dact != NULL (bf16 [T,K], the y_dact output of the
+ *         *preceding* layer's forward) dx is multiplied element-wise by it, i.e. back through that QuickGELU
  *   d_lora_a [K,r] = x^T · dh             d_lora_b [r,N] = scaling · (h ⊙ s_eff[sample])^T · dy
  *   d_s_eff [n_samples,r] = scaling · sum_{t in sample} dzu ⊙ h
  *
@@ -93,7 +93,7 @@ int ffm_svlora_fwd(const void* x, const void* w, const float* bias, const float*
  *   h is the f32 [T,16] side output of ffm_svlora_fwd.
  */
 int ffm_svlora_bwd(const void* dy, const void* x, const void* w_t, const float* lora_a, const float* lora_b,
-                   const float* s_eff, const float* h, const void* gelu_pre, void* dx, float* d_lora_a,
+                   const float* s_eff, const float* h, const void* gelu_dact, void* dx, float* d_lora_a,
                    float* d_lora_b, float* d_s_eff, void* workspace, size_t workspace_bytes, int T, int K, int N,
                    int r, int n_samples, int b_prime, int num_slices, int row_div, float scaling,
                    ffm_stream_t stream);

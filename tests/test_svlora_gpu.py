@@ -108,7 +108,7 @@ def _raw_case(T, K, N, r, b_prime, num_slices, act, seed=0):
     y, y_pre, h = ops.svlora_fwd(d["x"], d["W"], d["bias"], d["A"], d["B"], d["s_eff"], scaling, b_prime, num_slices,
                                  act)
     Wt = d["W"].t().contiguous()
-    gelu_pre = torch.randn(T, K, generator=g).bfloat16().to(dev) if act else None
+    gelu_pre = torch.rand(T, K, generator=g).bfloat16().to(dev) if act else None   # a saved QuickGELU' tensor
     dx, dA, dB, dse = ops.svlora_bwd(d["dy"], d["x"], Wt, d["A"], d["B"], d["s_eff"], h, gelu_pre, scaling, b_prime,
                                      num_slices)
     torch.cuda.synchronize()
@@ -124,9 +124,7 @@ def _raw_case(T, K, N, r, b_prime, num_slices, act, seed=0):
     dh = dzu * (scaling * s_eff)[samp]
     dx_ref = dyf @ Wf + dh @ A.t()
     if act:
-        up = gelu_pre.float().cpu()
-        sg = torch.sigmoid(1.702 * up)
-        dx_ref = dx_ref * (sg * (1 + 1.702 * up * (1 - sg)))
+        dx_ref = dx_ref * gelu_pre.float().cpu()
     dA_ref = xf.t() @ dh
     dB_ref = z.t() @ dyf
     dse_ref = torch.zeros(nS, r).index_add_(0, samp, scaling * dzu * h_ref)
@@ -141,7 +139,9 @@ def _raw_case(T, K, N, r, b_prime, num_slices, act, seed=0):
     assert r == 16 or float(h[:, r:].abs().max()) == 0.0
     tight(y, y_ref, "y")
     if act:
-        tight(y_pre, u_ref, "y_pre")
+        sg_ref = torch.sigmoid(1.702 * u_ref)
+        dact_ref = sg_ref * (1 + 1.702 * u_ref * (1 - sg_ref))
+        assert float((y_pre.float().cpu() - dact_ref).abs().max()) <= 1.5e-2      # bf16 storage of a value in [-0.1, 1.1]
     tight(dx, dx_ref, "dx")
     assert _rel_to_max(dA, dA_ref) < 5e-3 and _rel_to_max(dB, dB_ref) < 5e-3 and _rel_to_max(dse, dse_ref) < 5e-3
 

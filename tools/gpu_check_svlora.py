@@ -111,8 +111,8 @@ def run_case(T, K, N, r, b_prime, num_slices, act, seed=0, verbose=True, timing=
         ok = False
         block_map(ey, "y")
     if act:
-        ep = (y_pre.float() - u_ref).abs()
-        relp = (ep / (2.0 ** -7 * u_ref.abs() + 2e-3 * u_ref.abs().max())).max().item() * 2e-2
+        ep = (y_pre.float() - quick_gelu_grad(u_ref)).abs()
+        relp = (ep / 1.5e-2).max().item() * 2e-2
         if verbose:
             print(f"  pre max abs err {ep.max().item():.3e} rel-ish {relp:.3e}")
         if relp > 2e-2:
@@ -128,7 +128,7 @@ def run_case(T, K, N, r, b_prime, num_slices, act, seed=0, verbose=True, timing=
     dse = torch.zeros(nS, r, device=dev)
     bws_bytes = lib.ffm_svlora_bwd_workspace_bytes(T, K, N, nS)
     bws = torch.empty(bws_bytes, device=dev, dtype=torch.uint8)
-    gelu_pre = (torch.randn(T, K, device=dev, generator=g)).to(torch.bfloat16) if act else None
+    gelu_pre = (torch.rand(T, K, device=dev, generator=g)).to(torch.bfloat16) if act else None
 
     def bwd():
         _cabi.call("ffm_svlora_bwd", ptr(dy), ptr(x), ptr(Wt), ptr(A), ptr(B), ptr(s_eff), ptr(h), ptr(gelu_pre),
@@ -142,7 +142,7 @@ def run_case(T, K, N, r, b_prime, num_slices, act, seed=0, verbose=True, timing=
     dh_ref = dzu_ref * (scaling * s_eff)[samp]
     dx_ref = dyf @ W.float() + dh_ref.to(torch.bfloat16).float() @ A16.t()
     if act:
-        dx_ref = dx_ref * quick_gelu_grad(gelu_pre.float())
+        dx_ref = dx_ref * gelu_pre.float()
     dA_ref = xf.t() @ dh_ref
     dB_ref = (h_ref * (scaling * s_eff)[samp]).t() @ dyf
     dse_ref = torch.zeros(nS, r, device=dev).index_add_(0, samp, scaling * dzu_ref * h_ref)
