@@ -138,6 +138,43 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, int ta
   }
 }
 
+// Hot-path wait for warp-uniform code (TMA producer / MMA issuer warps): the spin loop lives INSIDE the asm block, so
+// the compiler sees straight-line code and keeps loop-carried pipeline state (stage, phase, descriptors) in uniform
+// registers — a C++ spin loop or an `if (lane == 0)` region makes it treat them as divergent and emit an
+// ELECT / R2UR waterfall around every tcgen05.mma (measured: ~100 issue cycles per MMA, the MMA warp became the
+// bottleneck).  Bounded (~2^26 probes) so a protocol bug traps instead of hanging the GPU.
+__device__ __forceinline__ void mbar_wait_uniform(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p, q;\n\t"
+      ".reg .u32 n;\n\t"
+      "mov.u32 n, 0;\n\t"
+      "FFM_WAIT_LOOP:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra FFM_WAIT_DONE;\n\t"
+      "add.u32 n, n, 1;\n\t"
+      "setp.lt.u32 q, n, 0x4000000;\n\t"
+      "@q bra FFM_WAIT_LOOP;\n\t"
+      "trap;\n\t"
+      "FFM_WAIT_DONE:\n\t"
+      "}" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+
+// One lane of a fully converged warp (the tcgen05 / TMA issuing lane).  Keeps the surrounding control flow uniform.
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "elect.sync _|p, 0xFFFFFFFF;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t"
+      "}"
+      : "=r"(pred));
+  return pred != 0;
+}
+
 // ----------------------------------------------------------------------------------------------
 // Proxy fences
 // ----------------------------------------------------------------------------------------------
@@ -340,6 +377,26 @@ __device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity
   while (!mbar_try_wait_cluster(bar, parity)) {
     if (clock64() - t0 > 4000000000ll) mbar_timeout_trap(tag, parity);
   }
+}
+
+// warp-uniform form (see mbar_wait_uniform) with cluster-scope acquire: the barrier is arrived on by the peer CTA
+__device__ __forceinline__ void mbar_wait_cluster_uniform(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p, q;\n\t"
+      ".reg .u32 n;\n\t"
+      "mov.u32 n, 0;\n\t"
+      "FFM_WAITC_LOOP:\n\t"
+      "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra FFM_WAITC_DONE;\n\t"
+      "add.u32 n, n, 1;\n\t"
+      "setp.lt.u32 q, n, 0x4000000;\n\t"
+      "@q bra FFM_WAITC_LOOP;\n\t"
+      "trap;\n\t"
+      "FFM_WAITC_DONE:\n\t"
+      "}" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
 }
 
 // TMA load executed by either CTA of a pair; transaction bytes are credited to the LEADER CTA's mbarrier

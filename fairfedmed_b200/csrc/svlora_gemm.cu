@@ -12,23 +12,21 @@
 //             -> OUT = dx, H = dy·B^T (un-scaled dz)
 //
 // Structure (one CTA per SM, 384 threads, static round-robin tile scheduler):
-//   warp 0   : TMA producer  — X / Wmat / Aside k-slices into a 4-stage SW128 smem ring
+//   warp 0   : TMA producer  — X / Wmat / Aside k-slices into a 4-stage SW128 smem ring (warp-uniform loop, one
+//                              elected lane issues)
 //   warp 1   : MMA issuer    — one tcgen05.mma (M=128, N=192+16, K=16) per k-step: the W tile and the
 //                              Aside tile are adjacent in smem, so a single UMMA accumulates both
 //                              D (192 cols) and H (16 cols) into TMEM; later one K=16 "fix-up" UMMA
 //                              D += Z · Bside^T with Z = bf16(H ⊙ s_rows) staged by the epilogue warps
 //   warp 2   : TMEM allocator (512 columns = 2 accumulator stages x 256)
 //   warps 4-11: epilogue     — tcgen05.ld H -> scale -> Z (SW32 smem) -> signal; then tcgen05.ld D
-//                              -> +bias / QuickGELU / QuickGELU' -> bf16 -> SW128 smem -> TMA store
+//                              -> +bias / QuickGELU / QuickGELU' -> bf16 -> per-warp SW64 staging -> per-warp TMA
+//                              store (8 independent streams, no CTA-wide barrier)
 // TMEM accumulators are double buffered so tile i's epilogue overlaps tile i+1's mainloop; the
 // fix-up UMMA of tile i is slotted into tile i+1's k-loop as soon as Z(i) is ready.
 #include <stdarg.h>
 #include <stdlib.h>
 #include <string.h>
-
-#ifndef FFM_GEMM_PAIR_DEFAULT
-#define FFM_GEMM_PAIR_DEFAULT 0
-#endif
 
 #include <atomic>
 #include <mutex>
@@ -103,23 +101,22 @@ constexpr int UMMA_N_MAIN = BN + RP;  // 208: [D | H] in one instruction
 constexpr int STAGES = 4;
 constexpr int ACC_COLS = 256;       // TMEM columns per accumulator stage (208 used)
 constexpr int TMEM_COLS = 512;
-constexpr int OUT_CHUNK = 64;       // output columns per TMA-store unit (128 B of bf16)
 
 constexpr int X_TILE_BYTES = BM * BK * 2;   // 16384
 constexpr int W_TILE_BYTES = BN * BK * 2;   // 24576
 constexpr int A_TILE_BYTES = RP * BK * 2;   //  2048
 constexpr int STAGE_BYTES = X_TILE_BYTES + W_TILE_BYTES + A_TILE_BYTES;  // 43008 (1024-multiple)
-constexpr int OUT_TILE_BYTES = BM * OUT_CHUNK * 2;  // 16384
+constexpr int OUT_STAGING_BYTES = 8 * 2 * EPI_PIECE_BYTES;  // 8 epilogue warps x 2 buffers x 2 KB = 32768
 constexpr int Z_TILE_BYTES = BM * RP * 2;           //  4096
 constexpr int BS_TILE_BYTES = BN * RP * 2;          //  6144
-constexpr int BIAS_TILE_BYTES = BN * 4;             //   768
+constexpr int BIAS_BYTES = 8 * (BN / 2) * 4;          //  3072: per epilogue warp, the bias of its BN/2 columns
 
 constexpr int OFF_STAGES = 0;
 constexpr int OFF_OUT = OFF_STAGES + STAGES * STAGE_BYTES;
-constexpr int OFF_Z = OFF_OUT + 2 * OUT_TILE_BYTES;
+constexpr int OFF_Z = OFF_OUT + OUT_STAGING_BYTES;
 constexpr int OFF_BS = OFF_Z + 2 * Z_TILE_BYTES;
 constexpr int OFF_BIAS = OFF_BS + 2 * BS_TILE_BYTES;
-constexpr int OFF_BAR = OFF_BIAS + 2 * BIAS_TILE_BYTES;
+constexpr int OFF_BAR = OFF_BIAS + BIAS_BYTES;
 constexpr int NUM_BARS = 2 * STAGES + 5 * 2;
 constexpr int SMEM_USED = OFF_BAR + NUM_BARS * 8 + 16;
 constexpr int SMEM_BYTES = SMEM_USED + 1024;  // slack for manual 1024-B alignment
@@ -128,12 +125,11 @@ static_assert(STAGE_BYTES % 1024 == 0, "stage must keep 1024-B alignment of SW12
 static_assert((X_TILE_BYTES + W_TILE_BYTES) % 1024 == 0, "Aside tile must start on a swizzle atom");
 static_assert(OFF_OUT % 1024 == 0 && OFF_Z % 1024 == 0 && OFF_BS % 1024 == 0, "tile alignment");
 static_assert(SMEM_BYTES <= 232448, "exceeds 227 KB of shared memory per CTA");
-static_assert(BN % OUT_CHUNK == 0, "epilogue chunks");
+static_assert(BN % (2 * EPI_PIECE_COLS) == 0, "epilogue pieces");
 
 constexpr int NUM_THREADS = 384;   // 4 control warps (TMA, MMA, TMEM alloc, spare) + 8 epilogue warps
 constexpr int EPI_THREADS = 256;
 constexpr int Z_THREADS = 128;     // epilogue threads that write the Z tile (one per tile row)
-constexpr int EPI_BAR_ID = 1;
 
 
 __global__ void __launch_bounds__(NUM_THREADS, 1)
@@ -190,96 +186,119 @@ svlora_gemm_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_consta
   const uint32_t tmem_base = *tmem_ptr;
 
   if (warp == 0) {
-    // =========================== TMA producer ===========================
-    if (lane == 0) {
-      uint32_t stage = 0, phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const int m_blk = tile / p.n_tiles;
-        const int n_blk = tile - m_blk * p.n_tiles;
-        for (int kb = 0; kb < p.k_blocks; ++kb) {
-          mbar_wait(&empty_bar[stage], phase ^ 1u, 100 + stage);
+    // =========================== TMA producer (whole warp, one elected lane issues) ===========================
+    uint32_t stage = 0, phase = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      const int m_blk = tile / p.n_tiles;
+      const int n_blk = tile - m_blk * p.n_tiles;
+      for (int kb = 0; kb < p.k_blocks; ++kb) {
+        mbar_wait_uniform(&empty_bar[stage], phase ^ 1u);
+        if (elect_one()) {
           uint8_t* st = smem + OFF_STAGES + stage * STAGE_BYTES;
-          mbar_arrive_expect_tx(&full_bar[stage], STAGE_BYTES);
-          tma_load_2d(st, &tm_x, &full_bar[stage], kb * BK, m_blk * BM);
-          tma_load_2d(st + X_TILE_BYTES, &tm_w, &full_bar[stage], kb * BK, n_blk * BN);
-          tma_load_2d(st + X_TILE_BYTES + W_TILE_BYTES, &tm_a, &full_bar[stage], kb * BK, 0);
-          if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+          if (p.dbg & 2) {
+            mbar_arrive(&full_bar[stage]);
+          } else {
+            mbar_arrive_expect_tx(&full_bar[stage], STAGE_BYTES);
+            tma_load_2d(st, &tm_x, &full_bar[stage], kb * BK, m_blk * BM);
+            tma_load_2d(st + X_TILE_BYTES, &tm_w, &full_bar[stage], kb * BK, n_blk * BN);
+            tma_load_2d(st + X_TILE_BYTES + W_TILE_BYTES, &tm_a, &full_bar[stage], kb * BK, 0);
+          }
         }
+        __syncwarp();
+        if (++stage == STAGES) { stage = 0; phase ^= 1u; }
       }
     }
   } else if (warp == 1) {
-    // =========================== MMA issuer ===========================
-    if (lane == 0) {
-      constexpr uint32_t idesc_main = umma_idesc_bf16(BM, UMMA_N_MAIN);
-      constexpr uint32_t idesc_fix = umma_idesc_bf16(BM, BN);
-      uint32_t stage = 0, phase = 0;
-      int pend = -1;
-      uint32_t pend_phase = 0;
+    // =========================== MMA issuer (whole warp, one elected lane issues) ===========================
+    // Everything below is warp-uniform: the only per-lane decision is elect_one() around the tcgen05 instructions
+    // (an `if (lane == 0)` region makes nvcc wrap every tcgen05.mma in an ELECT/R2UR waterfall loop).
+    constexpr uint32_t idesc_main = umma_idesc_bf16(BM, UMMA_N_MAIN);
+    constexpr uint32_t idesc_fix = umma_idesc_bf16(BM, BN);
+    const uint32_t stages_base = smem_u32(smem + OFF_STAGES);
+    uint32_t stage = 0, phase = 0;
+    int pend = -1;
+    uint32_t pend_phase = 0;
 
-      auto fixup = [&](int s, uint32_t ph) {
-        // D[s] += Z[s] (128 x 16) · Bside[s]^T (16 x 192)
-        mbar_wait(&bs_full[s], ph, 200 + s);
-        tc_fence_after();
+    auto fixup = [&](int s, uint32_t ph) {
+      // D[s] += Z[s] (128 x 16) · Bside[s]^T (16 x 192)
+      mbar_wait_uniform(&bs_full[s], ph);
+      tc_fence_after();
+      if (elect_one()) {
         const uint64_t zd = umma_desc_sw32(smem_u32(smem + OFF_Z + s * Z_TILE_BYTES));
         const uint64_t bd = umma_desc_sw32(smem_u32(smem + OFF_BS + s * BS_TILE_BYTES));
         umma_bf16(tmem_base + s * ACC_COLS, zd, bd, idesc_fix, 1u);
         umma_commit(&d_full[s]);
-      };
+      }
+      __syncwarp();
+    };
 
-      int it = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
-        const int m_blk = tile / p.n_tiles;
-        const int n_blk = tile - m_blk * p.n_tiles;
-        const int s = it & 1;
-        const uint32_t aph = (it >> 1) & 1u;
-        mbar_wait(&tmem_empty[s], aph ^ 1u, 300 + s);   // epilogue drained tile it-2 (=> Bside[s], Z[s] free)
-        tc_fence_after();
+    int it = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+      const int n_blk = tile % p.n_tiles;
+      const int s = it & 1;
+      const uint32_t aph = (it >> 1) & 1u;
+      mbar_wait_uniform(&tmem_empty[s], aph ^ 1u);   // epilogue drained tile it-2 (=> Bside[s], Z[s] free)
+      tc_fence_after();
+      if (elect_one()) {
         mbar_arrive_expect_tx(&bs_full[s], BS_TILE_BYTES);
         tma_load_2d(smem + OFF_BS + s * BS_TILE_BYTES, &tm_b, &bs_full[s], 0, n_blk * BN);
+      }
+      __syncwarp();
 
-        const uint32_t d_tmem = tmem_base + s * ACC_COLS;
-        for (int kb = 0; kb < p.k_blocks; ++kb) {
-          if (pend >= 0 && mbar_test_wait(&z_full[pend], pend_phase)) {
+      const uint32_t d_tmem = tmem_base + s * ACC_COLS;
+      for (int kb = 0; kb < p.k_blocks; ++kb) {
+        if (pend >= 0 && (kb & 3) == 3) {
+          // Z of the previous tile ready?  (vote keeps the decision warp-uniform for the compiler)
+          if (__all_sync(0xffffffffu, mbar_test_wait(&z_full[pend], pend_phase))) {
             fixup(pend, pend_phase);
             pend = -1;
           }
-          mbar_wait(&full_bar[stage], phase, 400 + stage);
-          tc_fence_after();
-          const uint32_t st = smem_u32(smem + OFF_STAGES + stage * STAGE_BYTES);
+        }
+        mbar_wait_uniform(&full_bar[stage], phase);
+        tc_fence_after();
+        if (elect_one()) {
+          const uint32_t st = stages_base + stage * STAGE_BYTES;
           const uint64_t adesc = umma_desc_sw128(st);
           const uint64_t bdesc = umma_desc_sw128(st + X_TILE_BYTES);
+          if (!(p.dbg & 1)) {
 #pragma unroll
-          for (int k = 0; k < BK / UMMA_K; ++k) {
-            // advance 32 B along K inside the 128-B swizzle row: +2 in the (>>4) address field
-            umma_bf16(d_tmem, adesc + 2u * k, bdesc + 2u * k, idesc_main, (kb | k) != 0 ? 1u : 0u);
+            for (int k = 0; k < BK / UMMA_K; ++k) {
+              // advance 32 B along K inside the 128-B swizzle row: +2 in the (>>4) address field
+              umma_bf16(d_tmem, adesc + 2u * k, bdesc + 2u * k, idesc_main, (kb | k) != 0 ? 1u : 0u);
+            }
           }
           umma_commit(&empty_bar[stage]);
-          if (++stage == STAGES) { stage = 0; phase ^= 1u; }
         }
-        umma_commit(&h_full[s]);
-        if (pend >= 0) {
-          mbar_wait(&z_full[pend], pend_phase, 500 + pend);
-          fixup(pend, pend_phase);
-        }
-        pend = s;
-        pend_phase = aph;
-        (void)m_blk;
+        __syncwarp();
+        if (++stage == STAGES) { stage = 0; phase ^= 1u; }
       }
+      if (elect_one()) umma_commit(&h_full[s]);
+      __syncwarp();
       if (pend >= 0) {
-        mbar_wait(&z_full[pend], pend_phase, 510 + pend);
+        mbar_wait_uniform(&z_full[pend], pend_phase);
         fixup(pend, pend_phase);
       }
+      pend = s;
+      pend_phase = aph;
+    }
+    if (pend >= 0) {
+      mbar_wait_uniform(&z_full[pend], pend_phase);
+      fixup(pend, pend_phase);
     }
   } else if (warp >= 4) {
-    // =========================== epilogue (8 warps) ===========================
-    // Two warps share each TMEM lane quarter (a warp may only touch lanes 32*(warpid%4)..+31): warp w handles
-    // columns [0,32) of every 64-column chunk, warp w+4 columns [32,64).  One tile row per thread.
+    // =========================== epilogue (8 independent warps) ===========================
+    // Two warps share each TMEM lane quarter (a warp may only touch lanes 32*(warpid%4)..+31): warp w takes the even
+    // 32-column pieces of the tile, warp w+4 the odd ones.  One tile row per thread.  No CTA-wide barriers: each warp
+    // stages and TMA-stores its own pieces (epi_store_piece).
+    const uint32_t ew = warp - 4u;             // 0..7
     const uint32_t q = warp & 3u;
-    const uint32_t half = (warp - 4u) >> 2;
+    const uint32_t half = ew >> 2;
     const uint32_t row = q * 32u + lane;
-    const uint32_t et = threadIdx.x - 128u;    // 0..255
     const uint32_t lane_addr = (q * 32u) << 16;
-    uint32_t store_unit = 0;                   // running count of TMA-store units (buffer = unit & 1)
+    uint8_t* stage_w = smem + OFF_OUT + ew * (2 * EPI_PIECE_BYTES);
+    float* bias_w = reinterpret_cast<float*>(smem + OFF_BIAS) + ew * (BN / 2);
+    uint32_t unit = 0;                         // this warp's running count of TMA stores (buffer = unit & 1)
+    constexpr int PIECES = BN / (2 * EPI_PIECE_COLS);   // pieces per warp per tile
     int it = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
       const int m_blk = tile / p.n_tiles;
@@ -289,7 +308,13 @@ svlora_gemm_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_consta
       const int grow = m_blk * BM + static_cast<int>(row);   // global row
       const int n0 = n_blk * BN;
       const uint32_t acc = tmem_base + lane_addr + s * ACC_COLS;
-      float* bias_s = reinterpret_cast<float*>(smem + OFF_BIAS + s * BIAS_TILE_BYTES);
+
+      // bias of this warp's columns (warp-private smem, read back as broadcasts)
+#pragma unroll
+      for (int pc = 0; pc < PIECES; ++pc) {
+        const int col = n0 + (2 * pc + static_cast<int>(half)) * EPI_PIECE_COLS + static_cast<int>(lane);
+        bias_w[pc * EPI_PIECE_COLS + lane] = (p.bias != nullptr && col < p.N) ? __ldg(p.bias + col) : 0.0f;
+      }
 
       if (half == 0) {
         // ---- H -> Z (SW32 K-major A operand of the fix-up UMMA) ----
@@ -329,107 +354,32 @@ svlora_gemm_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_consta
         *reinterpret_cast<uint4*>(zrow + ((1u ^ sw) << 4)) = c1;
         fence_proxy_async_smem();
         mbar_arrive(&z_full[s]);
-      } else {
-        // bias slice of this n block, staged by the other four warps meanwhile
-        for (int j = et - 128; j < BN; j += 128) {
-          const int col = n0 + j;
-          bias_s[j] = (p.bias != nullptr && col < p.N) ? __ldg(p.bias + col) : 0.0f;
-        }
       }
-      named_bar_sync(EPI_BAR_ID, EPI_THREADS);   // bias_s visible to all epilogue threads
+      __syncwarp();                              // bias_w visible to the whole warp
 
       // ---- D -> OUT ----
       mbar_wait(&d_full[s], aph, 700 + s);
       tc_fence_after();
-      const int n_pass = (p.act == ACT_QUICKGELU && p.has_pre) ? 2 : 1;
 #pragma unroll 1
-      for (int c = 0; c < BN / OUT_CHUNK; ++c) {
-        const int cc = c * OUT_CHUNK + static_cast<int>(half) * 32;   // first tile column of this thread's slice
+      for (int pc = 0; pc < PIECES; ++pc) {
+        const int cc = (2 * pc + static_cast<int>(half)) * EPI_PIECE_COLS;   // first tile column of this piece
         uint32_t v[32];
         tmem_ld32(acc + cc, v);
         tmem_ld_wait();
-        if (c == BN / OUT_CHUNK - 1) {
+        if (pc == PIECES - 1) {
           // accumulator stage fully read by this warp: hand it back to the MMA warp
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(&tmem_empty[s]);
         }
-        float f[32], g2[32];
+        float f[32];
 #pragma unroll
-        for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]) + bias_s[cc + j];
-        const int col0 = n0 + c * OUT_CHUNK;     // first global column of the 64-wide store unit
-        if (p.act == ACT_QUICKGELU_GRAD) {
-          // f <- f * QuickGELU'(u), u = pre-activation saved by the forward pass
-          if (grow < p.T) {
-            const int gc = n0 + cc;
-            const __nv_bfloat16* up = p.aux + static_cast<size_t>(grow) * p.N + gc;
-            if (gc + 32 <= p.N) {
-#pragma unroll
-              for (int j8 = 0; j8 < 4; ++j8) {
-                const uint4 raw = __ldg(reinterpret_cast<const uint4*>(up) + j8);
-                const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&raw);
-#pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                  const float2 uu = __bfloat1622float2(h2[e]);
-                  f[j8 * 8 + 2 * e] *= uu.x;
-                  f[j8 * 8 + 2 * e + 1] *= uu.y;
-                }
-              }
-            } else {
-              for (int j = 0; j < 32; ++j)
-                if (gc + j < p.N) f[j] *= __bfloat162float(up[j]);
-            }
-          }
-        }
-#pragma unroll 1
-        for (int pass = 0; pass < n_pass; ++pass) {
-          // pass 0 of a dual store writes QuickGELU'(u) (tm_y2), the last pass the activated value
-          const uint32_t buf = store_unit & 1u;
-          uint8_t* ob = smem + OFF_OUT + buf * OUT_TILE_BYTES;
-          // the TMA store that last read this buffer (2 units ago) must have finished reading smem
-          if (et == 0) tma_store_wait_read<1>();
-          named_bar_sync(EPI_BAR_ID, EPI_THREADS);
-          uint8_t* orow = ob + row * 128u;
-          if (p.act == ACT_QUICKGELU) {   // warp-uniform branch: keep the MUFU work out of the plain-store path
-            if (n_pass == 2 && pass == 0) {
-              // first store of the dual store: QuickGELU'(u), all the backward pass needs (u itself is not kept)
-#pragma unroll
-              for (int j = 0; j < 32; ++j) {
-                const float sgm = fmaf(0.5f, tanh_approx(0.851f * f[j]), 0.5f);
-                g2[j] = f[j] * sgm;                                       // QuickGELU(u), stored by the next pass
-                f[j] = sgm * fmaf(1.702f * f[j], 1.0f - sgm, 1.0f);      // QuickGELU'(u)
-              }
-            } else if (n_pass == 2) {
-#pragma unroll
-              for (int j = 0; j < 32; ++j) f[j] = g2[j];
-            } else {
-#pragma unroll
-              for (int j = 0; j < 32; ++j) f[j] = quick_gelu(f[j]);
-            }
-          }
-#pragma unroll
-          for (int j8 = 0; j8 < 4; ++j8) {
-            uint4 pk;
-            pk.x = pack_bf16x2(f[j8 * 8 + 0], f[j8 * 8 + 1]);
-            pk.y = pack_bf16x2(f[j8 * 8 + 2], f[j8 * 8 + 3]);
-            pk.z = pack_bf16x2(f[j8 * 8 + 4], f[j8 * 8 + 5]);
-            pk.w = pack_bf16x2(f[j8 * 8 + 6], f[j8 * 8 + 7]);
-            // SW128: 16-B piece k of row r lives at piece (k ^ (r & 7)); this thread owns pieces half*4 .. +3
-            const uint32_t piece = half * 4u + static_cast<uint32_t>(j8);
-            *reinterpret_cast<uint4*>(orow + ((piece ^ (row & 7u)) << 4)) = pk;
-          }
-          fence_proxy_async_smem();
-          named_bar_sync(EPI_BAR_ID, EPI_THREADS);
-          if (et == 0) {
-            const CUtensorMap* tm = (n_pass == 2 && pass == 0) ? &tm_y2 : &tm_y;
-            tma_store_2d(tm, ob, col0, m_blk * BM);
-            tma_store_commit();
-          }
-          ++store_unit;
-        }
+        for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]) + bias_w[pc * EPI_PIECE_COLS + j];
+        epi_store_piece(p, f, &tm_y, &tm_y2, stage_w, unit, lane, grow, n0 + cc, m_blk * BM + static_cast<int>(q) * 32);
       }
+      __syncwarp();                              // all lanes done with bias_w before the next tile overwrites it
     }
-    if (et == 0) tma_store_wait_all<0>();
+    if (lane == 0) tma_store_wait_all<0>();
   }
 
   __syncwarp();
@@ -514,14 +464,28 @@ int make_map_bf16(CUtensorMap* out, const void* ptr, uint64_t rows, uint64_t col
 }
 
 
-// FFM_GEMM_PAIR=0 selects the single-CTA build (kept for A/B measurements); default is the CTA-pair build
-static bool use_pair_kernel() {
+// Which build runs: the CTA-pair kernel (deeper ring: 6 stages of 29 KB, half the issue overhead per FLOP) wins when a
+// tile has many k-blocks (K >= 2048: 51 us vs 58 us at T=12608, K=3072, N=768); with 12 k-blocks per tile (K = 768) its
+// per-tile hand-offs cost more than they save (72 us vs 61 us), so short contractions stay on the single-CTA kernel.
+// FFM_GEMM_PAIR=0 / 1 forces one build (A/B measurements).
+static bool use_pair_kernel(int K) {
+  static int v = -2;
+  if (v == -2) {
+    const char* e = getenv("FFM_GEMM_PAIR");
+    v = (e == nullptr) ? -1 : (e[0] != '0');
+  }
+  if (v >= 0) return v != 0;
+  return K >= 2048;
+}
+
+// FFM_GEMM_DBG: bottleneck experiments only (1: no MMA, 2: no TMA loads, 4: no TMA stores); results are garbage
+int gemm_debug_mask() {
   static int v = -1;
   if (v < 0) {
-    const char* e = getenv("FFM_GEMM_PAIR");
-    v = (e == nullptr) ? FFM_GEMM_PAIR_DEFAULT : (e[0] != '0');
+    const char* e = getenv("FFM_GEMM_DBG");
+    v = (e == nullptr) ? 0 : atoi(e);
   }
-  return v != 0;
+  return v;
 }
 
 static int launch_svlora_gemm(const GemmOperands& o, cudaStream_t stream) {
@@ -536,7 +500,7 @@ static int launch_svlora_gemm(const GemmOperands& o, cudaStream_t stream) {
                              reinterpret_cast<uintptr_t>(o.s_rows) | reinterpret_cast<uintptr_t>(o.h_out) |
                              reinterpret_cast<uintptr_t>(o.aux);
   FFM_CHECK_ARG((align_or & 15u) == 0, "svlora gemm: all device pointers must be 16-byte aligned");
-  if (use_pair_kernel()) return launch_svlora_gemm_pair(o, stream);
+  if (use_pair_kernel(o.K)) return launch_svlora_gemm_pair(o, stream);
 
   CUtensorMap tm_x, tm_w, tm_a, tm_b, tm_y, tm_y2;
   int rc;
@@ -544,9 +508,9 @@ static int launch_svlora_gemm(const GemmOperands& o, cudaStream_t stream) {
   if ((rc = make_map_bf16(&tm_w, o.wmat, o.N, o.K, BN, BK, CU_TENSOR_MAP_SWIZZLE_128B, true))) return rc;
   if ((rc = make_map_bf16(&tm_a, o.a_side, RP, o.K, RP, BK, CU_TENSOR_MAP_SWIZZLE_128B, true))) return rc;
   if ((rc = make_map_bf16(&tm_b, o.b_side, o.N, RP, BN, RP, CU_TENSOR_MAP_SWIZZLE_32B, false))) return rc;
-  if ((rc = make_map_bf16(&tm_y, o.out, o.T, o.N, BM, OUT_CHUNK, CU_TENSOR_MAP_SWIZZLE_128B, false))) return rc;
+  if ((rc = make_map_bf16(&tm_y, o.out, o.T, o.N, 32, EPI_PIECE_COLS, CU_TENSOR_MAP_SWIZZLE_64B, false))) return rc;
   const bool has_pre = (o.act == ACT_QUICKGELU && o.out_pre != nullptr);
-  if ((rc = make_map_bf16(&tm_y2, has_pre ? o.out_pre : o.out, o.T, o.N, BM, OUT_CHUNK, CU_TENSOR_MAP_SWIZZLE_128B,
+  if ((rc = make_map_bf16(&tm_y2, has_pre ? o.out_pre : o.out, o.T, o.N, 32, EPI_PIECE_COLS, CU_TENSOR_MAP_SWIZZLE_64B,
                           false)))
     return rc;
 
@@ -562,6 +526,7 @@ static int launch_svlora_gemm(const GemmOperands& o, cudaStream_t stream) {
   p.m_tiles = (o.T + BM - 1) / BM;
   p.n_tiles = (o.N + BN - 1) / BN;
   p.k_blocks = (o.K + BK - 1) / BK;
+  p.dbg = gemm_debug_mask();
 
   static std::once_flag attr_once;
   static cudaError_t attr_err = cudaSuccess;

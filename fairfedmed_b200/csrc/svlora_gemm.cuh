@@ -19,7 +19,10 @@ struct GemmParams {
   int act;
   int has_pre;                  // ACT_QUICKGELU: also store QuickGELU'(u) through tm_y2
   int m_tiles, n_tiles, k_blocks;
+  int dbg;                      // FFM_GEMM_DBG experiment mask (1: no MMA, 2: no TMA loads, 4: no TMA stores); 0 in production
 };
+
+int gemm_debug_mask();
 
 struct GemmOperands {
   const void* x;        // [T, K] bf16
@@ -64,6 +67,86 @@ __device__ __forceinline__ float quick_gelu(float u) {
 __device__ __forceinline__ float quick_gelu_grad(float u) {
   const float s = fmaf(0.5f, tanh_approx(0.851f * u), 0.5f);
   return s * fmaf(1.702f * u, 1.0f - s, 1.0f);
+}
+
+// ----------------------------------------------------------------------------------------------
+// Epilogue tail shared by the single-CTA and CTA-pair builds.  Every epilogue warp is an independent stream: it owns
+// 32 tile rows (lane = row), converts one 32-column piece at a time and ships it with its OWN TMA store from its OWN
+// double-buffered 2 KB staging area (SW64 rows of 64 B) — no CTA-wide barriers anywhere in the epilogue.
+// ----------------------------------------------------------------------------------------------
+constexpr int EPI_PIECE_COLS = 32;
+constexpr int EPI_PIECE_BYTES = 32 * EPI_PIECE_COLS * 2;   // 32 rows x 64 B
+
+// f[j] (+bias already added) -> optional x saved QuickGELU' (backward) -> optional QuickGELU (+ its derivative as a
+// second store) -> bf16 -> staging -> TMA store at (row0, gcol).  `unit` counts this warp's stores (buffer = unit&1).
+__device__ __forceinline__ void epi_store_piece(const GemmParams& p, float (&f)[32], const CUtensorMap* tm_y,
+                                                const CUtensorMap* tm_y2, uint8_t* stage_w, uint32_t& unit,
+                                                uint32_t lane, int grow, int gcol, int row0) {
+  if (p.act == ACT_QUICKGELU_GRAD && grow < p.T) {
+    const __nv_bfloat16* up = p.aux + static_cast<size_t>(grow) * p.N + gcol;
+    if (gcol + 32 <= p.N) {
+#pragma unroll
+      for (int j8 = 0; j8 < 4; ++j8) {
+        const uint4 raw = __ldg(reinterpret_cast<const uint4*>(up) + j8);
+        const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&raw);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const float2 uu = __bfloat1622float2(h2[e]);
+          f[j8 * 8 + 2 * e] *= uu.x;
+          f[j8 * 8 + 2 * e + 1] *= uu.y;
+        }
+      }
+    } else {
+      for (int j = 0; j < 32; ++j)
+        if (gcol + j < p.N) f[j] *= __bfloat162float(up[j]);
+    }
+  }
+  const int n_pass = (p.act == ACT_QUICKGELU && p.has_pre) ? 2 : 1;
+  float g2[32];
+#pragma unroll 1
+  for (int pass = 0; pass < n_pass; ++pass) {
+    uint8_t* ob = stage_w + (unit & 1u) * EPI_PIECE_BYTES;
+    // the TMA store that last read this buffer (2 units ago) must have finished reading smem
+    if (lane == 0) tma_store_wait_read<1>();
+    __syncwarp();
+    if (p.act == ACT_QUICKGELU) {
+      if (n_pass == 2 && pass == 0) {
+        // first store of the dual store: QuickGELU'(u), all the backward pass needs (u itself is not kept)
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          const float sgm = fmaf(0.5f, tanh_approx(0.851f * f[j]), 0.5f);
+          g2[j] = f[j] * sgm;                                       // QuickGELU(u), stored by the next pass
+          f[j] = sgm * fmaf(1.702f * f[j], 1.0f - sgm, 1.0f);      // QuickGELU'(u)
+        }
+      } else if (n_pass == 2) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) f[j] = g2[j];
+      } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) f[j] = quick_gelu(f[j]);
+      }
+    }
+    // SW64: 16-B chunk k of row r lives at chunk (k ^ ((r >> 1) & 3)) of the 64-B row
+    uint8_t* orow = ob + lane * 64u;
+    const uint32_t sw = (lane >> 1) & 3u;
+#pragma unroll
+    for (int j8 = 0; j8 < 4; ++j8) {
+      uint4 pk;
+      pk.x = pack_bf16x2(f[j8 * 8 + 0], f[j8 * 8 + 1]);
+      pk.y = pack_bf16x2(f[j8 * 8 + 2], f[j8 * 8 + 3]);
+      pk.z = pack_bf16x2(f[j8 * 8 + 4], f[j8 * 8 + 5]);
+      pk.w = pack_bf16x2(f[j8 * 8 + 6], f[j8 * 8 + 7]);
+      *reinterpret_cast<uint4*>(orow + ((static_cast<uint32_t>(j8) ^ sw) << 4)) = pk;
+    }
+    fence_proxy_async_smem();
+    __syncwarp();
+    if (lane == 0) {
+      const CUtensorMap* tm = (n_pass == 2 && pass == 0) ? tm_y2 : tm_y;
+      if (!(p.dbg & 4)) tma_store_2d(tm, ob, gcol, row0);
+      tma_store_commit();
+    }
+    ++unit;
+  }
 }
 #endif
 

@@ -40,24 +40,23 @@ constexpr int UMMA_N = 2 * BH;       // 208
 constexpr int STAGES = 6;
 constexpr int ACC_COLS = 256;
 constexpr int TMEM_COLS = 512;
-constexpr int OUT_CHUNK = 64;
 
 constexpr int X_TILE_BYTES = BM * BK * 2;     // 16384
 constexpr int W_TILE_BYTES = HN * BK * 2;     // 12288
 constexpr int A_TILE_BYTES = HR * BK * 2;     //  1024
 constexpr int STAGE_BYTES = X_TILE_BYTES + W_TILE_BYTES + A_TILE_BYTES;   // 29696 = 29 * 1024
-constexpr int OUT_TILE_BYTES = BM * OUT_CHUNK * 2;   // 16384
+constexpr int OUT_STAGING_BYTES = 8 * 2 * EPI_PIECE_BYTES;   // 8 epilogue warps x 2 buffers x 2 KB
 constexpr int Z_TILE_BYTES = BM * RP * 2;            //  4096
 constexpr int BS_LOAD_BYTES = HN * RP * 2;           //  3072 (TMA box)
 constexpr int BS_TILE_BYTES = 4096;                  //  104 rows x 32 B = 3328, padded
-constexpr int BIAS_TILE_BYTES = BN * 4;              //   768
+constexpr int BIAS_BYTES = 8 * (BN / 2) * 4;           //  3072
 
 constexpr int OFF_STAGES = 0;
 constexpr int OFF_OUT = OFF_STAGES + STAGES * STAGE_BYTES;
-constexpr int OFF_Z = OFF_OUT + 2 * OUT_TILE_BYTES;
+constexpr int OFF_Z = OFF_OUT + OUT_STAGING_BYTES;
 constexpr int OFF_BS = OFF_Z + 2 * Z_TILE_BYTES;
 constexpr int OFF_BIAS = OFF_BS + 2 * BS_TILE_BYTES;
-constexpr int OFF_BAR = OFF_BIAS + 2 * BIAS_TILE_BYTES;
+constexpr int OFF_BAR = OFF_BIAS + BIAS_BYTES;
 constexpr int NUM_BARS = 2 * STAGES + 5 * 2;
 constexpr int SMEM_USED = OFF_BAR + NUM_BARS * 8 + 16;
 constexpr int SMEM_BYTES = SMEM_USED + 1024;
@@ -70,7 +69,6 @@ static_assert(HN % 32 == 0, "a 32-column epilogue slice must not straddle the tw
 constexpr int NUM_THREADS = 384;
 constexpr int EPI_THREADS = 256;
 constexpr int Z_THREADS = 128;
-constexpr int EPI_BAR_ID = 1;
 
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
 svlora_gemm_pair_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_w,
@@ -140,95 +138,118 @@ svlora_gemm_pair_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_c
   const uint32_t tmem_base = *tmem_ptr;
 
   if (warp == 0) {
-    // =========================== TMA producer (both CTAs) ===========================
-    if (lane == 0) {
-      uint32_t stage = 0, phase = 0;
-      int it = 0;
-      for (int tile = cluster_id; tile < num_tiles; tile += num_clusters, ++it) {
-        const int m_pair = tile / p.n_tiles;
-        const int n_blk = tile - m_pair * p.n_tiles;
-        const int m_blk = m_pair * 2 + static_cast<int>(rank);
-        const int s = it & 1;
-        // Bside half for this tile; buffer s is free once the fix-up UMMA of tile it-2 completed
-        if (it >= 2) mbar_wait(&d_full[s], ((it - 2) >> 1) & 1u, 150 + s);
+    // =========================== TMA producer (both CTAs; whole warp, one elected lane issues) ===================
+    uint32_t stage = 0, phase = 0;
+    int it = 0;
+    for (int tile = cluster_id; tile < num_tiles; tile += num_clusters, ++it) {
+      const int m_pair = tile / p.n_tiles;
+      const int n_blk = tile - m_pair * p.n_tiles;
+      const int m_blk = m_pair * 2 + static_cast<int>(rank);
+      const int s = it & 1;
+      // Bside half for this tile; buffer s is free once the fix-up UMMA of tile it-2 completed
+      if (it >= 2) mbar_wait_uniform(&d_full[s], ((it - 2) >> 1) & 1u);
+      if (elect_one()) {
         if (leader) mbar_arrive_expect_tx(&bs_full[s], 2 * BS_LOAD_BYTES);
         tma_load_2d_pair(smem + OFF_BS + s * BS_TILE_BYTES, &tm_b, &bs_full[s], 0,
                          n_blk * BN + static_cast<int>(rank) * HN);
-        for (int kb = 0; kb < p.k_blocks; ++kb) {
-          mbar_wait(&empty_bar[stage], phase ^ 1u, 100 + stage);
+      }
+      __syncwarp();
+      for (int kb = 0; kb < p.k_blocks; ++kb) {
+        mbar_wait_uniform(&empty_bar[stage], phase ^ 1u);
+        if (elect_one()) {
           uint8_t* st = smem + OFF_STAGES + stage * STAGE_BYTES;
-          if (leader) mbar_arrive_expect_tx(&full_bar[stage], 2 * STAGE_BYTES);
-          tma_load_2d_pair(st, &tm_x, &full_bar[stage], kb * BK, m_blk * BM);
-          tma_load_2d_pair(st + X_TILE_BYTES, &tm_w, &full_bar[stage], kb * BK,
-                           n_blk * BN + static_cast<int>(rank) * HN);
-          tma_load_2d_pair(st + X_TILE_BYTES + W_TILE_BYTES, &tm_a, &full_bar[stage], kb * BK,
-                           static_cast<int>(rank) * HR);
-          if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+          if (p.dbg & 2) {
+            if (leader) mbar_arrive(&full_bar[stage]);
+          } else {
+            if (leader) mbar_arrive_expect_tx(&full_bar[stage], 2 * STAGE_BYTES);
+            tma_load_2d_pair(st, &tm_x, &full_bar[stage], kb * BK, m_blk * BM);
+            tma_load_2d_pair(st + X_TILE_BYTES, &tm_w, &full_bar[stage], kb * BK,
+                             n_blk * BN + static_cast<int>(rank) * HN);
+            tma_load_2d_pair(st + X_TILE_BYTES + W_TILE_BYTES, &tm_a, &full_bar[stage], kb * BK,
+                             static_cast<int>(rank) * HR);
+          }
         }
+        __syncwarp();
+        if (++stage == STAGES) { stage = 0; phase ^= 1u; }
       }
     }
   } else if (warp == 1) {
-    // =========================== MMA issuer (leader CTA only) ===========================
-    if (lane == 0 && leader) {
+    // =========================== MMA issuer (leader CTA only; whole warp, one elected lane issues) ==============
+    if (leader) {
       constexpr uint32_t idesc = umma_idesc_bf16(UMMA_M, UMMA_N);
+      const uint32_t stages_base = smem_u32(smem + OFF_STAGES);
       uint32_t stage = 0, phase = 0;
       int pend = -1;
       uint32_t pend_phase = 0;
 
       auto fixup = [&](int s, uint32_t ph) {
         // D[s] += Z[s] (256 x 16 over the pair) · [Bside | 0]^T (16 x 208)
-        mbar_wait(&bs_full[s], ph, 200 + s);
+        mbar_wait_uniform(&bs_full[s], ph);
         tc_fence_after();
-        const uint64_t zd = umma_desc_sw32(smem_u32(smem + OFF_Z + s * Z_TILE_BYTES));
-        const uint64_t bd = umma_desc_sw32(smem_u32(smem + OFF_BS + s * BS_TILE_BYTES));
-        umma_bf16_pair(tmem_base + s * ACC_COLS, zd, bd, idesc, 1u);
-        umma_commit_pair(&d_full[s]);
+        if (elect_one()) {
+          const uint64_t zd = umma_desc_sw32(smem_u32(smem + OFF_Z + s * Z_TILE_BYTES));
+          const uint64_t bd = umma_desc_sw32(smem_u32(smem + OFF_BS + s * BS_TILE_BYTES));
+          umma_bf16_pair(tmem_base + s * ACC_COLS, zd, bd, idesc, 1u);
+          umma_commit_pair(&d_full[s]);
+        }
+        __syncwarp();
       };
 
       int it = 0;
       for (int tile = cluster_id; tile < num_tiles; tile += num_clusters, ++it) {
         const int s = it & 1;
         const uint32_t aph = (it >> 1) & 1u;
-        mbar_wait_cluster(&tmem_empty[s], aph ^ 1u, 300 + s);   // both epilogues drained tile it-2
+        mbar_wait_cluster_uniform(&tmem_empty[s], aph ^ 1u);   // both epilogues drained tile it-2
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + s * ACC_COLS;
         for (int kb = 0; kb < p.k_blocks; ++kb) {
-          if (pend >= 0 && mbar_test_wait_cluster(&z_full[pend], pend_phase)) {
-            fixup(pend, pend_phase);
-            pend = -1;
+          if (pend >= 0) {
+            if (__all_sync(0xffffffffu, mbar_test_wait_cluster(&z_full[pend], pend_phase))) {
+              fixup(pend, pend_phase);
+              pend = -1;
+            }
           }
-          mbar_wait(&full_bar[stage], phase, 400 + stage);
+          mbar_wait_uniform(&full_bar[stage], phase);
           tc_fence_after();
-          const uint32_t st = smem_u32(smem + OFF_STAGES + stage * STAGE_BYTES);
-          const uint64_t adesc = umma_desc_sw128(st);
-          const uint64_t bdesc = umma_desc_sw128(st + X_TILE_BYTES);
+          if (elect_one()) {
+            const uint32_t st = stages_base + stage * STAGE_BYTES;
+            const uint64_t adesc = umma_desc_sw128(st);
+            const uint64_t bdesc = umma_desc_sw128(st + X_TILE_BYTES);
+            if (!(p.dbg & 1)) {
 #pragma unroll
-          for (int k = 0; k < BK / UMMA_K; ++k)
-            umma_bf16_pair(d_tmem, adesc + 2u * k, bdesc + 2u * k, idesc, (kb | k) != 0 ? 1u : 0u);
-          umma_commit_pair(&empty_bar[stage]);
+              for (int k = 0; k < BK / UMMA_K; ++k)
+                umma_bf16_pair(d_tmem, adesc + 2u * k, bdesc + 2u * k, idesc, (kb | k) != 0 ? 1u : 0u);
+            }
+            umma_commit_pair(&empty_bar[stage]);
+          }
+          __syncwarp();
           if (++stage == STAGES) { stage = 0; phase ^= 1u; }
         }
-        umma_commit_pair(&h_full[s]);
+        if (elect_one()) umma_commit_pair(&h_full[s]);
+        __syncwarp();
         if (pend >= 0) {
-          mbar_wait_cluster(&z_full[pend], pend_phase, 500 + pend);
+          mbar_wait_cluster_uniform(&z_full[pend], pend_phase);
           fixup(pend, pend_phase);
         }
         pend = s;
         pend_phase = aph;
       }
       if (pend >= 0) {
-        mbar_wait_cluster(&z_full[pend], pend_phase, 510 + pend);
+        mbar_wait_cluster_uniform(&z_full[pend], pend_phase);
         fixup(pend, pend_phase);
       }
     }
   } else if (warp >= 4) {
-    // =========================== epilogue (8 warps, both CTAs) ===========================
+    // =========================== epilogue (8 independent warps, both CTAs) ===========================
+    const uint32_t ew = warp - 4u;
     const uint32_t q = warp & 3u;
-    const uint32_t half = (warp - 4u) >> 2;
+    const uint32_t half = ew >> 2;
     const uint32_t row = q * 32u + lane;
-    const uint32_t et = threadIdx.x - 128u;
     const uint32_t lane_addr = (q * 32u) << 16;
-    uint32_t store_unit = 0;
+    uint8_t* stage_w = smem + OFF_OUT + ew * (2 * EPI_PIECE_BYTES);
+    float* bias_w = reinterpret_cast<float*>(smem + OFF_BIAS) + ew * (BN / 2);
+    uint32_t unit = 0;
+    constexpr int PIECES = BN / (2 * EPI_PIECE_COLS);
     int it = 0;
     for (int tile = cluster_id; tile < num_tiles; tile += num_clusters, ++it) {
       const int m_pair = tile / p.n_tiles;
@@ -239,7 +260,12 @@ svlora_gemm_pair_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_c
       const int grow = m_blk * BM + static_cast<int>(row);
       const int n0 = n_blk * BN;
       const uint32_t acc = tmem_base + lane_addr + s * ACC_COLS;
-      float* bias_s = reinterpret_cast<float*>(smem + OFF_BIAS + s * BIAS_TILE_BYTES);
+
+#pragma unroll
+      for (int pc = 0; pc < PIECES; ++pc) {
+        const int col = n0 + (2 * pc + static_cast<int>(half)) * EPI_PIECE_COLS + static_cast<int>(lane);
+        bias_w[pc * EPI_PIECE_COLS + lane] = (p.bias != nullptr && col < p.N) ? __ldg(p.bias + col) : 0.0f;
+      }
 
       if (half == 0) {
         // ---- H -> Z ----
@@ -277,102 +303,32 @@ svlora_gemm_pair_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_c
         *reinterpret_cast<uint4*>(zrow + ((1u ^ sw) << 4)) = c1;
         fence_proxy_async_smem();
         mbar_arrive_cluster(mapa_u32(smem_u32(&z_full[s]), 0));       // leader's barrier (local when rank 0)
-      } else {
-        for (int j = et - 128; j < BN; j += 128) {
-          const int col = n0 + j;
-          bias_s[j] = (p.bias != nullptr && col < p.N) ? __ldg(p.bias + col) : 0.0f;
-        }
       }
-      named_bar_sync(EPI_BAR_ID, EPI_THREADS);
+      __syncwarp();
 
       // ---- D -> OUT ----
       mbar_wait(&d_full[s], aph, 700 + s);
       tc_fence_after();
-      const int n_pass = (p.act == ACT_QUICKGELU && p.has_pre) ? 2 : 1;
 #pragma unroll 1
-      for (int c = 0; c < BN / OUT_CHUNK; ++c) {
-        const int cc = c * OUT_CHUNK + static_cast<int>(half) * 32;   // tile column of this thread's 32-wide slice
-        const int tcol = cc < HN ? cc : cc + HR;                        // accumulator column (skip the H block)
+      for (int pc = 0; pc < PIECES; ++pc) {
+        const int cc = (2 * pc + static_cast<int>(half)) * EPI_PIECE_COLS;   // tile column of this piece
+        const int tcol = cc < HN ? cc : cc + HR;                               // accumulator column (skip the H block)
         uint32_t v[32];
         tmem_ld32(acc + tcol, v);
         tmem_ld_wait();
-        if (c == BN / OUT_CHUNK - 1) {
+        if (pc == PIECES - 1) {
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive_cluster(mapa_u32(smem_u32(&tmem_empty[s]), 0));
         }
-        float f[32], g2[32];
+        float f[32];
 #pragma unroll
-        for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]) + bias_s[cc + j];
-        const int col0 = n0 + c * OUT_CHUNK;
-        if (p.act == ACT_QUICKGELU_GRAD) {
-          if (grow < p.T) {
-            const int gc = n0 + cc;
-            const __nv_bfloat16* up = p.aux + static_cast<size_t>(grow) * p.N + gc;
-            if (gc + 32 <= p.N) {
-#pragma unroll
-              for (int j8 = 0; j8 < 4; ++j8) {
-                const uint4 raw = __ldg(reinterpret_cast<const uint4*>(up) + j8);
-                const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&raw);
-#pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                  const float2 uu = __bfloat1622float2(h2[e]);
-                  f[j8 * 8 + 2 * e] *= uu.x;
-                  f[j8 * 8 + 2 * e + 1] *= uu.y;
-                }
-              }
-            } else {
-              for (int j = 0; j < 32; ++j)
-                if (gc + j < p.N) f[j] *= __bfloat162float(up[j]);
-            }
-          }
-        }
-#pragma unroll 1
-        for (int pass = 0; pass < n_pass; ++pass) {
-          const uint32_t buf = store_unit & 1u;
-          uint8_t* ob = smem + OFF_OUT + buf * OUT_TILE_BYTES;
-          if (et == 0) tma_store_wait_read<1>();
-          named_bar_sync(EPI_BAR_ID, EPI_THREADS);
-          uint8_t* orow = ob + row * 128u;
-          if (p.act == ACT_QUICKGELU) {   // warp-uniform branch: keep the MUFU work out of the plain-store path
-            if (n_pass == 2 && pass == 0) {
-              // first store of the dual store: QuickGELU'(u), all the backward pass needs (u itself is not kept)
-#pragma unroll
-              for (int j = 0; j < 32; ++j) {
-                const float sgm = fmaf(0.5f, tanh_approx(0.851f * f[j]), 0.5f);
-                g2[j] = f[j] * sgm;                                       // QuickGELU(u), stored by the next pass
-                f[j] = sgm * fmaf(1.702f * f[j], 1.0f - sgm, 1.0f);      // QuickGELU'(u)
-              }
-            } else if (n_pass == 2) {
-#pragma unroll
-              for (int j = 0; j < 32; ++j) f[j] = g2[j];
-            } else {
-#pragma unroll
-              for (int j = 0; j < 32; ++j) f[j] = quick_gelu(f[j]);
-            }
-          }
-#pragma unroll
-          for (int j8 = 0; j8 < 4; ++j8) {
-            uint4 pk;
-            pk.x = pack_bf16x2(f[j8 * 8 + 0], f[j8 * 8 + 1]);
-            pk.y = pack_bf16x2(f[j8 * 8 + 2], f[j8 * 8 + 3]);
-            pk.z = pack_bf16x2(f[j8 * 8 + 4], f[j8 * 8 + 5]);
-            pk.w = pack_bf16x2(f[j8 * 8 + 6], f[j8 * 8 + 7]);
-            const uint32_t piece = half * 4u + static_cast<uint32_t>(j8);
-            *reinterpret_cast<uint4*>(orow + ((piece ^ (row & 7u)) << 4)) = pk;
-          }
-          fence_proxy_async_smem();
-          named_bar_sync(EPI_BAR_ID, EPI_THREADS);
-          if (et == 0) {
-            const CUtensorMap* tm = (n_pass == 2 && pass == 0) ? &tm_y2 : &tm_y;
-            tma_store_2d(tm, ob, col0, m_blk * BM);
-            tma_store_commit();
-          }
-          ++store_unit;
-        }
+        for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]) + bias_w[pc * EPI_PIECE_COLS + j];
+        epi_store_piece(p, f, &tm_y, &tm_y2, stage_w, unit, lane, grow, n0 + cc, m_blk * BM + static_cast<int>(q) * 32);
       }
+      __syncwarp();
     }
-    if (et == 0) tma_store_wait_all<0>();
+    if (lane == 0) tma_store_wait_all<0>();
   }
 
   // teardown: nobody may leave while the peer can still address this CTA's barriers / TMEM
@@ -393,9 +349,9 @@ int launch_svlora_gemm_pair(const GemmOperands& o, cudaStream_t stream) {
   if ((rc = make_map_bf16(&tm_w, o.wmat, o.N, o.K, HN, BK, CU_TENSOR_MAP_SWIZZLE_128B, true))) return rc;
   if ((rc = make_map_bf16(&tm_a, o.a_side, RP, o.K, HR, BK, CU_TENSOR_MAP_SWIZZLE_128B, true))) return rc;
   if ((rc = make_map_bf16(&tm_b, o.b_side, o.N, RP, HN, RP, CU_TENSOR_MAP_SWIZZLE_32B, false))) return rc;
-  if ((rc = make_map_bf16(&tm_y, o.out, o.T, o.N, BM, OUT_CHUNK, CU_TENSOR_MAP_SWIZZLE_128B, false))) return rc;
+  if ((rc = make_map_bf16(&tm_y, o.out, o.T, o.N, 32, EPI_PIECE_COLS, CU_TENSOR_MAP_SWIZZLE_64B, false))) return rc;
   const bool has_pre = (o.act == ACT_QUICKGELU && o.out_pre != nullptr);
-  if ((rc = make_map_bf16(&tm_y2, has_pre ? o.out_pre : o.out, o.T, o.N, BM, OUT_CHUNK, CU_TENSOR_MAP_SWIZZLE_128B,
+  if ((rc = make_map_bf16(&tm_y2, has_pre ? o.out_pre : o.out, o.T, o.N, 32, EPI_PIECE_COLS, CU_TENSOR_MAP_SWIZZLE_64B,
                           false)))
     return rc;
 
@@ -411,6 +367,7 @@ int launch_svlora_gemm_pair(const GemmOperands& o, cudaStream_t stream) {
   p.m_tiles = (o.T + BM - 1) / BM;
   p.n_tiles = (o.N + BN - 1) / BN;
   p.k_blocks = (o.K + BK - 1) / BK;
+  p.dbg = gemm_debug_mask();
 
   static thread_local int attr_dev = -1;
   int dev = 0;

@@ -33,8 +33,23 @@ fn = bwd if a.bwd else fwd
 for _ in range(3): fn()
 torch.cuda.synchronize()
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+import ctypes
+lib.ffm_profile_enable(1)
 e0.record()
 for _ in range(a.iters): fn()
 e1.record(); torch.cuda.synchronize()
+lib.ffm_profile_enable(0)
+ms_arr = (ctypes.c_float * 4096)(); tkn = (ctypes.c_int * (3 * 4096))()
+n = lib.ffm_profile_read(ms_arr, tkn, 4096)
+kern = sorted(ms_arr[i] for i in range(n))
 ms = e0.elapsed_time(e1) / a.iters
+kmed = kern[len(kern) // 2] if n > 0 else float('nan')
+print(f"  GEMM kernel only (events around the launch): median {kmed*1e3:.1f} us min {kern[0]*1e3:.1f} us -> {2.0*T*K*N/kmed/1e9:.1f} TFLOP/s")
+# cuBLAS reference on the same box / same clocks (plain x @ W^T, no adapter, no bias)
+for _ in range(3): torch.matmul(x, W.t())
+torch.cuda.synchronize(); e0.record()
+for _ in range(a.iters): torch.matmul(x, W.t())
+e1.record(); torch.cuda.synchronize()
+cms = e0.elapsed_time(e1) / a.iters
+print(f"  cuBLAS x@W^T on this box: {cms*1e3:.1f} us -> {2.0*T*K*N/cms/1e9:.1f} TFLOP/s")
 print(f"T={T} K={K} N={N} {'bwd' if a.bwd else 'fwd'} act={a.act}: {ms*1e3:.1f} us  {2.0*T*K*N/ms/1e9:.1f} TFLOP/s (base GEMM flops)")
