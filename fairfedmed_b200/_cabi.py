@@ -27,10 +27,12 @@ SIGNATURES = {
     "ffm_profile_read": (_i, [_vp, _vp, _i]),
     "ffm_svlora_fwd_workspace_bytes": (_sz, [_i, _i, _i, _i]),
     "ffm_svlora_bwd_workspace_bytes": (_sz, [_i, _i, _i, _i]),
-    "ffm_svlora_fwd": (_i, [_vp, _vp, _fp, _fp, _fp, _fp, _vp, _vp, _fp, _vp, _sz,
+    "ffm_svlora_fwd": (_i, [_vp, _vp, _fp, _fp, _fp, _fp, _vp, _vp, _fp, _vp, _vp, _sz,
                             _i, _i, _i, _i, _i, _i, _i, _i, _f, _i, _vp]),
-    "ffm_svlora_bwd": (_i, [_vp, _vp, _vp, _fp, _fp, _fp, _fp, _vp, _vp, _fp, _fp, _fp, _vp, _sz,
+    "ffm_svlora_bwd": (_i, [_vp, _vp, _vp, _fp, _fp, _fp, _fp, _vp, _vp, _vp, _vp, _fp, _fp, _fp, _vp, _sz,
                             _i, _i, _i, _i, _i, _i, _i, _i, _f, _vp]),
+    "ffm_add_layernorm_fwd": (_i, [_vp, _vp, _fp, _fp, _vp, _vp, _fp, _fp, _i, _i, _f, _vp]),
+    "ffm_add_layernorm_bwd": (_i, [_vp, _vp, _vp, _fp, _fp, _fp, _vp, _i, _i, _vp]),
     "ffm_seff": (_i, [_vp, _fp, _fp, _fp, _i, _i, _i, _f, _vp]),
     "ffm_ds": (_i, [_vp, _fp, _fp, _fp, _i, _i, _i, _f, _vp]),
     "ffm_ot_head_workspace_bytes": (_sz, [_i, _i, _i, _i, _i]),

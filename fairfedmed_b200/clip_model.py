@@ -157,10 +157,32 @@ class Transformer(nn.Module):
         self.resblocks = nn.ModuleList([ResidualAttentionBlock(width, heads, attn_mask, batch_first)
                                         for _ in range(layers)])
 
-    def forward(self, x: torch.Tensor, attr=None):
-        for block in self.resblocks:
-            x = block(x, attr)
-        return x
+    def _fusable(self, x: torch.Tensor) -> bool:
+        if not (x.is_cuda and x.dtype == torch.bfloat16 and self.width % 256 == 0 and self.width <= 1024):
+            return False
+        # the fused kernel has no LayerNorm-parameter gradients: FairLoRA freezes them (trainers/GLP_OT_SVLoRA.py:822-829)
+        return not any(p.requires_grad for blk in self.resblocks for ln in (blk.ln_1, blk.ln_2) for p in ln.parameters())
+
+    def forward(self, x: torch.Tensor, attr=None, final_ln: Optional[nn.LayerNorm] = None):
+        """Same computation as the chain of ResidualAttentionBlock.forward (clip/model.py:370-374), optionally followed
+        by `final_ln` (ln_post / ln_final of the caller).  On the device every `x = x + branch; h = LayerNorm(x)` pair
+        runs as ONE kernel (ops.add_layernorm): the residual stream is read and written once per half-block."""
+        if not self._fusable(x) or (final_ln is not None and any(p.requires_grad for p in final_ln.parameters())):
+            for block in self.resblocks:
+                x = block(x, attr)
+            return x if final_ln is None else final_ln(x)
+        blocks = self.resblocks
+        ln = blocks[0].ln_1
+        x, h = ops.add_layernorm(x, None, ln.weight, ln.bias, ln.eps)
+        for i, blk in enumerate(blocks):
+            a = blk.attention(h)
+            x, h = ops.add_layernorm(x, a, blk.ln_2.weight, blk.ln_2.bias, blk.ln_2.eps)
+            m = blk.mlp(h, attr=attr)
+            nxt = blocks[i + 1].ln_1 if i + 1 < len(blocks) else final_ln
+            if nxt is None:
+                return x + m
+            x, h = ops.add_layernorm(x, m, nxt.weight, nxt.bias, nxt.eps)
+        return h
 
 
 class ModifiedVisionTransformer(nn.Module, _Bf16Cache):
@@ -192,8 +214,7 @@ class ModifiedVisionTransformer(nn.Module, _Bf16Cache):
         cls = self._bf("cls", self.class_embedding, dt).expand(x.shape[0], 1, -1)
         x = torch.cat([cls, x], dim=1) + self._bf("pos", self.positional_embedding, dt)
         x = self.ln_pre(x)
-        x = self.transformer(x, attr=attr)
-        x = self.ln_post(x)
+        x = self.transformer(x, attr=attr, final_ln=self.ln_post)
         x = x @ self._bf("proj", self.proj, dt)                                                # [B', L, output_dim]
         return x.transpose(0, 1)                                                               # [L, B', output_dim]
 
@@ -213,8 +234,7 @@ class TextEncoder(nn.Module, _Bf16Cache):
     def forward(self, prompts: torch.Tensor, eot_index: torch.Tensor):
         dt = self.compute_dtype if prompts.is_cuda else prompts.dtype
         x = prompts.to(dt) + self._bf("pos", self.positional_embedding, dt)
-        x = self.transformer(x)                      # prompts are already [n_prompts * n_cls, 77, width]
-        x = self.ln_final(x)
+        x = self.transformer(x, final_ln=self.ln_final)   # prompts are already [n_prompts * n_cls, 77, width]
         x = x[torch.arange(x.shape[0], device=x.device), eot_index]
         return x.float() @ self.text_projection
 

@@ -352,6 +352,11 @@ svlora_gemm_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_consta
         c1.z = pack_bf16x2(zf[12], zf[13]); c1.w = pack_bf16x2(zf[14], zf[15]);
         *reinterpret_cast<uint4*>(zrow + ((0u ^ sw) << 4)) = c0;
         *reinterpret_cast<uint4*>(zrow + ((1u ^ sw) << 4)) = c1;
+        if (p.z_out != nullptr && n_blk == 0 && grow < p.T) {
+          uint4* zo = reinterpret_cast<uint4*>(p.z_out + static_cast<size_t>(grow) * RP);
+          zo[0] = c0;
+          zo[1] = c1;
+        }
         fence_proxy_async_smem();
         mbar_arrive(&z_full[s]);
       }
@@ -389,29 +394,43 @@ svlora_gemm_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_consta
 }
 
 // ----------------------------------------------------------------------------------------------
-// Prep kernel: fp32 master adapter parameters -> bf16 padded side tiles + scaled singular values.
-//   a_side[RP, Kdim]  (row j = column j of the [Kdim, r] matrix, or row j of an [r, Kdim] matrix)
-//   b_side[Ndim, RP]  (row n = column n of the [r, Ndim] matrix, or row n of an [Ndim, r] matrix)
-//   s_rows[nS, RP]    = scaling * s_eff[nS, r], zero padded
+// Prep kernel: fp32 master adapter parameters -> bf16 padded side tiles + scaled singular values, for BOTH directions
+// in one launch (the backward pass reuses the forward's tiles: A and B do not change in between).
+//   forward  (contraction over K): a_fwd[RP, K] = A^T (A is [K, r]),  b_fwd[N, RP] = B^T (B is [r, N])
+//   backward (contraction over N): a_bwd[RP, N] = B,                  b_bwd[K, RP] = A
+//   s_rows[nS, RP] = scaling * s_eff[nS, r], zero padded
+// Any output pointer may be null (skipped).
 // ----------------------------------------------------------------------------------------------
-__global__ void svlora_prep_kernel(const float* __restrict__ a_src, int a_transposed,  // a_transposed: src is [Kdim, r]
-                                   const float* __restrict__ b_src, int b_transposed,  // b_transposed: src is [r, Ndim]
-                                   const float* __restrict__ s_eff, __nv_bfloat16* __restrict__ a_side,
-                                   __nv_bfloat16* __restrict__ b_side, float* __restrict__ s_rows, int Kdim,
-                                   int Ndim, int r, int nS, float scaling) {
+__global__ void svlora_prep_kernel(const float* __restrict__ A, const float* __restrict__ B,
+                                   const float* __restrict__ s_eff, __nv_bfloat16* __restrict__ a_fwd,
+                                   __nv_bfloat16* __restrict__ b_fwd, __nv_bfloat16* __restrict__ a_bwd,
+                                   __nv_bfloat16* __restrict__ b_bwd, float* __restrict__ s_rows, int K, int N, int r,
+                                   int nS, float scaling) {
   const int tid = blockIdx.x * blockDim.x + threadIdx.x;
   const int nthreads = gridDim.x * blockDim.x;
-  for (int i = tid; i < RP * Kdim; i += nthreads) {
-    const int j = i / Kdim, k = i - j * Kdim;
-    float v = 0.f;
-    if (j < r) v = a_transposed ? a_src[static_cast<size_t>(k) * r + j] : a_src[static_cast<size_t>(j) * Kdim + k];
-    a_side[i] = __float2bfloat16(v);
+  if (a_fwd != nullptr) {
+    for (int i = tid; i < RP * K; i += nthreads) {
+      const int j = i / K, k = i - j * K;
+      a_fwd[i] = __float2bfloat16(j < r ? A[static_cast<size_t>(k) * r + j] : 0.f);
+    }
   }
-  for (int i = tid; i < Ndim * RP; i += nthreads) {
-    const int n = i / RP, j = i - n * RP;
-    float v = 0.f;
-    if (j < r) v = b_transposed ? b_src[static_cast<size_t>(j) * Ndim + n] : b_src[static_cast<size_t>(n) * r + j];
-    b_side[i] = __float2bfloat16(v);
+  if (b_bwd != nullptr) {
+    for (int i = tid; i < K * RP; i += nthreads) {
+      const int k = i / RP, j = i - k * RP;
+      b_bwd[i] = __float2bfloat16(j < r ? A[static_cast<size_t>(k) * r + j] : 0.f);
+    }
+  }
+  if (b_fwd != nullptr) {
+    for (int i = tid; i < N * RP; i += nthreads) {
+      const int n = i / RP, j = i - n * RP;
+      b_fwd[i] = __float2bfloat16(j < r ? B[static_cast<size_t>(j) * N + n] : 0.f);
+    }
+  }
+  if (a_bwd != nullptr) {
+    for (int i = tid; i < RP * N; i += nthreads) {
+      const int j = i / N, n = i - j * N;
+      a_bwd[i] = __float2bfloat16(j < r ? B[static_cast<size_t>(j) * N + n] : 0.f);
+    }
   }
   for (int i = tid; i < nS * RP; i += nthreads) {
     const int b = i / RP, j = i - b * RP;
@@ -498,6 +517,7 @@ static int launch_svlora_gemm(const GemmOperands& o, cudaStream_t stream) {
                              reinterpret_cast<uintptr_t>(o.a_side) | reinterpret_cast<uintptr_t>(o.b_side) |
                              reinterpret_cast<uintptr_t>(o.out) | reinterpret_cast<uintptr_t>(o.out_pre) |
                              reinterpret_cast<uintptr_t>(o.s_rows) | reinterpret_cast<uintptr_t>(o.h_out) |
+                             reinterpret_cast<uintptr_t>(o.z_out) |
                              reinterpret_cast<uintptr_t>(o.aux);
   FFM_CHECK_ARG((align_or & 15u) == 0, "svlora gemm: all device pointers must be 16-byte aligned");
   if (use_pair_kernel(o.K)) return launch_svlora_gemm_pair(o, stream);
@@ -518,6 +538,7 @@ static int launch_svlora_gemm(const GemmOperands& o, cudaStream_t stream) {
   p.bias = o.bias;
   p.s_rows = o.s_rows;
   p.h_out = o.h_out;
+  p.z_out = reinterpret_cast<__nv_bfloat16*>(o.z_out);
   p.aux = reinterpret_cast<const __nv_bfloat16*>(o.aux);
   p.T = o.T; p.K = o.K; p.N = o.N;
   p.b_prime = o.b_prime; p.num_slices = o.num_slices; p.row_div = o.row_div;
@@ -555,39 +576,41 @@ static int launch_svlora_gemm(const GemmOperands& o, cudaStream_t stream) {
   return gemm_profile_end(&prof, o.T, o.K, o.N, stream);
 }
 
-// workspace carve-up shared by fwd and bwd (all offsets 256-B aligned)
-struct SvloraWorkspace {
-  __nv_bfloat16* a_side;  // [RP, Kdim]
-  __nv_bfloat16* b_side;  // [Ndim, RP]
+// Adapter tiles prepared by svlora_prep_kernel (all offsets 256-B aligned).  The forward workspace holds the tiles of
+// both directions so that the backward pass can skip its own prep launch.
+struct SvloraTiles {
+  __nv_bfloat16* a_fwd;   // [RP, K]
+  __nv_bfloat16* b_fwd;   // [N, RP]
   float* s_rows;          // [nS, RP]
-  uint8_t* rest;          // remaining bytes (bwd partials)
-  size_t rest_bytes;
+  __nv_bfloat16* a_bwd;   // [RP, N]
+  __nv_bfloat16* b_bwd;   // [K, RP]
 };
 
 static size_t align256(size_t v) { return (v + 255) & ~size_t(255); }
 
-static size_t svlora_ws_prefix(int Kdim, int Ndim, int nS) {
-  return align256(static_cast<size_t>(RP) * Kdim * 2) + align256(static_cast<size_t>(Ndim) * RP * 2) +
+static size_t svlora_tiles_bytes(int K, int N, int nS) {
+  return 2 * (align256(static_cast<size_t>(RP) * K * 2) + align256(static_cast<size_t>(N) * RP * 2)) +
          align256(static_cast<size_t>(nS) * RP * 4);
 }
 
-static void carve(SvloraWorkspace* w, void* ws, size_t ws_bytes, int Kdim, int Ndim, int nS) {
+static void carve_tiles(SvloraTiles* w, void* ws, int K, int N, int nS) {
   uint8_t* p = static_cast<uint8_t*>(ws);
-  w->a_side = reinterpret_cast<__nv_bfloat16*>(p);
-  p += align256(static_cast<size_t>(RP) * Kdim * 2);
-  w->b_side = reinterpret_cast<__nv_bfloat16*>(p);
-  p += align256(static_cast<size_t>(Ndim) * RP * 2);
+  w->a_fwd = reinterpret_cast<__nv_bfloat16*>(p);
+  p += align256(static_cast<size_t>(RP) * K * 2);
+  w->b_fwd = reinterpret_cast<__nv_bfloat16*>(p);
+  p += align256(static_cast<size_t>(N) * RP * 2);
   w->s_rows = reinterpret_cast<float*>(p);
   p += align256(static_cast<size_t>(nS) * RP * 4);
-  w->rest = p;
-  w->rest_bytes = ws_bytes - static_cast<size_t>(p - static_cast<uint8_t*>(ws));
+  w->a_bwd = reinterpret_cast<__nv_bfloat16*>(p);
+  p += align256(static_cast<size_t>(RP) * N * 2);
+  w->b_bwd = reinterpret_cast<__nv_bfloat16*>(p);
 }
 
 // implemented in svlora_small.cu
 int launch_svlora_bwd_small(const __nv_bfloat16* x, const __nv_bfloat16* dy, const float* h, const float* dzu,
-                            const float* s_rows, float* dA, float* dB, float* ds_eff, void* scratch,
-                            size_t scratch_bytes, int T, int K, int N, int r, int nS, int b_prime, int num_slices,
-                            int row_div, float scaling, cudaStream_t stream);
+                            const __nv_bfloat16* z, const __nv_bfloat16* dh, float* dA, float* dB, float* ds_eff,
+                            void* scratch, size_t scratch_bytes, int T, int K, int N, int r, int nS, int b_prime,
+                            int num_slices, int row_div, float scaling, cudaStream_t stream);
 size_t svlora_bwd_small_scratch_bytes(int T, int K, int N);
 
 }  // namespace ffm
@@ -598,7 +621,7 @@ extern "C" {
 
 const char* ffm_last_error(void) { return g_last_error; }
 
-int ffm_version(void) { return 100; }
+int ffm_version(void) { return 101; }
 
 int ffm_svlora_max_rank(void) { return RP; }
 
@@ -640,19 +663,19 @@ int ffm_profile_read(float* ms_host, int* tkn_host, int max_records) {
 
 size_t ffm_svlora_fwd_workspace_bytes(int T, int K, int N, int n_samples) {
   (void)T;
-  return svlora_ws_prefix(K, N, n_samples);
+  return svlora_tiles_bytes(K, N, n_samples);
 }
 
 size_t ffm_svlora_bwd_workspace_bytes(int T, int K, int N, int n_samples) {
-  // backward GEMM contracts over N and produces K columns
-  return svlora_ws_prefix(N, K, n_samples) + align256(static_cast<size_t>(T) * RP * 4) +
-         svlora_bwd_small_scratch_bytes(T, K, N);
+  // own tiles (only used when the forward workspace is not handed over) + dzu f32 [T,16] + dh bf16 [T,16] + partials
+  return svlora_tiles_bytes(K, N, n_samples) + align256(static_cast<size_t>(T) * RP * 4) +
+         align256(static_cast<size_t>(T) * RP * 2) + svlora_bwd_small_scratch_bytes(T, K, N);
 }
 
 int ffm_svlora_fwd(const void* x, const void* w, const float* bias, const float* lora_a, const float* lora_b,
-                   const float* s_eff, void* y, void* y_dact, float* h_out, void* workspace, size_t workspace_bytes,
-                   int T, int K, int N, int r, int n_samples, int b_prime, int num_slices, int row_div, float scaling,
-                   int act, cudaStream_t stream) {
+                   const float* s_eff, void* y, void* y_dact, float* h_out, void* z_out, void* workspace,
+                   size_t workspace_bytes, int T, int K, int N, int r, int n_samples, int b_prime, int num_slices,
+                   int row_div, float scaling, int act, cudaStream_t stream) {
   FFM_CHECK_ARG(x && w && lora_a && lora_b && s_eff && y && workspace, "ffm_svlora_fwd: null pointer argument");
   FFM_CHECK_ARG(row_div >= 1, "ffm_svlora_fwd: row_div must be >= 1");
   FFM_CHECK_ARG(r >= 1 && r <= RP, "ffm_svlora_fwd: rank %d not in [1, %d]", r, RP);
@@ -663,26 +686,25 @@ int ffm_svlora_fwd(const void* x, const void* w, const float* bias, const float*
   FFM_CHECK_ARG(act == ACT_NONE || act == ACT_QUICKGELU, "ffm_svlora_fwd: act must be 0 or 1");
   FFM_CHECK_ARG(workspace_bytes >= ffm_svlora_fwd_workspace_bytes(T, K, N, n_samples),
                 "ffm_svlora_fwd: workspace too small");
-  SvloraWorkspace ws;
-  carve(&ws, workspace, workspace_bytes, K, N, n_samples);
-  // forward: Aside = A^T (A is [K, r]), Bside = B^T (B is [r, N])
-  svlora_prep_kernel<<<64, 256, 0, stream>>>(lora_a, 1, lora_b, 1, s_eff, ws.a_side, ws.b_side, ws.s_rows, K, N, r,
-                                             n_samples, scaling);
+  SvloraTiles ws;
+  carve_tiles(&ws, workspace, K, N, n_samples);
+  svlora_prep_kernel<<<96, 256, 0, stream>>>(lora_a, lora_b, s_eff, ws.a_fwd, ws.b_fwd, ws.a_bwd, ws.b_bwd, ws.s_rows,
+                                             K, N, r, n_samples, scaling);
   FFM_CHECK_CUDA(cudaGetLastError());
   count_launch();
   GemmOperands o;
-  o.x = x; o.wmat = w; o.a_side = ws.a_side; o.b_side = ws.b_side; o.s_rows = ws.s_rows; o.bias = bias;
-  o.out = y; o.out_pre = y_dact; o.h_out = h_out; o.aux = nullptr;
+  o.x = x; o.wmat = w; o.a_side = ws.a_fwd; o.b_side = ws.b_fwd; o.s_rows = ws.s_rows; o.bias = bias;
+  o.out = y; o.out_pre = y_dact; o.h_out = h_out; o.z_out = z_out; o.aux = nullptr;
   o.T = T; o.K = K; o.N = N; o.b_prime = b_prime; o.num_slices = num_slices; o.row_div = row_div; o.act = act;
   return launch_svlora_gemm(o, stream);
 }
 
 int ffm_svlora_bwd(const void* dy, const void* x, const void* w_t, const float* lora_a, const float* lora_b,
-                   const float* s_eff, const float* h, const void* gelu_dact, void* dx, float* d_lora_a,
-                   float* d_lora_b, float* d_s_eff, void* workspace, size_t workspace_bytes, int T, int K, int N,
-                   int r, int n_samples, int b_prime, int num_slices, int row_div, float scaling,
-                   cudaStream_t stream) {
-  FFM_CHECK_ARG(dy && x && w_t && lora_a && lora_b && s_eff && h && dx && d_lora_a && d_lora_b && d_s_eff &&
+                   const float* s_eff, const float* h, const void* z, const void* fwd_workspace,
+                   const void* gelu_dact, void* dx, float* d_lora_a, float* d_lora_b, float* d_s_eff, void* workspace,
+                   size_t workspace_bytes, int T, int K, int N, int r, int n_samples, int b_prime, int num_slices,
+                   int row_div, float scaling, cudaStream_t stream) {
+  FFM_CHECK_ARG(dy && x && w_t && lora_a && lora_b && s_eff && h && z && dx && d_lora_a && d_lora_b && d_s_eff &&
                     workspace,
                 "ffm_svlora_bwd: null pointer argument");
   FFM_CHECK_ARG(r >= 1 && r <= RP, "ffm_svlora_bwd: rank %d not in [1, %d]", r, RP);
@@ -690,26 +712,36 @@ int ffm_svlora_bwd(const void* dy, const void* x, const void* w_t, const float* 
                 "ffm_svlora_bwd: sample mapping exceeds n_samples");
   FFM_CHECK_ARG(workspace_bytes >= ffm_svlora_bwd_workspace_bytes(T, K, N, n_samples),
                 "ffm_svlora_bwd: workspace too small");
-  SvloraWorkspace ws;
-  carve(&ws, workspace, workspace_bytes, N, K, n_samples);
-  float* dzu = reinterpret_cast<float*>(ws.rest);
-  uint8_t* scratch = ws.rest + align256(static_cast<size_t>(T) * RP * 4);
-  const size_t scratch_bytes = ws.rest_bytes - align256(static_cast<size_t>(T) * RP * 4);
-  // backward: contraction over N.  Aside = B (already [r, N]), Bside = A (already [K, r]).
-  svlora_prep_kernel<<<64, 256, 0, stream>>>(lora_b, 0, lora_a, 0, s_eff, ws.a_side, ws.b_side, ws.s_rows, N, K, r,
-                                             n_samples, scaling);
-  FFM_CHECK_CUDA(cudaGetLastError());
-  count_launch();
+  SvloraTiles ws;
+  uint8_t* rest = static_cast<uint8_t*>(workspace) + svlora_tiles_bytes(K, N, n_samples);
+  if (fwd_workspace != nullptr) {
+    // tiles prepared by ffm_svlora_fwd of the same step (A, B, s_eff unchanged since): no prep launch
+    carve_tiles(&ws, const_cast<void*>(fwd_workspace), K, N, n_samples);
+  } else {
+    carve_tiles(&ws, workspace, K, N, n_samples);
+    svlora_prep_kernel<<<96, 256, 0, stream>>>(lora_a, lora_b, s_eff, nullptr, nullptr, ws.a_bwd, ws.b_bwd, ws.s_rows,
+                                               K, N, r, n_samples, scaling);
+    FFM_CHECK_CUDA(cudaGetLastError());
+    count_launch();
+  }
+  float* dzu = reinterpret_cast<float*>(rest);
+  rest += align256(static_cast<size_t>(T) * RP * 4);
+  __nv_bfloat16* dh = reinterpret_cast<__nv_bfloat16*>(rest);
+  rest += align256(static_cast<size_t>(T) * RP * 2);
+  const size_t scratch_bytes = workspace_bytes - static_cast<size_t>(rest - static_cast<uint8_t*>(workspace));
+  // backward: contraction over N.  Aside = B ([r, N]), Bside = A ([K, r]); side outputs dzu = dy·B^T (f32) and
+  // dh = bf16(dzu ⊙ s_rows), the operand of dA.
   GemmOperands o;
-  o.x = dy; o.wmat = w_t; o.a_side = ws.a_side; o.b_side = ws.b_side; o.s_rows = ws.s_rows; o.bias = nullptr;
-  o.out = dx; o.out_pre = nullptr; o.h_out = dzu; o.aux = gelu_dact;
+  o.x = dy; o.wmat = w_t; o.a_side = ws.a_bwd; o.b_side = ws.b_bwd; o.s_rows = ws.s_rows; o.bias = nullptr;
+  o.out = dx; o.out_pre = nullptr; o.h_out = dzu; o.z_out = dh; o.aux = gelu_dact;
   o.T = T; o.K = N; o.N = K; o.b_prime = b_prime; o.num_slices = num_slices; o.row_div = row_div;
   o.act = gelu_dact != nullptr ? ACT_QUICKGELU_GRAD : ACT_NONE;
   int rc = launch_svlora_gemm(o, stream);
   if (rc != FFM_OK) return rc;
   return launch_svlora_bwd_small(reinterpret_cast<const __nv_bfloat16*>(x), reinterpret_cast<const __nv_bfloat16*>(dy),
-                                 h, dzu, ws.s_rows, d_lora_a, d_lora_b, d_s_eff, scratch, scratch_bytes, T, K, N, r,
-                                 n_samples, b_prime, num_slices, row_div, scaling, stream);
+                                 h, dzu, reinterpret_cast<const __nv_bfloat16*>(z), dh, d_lora_a, d_lora_b, d_s_eff,
+                                 rest, scratch_bytes, T, K, N, r, n_samples, b_prime, num_slices, row_div, scaling,
+                                 stream);
 }
 
 }  // extern "C"

@@ -12,6 +12,7 @@ struct GemmParams {
   const float* bias;            // [N] or nullptr
   const float* s_rows;          // [n_samples, RP] fp32 (already multiplied by alpha/r)
   float* h_out;                 // [T, RP] fp32 or nullptr
+  __nv_bfloat16* z_out;         // [T, RP] bf16 or nullptr: Z = bf16(H ⊙ s_rows), the operand the adapter gradients need
   const __nv_bfloat16* aux;     // ACT_QUICKGELU_GRAD: QuickGELU'(u) saved by the forward [T, N]
   int T, K, N;
   int b_prime, num_slices;      // sample(t) = ((t / row_div) % b_prime) / num_slices
@@ -34,6 +35,7 @@ struct GemmOperands {
   void* out;            // [T, N] bf16
   void* out_pre;        // [T, N] bf16 or null (ACT_QUICKGELU only): receives QuickGELU'(u)
   float* h_out;         // [T, RP] or null
+  void* z_out;          // [T, RP] bf16 or null
   const void* aux;      // [T, N] bf16 (ACT_QUICKGELU_GRAD)
   int T, K, N, b_prime, num_slices, row_div, act;
 };

@@ -301,6 +301,11 @@ svlora_gemm_pair_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_c
         c1.z = pack_bf16x2(zf[12], zf[13]); c1.w = pack_bf16x2(zf[14], zf[15]);
         *reinterpret_cast<uint4*>(zrow + ((0u ^ sw) << 4)) = c0;
         *reinterpret_cast<uint4*>(zrow + ((1u ^ sw) << 4)) = c1;
+        if (p.z_out != nullptr && n_blk == 0 && grow < p.T) {
+          uint4* zo = reinterpret_cast<uint4*>(p.z_out + static_cast<size_t>(grow) * RP);
+          zo[0] = c0;
+          zo[1] = c1;
+        }
         fence_proxy_async_smem();
         mbar_arrive_cluster(mapa_u32(smem_u32(&z_full[s]), 0));       // leader's barrier (local when rank 0)
       }
@@ -359,6 +364,7 @@ int launch_svlora_gemm_pair(const GemmOperands& o, cudaStream_t stream) {
   p.bias = o.bias;
   p.s_rows = o.s_rows;
   p.h_out = o.h_out;
+  p.z_out = reinterpret_cast<__nv_bfloat16*>(o.z_out);
   p.aux = reinterpret_cast<const __nv_bfloat16*>(o.aux);
   p.T = o.T; p.K = o.K; p.N = o.N;
   p.b_prime = o.b_prime; p.num_slices = o.num_slices; p.row_div = o.row_div;

@@ -34,46 +34,61 @@ __global__ void seff_kernel(const long long* __restrict__ attr, const float* __r
   s_eff[i] = acc;
 }
 
+// dS[g, j] = sum_b pi[b, g] ds_eff[b, j] (+ the plain sum for the optional global singular values).  8 threads per
+// output element split the samples, a shuffle folds them (fixed order: deterministic).
+constexpr int DS_SPLIT = 8;
 __global__ void ds_kernel(const long long* __restrict__ attr, const float* __restrict__ ds_eff,
                           float* __restrict__ dS, float* __restrict__ dS_global, int nS, int G, int r,
                           float lambda) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= (G + 1) * r) return;
-  const int g = i / r, j = i - g * r;
+  const int tid = blockIdx.x * blockDim.x + threadIdx.x;
+  const int i = tid / DS_SPLIT, part = tid % DS_SPLIT;
+  const bool valid = i < (G + 1) * r;
+  const int g = valid ? i / r : 0, j = valid ? i - g * r : 0;
   float acc = 0.f;
-  if (g == G) {  // gradient of the optional global singular values: plain sum over samples
-    if (dS_global == nullptr) return;
-    for (int b = 0; b < nS; ++b) acc += ds_eff[b * r + j];
-    dS_global[j] = acc;
-    return;
+  if (valid) {
+    if (g == G) {  // gradient of the optional global singular values: plain sum over samples
+      if (dS_global != nullptr)
+        for (int b = part; b < nS; b += DS_SPLIT) acc += ds_eff[b * r + j];
+    } else if (attr == nullptr) {
+      const float w = 1.0f / static_cast<float>(G);
+      for (int b = part; b < nS; b += DS_SPLIT) acc += w * ds_eff[b * r + j];
+    } else {
+      const float off = (1.0f - lambda) / static_cast<float>(G - 1);
+      for (int b = part; b < nS; b += DS_SPLIT)
+        acc += ((static_cast<int>(attr[b]) == g) ? lambda : off) * ds_eff[b * r + j];
+    }
   }
-  if (attr == nullptr) {
-    const float w = 1.0f / static_cast<float>(G);
-    for (int b = 0; b < nS; ++b) acc += w * ds_eff[b * r + j];
+#pragma unroll
+  for (int o = DS_SPLIT / 2; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if (!valid || part != 0) return;
+  if (g == G) {
+    if (dS_global != nullptr) dS_global[j] = acc;
   } else {
-    const float off = (1.0f - lambda) / static_cast<float>(G - 1);
-    for (int b = 0; b < nS; ++b) acc += ((static_cast<int>(attr[b]) == g) ? lambda : off) * ds_eff[b * r + j];
+    dS[i] = acc;
   }
-  dS[i] = acc;
 }
 
 // ----------------------------------------------------------------------------------------------
-// out[c, j] = sum_t M[t, c] * v[t, j],  v[t, j] = bf16(src[t, j] * s_rows[sample(t), j])
-// bf16 M [T, C] (x or dy), fp32 src [T, 16] (dzu or h).  A skinny contraction over the T rows: M is read from HBM
-// exactly once (T*C*2 bytes) and that is the bound.  CUDA-core FMAs cannot keep up (16 FMA per 2 bytes), so the
-// products run on the legacy tensor path: mma.sync m16n8k16 with A = M^T and B = v, both fetched from shared memory
-// with ldmatrix.trans (the tiles sit in smem exactly as they sit in HBM: rows = t).
-//   CTA = 8 warps, tile = 128 columns x 64 rows per stage, 3-stage cp.async ring; warp w owns columns 16w..16w+15
-//   and all 16 ranks (two n-tiles).  Row chunks write fp32 partials; colsum_reduce_kernel folds them (deterministic).
+// Adapter gradients: two skinny contractions over the T rows in ONE launch,
+//     dA[K, r]   = x^T  · dh     (dh = bf16(scaling · dzu ⊙ s_eff[sample]), side output of the dX GEMM)
+//     dB[r, N]^T = dy^T · z      (z  = bf16(scaling · h   ⊙ s_eff[sample]), side output of the forward GEMM)
+// i.e. out[c, j] = sum_t M[t, c] * v[t, j] with bf16 M [T, C] and bf16 v [T, 16].  M is read from HBM exactly once
+// (T*C*2 bytes) and that is the bound.  CUDA-core FMAs cannot keep up (16 FMA per 2 bytes), so the products run on
+// the legacy tensor path: mma.sync m16n8k16 with A = M^T and B = v, both fetched from shared memory with
+// ldmatrix.trans (the tiles sit in smem exactly as they sit in HBM: rows = t).  Both tiles arrive through cp.async
+// (nothing in the loop waits on a synchronous global load).
+//   CTA = 8 warps, tile = 128 columns x 64 rows per stage, 4-stage ring; warp w owns columns 16w..16w+15 and all
+//   16 ranks (two n-tiles).  blockIdx.y < groups_a: column group of x (-> dA), else of dy (-> dB).
+//   Row chunks write fp32 partials; adapter_grad_finalize_kernel folds them in a fixed order (deterministic).
 // ----------------------------------------------------------------------------------------------
 constexpr int CS_THREADS = 256;
 constexpr int CS_COLS = 128;             // columns per CTA
 constexpr int CS_ROWS = 64;              // rows per stage
-constexpr int CS_STAGES = 3;
+constexpr int CS_STAGES = 4;
 constexpr int CS_MSTRIDE = CS_COLS * 2 + 16;   // 272 B: rows 16 B apart mod 128 -> conflict-free ldmatrix
 constexpr int CS_VSTRIDE = 48;                 // 16 bf16 = 32 B padded to 48 B, same reason
 constexpr int CS_STAGE_BYTES = CS_ROWS * CS_MSTRIDE + CS_ROWS * CS_VSTRIDE;   // 20480
-constexpr int CS_SMEM_BYTES = CS_STAGES * CS_STAGE_BYTES;                      // 61440
+constexpr int CS_SMEM_BYTES = CS_STAGES * CS_STAGE_BYTES;                      // 81920
 
 __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem_dst)), "l"(gmem_src) : "memory");
@@ -96,17 +111,23 @@ __device__ __forceinline__ void mma_bf16_16816(float (&d)[4], const uint32_t (&a
 }
 
 __global__ void __launch_bounds__(CS_THREADS)
-colsum16_kernel(const __nv_bfloat16* __restrict__ M, const float* __restrict__ src,
-                const float* __restrict__ s_rows, float* __restrict__ partial, int T, int C, int rows_per_chunk,
-                int b_prime, int num_slices, int row_div) {
+adapter_grad_kernel(const __nv_bfloat16* __restrict__ Ma, const __nv_bfloat16* __restrict__ va,
+                    float* __restrict__ partial_a, int Ca, int groups_a, const __nv_bfloat16* __restrict__ Mb,
+                    const __nv_bfloat16* __restrict__ vb, float* __restrict__ partial_b, int Cb, int T,
+                    int rows_per_chunk) {
   extern __shared__ __align__(16) uint8_t cs_smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int c_base = blockIdx.y * CS_COLS;
+  const bool is_a = static_cast<int>(blockIdx.y) < groups_a;
+  const __nv_bfloat16* __restrict__ M = is_a ? Ma : Mb;
+  const __nv_bfloat16* __restrict__ v = is_a ? va : vb;
+  float* __restrict__ partial = is_a ? partial_a : partial_b;
+  const int C = is_a ? Ca : Cb;
+  const int c_base = (is_a ? blockIdx.y : blockIdx.y - groups_a) * CS_COLS;
   const int t_begin = blockIdx.x * rows_per_chunk;
   const int t_end = min(T, t_begin + rows_per_chunk);
   const int n_stages = (t_end - t_begin + CS_ROWS - 1) / CS_ROWS;
 
-  // stage loader: M tile via cp.async (16 B = 8 columns per request), v tile computed and stored as bf16
+  // stage loader: M tile (16 B = 8 columns per request) and v tile (2 x 16 B per row), all cp.async
   auto load_stage = [&](int st_idx, int buf) {
     uint8_t* mt = cs_smem + buf * CS_STAGE_BYTES;
     uint8_t* vt = mt + CS_ROWS * CS_MSTRIDE;
@@ -120,19 +141,12 @@ colsum16_kernel(const __nv_bfloat16* __restrict__ M, const float* __restrict__ s
       if (t < t_end && c < C) cp_async16(dst, M + static_cast<size_t>(t) * C + c);
       else *reinterpret_cast<uint4*>(dst) = make_uint4(0u, 0u, 0u, 0u);
     }
-    {
-      // 64 rows x 16 ranks = 1024 values, 4 consecutive ranks per thread
-      const int rr = threadIdx.x >> 2, j0 = (threadIdx.x & 3) * 4;
+    if (threadIdx.x < CS_ROWS * 2) {
+      const int rr = threadIdx.x >> 1, hf = threadIdx.x & 1;
       const int t = t0 + rr;
-      uint2 packed = make_uint2(0u, 0u);
-      if (t < t_end) {
-        const int sample = ((t / row_div) % b_prime) / num_slices;
-        const float4 a = __ldg(reinterpret_cast<const float4*>(src + static_cast<size_t>(t) * RPS + j0));
-        const float4 sv = __ldg(reinterpret_cast<const float4*>(s_rows + sample * RPS + j0));
-        packed.x = pack_bf16x2(a.x * sv.x, a.y * sv.y);
-        packed.y = pack_bf16x2(a.z * sv.z, a.w * sv.w);
-      }
-      *reinterpret_cast<uint2*>(vt + rr * CS_VSTRIDE + j0 * 2) = packed;
+      uint8_t* dst = vt + rr * CS_VSTRIDE + hf * 16;
+      if (t < t_end) cp_async16(dst, v + static_cast<size_t>(t) * RPS + hf * 8);
+      else *reinterpret_cast<uint4*>(dst) = make_uint4(0u, 0u, 0u, 0u);
     }
   };
 
@@ -148,7 +162,7 @@ colsum16_kernel(const __nv_bfloat16* __restrict__ M, const float* __restrict__ s
     if (s0 < n_stages) load_stage(s0, s0);
     cp_async_commit();
   }
-  // ldmatrix lane roles (see header comment): matrix id = lane / 8, row inside the 8x8 block = lane % 8
+  // ldmatrix lane roles: matrix id = lane / 8, row inside the 8x8 block = lane % 8
   const int mi = lane >> 3, r8 = lane & 7;
   const uint32_t a_lane_off = (r8 + 8 * (mi >> 1)) * CS_MSTRIDE + (warp * 16 + 8 * (mi & 1)) * 2;
   const uint32_t b_lane_off = (r8 + 8 * (mi & 1)) * CS_VSTRIDE + (8 * (mi >> 1)) * 2;
@@ -187,38 +201,46 @@ colsum16_kernel(const __nv_bfloat16* __restrict__ M, const float* __restrict__ s
   }
 }
 
-// out = sum over chunks of partial[chunk, c, j]; transposed==0: out[c*r + j] ([C, r]); ==1: out[j*C + c] ([r, C])
-__global__ void colsum_reduce_kernel(const float* __restrict__ partial, float* __restrict__ out, int n_chunks, int C,
-                                     int r, int transposed) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= C * RPS) return;
-  const int c = i / RPS, j = i - c * RPS;
-  float acc = 0.f;
-#pragma unroll 8
-  for (int k = 0; k < n_chunks; ++k) acc += partial[(static_cast<size_t>(k) * C + c) * RPS + j];
-  if (j >= r) return;
-  if (transposed) out[static_cast<size_t>(j) * C + c] = acc;
-  else out[static_cast<size_t>(c) * r + j] = acc;
-}
-
 // ----------------------------------------------------------------------------------------------
-// ds_eff[b, j] = scaling * sum_{t : sample(t) == b} dzu[t, j] * h[t, j]
-// The segmented reduction keyed by sample id: one CTA per sample; its rows sit at stride b_prime in the
-// sequence-first [L, B', .] layout (stride 1 inside a contiguous block for batch-first rows). 16 lanes cover the 16 components of a row, 16 rows per pass, then a fixed-order
-// shared-memory fold (deterministic).
+// One launch that finishes the adapter gradients of a layer.  Block roles by blockIdx.x:
+//   [0, blocks_a)            dA[c*r + j]  = sum over row chunks of partial_a[chunk, c, j]
+//   [blocks_a, +blocks_b)    dB[j*N + c]  = sum over row chunks of partial_b[chunk, c, j]        (transposed store)
+//   the rest, one per sample ds_eff[b, j] = scaling * sum_{t : sample(t) == b} dzu[t, j] * h[t, j]
+// The last role is the segmented reduction keyed by sample id: a sample's rows sit at stride b_prime in the
+// sequence-first [L, B', .] layout (contiguous blocks for batch-first rows).  16 lanes cover the 16 components of a
+// row, 16 rows per pass, then a fixed-order shared-memory fold (deterministic).
 // ----------------------------------------------------------------------------------------------
-constexpr int DS_THREADS = 256;
+constexpr int FIN_THREADS = 256;
 
-__global__ void __launch_bounds__(DS_THREADS)
-dseff_kernel(const float* __restrict__ h, const float* __restrict__ dzu, float* __restrict__ ds_eff, int T, int r,
-             int nS, int b_prime, int num_slices, int row_div, float scaling) {
-  __shared__ float red[DS_THREADS / RPS][RPS];
-  const int b = blockIdx.x;
+__global__ void __launch_bounds__(FIN_THREADS)
+adapter_grad_finalize_kernel(const float* __restrict__ partial_a, const float* __restrict__ partial_b,
+                             float* __restrict__ dA, float* __restrict__ dB, int n_chunks, int K, int N, int r,
+                             int blocks_a, int blocks_b, const float* __restrict__ h, const float* __restrict__ dzu,
+                             float* __restrict__ ds_eff, int T, int b_prime, int num_slices, int row_div,
+                             float scaling) {
+  __shared__ float red[FIN_THREADS / RPS][RPS];
+  int blk = blockIdx.x;
+  if (blk < blocks_a + blocks_b) {
+    const bool is_a = blk < blocks_a;
+    const float* __restrict__ partial = is_a ? partial_a : partial_b;
+    const int C = is_a ? K : N;
+    const int i = (is_a ? blk : blk - blocks_a) * FIN_THREADS + threadIdx.x;
+    if (i >= C * RPS) return;
+    const int c = i / RPS, j = i - c * RPS;
+    float acc = 0.f;
+#pragma unroll 4
+    for (int k = 0; k < n_chunks; ++k) acc += partial[(static_cast<size_t>(k) * C + c) * RPS + j];
+    if (j >= r) return;
+    if (is_a) dA[static_cast<size_t>(c) * r + j] = acc;
+    else dB[static_cast<size_t>(j) * N + c] = acc;
+    return;
+  }
+  const int b = blk - blocks_a - blocks_b;
   const int j = threadIdx.x % RPS, lane_row = threadIdx.x / RPS;
   const int L = T / b_prime;
   const int rows = L * num_slices;
   float acc = 0.f;
-  for (int i = lane_row; i < rows; i += DS_THREADS / RPS) {
+  for (int i = lane_row; i < rows; i += FIN_THREADS / RPS) {
     const int l = i / num_slices, sl = i - l * num_slices;
     // sequence-first rows: t = l*B' + column; batch-first rows (row_div = L): t = column*L + l
     const size_t col = static_cast<size_t>(b) * num_slices + sl;
@@ -230,16 +252,16 @@ dseff_kernel(const float* __restrict__ h, const float* __restrict__ dzu, float* 
   if (lane_row == 0 && j < r) {
     float tot = 0.f;
 #pragma unroll
-    for (int k = 0; k < DS_THREADS / RPS; ++k) tot += red[k][j];
+    for (int k = 0; k < FIN_THREADS / RPS; ++k) tot += red[k][j];
     ds_eff[b * r + j] = tot * scaling;
   }
 }
 
-constexpr int CS_MAX_CHUNKS = 148;  // row chunks per column group (partials: chunks x C x 16 fp32)
+constexpr int CS_MAX_CHUNKS = 64;  // row chunks (partials: chunks x C x 16 fp32)
 
-// about two CTAs per SM in total (61 KB of smem each, 3 fit): enough loads in flight without a ragged second wave
-static int pick_chunks(int T, int C) {
-  const int col_groups = (C + CS_COLS - 1) / CS_COLS;
+// about two CTAs per SM in total over both contractions: enough loads in flight without a ragged second wave
+static int pick_chunks(int T, int K, int N) {
+  const int col_groups = (K + CS_COLS - 1) / CS_COLS + (N + CS_COLS - 1) / CS_COLS;
   int chunks = (2 * num_sms() + col_groups - 1) / col_groups;
   if (chunks > CS_MAX_CHUNKS) chunks = CS_MAX_CHUNKS;
   const int max_chunks = (T + CS_ROWS - 1) / CS_ROWS;
@@ -249,53 +271,42 @@ static int pick_chunks(int T, int C) {
 }
 
 size_t svlora_bwd_small_scratch_bytes(int T, int K, int N) {
-  const size_t a = static_cast<size_t>(pick_chunks(T, K)) * K;
-  const size_t b = static_cast<size_t>(pick_chunks(T, N)) * N;
-  return (a > b ? a : b) * RPS * 4 + 256;
+  return static_cast<size_t>(pick_chunks(T, K, N)) * (static_cast<size_t>(K) + N) * RPS * 4 + 256;
 }
 
 int launch_svlora_bwd_small(const __nv_bfloat16* x, const __nv_bfloat16* dy, const float* h, const float* dzu,
-                            const float* s_rows, float* dA, float* dB, float* ds_eff, void* scratch,
-                            size_t scratch_bytes, int T, int K, int N, int r, int nS, int b_prime, int num_slices,
-                            int row_div, float scaling, cudaStream_t stream) {
+                            const __nv_bfloat16* z, const __nv_bfloat16* dh, float* dA, float* dB, float* ds_eff,
+                            void* scratch, size_t scratch_bytes, int T, int K, int N, int r, int nS, int b_prime,
+                            int num_slices, int row_div, float scaling, cudaStream_t stream) {
   FFM_CHECK_ARG(row_div == 1 || row_div * b_prime == T, "svlora bwd: batch-first rows need row_div * b_prime == T");
+  FFM_CHECK_ARG(T % b_prime == 0, "svlora bwd: T (%d) must be a multiple of b_prime (%d)", T, b_prime);
   {
     static thread_local int attr_dev = -1;
     int dev = 0;
     FFM_CHECK_CUDA(cudaGetDevice(&dev));
     if (dev != attr_dev) {
-      FFM_CHECK_CUDA(cudaFuncSetAttribute(colsum16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+      FFM_CHECK_CUDA(cudaFuncSetAttribute(adapter_grad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                           CS_SMEM_BYTES));
       attr_dev = dev;
     }
   }
-  FFM_CHECK_ARG(T % b_prime == 0, "svlora bwd: T (%d) must be a multiple of b_prime (%d)", T, b_prime);
-  float* partial = static_cast<float*>(scratch);
-  // dA[K, r] = x^T · (dzu ⊙ s_rows)
-  {
-    const int chunks = pick_chunks(T, K);
-    FFM_CHECK_ARG(static_cast<size_t>(chunks) * K * RPS * 4 <= scratch_bytes, "svlora bwd: scratch too small (dA)");
-    const int rows_per_chunk = (T + chunks - 1) / chunks;
-    dim3 grid(chunks, (K + CS_COLS - 1) / CS_COLS);
-    colsum16_kernel<<<grid, CS_THREADS, CS_SMEM_BYTES, stream>>>(x, dzu, s_rows, partial, T, K, rows_per_chunk, b_prime,
-                                                     num_slices, row_div);
-    colsum_reduce_kernel<<<(K * RPS + 255) / 256, 256, 0, stream>>>(partial, dA, chunks, K, r, 0);
-  }
-  // dB[r, N] = (h ⊙ s_rows)^T · dy
-  {
-    const int chunks = pick_chunks(T, N);
-    FFM_CHECK_ARG(static_cast<size_t>(chunks) * N * RPS * 4 <= scratch_bytes, "svlora bwd: scratch too small (dB)");
-    const int rows_per_chunk = (T + chunks - 1) / chunks;
-    dim3 grid(chunks, (N + CS_COLS - 1) / CS_COLS);
-    colsum16_kernel<<<grid, CS_THREADS, CS_SMEM_BYTES, stream>>>(dy, h, s_rows, partial, T, N, rows_per_chunk, b_prime,
-                                                     num_slices, row_div);
-    colsum_reduce_kernel<<<(N * RPS + 255) / 256, 256, 0, stream>>>(partial, dB, chunks, N, r, 1);
-  }
-  count_launch(4);
-  // ds_eff[nS, r]: one warp per sample
-  dseff_kernel<<<nS, DS_THREADS, 0, stream>>>(h, dzu, ds_eff, T, r, nS, b_prime, num_slices, row_div, scaling);
+  const int chunks = pick_chunks(T, K, N);
+  FFM_CHECK_ARG(static_cast<size_t>(chunks) * (static_cast<size_t>(K) + N) * RPS * 4 <= scratch_bytes,
+                "svlora bwd: scratch too small");
+  float* partial_a = static_cast<float*>(scratch);
+  float* partial_b = partial_a + static_cast<size_t>(chunks) * K * RPS;
+  const int rows_per_chunk = (T + chunks - 1) / chunks;
+  const int groups_a = (K + CS_COLS - 1) / CS_COLS, groups_b = (N + CS_COLS - 1) / CS_COLS;
+  // dA[K, r] = x^T · dh   and   dB[r, N] = z^T · dy
+  adapter_grad_kernel<<<dim3(chunks, groups_a + groups_b), CS_THREADS, CS_SMEM_BYTES, stream>>>(
+      x, dh, partial_a, K, groups_a, dy, z, partial_b, N, T, rows_per_chunk);
   FFM_CHECK_CUDA(cudaGetLastError());
-  count_launch();
+  const int blocks_a = (K * RPS + FIN_THREADS - 1) / FIN_THREADS, blocks_b = (N * RPS + FIN_THREADS - 1) / FIN_THREADS;
+  adapter_grad_finalize_kernel<<<blocks_a + blocks_b + nS, FIN_THREADS, 0, stream>>>(
+      partial_a, partial_b, dA, dB, chunks, K, N, r, blocks_a, blocks_b, h, dzu, ds_eff, T, b_prime, num_slices,
+      row_div, scaling);
+  FFM_CHECK_CUDA(cudaGetLastError());
+  count_launch(2);
   return FFM_OK;
 }
 
@@ -321,7 +332,7 @@ int ffm_ds(const long long* attr, const float* ds_eff, float* dS, float* dS_glob
            float lambda, cudaStream_t stream) {
   FFM_CHECK_ARG(ds_eff && dS, "ffm_ds: null pointer argument");
   FFM_CHECK_ARG(n_samples >= 1 && G >= 1 && r >= 1, "ffm_ds: bad sizes");
-  const int n = (G + 1) * r;
+  const int n = (G + 1) * r * DS_SPLIT;
   ds_kernel<<<(n + 127) / 128, 128, 0, stream>>>(attr, ds_eff, dS, dS_global, n_samples, G, r, lambda);
   FFM_CHECK_CUDA(cudaGetLastError());
   count_launch();

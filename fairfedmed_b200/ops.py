@@ -38,8 +38,10 @@ def _need_cuda(*tensors):
 @torch.library.custom_op("ffm::svlora_fwd", mutates_args=())
 def svlora_fwd(x: Tensor, w: Tensor, bias: Optional[Tensor], lora_a: Tensor, lora_b: Tensor, s_eff: Tensor,
                scaling: float, b_prime: int, num_slices: int, act: int,
-               row_div: int = 1) -> Tuple[Tensor, Tensor, Tensor]:
-    """y, y_dact, h = fused FairLoRA linear (y_dact = QuickGELU'(u) when act = 1, else empty).  x [T,K] bf16, w [N,K] bf16, lora_a [K,r], lora_b [r,N], s_eff [nS,r].
+               row_div: int = 1) -> Tuple[Tensor, Tensor, Tensor, Tensor, Tensor]:
+    """y, y_dact, h, z, tiles = fused FairLoRA linear.  x [T,K] bf16, w [N,K] bf16, lora_a [K,r], lora_b [r,N],
+    s_eff [nS,r].  y_dact = QuickGELU'(u) when act = 1 (else empty); h = x·A (f32 [T,16]); z = bf16(scaling·h⊙s_eff)
+    ([T,16]); tiles = the call's workspace holding the prepared bf16 adapter tiles (hand it to svlora_bwd).
     Row t of x belongs to sample ((t // row_div) % b_prime) // num_slices (row_div = 1: sequence-first rows)."""
     _need_cuda(x, w, lora_a, lora_b, s_eff)
     T, K = x.shape
@@ -47,29 +49,32 @@ def svlora_fwd(x: Tensor, w: Tensor, bias: Optional[Tensor], lora_a: Tensor, lor
     r = lora_a.shape[1]
     nS = s_eff.shape[0]
     y = torch.empty((T, N), device=x.device, dtype=torch.bfloat16)
-    y_pre = torch.empty((T, N), device=x.device, dtype=torch.bfloat16) if act else y.new_empty((0,))
+    y_dact = torch.empty((T, N), device=x.device, dtype=torch.bfloat16) if act else y.new_empty((0,))
     h = torch.empty((T, RP), device=x.device, dtype=torch.float32)
+    z = torch.empty((T, RP), device=x.device, dtype=torch.bfloat16)
     lib = _cabi.load()
     ws_bytes = lib.ffm_svlora_fwd_workspace_bytes(T, K, N, nS)
     ws = torch.empty((ws_bytes,), device=x.device, dtype=torch.uint8)
     _cabi.call("ffm_svlora_fwd", _ptr(x), _ptr(w), _ptr(bias), _ptr(lora_a), _ptr(lora_b), _ptr(s_eff), _ptr(y),
-               _ptr(y_pre) if act else 0, _ptr(h), _ptr(ws), ws_bytes, T, K, N, r, nS, b_prime, num_slices,
+               _ptr(y_dact) if act else 0, _ptr(h), _ptr(z), _ptr(ws), ws_bytes, T, K, N, r, nS, b_prime, num_slices,
                int(row_div), float(scaling), int(act), _stream())
-    return y, y_pre, h
+    return y, y_dact, h, z, ws
 
 
 @svlora_fwd.register_fake
 def _(x, w, bias, lora_a, lora_b, s_eff, scaling, b_prime, num_slices, act, row_div=1):
     T, N = x.shape[0], w.shape[0]
     y = x.new_empty((T, N))
-    return y, (x.new_empty((T, N)) if act else x.new_empty((0,))), x.new_empty((T, RP), dtype=torch.float32)
+    return (y, (x.new_empty((T, N)) if act else x.new_empty((0,))), x.new_empty((T, RP), dtype=torch.float32),
+            x.new_empty((T, RP)), x.new_empty((1,), dtype=torch.uint8))
 
 
 @torch.library.custom_op("ffm::svlora_bwd", mutates_args=())
 def svlora_bwd(dy: Tensor, x: Tensor, w_t: Tensor, lora_a: Tensor, lora_b: Tensor, s_eff: Tensor, h: Tensor,
-               gelu_pre: Optional[Tensor], scaling: float, b_prime: int, num_slices: int,
-               row_div: int = 1) -> Tuple[Tensor, Tensor, Tensor, Tensor]:
-    """dx, d_lora_a, d_lora_b, d_s_eff.  dy [T,N] bf16, x [T,K] bf16, w_t [K,N] bf16 (transposed frozen weight)."""
+               z: Tensor, tiles: Optional[Tensor], gelu_dact: Optional[Tensor], scaling: float, b_prime: int,
+               num_slices: int, row_div: int = 1) -> Tuple[Tensor, Tensor, Tensor, Tensor]:
+    """dx, d_lora_a, d_lora_b, d_s_eff.  dy [T,N] bf16, x [T,K] bf16, w_t [K,N] bf16 (transposed frozen weight);
+    h, z, tiles are the side outputs of svlora_fwd (tiles may be None: the adapter tiles are then prepared again)."""
     _need_cuda(dy, x, w_t)
     T, N = dy.shape
     K = x.shape[1]
@@ -83,13 +88,13 @@ def svlora_bwd(dy: Tensor, x: Tensor, w_t: Tensor, lora_a: Tensor, lora_b: Tenso
     ws_bytes = lib.ffm_svlora_bwd_workspace_bytes(T, K, N, nS)
     ws = torch.empty((ws_bytes,), device=x.device, dtype=torch.uint8)
     _cabi.call("ffm_svlora_bwd", _ptr(dy), _ptr(x), _ptr(w_t), _ptr(lora_a), _ptr(lora_b), _ptr(s_eff), _ptr(h),
-               _ptr(gelu_pre), _ptr(dx), _ptr(dA), _ptr(dB), _ptr(dse), _ptr(ws), ws_bytes, T, K, N, r, nS, b_prime,
-               num_slices, int(row_div), float(scaling), _stream())
+               _ptr(z), _ptr(tiles), _ptr(gelu_dact), _ptr(dx), _ptr(dA), _ptr(dB), _ptr(dse), _ptr(ws), ws_bytes,
+               T, K, N, r, nS, b_prime, num_slices, int(row_div), float(scaling), _stream())
     return dx, dA, dB, dse
 
 
 @svlora_bwd.register_fake
-def _(dy, x, w_t, lora_a, lora_b, s_eff, h, gelu_pre, scaling, b_prime, num_slices, row_div=1):
+def _(dy, x, w_t, lora_a, lora_b, s_eff, h, z, tiles, gelu_dact, scaling, b_prime, num_slices, row_div=1):
     return (x.new_empty(x.shape), lora_a.new_empty(lora_a.shape), lora_b.new_empty(lora_b.shape),
             s_eff.new_empty(s_eff.shape))
 
@@ -155,17 +160,17 @@ class _SVLoRALinear(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, x2d, w, w_t, bias, lora_a, lora_b, s_eff, scaling, b_prime, num_slices, row_div):
-        y, _, h = svlora_fwd(x2d, w, bias, lora_a, lora_b, s_eff, scaling, b_prime, num_slices, 0, row_div)
-        ctx.save_for_backward(x2d, w_t, lora_a, lora_b, s_eff, h)
+        y, _, h, z, tiles = svlora_fwd(x2d, w, bias, lora_a, lora_b, s_eff, scaling, b_prime, num_slices, 0, row_div)
+        ctx.save_for_backward(x2d, w_t, lora_a, lora_b, s_eff, h, z, tiles)
         ctx.cfg = (scaling, b_prime, num_slices, row_div)
         return y
 
     @staticmethod
     def backward(ctx, dy):
-        x2d, w_t, lora_a, lora_b, s_eff, h = ctx.saved_tensors
+        x2d, w_t, lora_a, lora_b, s_eff, h, z, tiles = ctx.saved_tensors
         scaling, b_prime, num_slices, row_div = ctx.cfg
-        dx, dA, dB, dse = svlora_bwd(dy.contiguous(), x2d, w_t, lora_a, lora_b, s_eff, h, None, scaling, b_prime,
-                                     num_slices, row_div)
+        dx, dA, dB, dse = svlora_bwd(dy.contiguous(), x2d, w_t, lora_a, lora_b, s_eff, h, z, tiles, None, scaling,
+                                     b_prime, num_slices, row_div)
         return dx, None, None, None, dA, dB, dse, None, None, None, None
 
 
@@ -182,19 +187,20 @@ class _SVLoRAMLP(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x2d, w1, w1_t, b1, a1, bb1, s1, w2, w2_t, b2, a2, bb2, s2, scaling, b_prime, num_slices,
                 row_div):
-        g, u, h1 = svlora_fwd(x2d, w1, b1, a1, bb1, s1, scaling, b_prime, num_slices, 1, row_div)
-        y, _, h2 = svlora_fwd(g, w2, b2, a2, bb2, s2, scaling, b_prime, num_slices, 0, row_div)
-        ctx.save_for_backward(x2d, g, u, h1, h2, w1_t, a1, bb1, s1, w2_t, a2, bb2, s2)
+        g, u, h1, z1, t1 = svlora_fwd(x2d, w1, b1, a1, bb1, s1, scaling, b_prime, num_slices, 1, row_div)
+        y, _, h2, z2, t2 = svlora_fwd(g, w2, b2, a2, bb2, s2, scaling, b_prime, num_slices, 0, row_div)
+        ctx.save_for_backward(x2d, g, u, h1, h2, w1_t, a1, bb1, s1, w2_t, a2, bb2, s2, z1, t1, z2, t2)
         ctx.cfg = (scaling, b_prime, num_slices, row_div)
         return y
 
     @staticmethod
     def backward(ctx, dy):
-        x2d, g, u, h1, h2, w1_t, a1, bb1, s1, w2_t, a2, bb2, s2 = ctx.saved_tensors
+        x2d, g, u, h1, h2, w1_t, a1, bb1, s1, w2_t, a2, bb2, s2, z1, t1, z2, t2 = ctx.saved_tensors
         scaling, b_prime, num_slices, row_div = ctx.cfg
-        du, dA2, dB2, ds2 = svlora_bwd(dy.contiguous(), g, w2_t, a2, bb2, s2, h2, u, scaling, b_prime, num_slices,
+        du, dA2, dB2, ds2 = svlora_bwd(dy.contiguous(), g, w2_t, a2, bb2, s2, h2, z2, t2, u, scaling, b_prime,
+                                       num_slices, row_div)
+        dx, dA1, dB1, ds1 = svlora_bwd(du, x2d, w1_t, a1, bb1, s1, h1, z1, t1, None, scaling, b_prime, num_slices,
                                        row_div)
-        dx, dA1, dB1, ds1 = svlora_bwd(du, x2d, w1_t, a1, bb1, s1, h1, None, scaling, b_prime, num_slices, row_div)
         return dx, None, None, None, dA1, dB1, ds1, None, None, None, dA2, dB2, ds2, None, None, None, None
 
 
@@ -206,6 +212,81 @@ def svlora_mlp(x2d, fc, proj, scaling: float, b_prime: int, num_slices: int, row
 # =====================================================================================================
 # GLP_OT head
 # =====================================================================================================
+# =====================================================================================================
+# residual add + LayerNorm (frozen glue between the adapted MLP and attention)
+# =====================================================================================================
+@torch.library.custom_op("ffm::add_layernorm_fwd", mutates_args=())
+def add_layernorm_fwd(x: Tensor, res: Optional[Tensor], gamma: Tensor, beta: Tensor,
+                      eps: float) -> Tuple[Tensor, Tensor, Tensor, Tensor]:
+    """s, ln, mean, rstd: s = bf16(x + res) (empty when res is None: s is x itself), ln = LayerNorm(s)."""
+    _need_cuda(x, res, gamma, beta)
+    C = x.shape[-1]
+    rows = x.numel() // C
+    s = torch.empty_like(x) if res is not None else x.new_empty((0,))
+    ln = torch.empty_like(x)
+    mean = torch.empty((rows,), device=x.device, dtype=torch.float32)
+    rstd = torch.empty((rows,), device=x.device, dtype=torch.float32)
+    _cabi.call("ffm_add_layernorm_fwd", _ptr(x), _ptr(res), _ptr(gamma), _ptr(beta), _ptr(s) if res is not None else 0,
+               _ptr(ln), _ptr(mean), _ptr(rstd), rows, C, float(eps), _stream())
+    return s, ln, mean, rstd
+
+
+@add_layernorm_fwd.register_fake
+def _(x, res, gamma, beta, eps):
+    rows = x.numel() // x.shape[-1]
+    return (torch.empty_like(x) if res is not None else x.new_empty((0,)), torch.empty_like(x),
+            x.new_empty((rows,), dtype=torch.float32), x.new_empty((rows,), dtype=torch.float32))
+
+
+@torch.library.custom_op("ffm::add_layernorm_bwd", mutates_args=())
+def add_layernorm_bwd(d_ln: Tensor, d_res: Optional[Tensor], s: Tensor, gamma: Tensor, mean: Tensor,
+                      rstd: Tensor) -> Tensor:
+    _need_cuda(d_ln, d_res, s)
+    C = s.shape[-1]
+    dx = torch.empty_like(s)
+    _cabi.call("ffm_add_layernorm_bwd", _ptr(d_ln), _ptr(d_res), _ptr(s), _ptr(gamma), _ptr(mean), _ptr(rstd), _ptr(dx),
+               s.numel() // C, C, _stream())
+    return dx
+
+
+@add_layernorm_bwd.register_fake
+def _(d_ln, d_res, s, gamma, mean, rstd):
+    return torch.empty_like(s)
+
+
+class _AddLayerNorm(torch.autograd.Function):
+    """(x, res) -> (x + res, LayerNorm(x + res)); the LayerNorm parameters are frozen (no gradient)."""
+
+    @staticmethod
+    def forward(ctx, x, res, gamma, beta, eps):
+        s, ln, mean, rstd = add_layernorm_fwd(x, res, gamma, beta, eps)
+        if res is None:
+            s = x
+        ctx.save_for_backward(s, gamma, mean, rstd)
+        ctx.has_res = res is not None
+        return s, ln
+
+    @staticmethod
+    def backward(ctx, d_s, d_ln):
+        s, gamma, mean, rstd = ctx.saved_tensors
+        if d_ln is None:
+            dx = d_s
+        else:
+            dx = add_layernorm_bwd(d_ln.contiguous(), None if d_s is None else d_s.contiguous(), s, gamma, mean, rstd)
+        return dx, (dx if ctx.has_res else None), None, None, None
+
+
+def add_layernorm(x: Tensor, res: Optional[Tensor], gamma: Tensor, beta: Tensor, eps: float = 1e-5):
+    """Residual update + LayerNorm in one pass: returns (x + res, LayerNorm(x + res)); res=None: (x, LayerNorm(x)).
+    bf16 activations [..., C], fp32 frozen gamma/beta (clip/model.py:304-310, :354-357)."""
+    if gamma.requires_grad or beta.requires_grad:
+        raise _cabi.FfmError("add_layernorm: LayerNorm parameters must be frozen (FairLoRA trains adapters and prompts only)")
+    x = x.contiguous()
+    if res is not None:
+        res = res.contiguous()
+    return _AddLayerNorm.apply(x, res, gamma, beta, eps)
+
+
 @torch.library.custom_op("ffm::ot_head_fwd", mutates_args=())
 def ot_head_fwd(img: Tensor, txt: Tensor, logit_scale: Tensor, num_slices: int, mode: int, eps: float, thresh: float,
                 max_iter: int, top_percent: float) -> Tuple[Tensor, Tensor, Tensor, Tensor, Tensor, Tensor]:

@@ -71,14 +71,20 @@ size_t ffm_svlora_bwd_workspace_bytes(int T, int K, int N, int n_samples);
  *               (used by fairfedmed_b200.clip_model so attention needs no transposes).  OCT volumes fold
  *               num_slices slice-images per sample into B' (trainers/GLP_OT_SVLoRA.py:473-475).
  *
+ *   z[t,:]  = bf16(scaling · h[t,:] ⊙ s_eff[sample(t),:])   (bf16 [T,16], optional): the operand d_lora_b needs,
+ *             produced by the epilogue anyway (it feeds the rank-16 tensor-core update), so the backward pass does not
+ *             recompute it.
+ *
  *   x [T,K] bf16, W [N,K] bf16 (frozen nn.Linear weight), bias [N] f32 or NULL,
- *   lora_a [K,r] f32, lora_b [r,N] f32, s_eff [n_samples,r] f32 (from ffm_seff), y / y_pre [T,N] bf16.
+ *   lora_a [K,r] f32, lora_b [r,N] f32, s_eff [n_samples,r] f32 (from ffm_seff), y / y_dact [T,N] bf16.
+ *   workspace: ffm_svlora_fwd_workspace_bytes(); afterwards it holds the bf16 adapter tiles of BOTH directions.  Keep it
+ *   alive and pass it to ffm_svlora_bwd as fwd_workspace to save that call its own preparation launch.
  *   Requirements: K % 8 == 0, N % 8 == 0, 1 <= r <= ffm_svlora_max_rank(), 16-byte aligned pointers.
  */
 int ffm_svlora_fwd(const void* x, const void* w, const float* bias, const float* lora_a, const float* lora_b,
-                   const float* s_eff, void* y, void* y_dact, float* h_out, void* workspace, size_t workspace_bytes,
-                   int T, int K, int N, int r, int n_samples, int b_prime, int num_slices, int row_div, float scaling,
-                   int act, ffm_stream_t stream);
+                   const float* s_eff, void* y, void* y_dact, float* h_out, void* z_out, void* workspace,
+                   size_t workspace_bytes, int T, int K, int N, int r, int n_samples, int b_prime, int num_slices,
+                   int row_div, float scaling, int act, ffm_stream_t stream);
 
 /*
  * Backward of the same module (autograd of trainers/GLP_OT_SVLoRA.py:450-482; W and bias frozen :375-376).
@@ -86,17 +92,37 @@ int ffm_svlora_fwd(const void* x, const void* w, const float* bias, const float*
  *   dzu = dy · B^T                         dz = scaling·dzu       dh = dz ⊙ s_eff[sample]
  *   dx  = dy · W + dh · A^T               (bf16 [T,K]); if gelu_dact != NULL (bf16 [T,K], the y_dact output of the
  *         *preceding* layer's forward) dx is multiplied element-wise by it, i.e. back through that QuickGELU
- *   d_lora_a [K,r] = x^T · dh             d_lora_b [r,N] = scaling · (h ⊙ s_eff[sample])^T · dy
+ *   d_lora_a [K,r] = x^T · dh             d_lora_b [r,N] = z^T · dy       (z from ffm_svlora_fwd)
  *   d_s_eff [n_samples,r] = scaling · sum_{t in sample} dzu ⊙ h
  *
+ *   Three launches: the fused tcgen05 GEMM (dx, dzu, dh), one kernel for both adapter contractions (x and dy are
+ *   each read from HBM once), one kernel that folds their partials and does the per-sample segmented reduction.
  *   w_t is W transposed, [K,N] bf16 (the frozen weight is transposed once at module construction).
- *   h is the f32 [T,16] side output of ffm_svlora_fwd.
+ *   h (f32 [T,16]) and z (bf16 [T,16]) are the side outputs of ffm_svlora_fwd; fwd_workspace is that call's workspace
+ *   (adapter tiles already prepared) or NULL (then lora_a / lora_b / s_eff are converted again here).
  */
 int ffm_svlora_bwd(const void* dy, const void* x, const void* w_t, const float* lora_a, const float* lora_b,
-                   const float* s_eff, const float* h, const void* gelu_dact, void* dx, float* d_lora_a,
-                   float* d_lora_b, float* d_s_eff, void* workspace, size_t workspace_bytes, int T, int K, int N,
-                   int r, int n_samples, int b_prime, int num_slices, int row_div, float scaling,
-                   ffm_stream_t stream);
+                   const float* s_eff, const float* h, const void* z, const void* fwd_workspace,
+                   const void* gelu_dact, void* dx, float* d_lora_a, float* d_lora_b, float* d_s_eff, void* workspace,
+                   size_t workspace_bytes, int T, int K, int N, int r, int n_samples, int b_prime, int num_slices,
+                   int row_div, float scaling, ffm_stream_t stream);
+
+/* ------------------------------------------------- residual add + LayerNorm (frozen blocks) -- */
+/*
+ * The glue between the adapted MLP and the frozen attention of ResidualAttentionBlock (clip/model.py:354-357):
+ *   x = x + branch;  h = LayerNorm(x)        LayerNorm with fp32 statistics like clip/model.py:304-310
+ * fused into one pass (row-sized tensors moved: 2 reads + 2 writes instead of 3 reads + 2 writes + 1 read + 1 write).
+ *   x, res, sum_out, ln_out: bf16 [rows, C];  gamma, beta: f32 [C] (frozen);  mean_out, rstd_out: f32 [rows] (saved
+ *   for the backward).  res == NULL: plain LayerNorm of x (sum_out unused).  C in {256, 512, 768, 1024}.
+ * Backward (LayerNorm weights are frozen in the FairLoRA recipe, trainers/GLP_OT_SVLoRA.py:822-829):
+ *   dx = LayerNorm'(d_ln; s, mean, rstd, gamma) + d_res        (d_res == NULL: no residual gradient to merge)
+ *   the same dx is the gradient of both x and res.
+ */
+int ffm_add_layernorm_fwd(const void* x, const void* res, const float* gamma, const float* beta, void* sum_out,
+                          void* ln_out, float* mean_out, float* rstd_out, int rows, int C, float eps,
+                          ffm_stream_t stream);
+int ffm_add_layernorm_bwd(const void* d_ln, const void* d_res, const void* s, const float* gamma, const float* mean,
+                          const float* rstd, void* dx, int rows, int C, ffm_stream_t stream);
 
 /*
  * Group mixing of singular values — trainers/GLP_OT_SVLoRA.py:453-467.

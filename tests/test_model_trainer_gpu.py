@@ -157,3 +157,35 @@ def test_two_client_round_and_evaluation():
         torch.testing.assert_close(got[k2].cpu(), ref[k2], rtol=1e-3, atol=1e-5)
     res = fed.test(idx=0, current_epoch=0)
     assert len(res) == 13 and 0 <= res[0] <= 100 and 0 <= res[3] <= 100
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("C,rows,with_res", [(768, 197 * 8, True), (768, 333, False), (512, 4 * 77, True), (1024, 64, True)])
+def test_add_layernorm_matches_torch(C, rows, with_res):
+    """ops.add_layernorm (fused residual add + LayerNorm, fp32 statistics) vs torch on the same bf16 operands:
+    forward within bf16 rounding, backward (dx for both inputs; frozen gamma/beta) within 2^-7 relative + 2e-3 of max."""
+    import torch.nn.functional as F
+    from fairfedmed_b200 import ops
+    dev = torch.device("cuda:0")
+    g = torch.Generator().manual_seed(3)
+    x = torch.randn(rows, C, generator=g).bfloat16().to(dev).requires_grad_(True)
+    res = (0.5 * torch.randn(rows, C, generator=g)).bfloat16().to(dev).requires_grad_(True) if with_res else None
+    gamma = (1 + 0.1 * torch.randn(C, generator=g)).to(dev)
+    beta = (0.1 * torch.randn(C, generator=g)).to(dev)
+    d_s = torch.randn(rows, C, generator=g).bfloat16().to(dev)
+    d_ln = torch.randn(rows, C, generator=g).bfloat16().to(dev)
+    s, ln = ops.add_layernorm(x, res, gamma, beta, 1e-5)
+    ((s.float() * d_s.float()).sum() + (ln.float() * d_ln.float()).sum()).backward()
+    gx, gres = x.grad.clone(), (res.grad.clone() if with_res else None)
+    # torch reference on the same rounded operands
+    xr = x.detach().clone().requires_grad_(True)
+    rr = res.detach().clone().requires_grad_(True) if with_res else None
+    s_ref = (xr + rr) if with_res else xr
+    ln_ref = F.layer_norm(s_ref.float(), (C,), gamma, beta, 1e-5)
+    ((s_ref.float() * d_s.float()).sum() + (ln_ref * d_ln.float()).sum()).backward()
+    assert torch.equal(s.detach(), s_ref.detach())
+    assert float((ln.float() - ln_ref).abs().max()) <= 2.0 ** -7 * float(ln_ref.abs().max())
+    lim = 2.0 ** -7 * xr.grad.float().abs() + 2e-3 * float(xr.grad.float().abs().max())
+    assert bool(((gx.float() - xr.grad.float()).abs() <= lim).all())
+    if with_res:
+        assert torch.equal(gx, gres)

@@ -105,12 +105,16 @@ def _raw_case(T, K, N, r, b_prime, num_slices, act, seed=0):
     scaling = 2.0 / r
     dy = (torch.randn(T, N, generator=g) * 0.1).bfloat16()
     d = {k: v.to(dev) for k, v in dict(x=x, W=W, bias=bias, A=A, B=B, s_eff=s_eff, dy=dy).items()}
-    y, y_pre, h = ops.svlora_fwd(d["x"], d["W"], d["bias"], d["A"], d["B"], d["s_eff"], scaling, b_prime, num_slices,
-                                 act)
+    y, y_pre, h, z_dev, tiles = ops.svlora_fwd(d["x"], d["W"], d["bias"], d["A"], d["B"], d["s_eff"], scaling, b_prime,
+                                               num_slices, act)
     Wt = d["W"].t().contiguous()
     gelu_pre = torch.rand(T, K, generator=g).bfloat16().to(dev) if act else None   # a saved QuickGELU' tensor
-    dx, dA, dB, dse = ops.svlora_bwd(d["dy"], d["x"], Wt, d["A"], d["B"], d["s_eff"], h, gelu_pre, scaling, b_prime,
-                                     num_slices)
+    # first through the forward's prepared tiles, then (tiles=None) through the backward's own preparation launch
+    dx, dA, dB, dse = ops.svlora_bwd(d["dy"], d["x"], Wt, d["A"], d["B"], d["s_eff"], h, z_dev, tiles, gelu_pre,
+                                     scaling, b_prime, num_slices)
+    dx_b, dA_b, dB_b, dse_b = ops.svlora_bwd(d["dy"], d["x"], Wt, d["A"], d["B"], d["s_eff"], h, z_dev, None, gelu_pre,
+                                             scaling, b_prime, num_slices)
+    assert torch.equal(dx, dx_b) and torch.equal(dA, dA_b) and torch.equal(dB, dB_b) and torch.equal(dse, dse_b)
     torch.cuda.synchronize()
     # ---- oracle (CPU fp32 on the same rounded operands) ----
     samp = (torch.arange(T) % b_prime) // num_slices
@@ -172,9 +176,9 @@ def test_config2_full_size_properties():
     s1 = (torch.rand(B, r, generator=g) + 0.1).to(dev)
     zero = torch.zeros_like(s1)
     sc = 1.0 / 6
-    y0, _, h0 = ops.svlora_fwd(x, W, None, A, Bm, zero, sc, B, 1, 0)       # adapter switched off: plain GEMM
-    y1, _, h1 = ops.svlora_fwd(x, W, None, A, Bm, s1, sc, B, 1, 0)
-    y2, _, _ = ops.svlora_fwd(x, W, None, A, Bm, 2 * s1, sc, B, 1, 0)
+    y0, _, h0, _, _ = ops.svlora_fwd(x, W, None, A, Bm, zero, sc, B, 1, 0)       # adapter switched off: plain GEMM
+    y1, _, h1, _, _ = ops.svlora_fwd(x, W, None, A, Bm, s1, sc, B, 1, 0)
+    y2, _, _, _, _ = ops.svlora_fwd(x, W, None, A, Bm, 2 * s1, sc, B, 1, 0)
     assert torch.equal(h0, h1)                                             # H does not depend on s
     rows = torch.randint(0, T, (64,), generator=g).to(dev)
     ref0 = x[rows].float() @ W.float().t()
@@ -201,12 +205,12 @@ def test_batch_first_rows_equal_sequence_first_rows():
     Bm = torch.randn(r, N, generator=g).to(dev)
     s = (torch.rand(Bp // slices, r, generator=g) + 0.1).to(dev)
     Wt = W.t().contiguous()
-    y1, _, h1 = ops.svlora_fwd(x.reshape(L * Bp, K), W, None, A, Bm, s, 1 / 6, Bp, slices, 0, 1)
-    g1 = ops.svlora_bwd(dy.reshape(L * Bp, N), x.reshape(L * Bp, K), Wt, A, Bm, s, h1, None, 1 / 6, Bp, slices, 1)
+    y1, _, h1, z1, t1 = ops.svlora_fwd(x.reshape(L * Bp, K), W, None, A, Bm, s, 1 / 6, Bp, slices, 0, 1)
+    g1 = ops.svlora_bwd(dy.reshape(L * Bp, N), x.reshape(L * Bp, K), Wt, A, Bm, s, h1, z1, t1, None, 1 / 6, Bp, slices, 1)
     xb = x.transpose(0, 1).contiguous()
     dyb = dy.transpose(0, 1).contiguous()
-    y2, _, h2 = ops.svlora_fwd(xb.reshape(L * Bp, K), W, None, A, Bm, s, 1 / 6, Bp, slices, 0, L)
-    g2 = ops.svlora_bwd(dyb.reshape(L * Bp, N), xb.reshape(L * Bp, K), Wt, A, Bm, s, h2, None, 1 / 6, Bp, slices, L)
+    y2, _, h2, z2, t2 = ops.svlora_fwd(xb.reshape(L * Bp, K), W, None, A, Bm, s, 1 / 6, Bp, slices, 0, L)
+    g2 = ops.svlora_bwd(dyb.reshape(L * Bp, N), xb.reshape(L * Bp, K), Wt, A, Bm, s, h2, z2, t2, None, 1 / 6, Bp, slices, L)
     assert torch.equal(y2.view(Bp, L, N).transpose(0, 1), y1.view(L, Bp, N))
     assert torch.equal(g2[0].view(Bp, L, K).transpose(0, 1), g1[0].view(L, Bp, K))
     for a, b in zip(g1[1:], g2[1:]):          # dA, dB, ds_eff: same sums in a different row order

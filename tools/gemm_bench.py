@@ -16,18 +16,18 @@ x = torch.randn(T, K, device=dev).bfloat16(); W = (torch.randn(N, K, device=dev)
 bias = torch.randn(N, device=dev); A = torch.randn(K, r, device=dev) * 0.05; Bm = torch.randn(r, N, device=dev)
 s_eff = torch.rand(B, r, device=dev); y = torch.empty(T, N, device=dev, dtype=torch.bfloat16)
 ypre = torch.empty_like(y) if a.act else None
-h = torch.zeros(T, 16, device=dev); lib = _cabi.load()
+h = torch.zeros(T, 16, device=dev); zz = torch.zeros(T, 16, device=dev, dtype=torch.bfloat16); lib = _cabi.load()
 wsb = lib.ffm_svlora_fwd_workspace_bytes(T, K, N, B); ws = torch.empty(wsb, device=dev, dtype=torch.uint8)
 st = torch.cuda.current_stream().cuda_stream
 p = lambda t: 0 if t is None else t.data_ptr()
 def fwd():
-    _cabi.call("ffm_svlora_fwd", p(x), p(W), p(bias), p(A), p(Bm), p(s_eff), p(y), p(ypre), p(h), p(ws), wsb,
+    _cabi.call("ffm_svlora_fwd", p(x), p(W), p(bias), p(A), p(Bm), p(s_eff), p(y), p(ypre), p(h), p(zz), p(ws), wsb,
                T, K, N, r, B, B, 1, 1, 1.0 / 6, a.act, st)
 dy = torch.randn(T, N, device=dev).bfloat16(); Wt = W.t().contiguous(); dx = torch.empty_like(x)
 dA = torch.zeros(K, r, device=dev); dB = torch.zeros(r, N, device=dev); dse = torch.zeros(B, r, device=dev)
 bwsb = lib.ffm_svlora_bwd_workspace_bytes(T, K, N, B); bws = torch.empty(bwsb, device=dev, dtype=torch.uint8)
 def bwd():
-    _cabi.call("ffm_svlora_bwd", p(dy), p(x), p(Wt), p(A), p(Bm), p(s_eff), p(h), 0, p(dx), p(dA), p(dB), p(dse),
+    _cabi.call("ffm_svlora_bwd", p(dy), p(x), p(Wt), p(A), p(Bm), p(s_eff), p(h), p(zz), p(ws), 0, p(dx), p(dA), p(dB), p(dse),
                p(bws), bwsb, T, K, N, r, B, B, 1, 1, 1.0 / 6, st)
 fn = bwd if a.bwd else fwd
 for _ in range(3): fn()

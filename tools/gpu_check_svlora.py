@@ -72,13 +72,14 @@ def run_case(T, K, N, r, b_prime, num_slices, act, seed=0, verbose=True, timing=
     y = torch.empty(T, N, device=dev, dtype=torch.bfloat16)
     y_pre = torch.empty(T, N, device=dev, dtype=torch.bfloat16) if act else None
     h = torch.zeros(T, RP, device=dev)
+    zz = torch.zeros(T, RP, device=dev, dtype=torch.bfloat16)
     lib = _cabi.load()
     ws_bytes = lib.ffm_svlora_fwd_workspace_bytes(T, K, N, nS)
     ws = torch.empty(ws_bytes, device=dev, dtype=torch.uint8)
 
     def fwd():
         _cabi.call("ffm_svlora_fwd", ptr(x), ptr(W), ptr(bias), ptr(A), ptr(B), ptr(s_eff), ptr(y), ptr(y_pre),
-                   ptr(h), ptr(ws), ws_bytes, T, K, N, r, nS, b_prime, num_slices, 1, scaling, act, stream())
+                   ptr(h), ptr(zz), ptr(ws), ws_bytes, T, K, N, r, nS, b_prime, num_slices, 1, scaling, act, stream())
 
     fwd()
     torch.cuda.synchronize()
@@ -131,8 +132,8 @@ def run_case(T, K, N, r, b_prime, num_slices, act, seed=0, verbose=True, timing=
     gelu_pre = (torch.rand(T, K, device=dev, generator=g)).to(torch.bfloat16) if act else None
 
     def bwd():
-        _cabi.call("ffm_svlora_bwd", ptr(dy), ptr(x), ptr(Wt), ptr(A), ptr(B), ptr(s_eff), ptr(h), ptr(gelu_pre),
-                   ptr(dx), ptr(dA), ptr(dB), ptr(dse), ptr(bws), bws_bytes, T, K, N, r, nS, b_prime, num_slices,
+        _cabi.call("ffm_svlora_bwd", ptr(dy), ptr(x), ptr(Wt), ptr(A), ptr(B), ptr(s_eff), ptr(h), ptr(zz), ptr(ws),
+                   ptr(gelu_pre), ptr(dx), ptr(dA), ptr(dB), ptr(dse), ptr(bws), bws_bytes, T, K, N, r, nS, b_prime, num_slices,
                    1, scaling, stream())
 
     bwd()
