@@ -132,6 +132,7 @@ constexpr int EPI_THREADS = 256;
 constexpr int Z_THREADS = 128;     // epilogue threads that write the Z tile (one per tile row)
 
 
+template <int ACT>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 svlora_gemm_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_w,
                    const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b,
@@ -363,10 +364,15 @@ svlora_gemm_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_consta
       __syncwarp();                              // bias_w visible to the whole warp
 
       // ---- D -> OUT ----
+      EpiAux aux_cur, aux_nxt;
+      epi_load_aux<ACT>(p, aux_nxt, grow, n0 + static_cast<int>(half) * EPI_PIECE_COLS);   // piece 0, before the wait
       mbar_wait(&d_full[s], aph, 700 + s);
       tc_fence_after();
 #pragma unroll 1
       for (int pc = 0; pc < PIECES; ++pc) {
+        aux_cur = aux_nxt;
+        if (pc + 1 < PIECES)
+          epi_load_aux<ACT>(p, aux_nxt, grow, n0 + (2 * (pc + 1) + static_cast<int>(half)) * EPI_PIECE_COLS);
         const int cc = (2 * pc + static_cast<int>(half)) * EPI_PIECE_COLS;   // first tile column of this piece
         uint32_t v[32];
         tmem_ld32(acc + cc, v);
@@ -380,7 +386,7 @@ svlora_gemm_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_consta
         float f[32];
 #pragma unroll
         for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]) + bias_w[pc * EPI_PIECE_COLS + j];
-        epi_store_piece(p, f, &tm_y, &tm_y2, stage_w, unit, lane, grow, n0 + cc, m_blk * BM + static_cast<int>(q) * 32);
+        epi_store_piece<ACT>(p, f, aux_cur, &tm_y, &tm_y2, stage_w, unit, lane, grow, n0 + cc, m_blk * BM + static_cast<int>(q) * 32);
       }
       __syncwarp();                              // all lanes done with bias_w before the next tile overwrites it
     }
@@ -549,28 +555,37 @@ static int launch_svlora_gemm(const GemmOperands& o, cudaStream_t stream) {
   p.k_blocks = (o.K + BK - 1) / BK;
   p.dbg = gemm_debug_mask();
 
-  static std::once_flag attr_once;
-  static cudaError_t attr_err = cudaSuccess;
-  std::call_once(attr_once, [] {
-    attr_err = cudaFuncSetAttribute(svlora_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
-  });
-  // the attribute is per-device; re-apply cheaply when several devices are used from one process
-  if (attr_err == cudaSuccess) {
+  // dynamic-smem opt-in of the three epilogue variants; the attribute is per device
+  {
     static thread_local int attr_dev = -1;
     int dev = 0;
-    cudaGetDevice(&dev);
+    FFM_CHECK_CUDA(cudaGetDevice(&dev));
     if (dev != attr_dev) {
-      attr_err = cudaFuncSetAttribute(svlora_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+      FFM_CHECK_CUDA(cudaFuncSetAttribute(svlora_gemm_kernel<ACT_NONE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          SMEM_BYTES));
+      FFM_CHECK_CUDA(cudaFuncSetAttribute(svlora_gemm_kernel<ACT_QUICKGELU>,
+                                          cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+      FFM_CHECK_CUDA(cudaFuncSetAttribute(svlora_gemm_kernel<ACT_QUICKGELU_GRAD>,
+                                          cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
       attr_dev = dev;
     }
   }
-  FFM_CHECK_CUDA(attr_err);
 
   const int tiles = p.m_tiles * p.n_tiles;
   const int grid = tiles < num_sms() ? tiles : num_sms();
   GemmProfileScope prof;
   if ((rc = gemm_profile_begin(&prof, stream))) return rc;
-  svlora_gemm_kernel<<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(tm_x, tm_w, tm_a, tm_b, tm_y, tm_y2, p);
+  switch (p.act) {
+    case ACT_QUICKGELU:
+      svlora_gemm_kernel<ACT_QUICKGELU><<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(tm_x, tm_w, tm_a, tm_b, tm_y, tm_y2, p);
+      break;
+    case ACT_QUICKGELU_GRAD:
+      svlora_gemm_kernel<ACT_QUICKGELU_GRAD><<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(tm_x, tm_w, tm_a, tm_b, tm_y,
+                                                                                        tm_y2, p);
+      break;
+    default:
+      svlora_gemm_kernel<ACT_NONE><<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(tm_x, tm_w, tm_a, tm_b, tm_y, tm_y2, p);
+  }
   FFM_CHECK_CUDA(cudaGetLastError());
   count_launch();
   return gemm_profile_end(&prof, o.T, o.K, o.N, stream);

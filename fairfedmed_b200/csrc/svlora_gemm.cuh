@@ -81,16 +81,33 @@ constexpr int EPI_PIECE_BYTES = 32 * EPI_PIECE_COLS * 2;   // 32 rows x 64 B
 
 // f[j] (+bias already added) -> optional x saved QuickGELU' (backward) -> optional QuickGELU (+ its derivative as a
 // second store) -> bf16 -> staging -> TMA store at (row0, gcol).  `unit` counts this warp's stores (buffer = unit&1).
-__device__ __forceinline__ void epi_store_piece(const GemmParams& p, float (&f)[32], const CUtensorMap* tm_y,
-                                                const CUtensorMap* tm_y2, uint8_t* stage_w, uint32_t& unit,
-                                                uint32_t lane, int grow, int gcol, int row0) {
-  if (p.act == ACT_QUICKGELU_GRAD && grow < p.T) {
-    const __nv_bfloat16* up = p.aux + static_cast<size_t>(grow) * p.N + gcol;
-    if (gcol + 32 <= p.N) {
+// Saved QuickGELU'(u) values of one piece (ACT_QUICKGELU_GRAD): 64 contiguous bytes of this lane's row.  Issued one
+// piece ahead by the callers so the global-load latency overlaps the TMEM read / conversion of the current piece.
+struct EpiAux {
+  uint4 v[4];
+  bool ready;     // false: ragged / out-of-range piece, epi_store_piece falls back to guarded scalar loads
+};
+template <int ACT>
+__device__ __forceinline__ void epi_load_aux(const GemmParams& p, EpiAux& a, int grow, int gcol) {
+  a.ready = false;
+  if (ACT != ACT_QUICKGELU_GRAD) return;
+  if (grow < p.T && gcol + 32 <= p.N) {
+    const uint4* up = reinterpret_cast<const uint4*>(p.aux + static_cast<size_t>(grow) * p.N + gcol);
+#pragma unroll
+    for (int j8 = 0; j8 < 4; ++j8) a.v[j8] = __ldg(up + j8);
+    a.ready = true;
+  }
+}
+
+template <int ACT>
+__device__ __forceinline__ void epi_store_piece(const GemmParams& p, float (&f)[32], const EpiAux& aux,
+                                                const CUtensorMap* tm_y, const CUtensorMap* tm_y2, uint8_t* stage_w,
+                                                uint32_t& unit, uint32_t lane, int grow, int gcol, int row0) {
+  if (ACT == ACT_QUICKGELU_GRAD && grow < p.T) {
+    if (aux.ready) {
 #pragma unroll
       for (int j8 = 0; j8 < 4; ++j8) {
-        const uint4 raw = __ldg(reinterpret_cast<const uint4*>(up) + j8);
-        const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&raw);
+        const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&aux.v[j8]);
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
           const float2 uu = __bfloat1622float2(h2[e]);
@@ -99,11 +116,12 @@ __device__ __forceinline__ void epi_store_piece(const GemmParams& p, float (&f)[
         }
       }
     } else {
+      const __nv_bfloat16* up = p.aux + static_cast<size_t>(grow) * p.N + gcol;
       for (int j = 0; j < 32; ++j)
         if (gcol + j < p.N) f[j] *= __bfloat162float(up[j]);
     }
   }
-  const int n_pass = (p.act == ACT_QUICKGELU && p.has_pre) ? 2 : 1;
+  const int n_pass = (ACT == ACT_QUICKGELU && p.has_pre) ? 2 : 1;
   float g2[32];
 #pragma unroll 1
   for (int pass = 0; pass < n_pass; ++pass) {
@@ -111,7 +129,7 @@ __device__ __forceinline__ void epi_store_piece(const GemmParams& p, float (&f)[
     // the TMA store that last read this buffer (2 units ago) must have finished reading smem
     if (lane == 0) tma_store_wait_read<1>();
     __syncwarp();
-    if (p.act == ACT_QUICKGELU) {
+    if (ACT == ACT_QUICKGELU) {
       if (n_pass == 2 && pass == 0) {
         // first store of the dual store: QuickGELU'(u), all the backward pass needs (u itself is not kept)
 #pragma unroll

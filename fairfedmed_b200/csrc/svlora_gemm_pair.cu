@@ -70,6 +70,7 @@ constexpr int NUM_THREADS = 384;
 constexpr int EPI_THREADS = 256;
 constexpr int Z_THREADS = 128;
 
+template <int ACT>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
 svlora_gemm_pair_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_w,
                         const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b,
@@ -145,15 +146,6 @@ svlora_gemm_pair_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_c
       const int m_pair = tile / p.n_tiles;
       const int n_blk = tile - m_pair * p.n_tiles;
       const int m_blk = m_pair * 2 + static_cast<int>(rank);
-      const int s = it & 1;
-      // Bside half for this tile; buffer s is free once the fix-up UMMA of tile it-2 completed
-      if (it >= 2) mbar_wait_uniform(&d_full[s], ((it - 2) >> 1) & 1u);
-      if (elect_one()) {
-        if (leader) mbar_arrive_expect_tx(&bs_full[s], 2 * BS_LOAD_BYTES);
-        tma_load_2d_pair(smem + OFF_BS + s * BS_TILE_BYTES, &tm_b, &bs_full[s], 0,
-                         n_blk * BN + static_cast<int>(rank) * HN);
-      }
-      __syncwarp();
       for (int kb = 0; kb < p.k_blocks; ++kb) {
         mbar_wait_uniform(&empty_bar[stage], phase ^ 1u);
         if (elect_one()) {
@@ -201,6 +193,13 @@ svlora_gemm_pair_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_c
         const uint32_t aph = (it >> 1) & 1u;
         mbar_wait_cluster_uniform(&tmem_empty[s], aph ^ 1u);   // both epilogues drained tile it-2
         tc_fence_after();
+        // Bside halves of this tile (buffer s was last read by the fix-up UMMA of tile it-2, long complete): loaded from
+        // here and from the peer's otherwise idle warp 1, so the k-slice producers never wait on a per-tile event
+        if (elect_one()) {
+          mbar_arrive_expect_tx(&bs_full[s], 2 * BS_LOAD_BYTES);
+          tma_load_2d_pair(smem + OFF_BS + s * BS_TILE_BYTES, &tm_b, &bs_full[s], 0, (tile % p.n_tiles) * BN);
+        }
+        __syncwarp();
         const uint32_t d_tmem = tmem_base + s * ACC_COLS;
         for (int kb = 0; kb < p.k_blocks; ++kb) {
           if (pend >= 0) {
@@ -237,6 +236,17 @@ svlora_gemm_pair_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_c
       if (pend >= 0) {
         mbar_wait_cluster_uniform(&z_full[pend], pend_phase);
         fixup(pend, pend_phase);
+      }
+    } else {
+      // peer CTA: its half of every tile's Bside (credited to the leader's bs_full barrier)
+      int it = 0;
+      for (int tile = cluster_id; tile < num_tiles; tile += num_clusters, ++it) {
+        const int s = it & 1;
+        // buffer s is free once the fix-up UMMA of tile it-2 completed (multicast commit reaches this CTA's d_full)
+        if (it >= 2) mbar_wait_uniform(&d_full[s], ((it - 2) >> 1) & 1u);
+        if (elect_one())
+          tma_load_2d_pair(smem + OFF_BS + s * BS_TILE_BYTES, &tm_b, &bs_full[s], 0, (tile % p.n_tiles) * BN + HN);
+        __syncwarp();
       }
     }
   } else if (warp >= 4) {
@@ -312,10 +322,15 @@ svlora_gemm_pair_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_c
       __syncwarp();
 
       // ---- D -> OUT ----
+      EpiAux aux_cur, aux_nxt;
+      epi_load_aux<ACT>(p, aux_nxt, grow, n0 + static_cast<int>(half) * EPI_PIECE_COLS);   // piece 0, before the wait
       mbar_wait(&d_full[s], aph, 700 + s);
       tc_fence_after();
 #pragma unroll 1
       for (int pc = 0; pc < PIECES; ++pc) {
+        aux_cur = aux_nxt;
+        if (pc + 1 < PIECES)
+          epi_load_aux<ACT>(p, aux_nxt, grow, n0 + (2 * (pc + 1) + static_cast<int>(half)) * EPI_PIECE_COLS);
         const int cc = (2 * pc + static_cast<int>(half)) * EPI_PIECE_COLS;   // tile column of this piece
         const int tcol = cc < HN ? cc : cc + HR;                               // accumulator column (skip the H block)
         uint32_t v[32];
@@ -329,7 +344,7 @@ svlora_gemm_pair_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_c
         float f[32];
 #pragma unroll
         for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]) + bias_w[pc * EPI_PIECE_COLS + j];
-        epi_store_piece(p, f, &tm_y, &tm_y2, stage_w, unit, lane, grow, n0 + cc, m_blk * BM + static_cast<int>(q) * 32);
+        epi_store_piece<ACT>(p, f, aux_cur, &tm_y, &tm_y2, stage_w, unit, lane, grow, n0 + cc, m_blk * BM + static_cast<int>(q) * 32);
       }
       __syncwarp();
     }
@@ -379,8 +394,12 @@ int launch_svlora_gemm_pair(const GemmOperands& o, cudaStream_t stream) {
   int dev = 0;
   FFM_CHECK_CUDA(cudaGetDevice(&dev));
   if (dev != attr_dev) {
-    FFM_CHECK_CUDA(cudaFuncSetAttribute(svlora_gemm_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    FFM_CHECK_CUDA(cudaFuncSetAttribute(svlora_gemm_pair_kernel<ACT_NONE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                         SMEM_BYTES));
+    FFM_CHECK_CUDA(cudaFuncSetAttribute(svlora_gemm_pair_kernel<ACT_QUICKGELU>,
+                                        cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    FFM_CHECK_CUDA(cudaFuncSetAttribute(svlora_gemm_pair_kernel<ACT_QUICKGELU_GRAD>,
+                                        cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
     attr_dev = dev;
   }
   const int pair_tiles = ((p.m_tiles + 1) / 2) * p.n_tiles;
@@ -388,7 +407,20 @@ int launch_svlora_gemm_pair(const GemmOperands& o, cudaStream_t stream) {
   const int clusters = pair_tiles < max_clusters ? pair_tiles : max_clusters;
   GemmProfileScope prof;
   if ((rc = gemm_profile_begin(&prof, stream))) return rc;
-  svlora_gemm_pair_kernel<<<2 * clusters, NUM_THREADS, SMEM_BYTES, stream>>>(tm_x, tm_w, tm_a, tm_b, tm_y, tm_y2, p);
+  const int grid = 2 * clusters;
+  switch (p.act) {
+    case ACT_QUICKGELU:
+      svlora_gemm_pair_kernel<ACT_QUICKGELU><<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(tm_x, tm_w, tm_a, tm_b, tm_y,
+                                                                                        tm_y2, p);
+      break;
+    case ACT_QUICKGELU_GRAD:
+      svlora_gemm_pair_kernel<ACT_QUICKGELU_GRAD><<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(tm_x, tm_w, tm_a, tm_b,
+                                                                                             tm_y, tm_y2, p);
+      break;
+    default:
+      svlora_gemm_pair_kernel<ACT_NONE><<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(tm_x, tm_w, tm_a, tm_b, tm_y, tm_y2,
+                                                                                   p);
+  }
   FFM_CHECK_CUDA(cudaGetLastError());
   count_launch();
   return gemm_profile_end(&prof, o.T, o.K, o.N, stream);
