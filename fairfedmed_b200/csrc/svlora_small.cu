@@ -77,18 +77,18 @@ __global__ void ds_kernel(const long long* __restrict__ attr, const float* __res
 // the legacy tensor path: mma.sync m16n8k16 with A = M^T and B = v, both fetched from shared memory with
 // ldmatrix.trans (the tiles sit in smem exactly as they sit in HBM: rows = t).  Both tiles arrive through cp.async
 // (nothing in the loop waits on a synchronous global load).
-//   CTA = 8 warps, tile = 128 columns x 64 rows per stage, 4-stage ring; warp w owns columns 16w..16w+15 and all
+//   CTA = 8 warps, tile = 128 columns x 64 rows per stage, 3-stage ring (3 CTAs per SM); warp w owns columns 16w..16w+15 and all
 //   16 ranks (two n-tiles).  blockIdx.y < groups_a: column group of x (-> dA), else of dy (-> dB).
 //   Row chunks write fp32 partials; adapter_grad_finalize_kernel folds them in a fixed order (deterministic).
 // ----------------------------------------------------------------------------------------------
 constexpr int CS_THREADS = 256;
 constexpr int CS_COLS = 128;             // columns per CTA
 constexpr int CS_ROWS = 64;              // rows per stage
-constexpr int CS_STAGES = 4;
+constexpr int CS_STAGES = 3;
 constexpr int CS_MSTRIDE = CS_COLS * 2 + 16;   // 272 B: rows 16 B apart mod 128 -> conflict-free ldmatrix
 constexpr int CS_VSTRIDE = 48;                 // 16 bf16 = 32 B padded to 48 B, same reason
 constexpr int CS_STAGE_BYTES = CS_ROWS * CS_MSTRIDE + CS_ROWS * CS_VSTRIDE;   // 20480
-constexpr int CS_SMEM_BYTES = CS_STAGES * CS_STAGE_BYTES;                      // 81920
+constexpr int CS_SMEM_BYTES = CS_STAGES * CS_STAGE_BYTES;                      // 61440: three CTAs per SM
 
 __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem_dst)), "l"(gmem_src) : "memory");
@@ -259,10 +259,11 @@ adapter_grad_finalize_kernel(const float* __restrict__ partial_a, const float* _
 
 constexpr int CS_MAX_CHUNKS = 64;  // row chunks (partials: chunks x C x 16 fp32)
 
-// about two CTAs per SM in total over both contractions: enough loads in flight without a ragged second wave
+// three CTAs fit per SM (61 KB of smem each): fill those slots in ONE wave — a ceil() here once produced 300 CTAs for
+// 296 slots and the four stragglers doubled the kernel time (ncu: DRAM 45 % busy)
 static int pick_chunks(int T, int K, int N) {
   const int col_groups = (K + CS_COLS - 1) / CS_COLS + (N + CS_COLS - 1) / CS_COLS;
-  int chunks = (2 * num_sms() + col_groups - 1) / col_groups;
+  int chunks = (3 * num_sms()) / col_groups;
   if (chunks > CS_MAX_CHUNKS) chunks = CS_MAX_CHUNKS;
   const int max_chunks = (T + CS_ROWS - 1) / CS_ROWS;
   if (chunks > max_chunks) chunks = max_chunks;
