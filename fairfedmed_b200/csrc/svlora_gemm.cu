@@ -248,7 +248,7 @@ svlora_gemm_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_consta
 
       const uint32_t d_tmem = tmem_base + s * ACC_COLS;
       for (int kb = 0; kb < p.k_blocks; ++kb) {
-        if (pend >= 0 && (kb & 3) == 3) {
+        if (pend >= 0) {
           // Z of the previous tile ready?  (vote keeps the decision warp-uniform for the compiler)
           if (__all_sync(0xffffffffu, mbar_test_wait(&z_full[pend], pend_phase))) {
             fixup(pend, pend_phase);
@@ -319,29 +319,26 @@ svlora_gemm_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_consta
 
       if (half == 0) {
         // ---- H -> Z (SW32 K-major A operand of the fix-up UMMA) ----
+        // this row's scaled singular values first: their global-load latency hides behind the wait for H
+        const int grow_c = grow < p.T ? grow : (p.T - 1);
+        const int sample = ((grow_c / p.row_div) % p.b_prime) / p.num_slices;
+        const float4* sr = reinterpret_cast<const float4*>(p.s_rows + static_cast<size_t>(sample) * RP);
+        float4 svv[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) svv[j] = __ldg(sr + j);
         mbar_wait(&h_full[s], aph, 600 + s);
         tc_fence_after();
         uint32_t hv[16];
         tmem_ld16(acc + BN, hv);
         tmem_ld_wait();
-        const int grow_c = grow < p.T ? grow : (p.T - 1);
-        const int sample = ((grow_c / p.row_div) % p.b_prime) / p.num_slices;
-        const float4* sr = reinterpret_cast<const float4*>(p.s_rows + static_cast<size_t>(sample) * RP);
         float zf[16];
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-          const float4 sv = __ldg(sr + j);
+          const float4 sv = svv[j];
           zf[4 * j + 0] = __uint_as_float(hv[4 * j + 0]) * sv.x;
           zf[4 * j + 1] = __uint_as_float(hv[4 * j + 1]) * sv.y;
           zf[4 * j + 2] = __uint_as_float(hv[4 * j + 2]) * sv.z;
           zf[4 * j + 3] = __uint_as_float(hv[4 * j + 3]) * sv.w;
-        }
-        if (p.h_out != nullptr && n_blk == 0 && grow < p.T) {
-          float4* ho = reinterpret_cast<float4*>(p.h_out + static_cast<size_t>(grow) * RP);
-#pragma unroll
-          for (int j = 0; j < 4; ++j)
-            ho[j] = make_float4(__uint_as_float(hv[4 * j]), __uint_as_float(hv[4 * j + 1]),
-                                __uint_as_float(hv[4 * j + 2]), __uint_as_float(hv[4 * j + 3]));
         }
         // row r at r*32 B, 16-B chunk c stored at chunk (c ^ ((r>>2)&1))
         uint8_t* zrow = smem + OFF_Z + s * Z_TILE_BYTES + row * 32u;
@@ -353,13 +350,23 @@ svlora_gemm_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_consta
         c1.z = pack_bf16x2(zf[12], zf[13]); c1.w = pack_bf16x2(zf[14], zf[15]);
         *reinterpret_cast<uint4*>(zrow + ((0u ^ sw) << 4)) = c0;
         *reinterpret_cast<uint4*>(zrow + ((1u ^ sw) << 4)) = c1;
-        if (p.z_out != nullptr && n_blk == 0 && grow < p.T) {
-          uint4* zo = reinterpret_cast<uint4*>(p.z_out + static_cast<size_t>(grow) * RP);
-          zo[0] = c0;
-          zo[1] = c1;
-        }
         fence_proxy_async_smem();
         mbar_arrive(&z_full[s]);
+        // side outputs to HBM after the signal: they are off the tile's critical chain
+        if (n_blk == 0 && grow < p.T) {
+          if (p.h_out != nullptr) {
+            float4* ho = reinterpret_cast<float4*>(p.h_out + static_cast<size_t>(grow) * RP);
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+              ho[j] = make_float4(__uint_as_float(hv[4 * j]), __uint_as_float(hv[4 * j + 1]),
+                                  __uint_as_float(hv[4 * j + 2]), __uint_as_float(hv[4 * j + 3]));
+          }
+          if (p.z_out != nullptr) {
+            uint4* zo = reinterpret_cast<uint4*>(p.z_out + static_cast<size_t>(grow) * RP);
+            zo[0] = c0;
+            zo[1] = c1;
+          }
+        }
       }
       __syncwarp();                              // bias_w visible to the whole warp
 

@@ -279,24 +279,20 @@ svlora_gemm_pair_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_c
 
       if (half == 0) {
         // ---- H -> Z ----
+        // this row's scaled singular values first: their global-load latency hides behind the wait for H
+        const int grow_c = grow < p.T ? grow : (p.T - 1);
+        const int sample = ((grow_c / p.row_div) % p.b_prime) / p.num_slices;
+        const float4* sr = reinterpret_cast<const float4*>(p.s_rows + static_cast<size_t>(sample) * RP);
+        const float4 s0 = __ldg(sr), s1 = __ldg(sr + 1), s2 = __ldg(sr + 2), s3 = __ldg(sr + 3);
         mbar_wait(&h_full[s], aph, 600 + s);
         tc_fence_after();
         uint32_t h0[8], h1[8];
         tmem_ld8(acc + HN, h0);            // H columns 0..7  (leader's Aside rows)
         tmem_ld8(acc + BH + HN, h1);       // H columns 8..15 (peer's Aside rows)
         tmem_ld_wait();
-        const int grow_c = grow < p.T ? grow : (p.T - 1);
-        const int sample = ((grow_c / p.row_div) % p.b_prime) / p.num_slices;
-        const float4* sr = reinterpret_cast<const float4*>(p.s_rows + static_cast<size_t>(sample) * RP);
-        const float4 s0 = __ldg(sr), s1 = __ldg(sr + 1), s2 = __ldg(sr + 2), s3 = __ldg(sr + 3);
         float hf[16];
 #pragma unroll
         for (int j = 0; j < 8; ++j) { hf[j] = __uint_as_float(h0[j]); hf[8 + j] = __uint_as_float(h1[j]); }
-        if (p.h_out != nullptr && n_blk == 0 && grow < p.T) {
-          float4* ho = reinterpret_cast<float4*>(p.h_out + static_cast<size_t>(grow) * RP);
-#pragma unroll
-          for (int j = 0; j < 4; ++j) ho[j] = make_float4(hf[4 * j], hf[4 * j + 1], hf[4 * j + 2], hf[4 * j + 3]);
-        }
         const float sv[16] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w,
                               s2.x, s2.y, s2.z, s2.w, s3.x, s3.y, s3.z, s3.w};
         float zf[16];
@@ -311,13 +307,21 @@ svlora_gemm_pair_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_c
         c1.z = pack_bf16x2(zf[12], zf[13]); c1.w = pack_bf16x2(zf[14], zf[15]);
         *reinterpret_cast<uint4*>(zrow + ((0u ^ sw) << 4)) = c0;
         *reinterpret_cast<uint4*>(zrow + ((1u ^ sw) << 4)) = c1;
-        if (p.z_out != nullptr && n_blk == 0 && grow < p.T) {
-          uint4* zo = reinterpret_cast<uint4*>(p.z_out + static_cast<size_t>(grow) * RP);
-          zo[0] = c0;
-          zo[1] = c1;
-        }
         fence_proxy_async_smem();
         mbar_arrive_cluster(mapa_u32(smem_u32(&z_full[s]), 0));       // leader's barrier (local when rank 0)
+        // side outputs to HBM after the signal: they are off the tile's critical chain
+        if (n_blk == 0 && grow < p.T) {
+          if (p.h_out != nullptr) {
+            float4* ho = reinterpret_cast<float4*>(p.h_out + static_cast<size_t>(grow) * RP);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) ho[j] = make_float4(hf[4 * j], hf[4 * j + 1], hf[4 * j + 2], hf[4 * j + 3]);
+          }
+          if (p.z_out != nullptr) {
+            uint4* zo = reinterpret_cast<uint4*>(p.z_out + static_cast<size_t>(grow) * RP);
+            zo[0] = c0;
+            zo[1] = c1;
+          }
+        }
       }
       __syncwarp();
 
