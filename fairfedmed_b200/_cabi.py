@@ -22,6 +22,7 @@ SIGNATURES = {
     "ffm_last_error": (C.c_char_p, []),
     "ffm_version": (_i, []),
     "ffm_svlora_max_rank": (_i, []),
+    "ffm_svlora_padded_rank": (_i, [_i]),
     "ffm_launch_count": (C.c_longlong, [_i]),
     "ffm_profile_enable": (_i, [_i]),
     "ffm_profile_read": (_i, [_vp, _vp, _i]),

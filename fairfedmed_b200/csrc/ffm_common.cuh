@@ -282,6 +282,17 @@ __device__ __forceinline__ uint64_t umma_desc_sw32(uint32_t smem_addr) {
   return d;
 }
 
+//   SW64 : rows of  64 B, 8-row swizzle atom =  512 B (SBO); tile base 512-B aligned.
+__device__ __forceinline__ uint64_t umma_desc_sw64(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((smem_addr & 0x3FFFFu) >> 4);
+  d |= static_cast<uint64_t>(1) << 16;
+  d |= static_cast<uint64_t>(512u >> 4) << 32;
+  d |= static_cast<uint64_t>(1) << 46;
+  d |= static_cast<uint64_t>(4) << 61;            // SWIZZLE_64B
+  return d;
+}
+
 // Instruction descriptor: bf16 A/B (K-major), fp32 accumulate, dense.
 __host__ __device__ constexpr uint32_t umma_idesc_bf16(int m, int n) {
   return (1u << 4)                       // D format = F32

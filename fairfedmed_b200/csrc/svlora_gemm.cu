@@ -97,34 +97,41 @@ constexpr int BM = 128;             // rows of X per tile      (UMMA M, one TMEM
 constexpr int BN = 192;             // rows of Wmat per tile   (output columns)
 constexpr int BK = 64;              // k-slice per stage = one 128-byte swizzle row of bf16
 constexpr int UMMA_K = 16;
-constexpr int UMMA_N_MAIN = BN + RP;  // 208: [D | H] in one instruction
-constexpr int STAGES = 4;
-constexpr int ACC_COLS = 256;       // TMEM columns per accumulator stage (208 used)
+constexpr int ACC_COLS = 256;       // TMEM columns per accumulator stage (BN + padded rank used)
 constexpr int TMEM_COLS = 512;
 
 constexpr int X_TILE_BYTES = BM * BK * 2;   // 16384
 constexpr int W_TILE_BYTES = BN * BK * 2;   // 24576
-constexpr int A_TILE_BYTES = RP * BK * 2;   //  2048
-constexpr int STAGE_BYTES = X_TILE_BYTES + W_TILE_BYTES + A_TILE_BYTES;  // 43008 (1024-multiple)
 constexpr int OUT_STAGING_BYTES = 8 * 2 * EPI_PIECE_BYTES;  // 8 epilogue warps x 2 buffers x 2 KB = 32768
-constexpr int Z_TILE_BYTES = BM * RP * 2;           //  4096
-constexpr int BS_TILE_BYTES = BN * RP * 2;          //  6144
 constexpr int BIAS_BYTES = 8 * (BN / 2) * 4;          //  3072: per epilogue warp, the bias of its BN/2 columns
 
-constexpr int OFF_STAGES = 0;
-constexpr int OFF_OUT = OFF_STAGES + STAGES * STAGE_BYTES;
-constexpr int OFF_Z = OFF_OUT + OUT_STAGING_BYTES;
-constexpr int OFF_BS = OFF_Z + 2 * Z_TILE_BYTES;
-constexpr int OFF_BIAS = OFF_BS + 2 * BS_TILE_BYTES;
-constexpr int OFF_BAR = OFF_BIAS + BIAS_BYTES;
-constexpr int NUM_BARS = 2 * STAGES + 5 * 2;
-constexpr int SMEM_USED = OFF_BAR + NUM_BARS * 8 + 16;
-constexpr int SMEM_BYTES = SMEM_USED + 1024;  // slack for manual 1024-B alignment
-
-static_assert(STAGE_BYTES % 1024 == 0, "stage must keep 1024-B alignment of SW128 tiles");
+// Everything that depends on the padded adapter rank R (16: ViT recipes r <= 16; 32: the RN50 recipe r = 32).
+// R = 16: Aside rides as 16 extra accumulator columns (UMMA N = 208), Z / Bside are SW32 tiles, 4-stage ring.
+// R = 32: UMMA N = 224, Z / Bside are SW64 tiles, the fix-up is two K = 16 UMMAs, 3-stage ring (smem).
+template <int R>
+struct GemmCfg {
+  static_assert(R == 16 || R == 32, "padded adapter rank must be 16 or 32");
+  static constexpr int UMMA_N_MAIN = BN + R;                 // [D | H] in one instruction
+  static constexpr int STAGES = (R == 16) ? 4 : 3;
+  static constexpr int A_TILE_BYTES = R * BK * 2;            // 2048 / 4096
+  static constexpr int STAGE_BYTES = X_TILE_BYTES + W_TILE_BYTES + A_TILE_BYTES;   // 43008 / 45056 (1024-multiples)
+  static constexpr int Z_TILE_BYTES = BM * R * 2;            // 4096 / 8192
+  static constexpr int BS_TILE_BYTES = BN * R * 2;           // 6144 / 12288
+  static constexpr int OFF_STAGES = 0;
+  static constexpr int OFF_OUT = OFF_STAGES + STAGES * STAGE_BYTES;
+  static constexpr int OFF_Z = OFF_OUT + OUT_STAGING_BYTES;
+  static constexpr int OFF_BS = OFF_Z + 2 * Z_TILE_BYTES;
+  static constexpr int OFF_BIAS = OFF_BS + 2 * BS_TILE_BYTES;
+  static constexpr int OFF_BAR = OFF_BIAS + BIAS_BYTES;
+  static constexpr int NUM_BARS = 2 * STAGES + 5 * 2;
+  static constexpr int SMEM_USED = OFF_BAR + NUM_BARS * 8 + 16;
+  static constexpr int SMEM_BYTES = SMEM_USED + 1024;        // slack for manual 1024-B alignment
+  static_assert(STAGE_BYTES % 1024 == 0, "stage must keep 1024-B alignment of SW128 tiles");
+  static_assert(OFF_OUT % 1024 == 0 && OFF_Z % 1024 == 0 && OFF_BS % 1024 == 0, "tile alignment");
+  static_assert(SMEM_BYTES <= 232448, "exceeds 227 KB of shared memory per CTA");
+  static_assert(UMMA_N_MAIN <= ACC_COLS && UMMA_N_MAIN % 16 == 0, "accumulator stage");
+};
 static_assert((X_TILE_BYTES + W_TILE_BYTES) % 1024 == 0, "Aside tile must start on a swizzle atom");
-static_assert(OFF_OUT % 1024 == 0 && OFF_Z % 1024 == 0 && OFF_BS % 1024 == 0, "tile alignment");
-static_assert(SMEM_BYTES <= 232448, "exceeds 227 KB of shared memory per CTA");
 static_assert(BN % (2 * EPI_PIECE_COLS) == 0, "epilogue pieces");
 
 constexpr int NUM_THREADS = 384;   // 4 control warps (TMA, MMA, TMEM alloc, spare) + 8 epilogue warps
@@ -132,12 +139,17 @@ constexpr int EPI_THREADS = 256;
 constexpr int Z_THREADS = 128;     // epilogue threads that write the Z tile (one per tile row)
 
 
-template <int ACT>
+template <int ACT, int R>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 svlora_gemm_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_w,
                    const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b,
                    const __grid_constant__ CUtensorMap tm_y, const __grid_constant__ CUtensorMap tm_y2,
                    const GemmParams p) {
+  using C = GemmCfg<R>;
+  constexpr int STAGES = C::STAGES, STAGE_BYTES = C::STAGE_BYTES, Z_TILE_BYTES = C::Z_TILE_BYTES;
+  constexpr int BS_TILE_BYTES = C::BS_TILE_BYTES, NUM_BARS = C::NUM_BARS, UMMA_N_MAIN = C::UMMA_N_MAIN;
+  constexpr int OFF_STAGES = C::OFF_STAGES, OFF_OUT = C::OFF_OUT, OFF_Z = C::OFF_Z, OFF_BS = C::OFF_BS;
+  constexpr int OFF_BIAS = C::OFF_BIAS, OFF_BAR = C::OFF_BAR;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
 
@@ -221,13 +233,18 @@ svlora_gemm_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_consta
     uint32_t pend_phase = 0;
 
     auto fixup = [&](int s, uint32_t ph) {
-      // D[s] += Z[s] (128 x 16) · Bside[s]^T (16 x 192)
+      // D[s] += Z[s] (128 x R) · Bside[s]^T (R x 192)
       mbar_wait_uniform(&bs_full[s], ph);
       tc_fence_after();
       if (elect_one()) {
-        const uint64_t zd = umma_desc_sw32(smem_u32(smem + OFF_Z + s * Z_TILE_BYTES));
-        const uint64_t bd = umma_desc_sw32(smem_u32(smem + OFF_BS + s * BS_TILE_BYTES));
-        umma_bf16(tmem_base + s * ACC_COLS, zd, bd, idesc_fix, 1u);
+        const uint32_t za = smem_u32(smem + OFF_Z + s * Z_TILE_BYTES), ba = smem_u32(smem + OFF_BS + s * BS_TILE_BYTES);
+        if constexpr (R == 16) {
+          umma_bf16(tmem_base + s * ACC_COLS, umma_desc_sw32(za), umma_desc_sw32(ba), idesc_fix, 1u);
+        } else {   // rank 32: rows of 64 B (SW64), two K = 16 steps 32 B apart inside the swizzle row
+          const uint64_t zd = umma_desc_sw64(za), bd = umma_desc_sw64(ba);
+          umma_bf16(tmem_base + s * ACC_COLS, zd, bd, idesc_fix, 1u);
+          umma_bf16(tmem_base + s * ACC_COLS, zd + 2u, bd + 2u, idesc_fix, 1u);
+        }
         umma_commit(&d_full[s]);
       }
       __syncwarp();
@@ -322,49 +339,53 @@ svlora_gemm_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_consta
         // this row's scaled singular values first: their global-load latency hides behind the wait for H
         const int grow_c = grow < p.T ? grow : (p.T - 1);
         const int sample = ((grow_c / p.row_div) % p.b_prime) / p.num_slices;
-        const float4* sr = reinterpret_cast<const float4*>(p.s_rows + static_cast<size_t>(sample) * RP);
-        float4 svv[4];
+        const float4* sr = reinterpret_cast<const float4*>(p.s_rows + static_cast<size_t>(sample) * R);
+        float4 svv[R / 4];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) svv[j] = __ldg(sr + j);
+        for (int j = 0; j < R / 4; ++j) svv[j] = __ldg(sr + j);
         mbar_wait(&h_full[s], aph, 600 + s);
         tc_fence_after();
-        uint32_t hv[16];
-        tmem_ld16(acc + BN, hv);
+        uint32_t hv[R];
+        if constexpr (R == 16) tmem_ld16(acc + BN, hv);
+        else tmem_ld32(acc + BN, hv);
         tmem_ld_wait();
-        float zf[16];
+        float zf[R];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
+        for (int j = 0; j < R / 4; ++j) {
           const float4 sv = svv[j];
           zf[4 * j + 0] = __uint_as_float(hv[4 * j + 0]) * sv.x;
           zf[4 * j + 1] = __uint_as_float(hv[4 * j + 1]) * sv.y;
           zf[4 * j + 2] = __uint_as_float(hv[4 * j + 2]) * sv.z;
           zf[4 * j + 3] = __uint_as_float(hv[4 * j + 3]) * sv.w;
         }
-        // row r at r*32 B, 16-B chunk c stored at chunk (c ^ ((r>>2)&1))
-        uint8_t* zrow = smem + OFF_Z + s * Z_TILE_BYTES + row * 32u;
-        const uint32_t sw = (row >> 2) & 1u;
-        uint4 c0, c1;
-        c0.x = pack_bf16x2(zf[0], zf[1]);   c0.y = pack_bf16x2(zf[2], zf[3]);
-        c0.z = pack_bf16x2(zf[4], zf[5]);   c0.w = pack_bf16x2(zf[6], zf[7]);
-        c1.x = pack_bf16x2(zf[8], zf[9]);   c1.y = pack_bf16x2(zf[10], zf[11]);
-        c1.z = pack_bf16x2(zf[12], zf[13]); c1.w = pack_bf16x2(zf[14], zf[15]);
-        *reinterpret_cast<uint4*>(zrow + ((0u ^ sw) << 4)) = c0;
-        *reinterpret_cast<uint4*>(zrow + ((1u ^ sw) << 4)) = c1;
+        // K-major A operand of the fix-up UMMA: row r at r * (2R) bytes; R = 16: SW32 (16-B chunk c at c ^ ((r>>2)&1)),
+        // R = 32: SW64 (chunk c at c ^ ((r>>1)&3))
+        uint8_t* zrow = smem + OFF_Z + s * Z_TILE_BYTES + row * (2u * R);
+        const uint32_t sw = (R == 16) ? ((row >> 2) & 1u) : ((row >> 1) & 3u);
+        uint4 zc[R / 8];
+#pragma unroll
+        for (int c = 0; c < R / 8; ++c) {
+          zc[c].x = pack_bf16x2(zf[8 * c + 0], zf[8 * c + 1]);
+          zc[c].y = pack_bf16x2(zf[8 * c + 2], zf[8 * c + 3]);
+          zc[c].z = pack_bf16x2(zf[8 * c + 4], zf[8 * c + 5]);
+          zc[c].w = pack_bf16x2(zf[8 * c + 6], zf[8 * c + 7]);
+          *reinterpret_cast<uint4*>(zrow + ((static_cast<uint32_t>(c) ^ sw) << 4)) = zc[c];
+        }
         fence_proxy_async_smem();
         mbar_arrive(&z_full[s]);
         // side outputs to HBM after the signal: they are off the tile's critical chain
         if (n_blk == 0 && grow < p.T) {
           if (p.h_out != nullptr) {
-            float4* ho = reinterpret_cast<float4*>(p.h_out + static_cast<size_t>(grow) * RP);
+            float4* ho = reinterpret_cast<float4*>(p.h_out + static_cast<size_t>(grow) * R);
 #pragma unroll
-            for (int j = 0; j < 4; ++j)
+            for (int j = 0; j < R / 4; ++j)
               ho[j] = make_float4(__uint_as_float(hv[4 * j]), __uint_as_float(hv[4 * j + 1]),
                                   __uint_as_float(hv[4 * j + 2]), __uint_as_float(hv[4 * j + 3]));
           }
           if (p.z_out != nullptr) {
-            uint4* zo = reinterpret_cast<uint4*>(p.z_out + static_cast<size_t>(grow) * RP);
-            zo[0] = c0;
-            zo[1] = c1;
+            uint4* zo = reinterpret_cast<uint4*>(p.z_out + static_cast<size_t>(grow) * R);
+#pragma unroll
+            for (int c = 0; c < R / 8; ++c) zo[c] = zc[c];
           }
         }
       }
@@ -411,14 +432,14 @@ svlora_gemm_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_consta
 // in one launch (the backward pass reuses the forward's tiles: A and B do not change in between).
 //   forward  (contraction over K): a_fwd[RP, K] = A^T (A is [K, r]),  b_fwd[N, RP] = B^T (B is [r, N])
 //   backward (contraction over N): a_bwd[RP, N] = B,                  b_bwd[K, RP] = A
-//   s_rows[nS, RP] = scaling * s_eff[nS, r], zero padded
+//   s_rows[nS, RP] = scaling * s_eff[nS, r], zero padded          (RP = padded rank, 16 or 32, a kernel argument)
 // Any output pointer may be null (skipped).
 // ----------------------------------------------------------------------------------------------
 __global__ void svlora_prep_kernel(const float* __restrict__ A, const float* __restrict__ B,
                                    const float* __restrict__ s_eff, __nv_bfloat16* __restrict__ a_fwd,
                                    __nv_bfloat16* __restrict__ b_fwd, __nv_bfloat16* __restrict__ a_bwd,
                                    __nv_bfloat16* __restrict__ b_bwd, float* __restrict__ s_rows, int K, int N, int r,
-                                   int nS, float scaling) {
+                                   int RP, int nS, float scaling) {
   const int tid = blockIdx.x * blockDim.x + threadIdx.x;
   const int nthreads = gridDim.x * blockDim.x;
   if (a_fwd != nullptr) {
@@ -520,32 +541,78 @@ int gemm_debug_mask() {
   return v;
 }
 
+template <int R>
+static int launch_single(const GemmOperands& o, const GemmParams& p0, cudaStream_t stream) {
+  using C = GemmCfg<R>;
+  CUtensorMap tm_x, tm_w, tm_a, tm_b, tm_y, tm_y2;
+  int rc;
+  if ((rc = make_map_bf16(&tm_x, o.x, o.T, o.K, BM, BK, CU_TENSOR_MAP_SWIZZLE_128B, true))) return rc;
+  if ((rc = make_map_bf16(&tm_w, o.wmat, o.N, o.K, BN, BK, CU_TENSOR_MAP_SWIZZLE_128B, true))) return rc;
+  if ((rc = make_map_bf16(&tm_a, o.a_side, R, o.K, R, BK, CU_TENSOR_MAP_SWIZZLE_128B, true))) return rc;
+  if ((rc = make_map_bf16(&tm_b, o.b_side, o.N, R, BN, R, R == 16 ? CU_TENSOR_MAP_SWIZZLE_32B : CU_TENSOR_MAP_SWIZZLE_64B,
+                          false)))
+    return rc;
+  if ((rc = make_map_bf16(&tm_y, o.out, o.T, o.N, 32, EPI_PIECE_COLS, CU_TENSOR_MAP_SWIZZLE_64B, false))) return rc;
+  const bool has_pre = p0.has_pre != 0;
+  if ((rc = make_map_bf16(&tm_y2, has_pre ? o.out_pre : o.out, o.T, o.N, 32, EPI_PIECE_COLS, CU_TENSOR_MAP_SWIZZLE_64B,
+                          false)))
+    return rc;
+  GemmParams p = p0;
+  p.m_tiles = (o.T + BM - 1) / BM;
+  p.n_tiles = (o.N + BN - 1) / BN;
+  p.k_blocks = (o.K + BK - 1) / BK;
+
+  // dynamic-smem opt-in of the three epilogue variants; the attribute is per device
+  {
+    static thread_local int attr_dev = -1;
+    int dev = 0;
+    FFM_CHECK_CUDA(cudaGetDevice(&dev));
+    if (dev != attr_dev) {
+      FFM_CHECK_CUDA(cudaFuncSetAttribute(svlora_gemm_kernel<ACT_NONE, R>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          C::SMEM_BYTES));
+      FFM_CHECK_CUDA(cudaFuncSetAttribute(svlora_gemm_kernel<ACT_QUICKGELU, R>,
+                                          cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
+      FFM_CHECK_CUDA(cudaFuncSetAttribute(svlora_gemm_kernel<ACT_QUICKGELU_GRAD, R>,
+                                          cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
+      attr_dev = dev;
+    }
+  }
+  const int tiles = p.m_tiles * p.n_tiles;
+  const int grid = tiles < num_sms() ? tiles : num_sms();
+  GemmProfileScope prof;
+  if ((rc = gemm_profile_begin(&prof, stream))) return rc;
+  switch (p.act) {
+    case ACT_QUICKGELU:
+      svlora_gemm_kernel<ACT_QUICKGELU, R><<<grid, NUM_THREADS, C::SMEM_BYTES, stream>>>(tm_x, tm_w, tm_a, tm_b, tm_y,
+                                                                                         tm_y2, p);
+      break;
+    case ACT_QUICKGELU_GRAD:
+      svlora_gemm_kernel<ACT_QUICKGELU_GRAD, R><<<grid, NUM_THREADS, C::SMEM_BYTES, stream>>>(tm_x, tm_w, tm_a, tm_b,
+                                                                                              tm_y, tm_y2, p);
+      break;
+    default:
+      svlora_gemm_kernel<ACT_NONE, R><<<grid, NUM_THREADS, C::SMEM_BYTES, stream>>>(tm_x, tm_w, tm_a, tm_b, tm_y, tm_y2,
+                                                                                    p);
+  }
+  FFM_CHECK_CUDA(cudaGetLastError());
+  count_launch();
+  return gemm_profile_end(&prof, o.T, o.K, o.N, stream);
+}
+
 static int launch_svlora_gemm(const GemmOperands& o, cudaStream_t stream) {
   FFM_CHECK_ARG(o.T > 0 && o.K > 0 && o.N > 0, "svlora gemm: empty problem T=%d K=%d N=%d", o.T, o.K, o.N);
   FFM_CHECK_ARG(o.K % 8 == 0 && o.N % 8 == 0, "svlora gemm: K (%d) and N (%d) must be multiples of 8 (TMA 16-B strides)",
                 o.K, o.N);
   FFM_CHECK_ARG(o.b_prime > 0 && o.num_slices > 0 && o.row_div > 0, "svlora gemm: b_prime/num_slices/row_div must be positive");
   FFM_CHECK_ARG(o.act != ACT_QUICKGELU_GRAD || o.aux != nullptr, "svlora gemm: ACT_QUICKGELU_GRAD needs aux");
+  FFM_CHECK_ARG(o.rp == RP || o.rp == RP_MAX, "svlora gemm: padded rank must be %d or %d", RP, RP_MAX);
   const uintptr_t align_or = reinterpret_cast<uintptr_t>(o.x) | reinterpret_cast<uintptr_t>(o.wmat) |
                              reinterpret_cast<uintptr_t>(o.a_side) | reinterpret_cast<uintptr_t>(o.b_side) |
                              reinterpret_cast<uintptr_t>(o.out) | reinterpret_cast<uintptr_t>(o.out_pre) |
                              reinterpret_cast<uintptr_t>(o.s_rows) | reinterpret_cast<uintptr_t>(o.h_out) |
-                             reinterpret_cast<uintptr_t>(o.z_out) |
-                             reinterpret_cast<uintptr_t>(o.aux);
+                             reinterpret_cast<uintptr_t>(o.z_out) | reinterpret_cast<uintptr_t>(o.aux);
   FFM_CHECK_ARG((align_or & 15u) == 0, "svlora gemm: all device pointers must be 16-byte aligned");
-  if (use_pair_kernel(o.K)) return launch_svlora_gemm_pair(o, stream);
-
-  CUtensorMap tm_x, tm_w, tm_a, tm_b, tm_y, tm_y2;
-  int rc;
-  if ((rc = make_map_bf16(&tm_x, o.x, o.T, o.K, BM, BK, CU_TENSOR_MAP_SWIZZLE_128B, true))) return rc;
-  if ((rc = make_map_bf16(&tm_w, o.wmat, o.N, o.K, BN, BK, CU_TENSOR_MAP_SWIZZLE_128B, true))) return rc;
-  if ((rc = make_map_bf16(&tm_a, o.a_side, RP, o.K, RP, BK, CU_TENSOR_MAP_SWIZZLE_128B, true))) return rc;
-  if ((rc = make_map_bf16(&tm_b, o.b_side, o.N, RP, BN, RP, CU_TENSOR_MAP_SWIZZLE_32B, false))) return rc;
-  if ((rc = make_map_bf16(&tm_y, o.out, o.T, o.N, 32, EPI_PIECE_COLS, CU_TENSOR_MAP_SWIZZLE_64B, false))) return rc;
-  const bool has_pre = (o.act == ACT_QUICKGELU && o.out_pre != nullptr);
-  if ((rc = make_map_bf16(&tm_y2, has_pre ? o.out_pre : o.out, o.T, o.N, 32, EPI_PIECE_COLS, CU_TENSOR_MAP_SWIZZLE_64B,
-                          false)))
-    return rc;
+  if (o.rp == RP && use_pair_kernel(o.K)) return launch_svlora_gemm_pair(o, stream);
 
   GemmParams p;
   p.bias = o.bias;
@@ -554,48 +621,13 @@ static int launch_svlora_gemm(const GemmOperands& o, cudaStream_t stream) {
   p.z_out = reinterpret_cast<__nv_bfloat16*>(o.z_out);
   p.aux = reinterpret_cast<const __nv_bfloat16*>(o.aux);
   p.T = o.T; p.K = o.K; p.N = o.N;
+  p.rp = o.rp;
   p.b_prime = o.b_prime; p.num_slices = o.num_slices; p.row_div = o.row_div;
   p.act = o.act;
-  p.has_pre = has_pre ? 1 : 0;
-  p.m_tiles = (o.T + BM - 1) / BM;
-  p.n_tiles = (o.N + BN - 1) / BN;
-  p.k_blocks = (o.K + BK - 1) / BK;
+  p.has_pre = (o.act == ACT_QUICKGELU && o.out_pre != nullptr) ? 1 : 0;
+  p.m_tiles = p.n_tiles = p.k_blocks = 0;
   p.dbg = gemm_debug_mask();
-
-  // dynamic-smem opt-in of the three epilogue variants; the attribute is per device
-  {
-    static thread_local int attr_dev = -1;
-    int dev = 0;
-    FFM_CHECK_CUDA(cudaGetDevice(&dev));
-    if (dev != attr_dev) {
-      FFM_CHECK_CUDA(cudaFuncSetAttribute(svlora_gemm_kernel<ACT_NONE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                          SMEM_BYTES));
-      FFM_CHECK_CUDA(cudaFuncSetAttribute(svlora_gemm_kernel<ACT_QUICKGELU>,
-                                          cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-      FFM_CHECK_CUDA(cudaFuncSetAttribute(svlora_gemm_kernel<ACT_QUICKGELU_GRAD>,
-                                          cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-      attr_dev = dev;
-    }
-  }
-
-  const int tiles = p.m_tiles * p.n_tiles;
-  const int grid = tiles < num_sms() ? tiles : num_sms();
-  GemmProfileScope prof;
-  if ((rc = gemm_profile_begin(&prof, stream))) return rc;
-  switch (p.act) {
-    case ACT_QUICKGELU:
-      svlora_gemm_kernel<ACT_QUICKGELU><<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(tm_x, tm_w, tm_a, tm_b, tm_y, tm_y2, p);
-      break;
-    case ACT_QUICKGELU_GRAD:
-      svlora_gemm_kernel<ACT_QUICKGELU_GRAD><<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(tm_x, tm_w, tm_a, tm_b, tm_y,
-                                                                                        tm_y2, p);
-      break;
-    default:
-      svlora_gemm_kernel<ACT_NONE><<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(tm_x, tm_w, tm_a, tm_b, tm_y, tm_y2, p);
-  }
-  FFM_CHECK_CUDA(cudaGetLastError());
-  count_launch();
-  return gemm_profile_end(&prof, o.T, o.K, o.N, stream);
+  return o.rp == RP ? launch_single<RP>(o, p, stream) : launch_single<RP_MAX>(o, p, stream);
 }
 
 // Adapter tiles prepared by svlora_prep_kernel (all offsets 256-B aligned).  The forward workspace holds the tiles of
@@ -610,28 +642,31 @@ struct SvloraTiles {
 
 static size_t align256(size_t v) { return (v + 255) & ~size_t(255); }
 
+// sized for the largest padded rank so the workspace queries need no rank argument
 static size_t svlora_tiles_bytes(int K, int N, int nS) {
-  return 2 * (align256(static_cast<size_t>(RP) * K * 2) + align256(static_cast<size_t>(N) * RP * 2)) +
-         align256(static_cast<size_t>(nS) * RP * 4);
+  return 2 * (align256(static_cast<size_t>(RP_MAX) * K * 2) + align256(static_cast<size_t>(N) * RP_MAX * 2)) +
+         align256(static_cast<size_t>(nS) * RP_MAX * 4);
 }
 
 static void carve_tiles(SvloraTiles* w, void* ws, int K, int N, int nS) {
   uint8_t* p = static_cast<uint8_t*>(ws);
   w->a_fwd = reinterpret_cast<__nv_bfloat16*>(p);
-  p += align256(static_cast<size_t>(RP) * K * 2);
+  p += align256(static_cast<size_t>(RP_MAX) * K * 2);
   w->b_fwd = reinterpret_cast<__nv_bfloat16*>(p);
-  p += align256(static_cast<size_t>(N) * RP * 2);
+  p += align256(static_cast<size_t>(N) * RP_MAX * 2);
   w->s_rows = reinterpret_cast<float*>(p);
-  p += align256(static_cast<size_t>(nS) * RP * 4);
+  p += align256(static_cast<size_t>(nS) * RP_MAX * 4);
   w->a_bwd = reinterpret_cast<__nv_bfloat16*>(p);
-  p += align256(static_cast<size_t>(RP) * N * 2);
+  p += align256(static_cast<size_t>(RP_MAX) * N * 2);
   w->b_bwd = reinterpret_cast<__nv_bfloat16*>(p);
 }
+
+static int padded_rank(int r) { return r <= RP ? RP : RP_MAX; }
 
 // implemented in svlora_small.cu
 int launch_svlora_bwd_small(const __nv_bfloat16* x, const __nv_bfloat16* dy, const float* h, const float* dzu,
                             const __nv_bfloat16* z, const __nv_bfloat16* dh, float* dA, float* dB, float* ds_eff,
-                            void* scratch, size_t scratch_bytes, int T, int K, int N, int r, int nS, int b_prime,
+                            void* scratch, size_t scratch_bytes, int T, int K, int N, int r, int rp, int nS, int b_prime,
                             int num_slices, int row_div, float scaling, cudaStream_t stream);
 size_t svlora_bwd_small_scratch_bytes(int T, int K, int N);
 
@@ -645,7 +680,9 @@ const char* ffm_last_error(void) { return g_last_error; }
 
 int ffm_version(void) { return 101; }
 
-int ffm_svlora_max_rank(void) { return RP; }
+int ffm_svlora_max_rank(void) { return RP_MAX; }
+
+int ffm_svlora_padded_rank(int r) { return (r >= 1 && r <= RP_MAX) ? padded_rank(r) : 0; }
 
 long long ffm_launch_count(int reset) {
   return reset ? g_launches.exchange(0) : g_launches.load();
@@ -690,8 +727,8 @@ size_t ffm_svlora_fwd_workspace_bytes(int T, int K, int N, int n_samples) {
 
 size_t ffm_svlora_bwd_workspace_bytes(int T, int K, int N, int n_samples) {
   // own tiles (only used when the forward workspace is not handed over) + dzu f32 [T,16] + dh bf16 [T,16] + partials
-  return svlora_tiles_bytes(K, N, n_samples) + align256(static_cast<size_t>(T) * RP * 4) +
-         align256(static_cast<size_t>(T) * RP * 2) + svlora_bwd_small_scratch_bytes(T, K, N);
+  return svlora_tiles_bytes(K, N, n_samples) + align256(static_cast<size_t>(T) * RP_MAX * 4) +
+         align256(static_cast<size_t>(T) * RP_MAX * 2) + svlora_bwd_small_scratch_bytes(T, K, N);
 }
 
 int ffm_svlora_fwd(const void* x, const void* w, const float* bias, const float* lora_a, const float* lora_b,
@@ -700,7 +737,7 @@ int ffm_svlora_fwd(const void* x, const void* w, const float* bias, const float*
                    int row_div, float scaling, int act, cudaStream_t stream) {
   FFM_CHECK_ARG(x && w && lora_a && lora_b && s_eff && y && workspace, "ffm_svlora_fwd: null pointer argument");
   FFM_CHECK_ARG(row_div >= 1, "ffm_svlora_fwd: row_div must be >= 1");
-  FFM_CHECK_ARG(r >= 1 && r <= RP, "ffm_svlora_fwd: rank %d not in [1, %d]", r, RP);
+  FFM_CHECK_ARG(r >= 1 && r <= RP_MAX, "ffm_svlora_fwd: rank %d not in [1, %d]", r, RP_MAX);
   FFM_CHECK_ARG(n_samples >= 1, "ffm_svlora_fwd: n_samples must be >= 1");
   FFM_CHECK_ARG(b_prime >= 1 && num_slices >= 1 && (b_prime - 1) / num_slices < n_samples,
                 "ffm_svlora_fwd: sample mapping (b_prime=%d, num_slices=%d) exceeds n_samples=%d", b_prime,
@@ -710,14 +747,16 @@ int ffm_svlora_fwd(const void* x, const void* w, const float* bias, const float*
                 "ffm_svlora_fwd: workspace too small");
   SvloraTiles ws;
   carve_tiles(&ws, workspace, K, N, n_samples);
+  const int rp = padded_rank(r);
   svlora_prep_kernel<<<96, 256, 0, stream>>>(lora_a, lora_b, s_eff, ws.a_fwd, ws.b_fwd, ws.a_bwd, ws.b_bwd, ws.s_rows,
-                                             K, N, r, n_samples, scaling);
+                                             K, N, r, rp, n_samples, scaling);
   FFM_CHECK_CUDA(cudaGetLastError());
   count_launch();
   GemmOperands o;
   o.x = x; o.wmat = w; o.a_side = ws.a_fwd; o.b_side = ws.b_fwd; o.s_rows = ws.s_rows; o.bias = bias;
   o.out = y; o.out_pre = y_dact; o.h_out = h_out; o.z_out = z_out; o.aux = nullptr;
   o.T = T; o.K = K; o.N = N; o.b_prime = b_prime; o.num_slices = num_slices; o.row_div = row_div; o.act = act;
+  o.rp = rp;
   return launch_svlora_gemm(o, stream);
 }
 
@@ -729,12 +768,13 @@ int ffm_svlora_bwd(const void* dy, const void* x, const void* w_t, const float* 
   FFM_CHECK_ARG(dy && x && w_t && lora_a && lora_b && s_eff && h && z && dx && d_lora_a && d_lora_b && d_s_eff &&
                     workspace,
                 "ffm_svlora_bwd: null pointer argument");
-  FFM_CHECK_ARG(r >= 1 && r <= RP, "ffm_svlora_bwd: rank %d not in [1, %d]", r, RP);
+  FFM_CHECK_ARG(r >= 1 && r <= RP_MAX, "ffm_svlora_bwd: rank %d not in [1, %d]", r, RP_MAX);
   FFM_CHECK_ARG(b_prime >= 1 && num_slices >= 1 && row_div >= 1 && (b_prime - 1) / num_slices < n_samples,
                 "ffm_svlora_bwd: sample mapping exceeds n_samples");
   FFM_CHECK_ARG(workspace_bytes >= ffm_svlora_bwd_workspace_bytes(T, K, N, n_samples),
                 "ffm_svlora_bwd: workspace too small");
   SvloraTiles ws;
+  const int rp = padded_rank(r);
   uint8_t* rest = static_cast<uint8_t*>(workspace) + svlora_tiles_bytes(K, N, n_samples);
   if (fwd_workspace != nullptr) {
     // tiles prepared by ffm_svlora_fwd of the same step (A, B, s_eff unchanged since): no prep launch
@@ -742,14 +782,14 @@ int ffm_svlora_bwd(const void* dy, const void* x, const void* w_t, const float* 
   } else {
     carve_tiles(&ws, workspace, K, N, n_samples);
     svlora_prep_kernel<<<96, 256, 0, stream>>>(lora_a, lora_b, s_eff, nullptr, nullptr, ws.a_bwd, ws.b_bwd, ws.s_rows,
-                                               K, N, r, n_samples, scaling);
+                                               K, N, r, rp, n_samples, scaling);
     FFM_CHECK_CUDA(cudaGetLastError());
     count_launch();
   }
   float* dzu = reinterpret_cast<float*>(rest);
-  rest += align256(static_cast<size_t>(T) * RP * 4);
+  rest += align256(static_cast<size_t>(T) * RP_MAX * 4);
   __nv_bfloat16* dh = reinterpret_cast<__nv_bfloat16*>(rest);
-  rest += align256(static_cast<size_t>(T) * RP * 2);
+  rest += align256(static_cast<size_t>(T) * RP_MAX * 2);
   const size_t scratch_bytes = workspace_bytes - static_cast<size_t>(rest - static_cast<uint8_t*>(workspace));
   // backward: contraction over N.  Aside = B ([r, N]), Bside = A ([K, r]); side outputs dzu = dy·B^T (f32) and
   // dh = bf16(dzu ⊙ s_rows), the operand of dA.
@@ -757,12 +797,13 @@ int ffm_svlora_bwd(const void* dy, const void* x, const void* w_t, const float* 
   o.x = dy; o.wmat = w_t; o.a_side = ws.a_bwd; o.b_side = ws.b_bwd; o.s_rows = ws.s_rows; o.bias = nullptr;
   o.out = dx; o.out_pre = nullptr; o.h_out = dzu; o.z_out = dh; o.aux = gelu_dact;
   o.T = T; o.K = N; o.N = K; o.b_prime = b_prime; o.num_slices = num_slices; o.row_div = row_div;
+  o.rp = rp;
   o.act = gelu_dact != nullptr ? ACT_QUICKGELU_GRAD : ACT_NONE;
   int rc = launch_svlora_gemm(o, stream);
   if (rc != FFM_OK) return rc;
   return launch_svlora_bwd_small(reinterpret_cast<const __nv_bfloat16*>(x), reinterpret_cast<const __nv_bfloat16*>(dy),
                                  h, dzu, reinterpret_cast<const __nv_bfloat16*>(z), dh, d_lora_a, d_lora_b, d_s_eff,
-                                 rest, scratch_bytes, T, K, N, r, n_samples, b_prime, num_slices, row_div, scaling,
+                                 rest, scratch_bytes, T, K, N, r, rp, n_samples, b_prime, num_slices, row_div, scaling,
                                  stream);
 }
 

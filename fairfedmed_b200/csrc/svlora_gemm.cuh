@@ -5,7 +5,8 @@
 
 namespace ffm {
 
-constexpr int RP = 16;              // padded adapter rank
+constexpr int RP = 16;              // padded adapter rank of the ViT recipes (r <= 16); the pair build is RP-only
+constexpr int RP_MAX = 32;          // largest padded rank (RN50 recipe r = 32): single-CTA build only
 enum : int { ACT_NONE = 0, ACT_QUICKGELU = 1, ACT_QUICKGELU_GRAD = 2 };
 
 struct GemmParams {
@@ -15,6 +16,7 @@ struct GemmParams {
   __nv_bfloat16* z_out;         // [T, RP] bf16 or nullptr: Z = bf16(H ⊙ s_rows), the operand the adapter gradients need
   const __nv_bfloat16* aux;     // ACT_QUICKGELU_GRAD: QuickGELU'(u) saved by the forward [T, N]
   int T, K, N;
+  int rp;                       // padded adapter rank (16 or 32): row stride of s_rows / h_out / z_out
   int b_prime, num_slices;      // sample(t) = ((t / row_div) % b_prime) / num_slices
   int row_div;                  // 1: sequence-first rows [L, B', C] (reference); L: batch-first rows [B', L, C]
   int act;
@@ -28,9 +30,9 @@ int gemm_debug_mask();
 struct GemmOperands {
   const void* x;        // [T, K] bf16
   const void* wmat;     // [N, K] bf16
-  const void* a_side;   // [RP, K] bf16
-  const void* b_side;   // [N, RP] bf16
-  const float* s_rows;  // [nS, RP]
+  const void* a_side;   // [rp, K] bf16
+  const void* b_side;   // [N, rp] bf16
+  const float* s_rows;  // [nS, rp]
   const float* bias;    // [N] or null
   void* out;            // [T, N] bf16
   void* out_pre;        // [T, N] bf16 or null (ACT_QUICKGELU only): receives QuickGELU'(u)
@@ -38,6 +40,7 @@ struct GemmOperands {
   void* z_out;          // [T, RP] bf16 or null
   const void* aux;      // [T, N] bf16 (ACT_QUICKGELU_GRAD)
   int T, K, N, b_prime, num_slices, row_div, act;
+  int rp;               // padded adapter rank: 16 or 32
 };
 
 // row-major bf16 matrix [rows, cols] (cols contiguous) -> 2-D tiled map with box [box_rows, box_cols]

@@ -386,6 +386,7 @@ int launch_svlora_gemm_pair(const GemmOperands& o, cudaStream_t stream) {
   p.z_out = reinterpret_cast<__nv_bfloat16*>(o.z_out);
   p.aux = reinterpret_cast<const __nv_bfloat16*>(o.aux);
   p.T = o.T; p.K = o.K; p.N = o.N;
+  p.rp = RP;
   p.b_prime = o.b_prime; p.num_slices = o.num_slices; p.row_div = o.row_div;
   p.act = o.act;
   p.has_pre = has_pre ? 1 : 0;

@@ -9,7 +9,7 @@
 
 namespace ffm {
 
-constexpr int RPS = 16;  // padded rank, must match svlora_gemm.cu
+constexpr int RPS_MAX = 32;  // largest padded rank (svlora_gemm.cuh RP_MAX); kernels take the actual one (16 or 32)
 
 // ----------------------------------------------------------------------------------------------
 // s_eff / dS
@@ -86,9 +86,11 @@ constexpr int CS_COLS = 128;             // columns per CTA
 constexpr int CS_ROWS = 64;              // rows per stage
 constexpr int CS_STAGES = 3;
 constexpr int CS_MSTRIDE = CS_COLS * 2 + 16;   // 272 B: rows 16 B apart mod 128 -> conflict-free ldmatrix
-constexpr int CS_VSTRIDE = 48;                 // 16 bf16 = 32 B padded to 48 B, same reason
-constexpr int CS_STAGE_BYTES = CS_ROWS * CS_MSTRIDE + CS_ROWS * CS_VSTRIDE;   // 20480
-constexpr int CS_SMEM_BYTES = CS_STAGES * CS_STAGE_BYTES;                      // 61440: three CTAs per SM
+template <int R> struct CsCfg {
+  static constexpr int VSTRIDE = R * 2 + 16;     // operand rows padded by 16 B -> conflict-free ldmatrix
+  static constexpr int STAGE_BYTES = CS_ROWS * CS_MSTRIDE + CS_ROWS * VSTRIDE;   // 20480 (R = 16) / 22528 (R = 32)
+  static constexpr int SMEM_BYTES = CS_STAGES * STAGE_BYTES;                      // 61440 / 67584: three CTAs per SM
+};
 
 __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem_dst)), "l"(gmem_src) : "memory");
@@ -110,11 +112,14 @@ __device__ __forceinline__ void mma_bf16_16816(float (&d)[4], const uint32_t (&a
       : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
 
+template <int R>
 __global__ void __launch_bounds__(CS_THREADS)
 adapter_grad_kernel(const __nv_bfloat16* __restrict__ Ma, const __nv_bfloat16* __restrict__ va,
                     float* __restrict__ partial_a, int Ca, int groups_a, const __nv_bfloat16* __restrict__ Mb,
                     const __nv_bfloat16* __restrict__ vb, float* __restrict__ partial_b, int Cb, int T,
                     int rows_per_chunk) {
+  constexpr int CS_VSTRIDE = CsCfg<R>::VSTRIDE, CS_STAGE_BYTES = CsCfg<R>::STAGE_BYTES;
+  constexpr int NT = R / 8;                // 8-rank n-tiles of the m16n8k16 MMA
   extern __shared__ __align__(16) uint8_t cs_smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const bool is_a = static_cast<int>(blockIdx.y) < groups_a;
@@ -127,7 +132,7 @@ adapter_grad_kernel(const __nv_bfloat16* __restrict__ Ma, const __nv_bfloat16* _
   const int t_end = min(T, t_begin + rows_per_chunk);
   const int n_stages = (t_end - t_begin + CS_ROWS - 1) / CS_ROWS;
 
-  // stage loader: M tile (16 B = 8 columns per request) and v tile (2 x 16 B per row), all cp.async
+  // stage loader: M tile (16 B = 8 columns per request) and v tile (R/8 x 16 B per row), all cp.async
   auto load_stage = [&](int st_idx, int buf) {
     uint8_t* mt = cs_smem + buf * CS_STAGE_BYTES;
     uint8_t* vt = mt + CS_ROWS * CS_MSTRIDE;
@@ -141,18 +146,18 @@ adapter_grad_kernel(const __nv_bfloat16* __restrict__ Ma, const __nv_bfloat16* _
       if (t < t_end && c < C) cp_async16(dst, M + static_cast<size_t>(t) * C + c);
       else *reinterpret_cast<uint4*>(dst) = make_uint4(0u, 0u, 0u, 0u);
     }
-    if (threadIdx.x < CS_ROWS * 2) {
-      const int rr = threadIdx.x >> 1, hf = threadIdx.x & 1;
+    if (threadIdx.x < CS_ROWS * NT) {
+      const int rr = threadIdx.x / NT, hf = threadIdx.x % NT;
       const int t = t0 + rr;
       uint8_t* dst = vt + rr * CS_VSTRIDE + hf * 16;
-      if (t < t_end) cp_async16(dst, v + static_cast<size_t>(t) * RPS + hf * 8);
+      if (t < t_end) cp_async16(dst, v + static_cast<size_t>(t) * R + hf * 8);
       else *reinterpret_cast<uint4*>(dst) = make_uint4(0u, 0u, 0u, 0u);
     }
   };
 
-  float acc[2][4];
+  float acc[NT][4];
 #pragma unroll
-  for (int n = 0; n < 2; ++n)
+  for (int n = 0; n < NT; ++n)
 #pragma unroll
     for (int e = 0; e < 4; ++e) acc[n][e] = 0.f;
 
@@ -179,11 +184,15 @@ adapter_grad_kernel(const __nv_bfloat16* __restrict__ Ma, const __nv_bfloat16* _
     const uint32_t vt = mt + CS_ROWS * CS_MSTRIDE;
 #pragma unroll
     for (int ks = 0; ks < CS_ROWS / 16; ++ks) {
-      uint32_t a[4], b[4];
+      uint32_t a[4];
       ldmatrix_x4_trans(mt + ks * 16 * CS_MSTRIDE + a_lane_off, a);   // A = M^T : 16 columns x 16 rows(t)
-      ldmatrix_x4_trans(vt + ks * 16 * CS_VSTRIDE + b_lane_off, b);   // B = v   : 16 rows(t) x 16 ranks
-      mma_bf16_16816(acc[0], a, b[0], b[1]);                           // ranks 0..7
-      mma_bf16_16816(acc[1], a, b[2], b[3]);                           // ranks 8..15
+#pragma unroll
+      for (int g16 = 0; g16 < R / 16; ++g16) {
+        uint32_t b[4];
+        ldmatrix_x4_trans(vt + ks * 16 * CS_VSTRIDE + b_lane_off + g16 * 32, b);   // B = v : 16 rows(t) x 16 ranks
+        mma_bf16_16816(acc[2 * g16], a, b[0], b[1]);                  // ranks 16*g16 + 0..7
+        mma_bf16_16816(acc[2 * g16 + 1], a, b[2], b[3]);              // ranks 16*g16 + 8..15
+      }
     }
   }
   cp_async_wait<0>();
@@ -194,9 +203,10 @@ adapter_grad_kernel(const __nv_bfloat16* __restrict__ Ma, const __nv_bfloat16* _
   for (int hrow = 0; hrow < 2; ++hrow) {
     const int c = c_base + warp * 16 + g + 8 * hrow;
     if (c < C) {
-      float* p0 = partial + (static_cast<size_t>(blockIdx.x) * C + c) * RPS;
-      *reinterpret_cast<float2*>(p0 + i2) = make_float2(acc[0][2 * hrow], acc[0][2 * hrow + 1]);
-      *reinterpret_cast<float2*>(p0 + 8 + i2) = make_float2(acc[1][2 * hrow], acc[1][2 * hrow + 1]);
+      float* p0 = partial + (static_cast<size_t>(blockIdx.x) * C + c) * R;
+#pragma unroll
+      for (int n = 0; n < NT; ++n)
+        *reinterpret_cast<float2*>(p0 + 8 * n + i2) = make_float2(acc[n][2 * hrow], acc[n][2 * hrow + 1]);
     }
   }
 }
@@ -217,8 +227,8 @@ adapter_grad_finalize_kernel(const float* __restrict__ partial_a, const float* _
                              float* __restrict__ dA, float* __restrict__ dB, int n_chunks, int K, int N, int r,
                              int blocks_a, int blocks_b, const float* __restrict__ h, const float* __restrict__ dzu,
                              float* __restrict__ ds_eff, int T, int b_prime, int num_slices, int row_div,
-                             float scaling) {
-  __shared__ float red[FIN_THREADS / RPS][RPS];
+                             float scaling, int RPS) {
+  __shared__ float red[FIN_THREADS / 16][RPS_MAX];
   int blk = blockIdx.x;
   if (blk < blocks_a + blocks_b) {
     const bool is_a = blk < blocks_a;
@@ -251,7 +261,6 @@ adapter_grad_finalize_kernel(const float* __restrict__ partial_a, const float* _
   __syncthreads();
   if (lane_row == 0 && j < r) {
     float tot = 0.f;
-#pragma unroll
     for (int k = 0; k < FIN_THREADS / RPS; ++k) tot += red[k][j];
     ds_eff[b * r + j] = tot * scaling;
   }
@@ -272,40 +281,50 @@ static int pick_chunks(int T, int K, int N) {
 }
 
 size_t svlora_bwd_small_scratch_bytes(int T, int K, int N) {
-  return static_cast<size_t>(pick_chunks(T, K, N)) * (static_cast<size_t>(K) + N) * RPS * 4 + 256;
+  return static_cast<size_t>(pick_chunks(T, K, N)) * (static_cast<size_t>(K) + N) * RPS_MAX * 4 + 256;
+}
+
+template <int R>
+static int launch_adapter_grad(const __nv_bfloat16* x, const __nv_bfloat16* dh, float* partial_a, int K, int groups_a,
+                               const __nv_bfloat16* dy, const __nv_bfloat16* z, float* partial_b, int N, int T,
+                               int rows_per_chunk, dim3 grid, cudaStream_t stream) {
+  static thread_local int attr_dev = -1;
+  int dev = 0;
+  FFM_CHECK_CUDA(cudaGetDevice(&dev));
+  if (dev != attr_dev) {
+    FFM_CHECK_CUDA(cudaFuncSetAttribute(adapter_grad_kernel<R>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        CsCfg<R>::SMEM_BYTES));
+    attr_dev = dev;
+  }
+  adapter_grad_kernel<R><<<grid, CS_THREADS, CsCfg<R>::SMEM_BYTES, stream>>>(x, dh, partial_a, K, groups_a, dy, z,
+                                                                            partial_b, N, T, rows_per_chunk);
+  FFM_CHECK_CUDA(cudaGetLastError());
+  return FFM_OK;
 }
 
 int launch_svlora_bwd_small(const __nv_bfloat16* x, const __nv_bfloat16* dy, const float* h, const float* dzu,
                             const __nv_bfloat16* z, const __nv_bfloat16* dh, float* dA, float* dB, float* ds_eff,
-                            void* scratch, size_t scratch_bytes, int T, int K, int N, int r, int nS, int b_prime,
+                            void* scratch, size_t scratch_bytes, int T, int K, int N, int r, int rp, int nS, int b_prime,
                             int num_slices, int row_div, float scaling, cudaStream_t stream) {
   FFM_CHECK_ARG(row_div == 1 || row_div * b_prime == T, "svlora bwd: batch-first rows need row_div * b_prime == T");
   FFM_CHECK_ARG(T % b_prime == 0, "svlora bwd: T (%d) must be a multiple of b_prime (%d)", T, b_prime);
-  {
-    static thread_local int attr_dev = -1;
-    int dev = 0;
-    FFM_CHECK_CUDA(cudaGetDevice(&dev));
-    if (dev != attr_dev) {
-      FFM_CHECK_CUDA(cudaFuncSetAttribute(adapter_grad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                          CS_SMEM_BYTES));
-      attr_dev = dev;
-    }
-  }
+  FFM_CHECK_ARG(rp == 16 || rp == RPS_MAX, "svlora bwd: padded rank must be 16 or %d", RPS_MAX);
   const int chunks = pick_chunks(T, K, N);
-  FFM_CHECK_ARG(static_cast<size_t>(chunks) * (static_cast<size_t>(K) + N) * RPS * 4 <= scratch_bytes,
+  FFM_CHECK_ARG(static_cast<size_t>(chunks) * (static_cast<size_t>(K) + N) * rp * 4 <= scratch_bytes,
                 "svlora bwd: scratch too small");
   float* partial_a = static_cast<float*>(scratch);
-  float* partial_b = partial_a + static_cast<size_t>(chunks) * K * RPS;
+  float* partial_b = partial_a + static_cast<size_t>(chunks) * K * rp;
   const int rows_per_chunk = (T + chunks - 1) / chunks;
   const int groups_a = (K + CS_COLS - 1) / CS_COLS, groups_b = (N + CS_COLS - 1) / CS_COLS;
   // dA[K, r] = x^T · dh   and   dB[r, N] = z^T · dy
-  adapter_grad_kernel<<<dim3(chunks, groups_a + groups_b), CS_THREADS, CS_SMEM_BYTES, stream>>>(
-      x, dh, partial_a, K, groups_a, dy, z, partial_b, N, T, rows_per_chunk);
-  FFM_CHECK_CUDA(cudaGetLastError());
-  const int blocks_a = (K * RPS + FIN_THREADS - 1) / FIN_THREADS, blocks_b = (N * RPS + FIN_THREADS - 1) / FIN_THREADS;
+  const dim3 grid(chunks, groups_a + groups_b);
+  int rc = rp == 16 ? launch_adapter_grad<16>(x, dh, partial_a, K, groups_a, dy, z, partial_b, N, T, rows_per_chunk, grid, stream)
+                    : launch_adapter_grad<32>(x, dh, partial_a, K, groups_a, dy, z, partial_b, N, T, rows_per_chunk, grid, stream);
+  if (rc != FFM_OK) return rc;
+  const int blocks_a = (K * rp + FIN_THREADS - 1) / FIN_THREADS, blocks_b = (N * rp + FIN_THREADS - 1) / FIN_THREADS;
   adapter_grad_finalize_kernel<<<blocks_a + blocks_b + nS, FIN_THREADS, 0, stream>>>(
       partial_a, partial_b, dA, dB, chunks, K, N, r, blocks_a, blocks_b, h, dzu, ds_eff, T, b_prime, num_slices,
-      row_div, scaling);
+      row_div, scaling, rp);
   FFM_CHECK_CUDA(cudaGetLastError());
   count_launch(2);
   return FFM_OK;

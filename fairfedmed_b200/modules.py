@@ -54,8 +54,7 @@ class _AdapterBase(nn.Module):
                 raise ValueError("only 1x1 convolutions can be wrapped")
             self.is_1x1_conv = True
             self.out_features, self.in_features = w.shape[:2]
-        if rank > ops.RP:
-            raise ValueError(f"rank {rank} exceeds the fused kernel's padded rank {ops.RP}")
+        ops.padded_rank(rank)          # raises for ranks the fused kernel was not built for (1..32)
         for p in self.original_linear.parameters():
             p.requires_grad = False
         self._cache_key = None

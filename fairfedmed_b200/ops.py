@@ -13,7 +13,11 @@ from torch import Tensor
 
 from . import _cabi
 
-RP = 16  # padded adapter rank of the fused GEMM (ffm_svlora_max_rank)
+def padded_rank(r: int) -> int:
+    """Row length of the h / z side outputs for adapter rank r (ffm_svlora_padded_rank: 16 for r <= 16, else 32)."""
+    if r < 1 or r > 32:
+        raise _cabi.FfmError(f"adapter rank {r} not supported by the fused kernel (1..32)")
+    return 16 if r <= 16 else 32
 
 OT_MODES = {"None": 0, "Sinkhorn": 1, "COT": 2}
 
@@ -40,8 +44,8 @@ def svlora_fwd(x: Tensor, w: Tensor, bias: Optional[Tensor], lora_a: Tensor, lor
                scaling: float, b_prime: int, num_slices: int, act: int,
                row_div: int = 1) -> Tuple[Tensor, Tensor, Tensor, Tensor, Tensor]:
     """y, y_dact, h, z, tiles = fused FairLoRA linear.  x [T,K] bf16, w [N,K] bf16, lora_a [K,r], lora_b [r,N],
-    s_eff [nS,r].  y_dact = QuickGELU'(u) when act = 1 (else empty); h = x·A (f32 [T,16]); z = bf16(scaling·h⊙s_eff)
-    ([T,16]); tiles = the call's workspace holding the prepared bf16 adapter tiles (hand it to svlora_bwd).
+    s_eff [nS,r].  y_dact = QuickGELU'(u) when act = 1 (else empty); h = x·A (f32 [T,rp]); z = bf16(scaling·h⊙s_eff)
+    ([T,rp], rp = padded_rank(r)); tiles = the call's workspace holding the prepared bf16 adapter tiles (hand it to svlora_bwd).
     Row t of x belongs to sample ((t // row_div) % b_prime) // num_slices (row_div = 1: sequence-first rows)."""
     _need_cuda(x, w, lora_a, lora_b, s_eff)
     T, K = x.shape
@@ -50,8 +54,9 @@ def svlora_fwd(x: Tensor, w: Tensor, bias: Optional[Tensor], lora_a: Tensor, lor
     nS = s_eff.shape[0]
     y = torch.empty((T, N), device=x.device, dtype=torch.bfloat16)
     y_dact = torch.empty((T, N), device=x.device, dtype=torch.bfloat16) if act else y.new_empty((0,))
-    h = torch.empty((T, RP), device=x.device, dtype=torch.float32)
-    z = torch.empty((T, RP), device=x.device, dtype=torch.bfloat16)
+    rp = padded_rank(r)
+    h = torch.empty((T, rp), device=x.device, dtype=torch.float32)
+    z = torch.empty((T, rp), device=x.device, dtype=torch.bfloat16)
     lib = _cabi.load()
     ws_bytes = lib.ffm_svlora_fwd_workspace_bytes(T, K, N, nS)
     ws = torch.empty((ws_bytes,), device=x.device, dtype=torch.uint8)
@@ -65,8 +70,9 @@ def svlora_fwd(x: Tensor, w: Tensor, bias: Optional[Tensor], lora_a: Tensor, lor
 def _(x, w, bias, lora_a, lora_b, s_eff, scaling, b_prime, num_slices, act, row_div=1):
     T, N = x.shape[0], w.shape[0]
     y = x.new_empty((T, N))
-    return (y, (x.new_empty((T, N)) if act else x.new_empty((0,))), x.new_empty((T, RP), dtype=torch.float32),
-            x.new_empty((T, RP)), x.new_empty((1,), dtype=torch.uint8))
+    rp = padded_rank(lora_a.shape[1])
+    return (y, (x.new_empty((T, N)) if act else x.new_empty((0,))), x.new_empty((T, rp), dtype=torch.float32),
+            x.new_empty((T, rp)), x.new_empty((1,), dtype=torch.uint8))
 
 
 @torch.library.custom_op("ffm::svlora_bwd", mutates_args=())

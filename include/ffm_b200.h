@@ -50,8 +50,11 @@ int ffm_profile_enable(int enable);
 int ffm_profile_read(float* ms_host, int* tkn_host, int max_records);
 
 /* ------------------------------------------------- FairLoRA / SVLoRA linear ------------------ */
-/* Maximum adapter rank the fused GEMM was built for (r is zero-padded to this). */
+/* Maximum adapter rank the fused GEMM was built for (32: the RN50 recipe, scripts/fairfedlora_fairfedmed_rn50.sh:37). */
 int ffm_svlora_max_rank(void);
+/* Padded rank used for rank r: 16 for r <= 16 (ViT recipes, r = 12), 32 for r <= 32; 0 if r is unsupported.  It is the
+ * row length of the h / z side outputs of ffm_svlora_fwd. */
+int ffm_svlora_padded_rank(int r);
 
 size_t ffm_svlora_fwd_workspace_bytes(int T, int K, int N, int n_samples);
 size_t ffm_svlora_bwd_workspace_bytes(int T, int K, int N, int n_samples);
@@ -60,7 +63,7 @@ size_t ffm_svlora_bwd_workspace_bytes(int T, int K, int N, int n_samples);
  * Forward of FairLoRALinear / SVLoRALinear / LoRALinear
  *   replaces trainers/GLP_OT_SVLoRA.py:450-482 (FairLoRALinear.forward), :308-312, :241-242.
  *
- *   h[t,:]  = x[t,:] · A                                      (f32 [T,16], columns >= r are 0)
+ *   h[t,:]  = x[t,:] · A                                      (f32 [T,rp], rp = ffm_svlora_padded_rank(r); columns >= r are 0)
  *   u[t,:]  = x[t,:] · W^T + bias + scaling · (h[t,:] ⊙ s_eff[sample(t),:]) · B
  *   y       = act ? QuickGELU(u) : u          (clip/model.py:313-315 fused when act = 1)
  *   y_dact  = QuickGELU'(u) (only when act = 1 and y_dact != NULL): the one thing the backward pass needs from the
@@ -71,7 +74,7 @@ size_t ffm_svlora_bwd_workspace_bytes(int T, int K, int N, int n_samples);
  *               (used by fairfedmed_b200.clip_model so attention needs no transposes).  OCT volumes fold
  *               num_slices slice-images per sample into B' (trainers/GLP_OT_SVLoRA.py:473-475).
  *
- *   z[t,:]  = bf16(scaling · h[t,:] ⊙ s_eff[sample(t),:])   (bf16 [T,16], optional): the operand d_lora_b needs,
+ *   z[t,:]  = bf16(scaling · h[t,:] ⊙ s_eff[sample(t),:])   (bf16 [T,rp], optional): the operand d_lora_b needs,
  *             produced by the epilogue anyway (it feeds the rank-16 tensor-core update), so the backward pass does not
  *             recompute it.
  *
@@ -98,7 +101,7 @@ int ffm_svlora_fwd(const void* x, const void* w, const float* bias, const float*
  *   Three launches: the fused tcgen05 GEMM (dx, dzu, dh), one kernel for both adapter contractions (x and dy are
  *   each read from HBM once), one kernel that folds their partials and does the per-sample segmented reduction.
  *   w_t is W transposed, [K,N] bf16 (the frozen weight is transposed once at module construction).
- *   h (f32 [T,16]) and z (bf16 [T,16]) are the side outputs of ffm_svlora_fwd; fwd_workspace is that call's workspace
+ *   h (f32 [T,rp]) and z (bf16 [T,rp]) are the side outputs of ffm_svlora_fwd; fwd_workspace is that call's workspace
  *   (adapter tiles already prepared) or NULL (then lora_a / lora_b / s_eff are converted again here).
  */
 int ffm_svlora_bwd(const void* dy, const void* x, const void* w_t, const float* lora_a, const float* lora_b,

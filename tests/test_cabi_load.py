@@ -29,7 +29,8 @@ def test_binding_covers_header():
 
 def test_no_compute_metadata_calls(lib):
     assert lib.ffm_version() >= 100
-    assert lib.ffm_svlora_max_rank() == 16
+    assert lib.ffm_svlora_max_rank() == 32
+    assert [lib.ffm_svlora_padded_rank(r) for r in (0, 1, 12, 16, 17, 32, 33)] == [0, 16, 16, 16, 32, 32, 0]
     assert lib.ffm_svlora_fwd_workspace_bytes(1576, 768, 3072, 8) > 0
     assert lib.ffm_svlora_bwd_workspace_bytes(1576, 768, 3072, 8) > lib.ffm_svlora_fwd_workspace_bytes(1576, 768, 3072, 8)
     assert lib.ffm_ot_head_workspace_bytes(196, 64, 512, 2, 2) > 0

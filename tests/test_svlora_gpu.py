@@ -140,7 +140,7 @@ def _raw_case(T, K, N, r, b_prime, num_slices, act, seed=0):
         assert bool((err <= lim).all()), f"{what}: max err {err.max().item():.3e}"
 
     assert float((h[:, :r].cpu() - h_ref).abs().max()) <= 1e-3 * max(1.0, float(h_ref.abs().max()))
-    assert r == 16 or float(h[:, r:].abs().max()) == 0.0
+    assert r == h.shape[1] or float(h[:, r:].abs().max()) == 0.0
     tight(y, y_ref, "y")
     if act:
         sg_ref = torch.sigmoid(1.702 * u_ref)
@@ -158,6 +158,10 @@ def _raw_case(T, K, N, r, b_prime, num_slices, act, seed=0):
     (1576, 3072, 768, 12, 8, 1, 0),   # config-1 c_proj
     (1576, 768, 3072, 16, 8, 4, 0),   # OCT slices (2 samples x 4 slice-images), full padded rank
     (788, 768, 3072, 12, 4, 4, 0),    # attr=None layout: one s_eff row for every column
+    (128, 64, 192, 32, 8, 1, 0),      # rank 32 (RN50 recipe r=32): padded rank 32 build, one tile, one k block
+    (392, 256, 64, 32, 8, 1, 0),      # RN50 layer1 conv3-like 1x1 conv, 8 images x 7x7 tokens
+    (1568, 1024, 2048, 32, 8, 1, 0),  # RN50 layer4-like, several tiles and k blocks
+    (1576, 768, 3072, 20, 8, 1, 1),   # rank 20 -> padded 32, fused QuickGELU + QuickGELU' backward
 ])
 def test_kernel_matches_oracle_on_rounded_operands(shape):
     _raw_case(*shape)
@@ -222,9 +226,9 @@ def test_invalid_arguments_raise():
     dev = _dev()
     x = torch.zeros(128, 64, device=dev, dtype=torch.bfloat16)
     W = torch.zeros(192, 64, device=dev, dtype=torch.bfloat16)
-    A = torch.zeros(64, 20, device=dev)
-    Bm = torch.zeros(20, 192, device=dev)
-    s = torch.ones(8, 20, device=dev)
+    A = torch.zeros(64, 40, device=dev)            # rank 40 > 32, the largest padded rank built
+    Bm = torch.zeros(40, 192, device=dev)
+    s = torch.ones(8, 40, device=dev)
     with pytest.raises(_cabi.FfmError, match="rank"):
         ops.svlora_fwd(x, W, None, A, Bm, s, 0.1, 8, 1, 0)
     A, Bm, s = A[:, :12].contiguous(), Bm[:12].contiguous(), s[:, :12].contiguous()
