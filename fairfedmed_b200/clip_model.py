@@ -24,6 +24,7 @@ import torch.nn.functional as F
 
 from . import ops
 from .modules import FairLoRALinear, LoRALinear, SVLoRALinear, _AdapterBase, _attr_on
+from .resnet_model import ModifiedResNet_GLP_OT
 
 PIXEL_MEAN = (0.48145466, 0.4578275, 0.40821073)
 PIXEL_STD = (0.26862954, 0.26130258, 0.27577711)
@@ -280,7 +281,7 @@ class CustomCLIP(nn.Module):
 
     def __init__(self, *, classnames: Sequence[str] = ("NOT Glaucoma", "Glaucoma"), n_prompts: int = 2, n_ctx: int = 4,
                  ot: str = "None", eps: float = 0.1, thresh: float = 1e-3, max_iter: int = 100,
-                 top_percent: float = 0.8, image_resolution: int = 224, vision_layers: int = 12,
+                 top_percent: float = 0.8, image_resolution: int = 224, vision_layers=12,
                  vision_width: int = 768, vision_patch_size: int = 16, embed_dim: int = 512, text_width: int = 512,
                  text_layers: int = 12, text_heads: int = 8, context_length: int = 77,
                  dim_per_3d_slice: Optional[int] = None, prompt_buffers=None, dataset: str = "FairFedMed",
@@ -300,8 +301,13 @@ class CustomCLIP(nn.Module):
             prompt_buffers = synthetic_prompt_buffers(n_prompts, self.n_cls, n_ctx, text_width, context_length,
                                                       seed=seed)
         self.prompt_learner = PromptLearner(n_prompts, n_ctx, text_width, self.n_cls, *prompt_buffers)
-        self.image_encoder = ModifiedVisionTransformer(image_resolution, vision_patch_size, vision_width,
-                                                       vision_layers, vision_width // 64, embed_dim)
+        if isinstance(vision_layers, (tuple, list)):
+            # CLIP ResNet (clip/model.py:484-492): heads = width * 32 / 64, attention pool returns all tokens
+            self.image_encoder = ModifiedResNet_GLP_OT(tuple(vision_layers), embed_dim, vision_width * 32 // 64,
+                                                       image_resolution, vision_width)
+        else:
+            self.image_encoder = ModifiedVisionTransformer(image_resolution, vision_patch_size, vision_width,
+                                                           vision_layers, vision_width // 64, embed_dim)
         self.text_encoder = TextEncoder(text_width, text_layers, text_heads, context_length, embed_dim)
         self.logit_scale = nn.Parameter(torch.ones([]) * math.log(1 / 0.07))
         self.compute_dtype = torch.bfloat16
@@ -314,7 +320,15 @@ class CustomCLIP(nn.Module):
         """Random init in the spirit of CLIP.initialize_parameters (clip/model.py:533-560); no checkpoints offline."""
         te, ve = self.text_encoder, self.image_encoder
         nn.init.normal_(te.positional_embedding, std=0.01)
-        for tower in (te.transformer, ve.transformer):
+        towers = (te.transformer, ve.transformer) if hasattr(ve, "transformer") else (te.transformer,)
+        if not hasattr(ve, "transformer"):           # ResNet: attention-pool init as in CLIP.initialize_parameters :536-547
+            std = ve.attnpool.c_proj.in_features ** -0.5
+            for lin in (ve.attnpool.q_proj, ve.attnpool.k_proj, ve.attnpool.v_proj, ve.attnpool.c_proj):
+                nn.init.normal_(lin.weight, std=std)
+            for layer in (ve.layer1, ve.layer2, ve.layer3, ve.layer4):
+                for block in layer:
+                    nn.init.zeros_(block.bn3.weight)
+        for tower in towers:
             proj_std = (tower.width ** -0.5) * ((2 * tower.layers) ** -0.5)
             attn_std = tower.width ** -0.5
             fc_std = (2 * tower.width) ** -0.5
@@ -342,7 +356,12 @@ class CustomCLIP(nn.Module):
         x = self.preprocess(image.float())
         dt = self.compute_dtype if x.is_cuda else x.dtype
         attr_dev = _attr_on(x.device, attr)
-        feats = self.image_encoder(x.to(dt), attr=attr_dev)                        # [M+1, B', D]
+        if isinstance(self.image_encoder, ModifiedResNet_GLP_OT):
+            # conv trunk with training-mode BatchNorm over small batches: keep fp32 activations (bf16 only inside the
+            # fused adapter kernels), batch statistics amplify bf16 rounding
+            feats = self.image_encoder(x, attr=attr_dev)
+        else:
+            feats = self.image_encoder(x.to(dt), attr=attr_dev)                    # [M+1, B', D]
         prompts = self.prompt_learner()
         txt = self.text_encoder(prompts, self.prompt_learner.eot_index)           # [N*n_cls, D] fp32
         num_slices = feats.shape[1] // b

@@ -1,0 +1,157 @@
+"""CLIP ModifiedResNet (RN50) image encoder with the reference's attribute-aware interfaces (scope row a8).
+
+Same class names, sub-module names (=> state-dict keys) and call signatures as clip/model.py:11-118 and :227-301 of
+the reference: `Bottleneck.forward(x, attr)` hands `attr` to its 1x1 convolutions `conv1` / `conv3`,
+`AttentionPool2d.forward(x, attr)` asks its projections for `.weight(x, attr)` / `.bias()`, and
+`ModifiedResNet_GLP_OT.forward(x, attr)` returns ALL tokens `[HW+1, B, output_dim]` (pooled token first).
+
+What runs where:
+  * the adapted 1x1 convolutions (FairLoRALinear wrapping an nn.Conv2d, rank 32 in the RN50 recipe) go through the
+    fused tcgen05 kernel — a 1x1 convolution is a linear layer over the B*H*W tokens (reference :469-480);
+  * the frozen 3x3 / stem / downsample convolutions, BatchNorm (trainable in the recipe, trainers/GLP_OT_SVLoRA.py:
+    825-827) and the attention pool are PyTorch library kernels on bf16 channels-last activations.
+"""
+from __future__ import annotations
+
+from collections import OrderedDict
+from typing import Optional, Sequence
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from .modules import _AdapterBase, _attr_on
+
+
+def _conv(owner: nn.Module, name: str, conv: nn.Module, x: torch.Tensor, attr):
+    """Adapter-wrapped convolutions take (x, attr); frozen ones run on a cached copy of the weight in x's dtype."""
+    if isinstance(conv, _AdapterBase):
+        return conv(x, attr)
+    w = conv.weight
+    if w.dtype != x.dtype:
+        store = owner.__dict__.setdefault("_w_store", {})
+        key = (w.data_ptr(), w._version, w.device, x.dtype)
+        hit = store.get(name)
+        if hit is None or hit[0] != key:
+            store[name] = (key, w.detach().to(x.dtype).contiguous(memory_format=torch.channels_last))
+            hit = store[name]
+        w = hit[1] if not conv.weight.requires_grad else conv.weight.to(x.dtype)
+    return F.conv2d(x, w, None, conv.stride, conv.padding)
+
+
+class Bottleneck(nn.Module):
+    expansion = 4
+
+    def __init__(self, inplanes: int, planes: int, stride: int = 1):
+        super().__init__()
+        # all convolutions have stride 1; an average pool follows the second one when stride > 1 (anti-aliasing)
+        self.conv1 = nn.Conv2d(inplanes, planes, 1, bias=False)
+        self.bn1 = nn.BatchNorm2d(planes)
+        self.conv2 = nn.Conv2d(planes, planes, 3, padding=1, bias=False)
+        self.bn2 = nn.BatchNorm2d(planes)
+        self.avgpool = nn.AvgPool2d(stride) if stride > 1 else nn.Identity()
+        self.conv3 = nn.Conv2d(planes, planes * self.expansion, 1, bias=False)
+        self.bn3 = nn.BatchNorm2d(planes * self.expansion)
+        self.relu = nn.ReLU(inplace=True)
+        self.downsample = None
+        self.stride = stride
+        if stride > 1 or inplanes != planes * Bottleneck.expansion:
+            self.downsample = nn.Sequential(OrderedDict([
+                ("-1", nn.AvgPool2d(stride)),
+                ("0", nn.Conv2d(inplanes, planes * self.expansion, 1, stride=1, bias=False)),
+                ("1", nn.BatchNorm2d(planes * self.expansion)),
+            ]))
+
+    def forward(self, x: torch.Tensor, attr: Optional[torch.Tensor] = None):
+        identity = x
+        out = self.relu(self.bn1(_conv(self, "conv1", self.conv1, x, attr)))
+        out = self.relu(self.bn2(_conv(self, "conv2", self.conv2, out, None)))
+        out = self.avgpool(out)
+        out = self.bn3(_conv(self, "conv3", self.conv3, out, attr))
+        if self.downsample is not None:
+            identity = self.downsample[0](x)
+            identity = self.downsample[2](_conv(self, "downsample", self.downsample[1], identity, None))
+        return self.relu(out + identity)
+
+
+class AttentionPool2d(nn.Module):
+    """QKV attention over the HW tokens + their mean, every token as a query (clip/model.py:63-118)."""
+
+    def __init__(self, spacial_dim: int, embed_dim: int, num_heads: int, output_dim: Optional[int] = None):
+        super().__init__()
+        self.positional_embedding = nn.Parameter(torch.randn(spacial_dim ** 2 + 1, embed_dim) / embed_dim ** 0.5)
+        self.k_proj = nn.Linear(embed_dim, embed_dim)
+        self.q_proj = nn.Linear(embed_dim, embed_dim)
+        self.v_proj = nn.Linear(embed_dim, embed_dim)
+        self.c_proj = nn.Linear(embed_dim, output_dim or embed_dim)
+        self.num_heads, self.embed_dim, self.spacial_dim = num_heads, embed_dim, spacial_dim
+
+    @staticmethod
+    def _wb(layer, x, attr):
+        """(weight, bias): adapter projections expose the merged weight through .weight(x, attr) / .bias()."""
+        if isinstance(layer, _AdapterBase):
+            return layer.weight(x, attr), layer.bias()
+        return layer.weight, layer.bias
+
+    def forward(self, x: torch.Tensor, attr: Optional[torch.Tensor] = None):
+        b, c, h, w = x.shape
+        x = x.reshape(b, c, h * w).permute(2, 0, 1)                                   # NCHW -> (HW) N C
+        x = torch.cat([x.mean(dim=0, keepdim=True), x], dim=0)                         # (HW+1) N C
+        x = x + self.positional_embedding[:, None, :].to(x.dtype)
+        L = x.shape[0]
+        dt = x.dtype
+        hd = c // self.num_heads
+        proj = []
+        for layer in (self.q_proj, self.k_proj, self.v_proj):
+            wt, bs = self._wb(layer, x, attr)
+            proj.append(F.linear(x, wt.to(dt), None if bs is None else bs.to(dt)))
+        q, k, v = (t.reshape(L, b, self.num_heads, hd).permute(1, 2, 0, 3) for t in proj)      # [B, H, L, hd]
+        out = F.scaled_dot_product_attention(q, k, v)                                           # scale hd^-0.5
+        out = out.permute(2, 0, 1, 3).reshape(L, b, c)
+        wt, bs = self._wb(self.c_proj, x, attr)
+        return F.linear(out, wt.to(dt), None if bs is None else bs.to(dt))                      # [HW+1, B, output_dim]
+
+
+class ModifiedResNet_GLP_OT(nn.Module):
+    """3-conv stem with average pool, anti-aliased strided bottlenecks, attention pool returning all tokens
+    (clip/model.py:227-301)."""
+
+    def __init__(self, layers: Sequence[int], output_dim: int, heads: int, input_resolution: int = 224,
+                 width: int = 64):
+        super().__init__()
+        self.output_dim, self.input_resolution = output_dim, input_resolution
+        self.conv1 = nn.Conv2d(3, width // 2, kernel_size=3, stride=2, padding=1, bias=False)
+        self.bn1 = nn.BatchNorm2d(width // 2)
+        self.conv2 = nn.Conv2d(width // 2, width // 2, kernel_size=3, padding=1, bias=False)
+        self.bn2 = nn.BatchNorm2d(width // 2)
+        self.conv3 = nn.Conv2d(width // 2, width, kernel_size=3, padding=1, bias=False)
+        self.bn3 = nn.BatchNorm2d(width)
+        self.avgpool = nn.AvgPool2d(2)
+        self.relu = nn.ReLU(inplace=True)
+        self._inplanes = width
+        self.layer1 = self._make_layer(width, layers[0])
+        self.layer2 = self._make_layer(width * 2, layers[1], stride=2)
+        self.layer3 = self._make_layer(width * 4, layers[2], stride=2)
+        self.layer4 = self._make_layer(width * 8, layers[3], stride=2)
+        embed_dim = width * 32
+        self.attnpool = AttentionPool2d(input_resolution // 32, embed_dim, heads, output_dim)
+
+    def _make_layer(self, planes: int, blocks: int, stride: int = 1):
+        layers = [Bottleneck(self._inplanes, planes, stride)]
+        self._inplanes = planes * Bottleneck.expansion
+        for _ in range(1, blocks):
+            layers.append(Bottleneck(self._inplanes, planes))
+        return nn.ModuleList(layers)                       # a ModuleList, as upstream: blocks are called with attr
+
+    def forward(self, x: torch.Tensor, attr: Optional[torch.Tensor] = None):
+        attr = _attr_on(x.device, attr)
+        if x.is_cuda:
+            x = x.contiguous(memory_format=torch.channels_last)
+        for name, conv, bn in (("conv1", self.conv1, self.bn1), ("conv2", self.conv2, self.bn2),
+                               ("conv3", self.conv3, self.bn3)):
+            x = self.relu(bn(_conv(self, name, conv, x, None)))
+        x = self.avgpool(x)
+        for layer in (self.layer1, self.layer2, self.layer3, self.layer4):
+            for block in layer:
+                x = block(x, attr)
+        return self.attnpool(x, attr)                       # [HW+1, B, output_dim]

@@ -78,16 +78,23 @@ class GLP_OT_SVLoRA:
         ot = cfg.TRAINER.GLP_OT
         torch.manual_seed(cfg.SEED)
         is_3d = cfg.DATASET.MODALITY_TYPE in {"oct_bscans", "oct_bscans_3d", "mac_onh", "onh_mac"}
+        vision_layers, vision_width, embed = arch.VISION_LAYERS, arch.VISION_WIDTH, arch.EMBED
+        if cfg.MODEL.BACKBONE.NAME == "RN50" and not isinstance(vision_layers, (tuple, list)):
+            # CLIP RN50 (clip/clip.py _MODELS "RN50"): bottleneck counts (3, 4, 6, 3), stem width 64, embed_dim 1024
+            vision_layers, vision_width, embed = (3, 4, 6, 3), 64, 1024
         self.model = CustomCLIP(
             classnames=self.dm.dataset.classnames, n_prompts=ot.N, n_ctx=ot.N_CTX, ot=ot.OT, eps=ot.EPS,
             thresh=ot.THRESH, max_iter=ot.MAX_ITER, top_percent=ot.TOP_PERCENT, image_resolution=cfg.INPUT.SIZE[0],
-            vision_layers=arch.VISION_LAYERS, vision_width=arch.VISION_WIDTH, vision_patch_size=arch.PATCH,
-            embed_dim=arch.EMBED, text_width=arch.TEXT_WIDTH, text_layers=arch.TEXT_LAYERS,
+            vision_layers=vision_layers, vision_width=vision_width, vision_patch_size=arch.PATCH,
+            embed_dim=embed, text_width=arch.TEXT_WIDTH, text_layers=arch.TEXT_LAYERS,
             text_heads=arch.TEXT_HEADS, context_length=arch.CONTEXT,
             dim_per_3d_slice=cfg.DATASET.DIM_PER_3D_SLICE if is_3d else None, dataset=cfg.DATASET.NAME, seed=cfg.SEED)
-        # freeze everything but the prompt learner / OCT projection (:822-829), then wrap the MLP linears (:834-842)
+        # freeze everything but the prompt learner / OCT projection / BatchNorm2d affine parameters of the ResNet trunk
+        # (:822-829), then wrap the MLP linears or the 1x1 convolutions (:834-842)
+        bn_params = {id(p) for m_ in self.model.modules() if isinstance(m_, torch.nn.BatchNorm2d)
+                     for p in m_.parameters()}
         for name, p in self.model.named_parameters():
-            p.requires_grad_("prompt_learner" in name or "proj_per_3d_slice" in name)
+            p.requires_grad_("prompt_learner" in name or "proj_per_3d_slice" in name or id(p) in bn_params)
         lora = cfg.TRAINER.GLP_OT_LORA
         apply_lora_to_model(self.model, lora.UNFREEZE_IMAGE_ENCODER, rank=lora.RANK, alpha=lora.ALPHA,
                             lora_type=lora.TYPE, global_s=lora.GLOBAL_S, num_attrs=self.num_groups)

@@ -283,6 +283,60 @@ def text_encoder(prompts, eot_index, p, *, n_layers=12, n_head=8, pre="text_enco
     return x[torch.arange(x.shape[0]), eot_index] @ p[pre + "text_projection"]
 
 
+def _bn_train(x, p, pre, eps=1e-5):
+    """nn.BatchNorm2d in training mode (batch statistics, biased variance for the normalisation) — the reference never
+    calls .eval() on the trunk while training (Dassl/dassl/engine/trainer.py:156-165 sets train mode)."""
+    return F.batch_norm(x, None, None, p[pre + "weight"], p[pre + "bias"], True, 0.0, eps)
+
+
+def _rn_conv1x1(x, p, pre, attr, scaling):
+    """A 1x1 conv of a Bottleneck: FairLoRA-wrapped (keys under `original_linear`) or plain."""
+    if pre + "lora_A.weight" in p:
+        return fairlora_conv1x1(x, p[pre + "original_linear.weight"], None, p[pre + "lora_A.weight"],
+                                p[pre + "lora_S.weight"], p[pre + "lora_B.weight"], attr, scaling)
+    return F.conv2d(x, p[pre + "weight"])
+
+
+def resnet_image_encoder(image, p, attr, *, layers=(3, 4, 6, 3), n_head=32, scaling=0.25, pre="image_encoder."):
+    """ModifiedResNet_GLP_OT.forward (clip/model.py:270-301) with Bottleneck.forward (:41-60) and
+    AttentionPool2d.forward (:75-118): returns all tokens [HW+1, B, output_dim]."""
+    x = image
+    for i, stride in ((1, 2), (2, 1), (3, 1)):                                           # 3-conv stem
+        x = F.relu(_bn_train(F.conv2d(x, p[f"{pre}conv{i}.weight"], stride=stride, padding=1), p, f"{pre}bn{i}."))
+    x = F.avg_pool2d(x, 2)
+    for li, n_blocks in enumerate(layers, start=1):
+        for bi in range(n_blocks):
+            bp = f"{pre}layer{li}.{bi}."
+            stride = 2 if (li > 1 and bi == 0) else 1
+            identity = x
+            out = F.relu(_bn_train(_rn_conv1x1(x, p, bp + "conv1.", attr, scaling), p, bp + "bn1."))
+            out = F.relu(_bn_train(F.conv2d(out, p[bp + "conv2.weight"], padding=1), p, bp + "bn2."))
+            if stride > 1:
+                out = F.avg_pool2d(out, stride)
+            out = _bn_train(_rn_conv1x1(out, p, bp + "conv3.", attr, scaling), p, bp + "bn3.")
+            if bp + "downsample.0.weight" in p:
+                identity = F.avg_pool2d(x, stride) if stride > 1 else x
+                identity = _bn_train(F.conv2d(identity, p[bp + "downsample.0.weight"]), p, bp + "downsample.1.")
+            x = F.relu(out + identity)
+    # attention pool: every token (mean first) is a query; projections are plain-LoRA merged weights (:235-236)
+    b, c, hh, ww = x.shape
+    t = x.reshape(b, c, hh * ww).permute(2, 0, 1)
+    t = torch.cat([t.mean(dim=0, keepdim=True), t], dim=0) + p[pre + "attnpool.positional_embedding"][:, None, :]
+    ap = pre + "attnpool."
+
+    def wb(name):
+        if ap + name + ".lora_A.weight" in p:
+            w = lora_merged_weight(p[ap + name + ".original_linear.weight"], p[ap + name + ".lora_A.weight"],
+                                   p[ap + name + ".lora_B.weight"], scaling)
+            return w, p[ap + name + ".original_linear.bias"]
+        return p[ap + name + ".weight"], p[ap + name + ".bias"]
+    L, hd = t.shape[0], c // n_head
+    q, k, v = (F.linear(t, *wb(nm)).reshape(L, b, n_head, hd).permute(1, 2, 0, 3) for nm in ("q_proj", "k_proj", "v_proj"))
+    att = torch.softmax((q * hd ** -0.5) @ k.transpose(-1, -2), dim=-1) @ v                # [B, H, L, hd]
+    out = att.permute(2, 0, 1, 3).reshape(L, b, c)
+    return F.linear(out, *wb("c_proj"))
+
+
 def custom_clip_forward(image, attr, p, eot_index, *, n_prompts=2, n_cls=2, ot="None", eps=0.1, thresh=1e-3,
                         max_iter=100, top_percent=0.8, vision_layers=12, vision_heads=12, text_layers=12,
                         text_heads=8, scaling=1.0 / 6.0, lora_type="FairLoRA", dim_per_3d_slice=None):
@@ -299,8 +353,11 @@ def custom_clip_forward(image, attr, p, eot_index, *, n_prompts=2, n_cls=2, ot="
     mean = torch.tensor(PIXEL_MEAN, dtype=image.dtype).reshape(1, -1, 1, 1)
     std = torch.tensor(PIXEL_STD, dtype=image.dtype).reshape(1, -1, 1, 1)
     image = (image - mean) / std
-    feats = vit_image_encoder(image, p, attr, n_layers=vision_layers, n_head=vision_heads, scaling=scaling,
-                              lora_type=lora_type)
+    if isinstance(vision_layers, (tuple, list)):       # CLIP ResNet backbone: vision_heads = width * 32 // 64
+        feats = resnet_image_encoder(image, p, attr, layers=tuple(vision_layers), n_head=vision_heads, scaling=scaling)
+    else:
+        feats = vit_image_encoder(image, p, attr, n_layers=vision_layers, n_head=vision_heads, scaling=scaling,
+                                  lora_type=lora_type)
     prompts = prompt_embeddings(p, n_prompts, n_cls)
     txt = text_encoder(prompts, eot_index, p, n_layers=text_layers, n_head=text_heads)
     return ot_head(feats, txt, p["logit_scale"], n_cls=n_cls, batch=b, ot=ot, eps=eps, thresh=thresh,

@@ -137,7 +137,8 @@ def golden_model(T, CM):
                              rc["t_heads"], rc["t_layers"], dd).float()
         model = T.CustomCLIP(cfg, list(recipes.CLASSNAMES), clip_model)
         for n_, p_ in model.named_parameters():
-            p_.requires_grad_("prompt_learner" in n_ or "proj_per_3d_slice" in n_)
+            p_.requires_grad_("prompt_learner" in n_ or "proj_per_3d_slice" in n_ or
+                              (rc.get("train_bn", False) and (".bn" in n_ or "downsample.1" in n_)))
         T.apply_lora_to_model(model, True, rank=rc["rank"], alpha=rc["alpha"], lora_type=rc["lora_type"],
                               global_s=False, num_attrs=rc["groups"])
         eot = model.tokenized_prompts.argmax(dim=-1)

@@ -159,6 +159,12 @@ MODEL_CASES = {
     "tiny_oct": dict(modality="oct_bscans", ot="Sinkhorn", res=32, embed=64, v_layers=1, v_width=128, t_width=64,
                      t_heads=2, t_layers=1, rank=12, alpha=2.0, lora_type="FairLoRA", groups=2, batch=2, seed=54,
                      dim_per_3d_slice=8, grad_filter=_adapter_grads),
+    # CLIP ResNet backbone (scope row a8): conv trunk with FairLoRA on the 1x1 convs (rank 32, alpha 8 — the RN50 script
+    # values) + plain LoRA on the attention pool; BatchNorm in training mode with trainable affine parameters
+    "tiny_rn50": dict(modality="slo_fundus", ot="Sinkhorn", res=128, embed=64, v_layers=(1, 1, 1, 1), v_width=16,
+                      t_width=64, t_heads=2, t_layers=1, rank=32, alpha=8.0, lora_type="FairLoRA", groups=3, batch=8,
+                      seed=55, train_bn=True,
+                      grad_filter=lambda n: _adapter_grads(n) or ".bn" in n or "downsample.1" in n),
 }
 
 
@@ -170,6 +176,14 @@ def model_params(rc, shapes: dict):
         shp = shapes[k]
         if k == "logit_scale":
             out[k] = torch.tensor(float(np.log(1 / 0.07)))
+        elif k.endswith("running_var"):
+            out[k] = torch.rand(shp, generator=g) + 0.5
+        elif k.endswith("num_batches_tracked"):
+            out[k] = torch.zeros(shp, dtype=torch.int64)
+        elif k.endswith("running_mean"):
+            out[k] = 0.1 * torch.randn(shp, generator=g)
+        elif (".bn" in k or "downsample.1" in k) and k.endswith("weight"):
+            out[k] = 1.0 + 0.1 * torch.randn(shp, generator=g)
         elif k.endswith("ln_1.weight") or k.endswith("ln_2.weight") or k.endswith("ln_pre.weight") or \
                 k.endswith("ln_post.weight") or k.endswith("ln_final.weight"):
             out[k] = 1.0 + 0.1 * torch.randn(shp, generator=g)

@@ -33,7 +33,8 @@ def _build(rc, gold, name):
                    text_layers=rc["t_layers"], text_heads=rc["t_heads"],
                    dim_per_3d_slice=rc.get("dim_per_3d_slice") if is_oct else None, prompt_buffers=bufs)
     for n_, p_ in m.named_parameters():
-        p_.requires_grad_("prompt_learner" in n_ or "proj_per_3d_slice" in n_)
+        p_.requires_grad_("prompt_learner" in n_ or "proj_per_3d_slice" in n_ or
+                          (rc.get("train_bn", False) and (".bn" in n_ or "downsample.1" in n_)))
     apply_lora_to_model(m, True, rank=rc["rank"], alpha=rc["alpha"], lora_type=rc["lora_type"],
                         num_attrs=rc["groups"])
     assert set(m.state_dict().keys()) == set(keys), "state-dict keys must equal the reference's"
@@ -66,9 +67,66 @@ def test_custom_clip_matches_reference_golden(name):
             continue
         cos = float(F.cosine_similarity(g, r, dim=0))
         rel = float((g - r).abs().max() / r.abs().max())
-        assert cos >= 0.99 and rel <= 6e-2, f"{n_}: cos {cos:.4f} rel {rel:.3e}"
+        if isinstance(rc["v_layers"], tuple):
+            # conv trunk: the backward of training-mode BatchNorm subtracts the batch mean of the incoming gradient, which
+            # amplifies the bf16 rounding of the adapters' dX (8 adapted 1x1 convs in a row); the wiring itself is
+            # checked to fp32 accuracy in test_rn50_wiring_is_exact_with_reference_math below
+            assert cos >= 0.90, f"{n_}: cos {cos:.4f} rel {rel:.3e}"
+        else:
+            assert cos >= 0.99 and rel <= 6e-2, f"{n_}: cos {cos:.4f} rel {rel:.3e}"
         checked += 1
     assert checked >= 7
+
+
+def test_rn50_wiring_is_exact_with_reference_math(monkeypatch):
+    """Scope row a8, structure: ModifiedResNet_GLP_OT / Bottleneck / AttentionPool2d of this repo with the adapters'
+    arithmetic swapped for plain fp32 torch math (the reference's formula, :450-482) must reproduce the reference golden
+    to fp32 accuracy — logits 2e-3, every adapter / BatchNorm / prompt gradient cos >= 0.9999.  The fused kernels' own
+    numerics are pinned separately (test_svlora_gpu.py, rank-32 cases)."""
+    from fairfedmed_b200 import modules
+    name = "tiny_rn50"
+    rc = recipes.MODEL_CASES[name]
+    gold = np.load(GOLD / "model.npz")
+
+    def run_ref(self, x, s_eff):
+        W = self.original_linear.weight.reshape(self.out_features, self.in_features).float()
+        b = self.original_linear.bias
+        if self.is_1x1_conv:
+            bb, c, h, w = x.shape
+            tok = x.float().reshape(bb, c, h * w).permute(2, 0, 1)                      # [hw, b, c]
+        else:
+            tok = x.float()
+        s_rows = s_eff.repeat_interleave(tok.shape[1] // s_eff.shape[0], dim=0)
+        y = F.linear(tok, W, None if b is None else b.float())
+        y = y + self.scaling * (((tok @ self.lora_A.weight) * s_rows.unsqueeze(0)) @ self.lora_B.weight)
+        if self.is_1x1_conv:
+            y = y.reshape(h, w, bb, -1).permute(2, 3, 0, 1)
+        return y.to(x.dtype)
+
+    monkeypatch.setattr(modules._AdapterBase, "_run", run_ref)
+    prev = torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cudnn.allow_tf32 = torch.backends.cuda.matmul.allow_tf32 = False
+    try:
+        m, params, _ = _build(rc, gold, name)
+        m.text_encoder.compute_dtype = torch.float32
+        image, label, attr = recipes.model_batch(rc)
+        logits = m(image.to(DEV), attr)
+        ref = torch.from_numpy(gold[f"{name}.logits"])
+        assert float((logits.detach().float().cpu() - ref).abs().max()) <= 2e-3 * float(ref.abs().max())
+        F.cross_entropy(logits.float(), label.to(DEV)).backward()
+    finally:
+        torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = prev
+    checked = 0
+    for n_, p_ in m.named_parameters():
+        gk = f"{name}.grad.{n_}"
+        if gk not in gold.files or p_.grad is None:
+            continue
+        g, r = p_.grad.float().cpu().reshape(-1), torch.from_numpy(gold[gk]).reshape(-1)
+        if float(r.abs().max()) < 1e-7:
+            continue
+        assert float(F.cosine_similarity(g, r, dim=0)) >= 0.9999, n_
+        checked += 1
+    assert checked >= 60
 
 
 def _tiny_cfg(ot="None", users=2, batch=8, n_train=16):
@@ -189,3 +247,38 @@ def test_add_layernorm_matches_torch(C, rows, with_res):
     assert bool(((gx.float() - xr.grad.float()).abs() <= lim).all())
     if with_res:
         assert torch.equal(gx, gres)
+
+
+def test_trainer_runs_rn50_backbone():
+    """Config 4 shape (shrunk): MODEL.BACKBONE.NAME = RN50 builds the conv trunk with rank-32 FairLoRA on the 1x1 convs,
+    plain LoRA on the attention pool and trainable BatchNorm; one training step is finite and moves every group of
+    trainable tensors (adapters, BatchNorm affine, prompts)."""
+    import fairfedmed_b200.trainer  # noqa: F401
+    from fairfedmed_b200.modules import FairLoRALinear, LoRALinear
+    from fairfedmed_b200.registry import build_trainer
+    cfg = _tiny_cfg(ot="Sinkhorn")
+    cfg.MODEL.BACKBONE.NAME = "RN50"
+    cfg.MODEL_ARCH.merge_from_dict(dict(VISION_LAYERS=(1, 1, 1, 1), VISION_WIDTH=16, EMBED=64))
+    cfg.TRAINER.GLP_OT_LORA.merge_from_dict(dict(RANK=32, ALPHA=8.0))
+    tr = build_trainer(cfg)
+    enc = tr.model.image_encoder
+    assert sum(isinstance(m_, FairLoRALinear) for m_ in enc.modules()) == 8          # conv1 + conv3 of 4 bottlenecks
+    assert sum(isinstance(m_, LoRALinear) for m_ in enc.attnpool.modules()) == 4
+    assert any(".bn1.weight" in n for n in tr.trainable_names)
+    with torch.no_grad():
+        for n_, p_ in tr.model.named_parameters():
+            if "lora_A" in n_:
+                p_.copy_(0.05 * torch.randn(p_.shape, generator=torch.Generator().manual_seed(2)).to(p_.device))
+            if ".bn3.weight" in n_:        # CLIP zero-initialises the last BatchNorm of every bottleneck: open the branch
+                p_.fill_(1.0)
+    before = tr.get_flat().clone()
+    batch = next(iter(tr.fed_train_loader_x_dict[0]))
+    tr.batch_idx, tr.num_batches = 0, 2
+    out = tr.forward_backward(batch)
+    assert np.isfinite(out["loss"])
+    moved = (tr.get_flat() - before).abs()
+    assert float(moved.max()) > 0
+    sd = dict(tr.model.named_parameters())
+    for frag in ("lora_B", "lora_S", ".bn3.weight", "prompt_learner.ctx", "attnpool.c_proj.lora_A"):
+        k = next(n for n in tr.trainable_names if frag in n)
+        assert float(sd[k].grad.abs().max()) > 0, k

@@ -156,14 +156,16 @@ def test_custom_clip_forward_backward_matches_reference(name):
     keys = [str(k) for k in gold[f"{name}.keys"]]
     shapes = {k: tuple(int(v) for v in str(s).split(",") if v != "") for k, s in zip(keys, gold[f"{name}.shapes"])}
     params = recipes.model_params(rc, shapes)
-    trainable = [k for k in params if recipes._adapter_grads(k)]
+    trainable = [k for k in params if rc["grad_filter"](k) and params[k].is_floating_point() and
+                 "running_" not in k]
     for k in trainable:
         params[k].requires_grad_(True)
     image, label, attr = recipes.model_batch(rc)
     eot = torch.from_numpy(gold[f"{name}.eot"])
     logits = rp.custom_clip_forward(
         image, attr, params, eot, n_prompts=2, n_cls=2, ot=rc["ot"], vision_layers=rc["v_layers"],
-        vision_heads=rc["v_width"] // 64, text_layers=rc["t_layers"], text_heads=rc["t_heads"],
+        vision_heads=(rc["v_width"] * 32 // 64) if isinstance(rc["v_layers"], tuple) else rc["v_width"] // 64,
+        text_layers=rc["t_layers"], text_heads=rc["t_heads"],
         scaling=rc["alpha"] / rc["rank"], lora_type=rc["lora_type"],
         dim_per_3d_slice=rc.get("dim_per_3d_slice") if rc["modality"] == "oct_bscans" else None)
     close(logits, gold[f"{name}.logits"], 2e-4, 2e-5)
