@@ -28,6 +28,7 @@ from .resnet_model import ModifiedResNet_GLP_OT
 
 PIXEL_MEAN = (0.48145466, 0.4578275, 0.40821073)
 PIXEL_STD = (0.26862954, 0.26130258, 0.27577711)
+_SIDE_STREAMS: dict = {}     # device index -> side stream of the text tower (module level: models stay picklable)
 
 
 class _Bf16Cache:
@@ -164,17 +165,23 @@ class Transformer(nn.Module):
         # the fused kernel has no LayerNorm-parameter gradients: FairLoRA freezes them (trainers/GLP_OT_SVLoRA.py:822-829)
         return not any(p.requires_grad for blk in self.resblocks for ln in (blk.ln_1, blk.ln_2) for p in ln.parameters())
 
-    def forward(self, x: torch.Tensor, attr=None, final_ln: Optional[nn.LayerNorm] = None):
+    def forward(self, x: torch.Tensor, attr=None, final_ln: Optional[nn.LayerNorm] = None,
+                h0: Optional[torch.Tensor] = None):
         """Same computation as the chain of ResidualAttentionBlock.forward (clip/model.py:370-374), optionally followed
         by `final_ln` (ln_post / ln_final of the caller).  On the device every `x = x + branch; h = LayerNorm(x)` pair
-        runs as ONE kernel (ops.add_layernorm): the residual stream is read and written once per half-block."""
+        runs as ONE kernel (ops.add_layernorm): the residual stream is read and written once per half-block.
+        `h0`: ln_1 of the first block already applied to x by the caller (ops.vit_embed_ln)."""
         if not self._fusable(x) or (final_ln is not None and any(p.requires_grad for p in final_ln.parameters())):
+            assert h0 is None
             for block in self.resblocks:
                 x = block(x, attr)
             return x if final_ln is None else final_ln(x)
         blocks = self.resblocks
         ln = blocks[0].ln_1
-        x, h = ops.add_layernorm(x, None, ln.weight, ln.bias, ln.eps)
+        if h0 is None:
+            x, h = ops.add_layernorm(x, None, ln.weight, ln.bias, ln.eps)
+        else:
+            h = h0
         for i, blk in enumerate(blocks):
             a = blk.attention(h)
             x, h = ops.add_layernorm(x, a, blk.ln_2.weight, blk.ln_2.bias, blk.ln_2.eps)
@@ -211,7 +218,29 @@ class ModifiedVisionTransformer(nn.Module, _Bf16Cache):
         ps = self.patch_size
         gh, gw = hh // ps, ww // ps
         patches = x.view(bp, ch, gh, ps, gw, ps).permute(0, 2, 4, 1, 3, 5).reshape(bp, gh * gw, ch * ps * ps)
+        return self.forward_patches(patches, attr)
+
+    def _frozen_input_side(self) -> bool:
+        tr = self.transformer
+        params = [self.conv1.weight, self.class_embedding, self.positional_embedding, *self.ln_pre.parameters(),
+                  *self.ln_post.parameters(), *tr.resblocks[0].ln_1.parameters()]
+        return not any(p.requires_grad for p in params)
+
+    def forward_patches(self, patches: torch.Tensor, attr: Optional[torch.Tensor] = None):
+        """`forward` from the im2col'ed, normalised image on (patches [B', G, 3*P*P], e.g. ops.patchify_normalize)."""
+        dt = patches.dtype
         x = patches @ self._bf("conv1", self.conv1.weight, dt).flatten(1).t()                  # [B', g*g, width]
+        tr = self.transformer
+        if x.is_cuda and dt == torch.bfloat16 and not x.requires_grad and tr._fusable(x) and self._frozen_input_side():
+            # class token + positions + ln_pre + the first block's ln_1 in one pass over the tokens (forward only:
+            # nothing on this side of the residual stream is trainable)
+            ln1 = tr.resblocks[0].ln_1
+            x0, h0 = ops.vit_embed_ln(x.contiguous(), self.class_embedding.detach(), self.positional_embedding.detach(),
+                                      self.ln_pre.weight.detach(), self.ln_pre.bias.detach(), ln1.weight.detach(),
+                                      ln1.bias.detach(), self.ln_pre.eps, ln1.eps)
+            x = tr(x0, attr=attr, final_ln=self.ln_post, h0=h0)
+            x = x @ self._bf("proj", self.proj, dt)
+            return x.transpose(0, 1)
         cls = self._bf("cls", self.class_embedding, dt).expand(x.shape[0], 1, -1)
         x = torch.cat([cls, x], dim=1) + self._bf("pos", self.positional_embedding, dt)
         x = self.ln_pre(x)
@@ -353,17 +382,44 @@ class CustomCLIP(nn.Module):
 
     def forward(self, image: torch.Tensor, attr: Optional[torch.Tensor] = None):
         b = image.shape[0]
-        x = self.preprocess(image.float())
-        dt = self.compute_dtype if x.is_cuda else x.dtype
-        attr_dev = _attr_on(x.device, attr)
+        # The text tower (4 prompts x 77 tokens: ~300 launches of tiny kernels forward + backward) does not depend on
+        # the image: fork it onto a side stream so it fills the gaps of the image tower instead of extending the
+        # critical path.  Autograd replays the backward of each node on its forward stream, so the text backward
+        # overlaps the image backward the same way; under CUDA-graph capture the fork/join become graph edges.
+        fork = image.is_cuda and self.overlap_text
+        if fork:
+            cur = torch.cuda.current_stream(image.device)
+            side = self._side_stream(image.device)
+            side.wait_stream(cur)
+            with torch.cuda.stream(side):
+                prompts = self.prompt_learner()
+                txt = self.text_encoder(prompts, self.prompt_learner.eot_index)
+        dt = self.compute_dtype if image.is_cuda else torch.float32
+        attr_dev = _attr_on(image.device, attr)
+        ve = self.image_encoder
+        fast_input = (image.is_cuda and not self.is_3d_input and isinstance(ve, ModifiedVisionTransformer)
+                      and image.shape[1] == self.pixel_mean.shape[1] and ve.patch_size % 8 == 0
+                      and image.shape[2] % ve.patch_size == 0 and image.shape[3] % ve.patch_size == 0
+                      and image.shape[3] % 4 == 0)
         if isinstance(self.image_encoder, ModifiedResNet_GLP_OT):
             # conv trunk with training-mode BatchNorm over small batches: keep fp32 activations (bf16 only inside the
             # fused adapter kernels), batch statistics amplify bf16 rounding
-            feats = self.image_encoder(x, attr=attr_dev)
+            feats = self.image_encoder(self.preprocess(image.float()), attr=attr_dev)
+        elif fast_input:
+            # /255, mean/std, bf16 cast and im2col in one pass over the raw image
+            ve = self.image_encoder
+            patches = ops.patchify_normalize(image.float().contiguous(), self.pixel_mean.reshape(-1),
+                                             self.pixel_std.reshape(-1), ve.patch_size, True)
+            feats = ve.forward_patches(patches, attr=attr_dev)
         else:
+            x = self.preprocess(image.float())
             feats = self.image_encoder(x.to(dt), attr=attr_dev)                    # [M+1, B', D]
-        prompts = self.prompt_learner()
-        txt = self.text_encoder(prompts, self.prompt_learner.eot_index)           # [N*n_cls, D] fp32
+        if fork:
+            cur.wait_stream(side)
+            txt.record_stream(cur)
+        else:
+            prompts = self.prompt_learner()
+            txt = self.text_encoder(prompts, self.prompt_learner.eot_index)       # [N*n_cls, D] fp32
         num_slices = feats.shape[1] // b
         logits, status, _ = ops.ot_head(feats, txt, self.logit_scale, n_cls=self.n_cls, num_slices=num_slices,
                                         ot=self.OT, eps=self.eps, thresh=self.thresh, max_iter=self.max_iter,
@@ -374,3 +430,11 @@ class CustomCLIP(nn.Module):
         return logits
 
     check_nan = True
+    overlap_text = True      # run the text tower on a side stream (CUDA only)
+
+    @staticmethod
+    def _side_stream(device):
+        key = torch.device(device).index
+        if key not in _SIDE_STREAMS:
+            _SIDE_STREAMS[key] = torch.cuda.Stream(device=device)
+        return _SIDE_STREAMS[key]

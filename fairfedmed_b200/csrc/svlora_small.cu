@@ -228,7 +228,7 @@ adapter_grad_finalize_kernel(const float* __restrict__ partial_a, const float* _
                              int blocks_a, int blocks_b, const float* __restrict__ h, const float* __restrict__ dzu,
                              float* __restrict__ ds_eff, int T, int b_prime, int num_slices, int row_div,
                              float scaling, int RPS) {
-  __shared__ float red[FIN_THREADS / 16][RPS_MAX];
+  __shared__ __align__(16) float red[FIN_THREADS / 32][RPS_MAX];
   int blk = blockIdx.x;
   if (blk < blocks_a + blocks_b) {
     const bool is_a = blk < blocks_a;
@@ -237,32 +237,61 @@ adapter_grad_finalize_kernel(const float* __restrict__ partial_a, const float* _
     const int i = (is_a ? blk : blk - blocks_a) * FIN_THREADS + threadIdx.x;
     if (i >= C * RPS) return;
     const int c = i / RPS, j = i - c * RPS;
-    float acc = 0.f;
-#pragma unroll 4
-    for (int k = 0; k < n_chunks; ++k) acc += partial[(static_cast<size_t>(k) * C + c) * RPS + j];
+    // four independent accumulators keep four loads in flight (fixed association order: deterministic)
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+    const size_t stride = static_cast<size_t>(C) * RPS;
+    const float* pp = partial + static_cast<size_t>(c) * RPS + j;
+    int k = 0;
+    for (; k + 4 <= n_chunks; k += 4) {
+      a0 += pp[(k + 0) * stride];
+      a1 += pp[(k + 1) * stride];
+      a2 += pp[(k + 2) * stride];
+      a3 += pp[(k + 3) * stride];
+    }
+    for (; k < n_chunks; ++k) a0 += pp[k * stride];
+    const float acc = (a0 + a1) + (a2 + a3);
     if (j >= r) return;
     if (is_a) dA[static_cast<size_t>(c) * r + j] = acc;
     else dB[static_cast<size_t>(j) * N + c] = acc;
     return;
   }
+  // ---- per-sample segmented reduction: RPS/4 threads per row (float4 each), FIN_THREADS*4/RPS rows per pass ----
   const int b = blk - blocks_a - blocks_b;
-  const int j = threadIdx.x % RPS, lane_row = threadIdx.x / RPS;
+  const int q4 = RPS >> 2;                       // 4 (rank 16) or 8 (rank 32) float4 lanes per row
+  const int j4 = threadIdx.x % q4, lane_row = threadIdx.x / q4;
+  const int rows_per_pass = FIN_THREADS / q4;
   const int L = T / b_prime;
   const int rows = L * num_slices;
-  float acc = 0.f;
-  for (int i = lane_row; i < rows; i += FIN_THREADS / RPS) {
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 4
+  for (int i = lane_row; i < rows; i += rows_per_pass) {
     const int l = i / num_slices, sl = i - l * num_slices;
     // sequence-first rows: t = l*B' + column; batch-first rows (row_div = L): t = column*L + l
     const size_t col = static_cast<size_t>(b) * num_slices + sl;
     const size_t t = (row_div == 1) ? static_cast<size_t>(l) * b_prime + col : col * row_div + l;
-    acc = fmaf(dzu[t * RPS + j], h[t * RPS + j], acc);
+    const float4 a = __ldg(reinterpret_cast<const float4*>(dzu + t * RPS) + j4);
+    const float4 c = __ldg(reinterpret_cast<const float4*>(h + t * RPS) + j4);
+    acc.x = fmaf(a.x, c.x, acc.x);
+    acc.y = fmaf(a.y, c.y, acc.y);
+    acc.z = fmaf(a.z, c.z, acc.z);
+    acc.w = fmaf(a.w, c.w, acc.w);
   }
-  red[lane_row][j] = acc;
+  // fold the rows of a warp with shuffles (lanes with equal j4 sit q4 apart), then the warps through shared memory:
+  // fixed order both times, so the result is deterministic
+  for (int off = q4; off < 32; off <<= 1) {
+    acc.x += __shfl_xor_sync(0xffffffffu, acc.x, off);
+    acc.y += __shfl_xor_sync(0xffffffffu, acc.y, off);
+    acc.z += __shfl_xor_sync(0xffffffffu, acc.z, off);
+    acc.w += __shfl_xor_sync(0xffffffffu, acc.w, off);
+  }
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (lane < q4) *reinterpret_cast<float4*>(&red[warp][4 * lane]) = acc;
   __syncthreads();
-  if (lane_row == 0 && j < r) {
+  if (threadIdx.x < r) {
     float tot = 0.f;
-    for (int k = 0; k < FIN_THREADS / RPS; ++k) tot += red[k][j];
-    ds_eff[b * r + j] = tot * scaling;
+#pragma unroll
+    for (int k = 0; k < FIN_THREADS / 32; ++k) tot += red[k][threadIdx.x];
+    ds_eff[b * r + threadIdx.x] = tot * scaling;
   }
 }
 

@@ -105,6 +105,55 @@ def _(dy, x, w_t, lora_a, lora_b, s_eff, h, z, tiles, gelu_dact, scaling, b_prim
             s_eff.new_empty(s_eff.shape))
 
 
+@torch.library.custom_op("ffm::svlora_bwd_into", mutates_args=("dA", "dB"))
+def svlora_bwd_into(dy: Tensor, x: Tensor, w_t: Tensor, lora_a: Tensor, lora_b: Tensor, s_eff: Tensor, h: Tensor,
+                    z: Tensor, tiles: Optional[Tensor], gelu_dact: Optional[Tensor], dA: Tensor, dB: Tensor,
+                    scaling: float, b_prime: int, num_slices: int, row_div: int = 1) -> Tuple[Tensor, Tensor]:
+    """svlora_bwd with the adapter gradients OVERWRITING caller-owned fp32 buffers dA [K,r] / dB [r,N] (the trainer's
+    flat gradient buffer: no allocation, no accumulate kernel).  Returns dx, d_s_eff."""
+    _need_cuda(dy, x, w_t, dA, dB)
+    T, N = dy.shape
+    K = x.shape[1]
+    r = lora_a.shape[1]
+    nS = s_eff.shape[0]
+    if not (dA.is_contiguous() and dB.is_contiguous() and dA.dtype == torch.float32 and dB.dtype == torch.float32
+            and tuple(dA.shape) == (K, r) and tuple(dB.shape) == (r, N)):
+        raise _cabi.FfmError("svlora_bwd_into: dA / dB must be contiguous fp32 [K,r] / [r,N]")
+    dx = torch.empty((T, K), device=x.device, dtype=torch.bfloat16)
+    dse = torch.empty((nS, r), device=x.device, dtype=torch.float32)
+    lib = _cabi.load()
+    ws_bytes = lib.ffm_svlora_bwd_workspace_bytes(T, K, N, nS)
+    ws = torch.empty((ws_bytes,), device=x.device, dtype=torch.uint8)
+    _cabi.call("ffm_svlora_bwd", _ptr(dy), _ptr(x), _ptr(w_t), _ptr(lora_a), _ptr(lora_b), _ptr(s_eff), _ptr(h),
+               _ptr(z), _ptr(tiles), _ptr(gelu_dact), _ptr(dx), _ptr(dA), _ptr(dB), _ptr(dse), _ptr(ws), ws_bytes,
+               T, K, N, r, nS, b_prime, num_slices, int(row_div), float(scaling), _stream())
+    return dx, dse
+
+
+@svlora_bwd_into.register_fake
+def _(dy, x, w_t, lora_a, lora_b, s_eff, h, z, tiles, gelu_dact, dA, dB, scaling, b_prime, num_slices, row_div=1):
+    return x.new_empty(x.shape), s_eff.new_empty(s_eff.shape)
+
+
+def _direct_grad(param: Tensor) -> Optional[Tensor]:
+    """Gradient buffer a trainer registered for direct writes (`param._ffm_direct_grad = view of its flat gradient
+    buffer`), or None: then the gradient is returned to autograd as usual."""
+    return getattr(param, "_ffm_direct_grad", None)
+
+
+def _svlora_bwd_dispatch(dy, x, w_t, lora_a, lora_b, s_eff, h, z, tiles, gelu_dact, scaling, b_prime, num_slices,
+                         row_div):
+    """-> dx, dA or None, dB or None, d_s_eff.  With registered direct-gradient buffers on BOTH adapter matrices the
+    kernels write there (overwrite semantics: one backward per zero_grad, which is what the trainer does) and autograd
+    gets None, which removes two fp32 accumulate launches per layer."""
+    ga, gb = _direct_grad(lora_a), _direct_grad(lora_b)
+    if ga is not None and gb is not None:
+        dx, dse = svlora_bwd_into(dy, x, w_t, lora_a, lora_b, s_eff, h, z, tiles, gelu_dact, ga, gb, scaling, b_prime,
+                                  num_slices, row_div)
+        return dx, None, None, dse
+    return svlora_bwd(dy, x, w_t, lora_a, lora_b, s_eff, h, z, tiles, gelu_dact, scaling, b_prime, num_slices, row_div)
+
+
 @torch.library.custom_op("ffm::seff", mutates_args=())
 def seff_op(attr: Optional[Tensor], S: Tensor, S_global: Optional[Tensor], lam: float) -> Tensor:
     """s_eff [nS, r] = pi(attr) @ S (+ S_global);  attr int64 [nS] on the device or None (=> nS = 1, pi = 1/G)."""
@@ -145,12 +194,21 @@ class _SEff(torch.autograd.Function):
     def forward(ctx, attr, S, S_global, lam):
         ctx.attr, ctx.lam, ctx.G = attr, lam, S.shape[0]
         ctx.has_global = S_global is not None
+        # trainer-registered gradient views (see _direct_grad): dS is then written in place, autograd gets None
+        ctx.direct = (_direct_grad(S), None if S_global is None else _direct_grad(S_global))
         ctx.sg_shape = None if S_global is None else S_global.shape
         sg = None if S_global is None else S_global.reshape(-1).contiguous()
         return seff_op(attr, S.contiguous(), sg, lam)
 
     @staticmethod
     def backward(ctx, ds_eff):
+        gS, gSg = ctx.direct
+        if gS is not None and (not ctx.has_global or gSg is not None):
+            ds_eff = ds_eff.contiguous()
+            nS, r = ds_eff.shape
+            _cabi.call("ffm_ds", _ptr(ctx.attr), _ptr(ds_eff), _ptr(gS), _ptr(gSg) if ctx.has_global else 0, nS, ctx.G,
+                       r, float(ctx.lam), _stream())
+            return None, None, None, None
         dS, dSg = ds_op(ctx.attr, ds_eff.contiguous(), ctx.G, ctx.lam, ctx.has_global)
         return None, dS, (dSg.reshape(ctx.sg_shape) if ctx.has_global else None), None
 
@@ -175,8 +233,8 @@ class _SVLoRALinear(torch.autograd.Function):
     def backward(ctx, dy):
         x2d, w_t, lora_a, lora_b, s_eff, h, z, tiles = ctx.saved_tensors
         scaling, b_prime, num_slices, row_div = ctx.cfg
-        dx, dA, dB, dse = svlora_bwd(dy.contiguous(), x2d, w_t, lora_a, lora_b, s_eff, h, z, tiles, None, scaling,
-                                     b_prime, num_slices, row_div)
+        dx, dA, dB, dse = _svlora_bwd_dispatch(dy.contiguous(), x2d, w_t, lora_a, lora_b, s_eff, h, z, tiles, None,
+                                               scaling, b_prime, num_slices, row_div)
         return dx, None, None, None, dA, dB, dse, None, None, None, None
 
 
@@ -203,10 +261,10 @@ class _SVLoRAMLP(torch.autograd.Function):
     def backward(ctx, dy):
         x2d, g, u, h1, h2, w1_t, a1, bb1, s1, w2_t, a2, bb2, s2, z1, t1, z2, t2 = ctx.saved_tensors
         scaling, b_prime, num_slices, row_div = ctx.cfg
-        du, dA2, dB2, ds2 = svlora_bwd(dy.contiguous(), g, w2_t, a2, bb2, s2, h2, z2, t2, u, scaling, b_prime,
-                                       num_slices, row_div)
-        dx, dA1, dB1, ds1 = svlora_bwd(du, x2d, w1_t, a1, bb1, s1, h1, z1, t1, None, scaling, b_prime, num_slices,
-                                       row_div)
+        du, dA2, dB2, ds2 = _svlora_bwd_dispatch(dy.contiguous(), g, w2_t, a2, bb2, s2, h2, z2, t2, u, scaling,
+                                                 b_prime, num_slices, row_div)
+        dx, dA1, dB1, ds1 = _svlora_bwd_dispatch(du, x2d, w1_t, a1, bb1, s1, h1, z1, t1, None, scaling, b_prime,
+                                                 num_slices, row_div)
         return dx, None, None, None, dA1, dB1, ds1, None, None, None, dA2, dB2, ds2, None, None, None, None
 
 
@@ -291,6 +349,51 @@ def add_layernorm(x: Tensor, res: Optional[Tensor], gamma: Tensor, beta: Tensor,
     if res is not None:
         res = res.contiguous()
     return _AddLayerNorm.apply(x, res, gamma, beta, eps)
+
+
+# =====================================================================================================
+# ViT input side: /255 + mean/std + im2col in one pass, class token + positions + ln_pre + first ln_1 in another
+# =====================================================================================================
+@torch.library.custom_op("ffm::patchify_normalize", mutates_args=())
+def patchify_normalize(image: Tensor, mean: Tensor, std: Tensor, patch: int, div255: bool) -> Tensor:
+    """image f32 [B', C, H, W] -> bf16 [B', G, C*patch*patch] = im2col of bf16(((image / 255) - mean) / std)
+    (trainers/GLP_OT_SVLoRA.py:679-693 + clip/model.py:431-433)."""
+    _need_cuda(image, mean, std)
+    if image.dtype != torch.float32 or not image.is_contiguous():
+        raise _cabi.FfmError("patchify_normalize: image must be contiguous fp32 [B', C, H, W]")
+    bp, c, h, w = image.shape
+    out = torch.empty((bp, (h // patch) * (w // patch), c * patch * patch), device=image.device, dtype=torch.bfloat16)
+    _cabi.call("ffm_patchify_normalize", _ptr(image), _ptr(out), _ptr(mean), _ptr(std), bp, c, h, w, int(patch),
+               int(bool(div255)), _stream())
+    return out
+
+
+@patchify_normalize.register_fake
+def _(image, mean, std, patch, div255):
+    bp, c, h, w = image.shape
+    return image.new_empty((bp, (h // patch) * (w // patch), c * patch * patch), dtype=torch.bfloat16)
+
+
+@torch.library.custom_op("ffm::vit_embed_ln", mutates_args=())
+def vit_embed_ln(patch_emb: Tensor, cls: Tensor, pos: Tensor, g_pre: Tensor, b_pre: Tensor, g_1: Tensor, b_1: Tensor,
+                 eps_pre: float, eps_1: float) -> Tuple[Tensor, Tensor]:
+    """x0 = LN_pre(cat(cls, patch_emb) + pos), h0 = LN_1(x0): bf16 [B', G+1, C] each (clip/model.py:434-440, :354).
+    patch_emb bf16 [B', G, C]; the tables and LayerNorm parameters are the frozen fp32 masters."""
+    _need_cuda(patch_emb, cls, pos, g_pre, b_pre, g_1, b_1)
+    if patch_emb.dtype != torch.bfloat16 or not patch_emb.is_contiguous():
+        raise _cabi.FfmError("vit_embed_ln: patch_emb must be contiguous bf16 [B', G, C]")
+    bp, G, C = patch_emb.shape
+    x0 = torch.empty((bp, G + 1, C), device=patch_emb.device, dtype=torch.bfloat16)
+    h0 = torch.empty_like(x0)
+    _cabi.call("ffm_vit_embed_ln", _ptr(patch_emb), _ptr(cls), _ptr(pos), _ptr(g_pre), _ptr(b_pre), _ptr(g_1),
+               _ptr(b_1), _ptr(x0), _ptr(h0), 0, 0, bp, G, C, float(eps_pre), float(eps_1), _stream())
+    return x0, h0
+
+
+@vit_embed_ln.register_fake
+def _(patch_emb, cls, pos, g_pre, b_pre, g_1, b_1, eps_pre, eps_1):
+    bp, G, C = patch_emb.shape
+    return patch_emb.new_empty((bp, G + 1, C)), patch_emb.new_empty((bp, G + 1, C))
 
 
 @torch.library.custom_op("ffm::ot_head_fwd", mutates_args=())

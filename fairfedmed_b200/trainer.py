@@ -111,11 +111,16 @@ class GLP_OT_SVLoRA:
         self.flat_grads = torch.zeros(total, device=self.device, dtype=torch.float32)
         self.flat_mom = torch.zeros(total, device=self.device, dtype=torch.float32)
         off = 0
-        for _, p in named:
+        for name, p in named:
             n = p.numel()
             self.flat_params[off:off + n].copy_(p.data.reshape(-1))
             p.data = self.flat_params[off:off + n].view(p.shape)
             p.grad = self.flat_grads[off:off + n].view(p.shape)
+            if any(k in name for k in ("lora_A", "lora_B", "lora_S")) and "attnpool" not in name:
+                # the fused backward kernels write these gradients straight into the flat buffer (ops._direct_grad):
+                # one backward per zero_grad, which is how every step of this trainer runs.  The attention-pool
+                # LoRA of the ResNet goes through merged weights and plain autograd, so it keeps accumulating.
+                p._ffm_direct_grad = p.grad
             off += n
         sd = {n: p for n, p in named}
         self.flat_spec: FlatSpec = build_spec(sd, keys=[n for n, _ in named],

@@ -127,6 +127,31 @@ int ffm_add_layernorm_fwd(const void* x, const void* res, const float* gamma, co
 int ffm_add_layernorm_bwd(const void* d_ln, const void* d_res, const void* s, const float* gamma, const float* mean,
                           const float* rstd, void* dx, int rows, int C, ffm_stream_t stream);
 
+/* ------------------------------------------------- ViT input side (scope row f3) -------------- */
+/*
+ * ffm_patchify_normalize — CustomCLIP.forward's `image / 255`, `(image - mean) / std`
+ * (trainers/GLP_OT_SVLoRA.py:679-693), the cast to half precision and the im2col of the stride-`patch` convolution
+ * ModifiedVisionTransformer.conv1 (clip/model.py:431-433) in one pass:
+ *   patches[b*G + gy*gw + gx, c*patch*patch + py*patch + px] =
+ *       bf16((image[b, c, gy*patch+py, gx*patch+px] / 255 - mean[c]) / std[c])         (IEEE fp32 divisions)
+ *   image f32 [Bp, C, H, W] (0..255; div255 = 0 skips the first division: OCT inputs are already min-max scaled),
+ *   patches bf16 [Bp*G, C*patch*patch], mean / std f32 [C].  patch % 8 == 0, H % patch == W % patch == 0.
+ * The patch embedding is then the GEMM patches · conv1.weight.flatten(1)^T.
+ *
+ * ffm_vit_embed_ln — clip/model.py:434-440 and the first block's ln_1 (:354):
+ *   x0[b, 0, :]   = LN_pre(class_embedding + positional_embedding[0])
+ *   x0[b, l>0, :] = LN_pre(patch_emb[b*G + l-1, :] + positional_embedding[l]),   h0 = LN_1(x0)
+ *   patch_emb bf16 [Bp*G, C]; tables / LayerNorm parameters f32; x0, h0 bf16 [Bp, G+1, C]; mean1 / rstd1 f32
+ *   [Bp*(G+1)] or NULL (statistics of LN_1, the format ffm_add_layernorm_bwd takes).  C in {256, 512, 768, 1024}.
+ * Forward only: conv1, the embeddings and ln_pre are frozen and the image needs no gradient.
+ */
+int ffm_patchify_normalize(const float* image, void* patches, const float* mean, const float* stdv, int Bp, int C,
+                           int H, int W, int patch, int div255, ffm_stream_t stream);
+int ffm_vit_embed_ln(const void* patch_emb, const float* class_embedding, const float* positional_embedding,
+                     const float* ln_pre_gamma, const float* ln_pre_beta, const float* ln1_gamma, const float* ln1_beta,
+                     void* x0, void* h0, float* mean1, float* rstd1, int Bp, int G, int C, float eps_pre, float eps_1,
+                     ffm_stream_t stream);
+
 /*
  * Group mixing of singular values — trainers/GLP_OT_SVLoRA.py:453-467.
  *   attr != NULL: pi[b,g] = lambda (0.7 in the reference) if attr[b]==g else (1-lambda)/(G-1)

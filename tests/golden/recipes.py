@@ -159,6 +159,11 @@ MODEL_CASES = {
     "tiny_oct": dict(modality="oct_bscans", ot="Sinkhorn", res=32, embed=64, v_layers=1, v_width=128, t_width=64,
                      t_heads=2, t_layers=1, rank=12, alpha=2.0, lora_type="FairLoRA", groups=2, batch=2, seed=54,
                      dim_per_3d_slice=8, grad_filter=_adapter_grads),
+    # width 256 (4 heads): the vision tower takes the fused device path end to end — patchify+normalise kernel,
+    # class/positional embedding + ln_pre + ln_1 kernel, add+LayerNorm kernels, fused MLP, text tower on a side stream
+    "small_fused": dict(modality="slo_fundus", ot="Sinkhorn", res=64, embed=64, v_layers=2, v_width=256, t_width=64,
+                        t_heads=2, t_layers=2, rank=12, alpha=2.0, lora_type="FairLoRA", groups=3, batch=4, seed=56,
+                        grad_filter=_adapter_grads),
     # CLIP ResNet backbone (scope row a8): conv trunk with FairLoRA on the 1x1 convs (rank 32, alpha 8 — the RN50 script
     # values) + plain LoRA on the attention pool; BatchNorm in training mode with trainable affine parameters
     "tiny_rn50": dict(modality="slo_fundus", ot="Sinkhorn", res=128, embed=64, v_layers=(1, 1, 1, 1), v_width=16,
