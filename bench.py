@@ -325,7 +325,10 @@ def run_ours(args):
             ev.synchronize()
             losses.append(float(loss_ring[slot]))      # the host reads EVERY step's loss inside the timed region
 
+    host_ts = []
+
     def step_host(i):
+        host_ts.append(time.perf_counter())
         if i not in staged:
             stage(i)
         batch, ev = staged.pop(i)
@@ -345,6 +348,11 @@ def run_ours(args):
     ms_e2e, _ = timed(step_host, args.steps, max(args.warmup, 3), finalize=lambda: drain(keep=0))
     staged.clear()
     e2e_value = BATCH * world * args.steps / (ms_e2e / 1e3)
+    if rank == 0 and len(host_ts) > args.steps:      # diagnostics only (stderr): host-side gaps between e2e steps
+        gaps = [1e3 * (b - a) for a, b in zip(host_ts[-args.steps:-1], host_ts[-args.steps + 1:])]
+        if gaps:
+            print(f"[bench] e2e host step gaps ms: median {statistics.median(gaps):.2f} max {max(gaps):.2f} "
+                  f"(n={len(gaps)})", file=sys.stderr)
 
     # ---- roofline of the dominant kernel, measured live with CUDA events on the launching stream ----
     lib.ffm_profile_enable(1)

@@ -28,6 +28,7 @@ SIGNATURES = {
     "ffm_profile_read": (_i, [_vp, _vp, _i]),
     "ffm_svlora_fwd_workspace_bytes": (_sz, [_i, _i, _i, _i]),
     "ffm_svlora_bwd_workspace_bytes": (_sz, [_i, _i, _i, _i]),
+    "ffm_svlora_prepare": (_i, [_fp, _fp, _fp, _vp, _sz, _i, _i, _i, _i, _f, _vp]),
     "ffm_svlora_fwd": (_i, [_vp, _vp, _fp, _fp, _fp, _fp, _vp, _vp, _fp, _vp, _vp, _sz,
                             _i, _i, _i, _i, _i, _i, _i, _i, _f, _i, _vp]),
     "ffm_svlora_bwd": (_i, [_vp, _vp, _vp, _fp, _fp, _fp, _fp, _vp, _vp, _vp, _vp, _fp, _fp, _fp, _vp, _sz,

@@ -28,7 +28,14 @@ from .resnet_model import ModifiedResNet_GLP_OT
 
 PIXEL_MEAN = (0.48145466, 0.4578275, 0.40821073)
 PIXEL_STD = (0.26862954, 0.26130258, 0.27577711)
-_SIDE_STREAMS: dict = {}     # device index -> side stream of the text tower (module level: models stay picklable)
+_SIDE_STREAMS: dict = {}     # (device index, role) -> side stream (module level: models stay picklable)
+
+
+def _side_stream(device, role: str):
+    key = (torch.device(device).index, role)
+    if key not in _SIDE_STREAMS:
+        _SIDE_STREAMS[key] = torch.cuda.Stream(device=device)
+    return _SIDE_STREAMS[key]
 
 
 class _Bf16Cache:
@@ -82,9 +89,21 @@ class MLP(nn.Module, _Bf16Cache):
             s_eff = torch.ones((1, layer.rank), device=device, dtype=torch.float32)
         return (w, w_t, bias, layer.lora_A.weight, layer.lora_B.weight, s_eff)
 
-    def forward(self, x: torch.Tensor, attr: Optional[torch.Tensor] = None):
-        fused = isinstance(self.c_fc, _AdapterBase) and isinstance(self.c_proj, _AdapterBase) and x.is_cuda \
-            and x.dim() == 3 and self.c_fc.scaling == self.c_proj.scaling
+    def _fusable(self) -> bool:
+        return isinstance(self.c_fc, _AdapterBase) and isinstance(self.c_proj, _AdapterBase) \
+            and self.c_fc.scaling == self.c_proj.scaling
+
+    def prepare(self, attr, device):
+        """Everything of the fused MLP that depends on parameters and `attr` only (s_eff of both adapters, their bf16
+        tiles): the caller may run this ahead of time on another stream and hand the result to forward(prepared=)."""
+        fc = self._adapter_operands(self.c_fc, attr, device)
+        pj = self._adapter_operands(self.c_proj, attr, device)
+        t1 = ops.svlora_prepare(fc[3].detach(), fc[4].detach(), fc[5].detach(), self.c_fc.scaling)
+        t2 = ops.svlora_prepare(pj[3].detach(), pj[4].detach(), pj[5].detach(), self.c_proj.scaling)
+        return fc, pj, t1, t2
+
+    def forward(self, x: torch.Tensor, attr: Optional[torch.Tensor] = None, prepared=None):
+        fused = self._fusable() and x.is_cuda and x.dim() == 3
         if fused:
             if self.batch_first:
                 bp, L, c = x.shape
@@ -92,13 +111,18 @@ class MLP(nn.Module, _Bf16Cache):
             else:
                 L, bp, c = x.shape
                 row_div = 1          # row t = position * B' + column (reference layout)
-            fc = self._adapter_operands(self.c_fc, attr, x.device)
-            pj = self._adapter_operands(self.c_proj, attr, x.device)
+            if prepared is not None:
+                fc, pj, t1, t2 = prepared
+                tiles = (t1, t2)
+            else:
+                fc = self._adapter_operands(self.c_fc, attr, x.device)
+                pj = self._adapter_operands(self.c_proj, attr, x.device)
+                tiles = None
             n_samples = fc[5].shape[0]
             x2d = x.reshape(L * bp, c)
             if x2d.dtype != torch.bfloat16:
                 x2d = x2d.to(torch.bfloat16)
-            y = ops.svlora_mlp(x2d.contiguous(), fc, pj, self.c_fc.scaling, bp, bp // n_samples, row_div)
+            y = ops.svlora_mlp(x2d.contiguous(), fc, pj, self.c_fc.scaling, bp, bp // n_samples, row_div, tiles)
             return y.reshape(x.shape[0], x.shape[1], -1).to(x.dtype)
         if isinstance(self.c_fc, _AdapterBase):
             if self.batch_first:     # the stand-alone adapter modules speak the reference's sequence-first layout
@@ -159,6 +183,30 @@ class Transformer(nn.Module):
         self.resblocks = nn.ModuleList([ResidualAttentionBlock(width, heads, attn_mask, batch_first)
                                         for _ in range(layers)])
 
+    hoist_adapter_prep = True     # issue every block's s_eff / adapter-tile kernels up front on a side stream
+
+    def _prepare_adapters(self, attr, device):
+        """The 4 tiny launches per block that only depend on parameters and `attr` (group mixing of the singular values
+        and the bf16 adapter tiles, for c_fc and c_proj) leave the critical path: they are issued for all blocks at
+        once on a side stream, each block waits for its own event.  Autograd runs the matching backward nodes (dS) on
+        that stream too."""
+        if not any(blk.mlp._fusable() for blk in self.resblocks):
+            return None
+        cur = torch.cuda.current_stream(device)
+        side = _side_stream(device, "prep")
+        side.wait_stream(cur)
+        out = []
+        with torch.cuda.stream(side):
+            for blk in self.resblocks:
+                if not blk.mlp._fusable():
+                    out.append(None)
+                    continue
+                pre = blk.mlp.prepare(attr, device)
+                ev = torch.cuda.Event()
+                ev.record(side)
+                out.append((pre, ev))
+        return out
+
     def _fusable(self, x: torch.Tensor) -> bool:
         if not (x.is_cuda and x.dtype == torch.bfloat16 and self.width % 256 == 0 and self.width <= 1024):
             return False
@@ -177,6 +225,7 @@ class Transformer(nn.Module):
                 x = block(x, attr)
             return x if final_ln is None else final_ln(x)
         blocks = self.resblocks
+        prepared = self._prepare_adapters(attr, x.device) if self.hoist_adapter_prep else None
         ln = blocks[0].ln_1
         if h0 is None:
             x, h = ops.add_layernorm(x, None, ln.weight, ln.bias, ln.eps)
@@ -185,7 +234,15 @@ class Transformer(nn.Module):
         for i, blk in enumerate(blocks):
             a = blk.attention(h)
             x, h = ops.add_layernorm(x, a, blk.ln_2.weight, blk.ln_2.bias, blk.ln_2.eps)
-            m = blk.mlp(h, attr=attr)
+            if prepared is not None and prepared[i] is not None:
+                pre, ev = prepared[i]
+                cur = torch.cuda.current_stream(x.device)
+                cur.wait_event(ev)
+                for t in (pre[0][5], pre[1][5], pre[2], pre[3]):     # s_eff x2, tiles x2: allocated on the side stream
+                    t.record_stream(cur)
+                m = blk.mlp(h, attr=attr, prepared=pre)
+            else:
+                m = blk.mlp(h, attr=attr)
             nxt = blocks[i + 1].ln_1 if i + 1 < len(blocks) else final_ln
             if nxt is None:
                 return x + m
@@ -434,7 +491,4 @@ class CustomCLIP(nn.Module):
 
     @staticmethod
     def _side_stream(device):
-        key = torch.device(device).index
-        if key not in _SIDE_STREAMS:
-            _SIDE_STREAMS[key] = torch.cuda.Stream(device=device)
-        return _SIDE_STREAMS[key]
+        return _side_stream(device, "text")

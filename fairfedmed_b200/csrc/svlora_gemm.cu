@@ -731,11 +731,30 @@ size_t ffm_svlora_bwd_workspace_bytes(int T, int K, int N, int n_samples) {
          align256(static_cast<size_t>(T) * RP_MAX * 2) + svlora_bwd_small_scratch_bytes(T, K, N);
 }
 
+int ffm_svlora_prepare(const float* lora_a, const float* lora_b, const float* s_eff, void* workspace,
+                       size_t workspace_bytes, int K, int N, int r, int n_samples, float scaling,
+                       cudaStream_t stream) {
+  FFM_CHECK_ARG(lora_a && lora_b && s_eff && workspace, "ffm_svlora_prepare: null pointer argument");
+  FFM_CHECK_ARG(r >= 1 && r <= RP_MAX, "ffm_svlora_prepare: rank %d not in [1, %d]", r, RP_MAX);
+  FFM_CHECK_ARG(n_samples >= 1 && K >= 1 && N >= 1, "ffm_svlora_prepare: bad sizes");
+  FFM_CHECK_ARG(workspace_bytes >= svlora_tiles_bytes(K, N, n_samples), "ffm_svlora_prepare: workspace too small");
+  SvloraTiles ws;
+  carve_tiles(&ws, workspace, K, N, n_samples);
+  svlora_prep_kernel<<<96, 256, 0, stream>>>(lora_a, lora_b, s_eff, ws.a_fwd, ws.b_fwd, ws.a_bwd, ws.b_bwd, ws.s_rows,
+                                             K, N, r, padded_rank(r), n_samples, scaling);
+  FFM_CHECK_CUDA(cudaGetLastError());
+  count_launch();
+  return FFM_OK;
+}
+
 int ffm_svlora_fwd(const void* x, const void* w, const float* bias, const float* lora_a, const float* lora_b,
                    const float* s_eff, void* y, void* y_dact, float* h_out, void* z_out, void* workspace,
                    size_t workspace_bytes, int T, int K, int N, int r, int n_samples, int b_prime, int num_slices,
                    int row_div, float scaling, int act, cudaStream_t stream) {
-  FFM_CHECK_ARG(x && w && lora_a && lora_b && s_eff && y && workspace, "ffm_svlora_fwd: null pointer argument");
+  FFM_CHECK_ARG(x && w && y && workspace, "ffm_svlora_fwd: null pointer argument");
+  // lora_a == lora_b == NULL: the workspace already holds the tiles (ffm_svlora_prepare, same K / N / n_samples)
+  const bool prepared = lora_a == nullptr && lora_b == nullptr;
+  FFM_CHECK_ARG(prepared || (lora_a && lora_b && s_eff), "ffm_svlora_fwd: lora_a, lora_b and s_eff go together");
   FFM_CHECK_ARG(row_div >= 1, "ffm_svlora_fwd: row_div must be >= 1");
   FFM_CHECK_ARG(r >= 1 && r <= RP_MAX, "ffm_svlora_fwd: rank %d not in [1, %d]", r, RP_MAX);
   FFM_CHECK_ARG(n_samples >= 1, "ffm_svlora_fwd: n_samples must be >= 1");
@@ -748,10 +767,12 @@ int ffm_svlora_fwd(const void* x, const void* w, const float* bias, const float*
   SvloraTiles ws;
   carve_tiles(&ws, workspace, K, N, n_samples);
   const int rp = padded_rank(r);
-  svlora_prep_kernel<<<96, 256, 0, stream>>>(lora_a, lora_b, s_eff, ws.a_fwd, ws.b_fwd, ws.a_bwd, ws.b_bwd, ws.s_rows,
-                                             K, N, r, rp, n_samples, scaling);
-  FFM_CHECK_CUDA(cudaGetLastError());
-  count_launch();
+  if (!prepared) {
+    svlora_prep_kernel<<<96, 256, 0, stream>>>(lora_a, lora_b, s_eff, ws.a_fwd, ws.b_fwd, ws.a_bwd, ws.b_bwd,
+                                               ws.s_rows, K, N, r, rp, n_samples, scaling);
+    FFM_CHECK_CUDA(cudaGetLastError());
+    count_launch();
+  }
   GemmOperands o;
   o.x = x; o.wmat = w; o.a_side = ws.a_fwd; o.b_side = ws.b_fwd; o.s_rows = ws.s_rows; o.bias = bias;
   o.out = y; o.out_pre = y_dact; o.h_out = h_out; o.z_out = z_out; o.aux = nullptr;

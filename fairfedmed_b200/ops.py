@@ -42,11 +42,13 @@ def _need_cuda(*tensors):
 @torch.library.custom_op("ffm::svlora_fwd", mutates_args=())
 def svlora_fwd(x: Tensor, w: Tensor, bias: Optional[Tensor], lora_a: Tensor, lora_b: Tensor, s_eff: Tensor,
                scaling: float, b_prime: int, num_slices: int, act: int,
-               row_div: int = 1) -> Tuple[Tensor, Tensor, Tensor, Tensor, Tensor]:
+               row_div: int = 1, prepared: Optional[Tensor] = None) -> Tuple[Tensor, Tensor, Tensor, Tensor, Tensor]:
     """y, y_dact, h, z, tiles = fused FairLoRA linear.  x [T,K] bf16, w [N,K] bf16, lora_a [K,r], lora_b [r,N],
     s_eff [nS,r].  y_dact = QuickGELU'(u) when act = 1 (else empty); h = x·A (f32 [T,rp]); z = bf16(scaling·h⊙s_eff)
     ([T,rp], rp = padded_rank(r)); tiles = the call's workspace holding the prepared bf16 adapter tiles (hand it to svlora_bwd).
-    Row t of x belongs to sample ((t // row_div) % b_prime) // num_slices (row_div = 1: sequence-first rows)."""
+    Row t of x belongs to sample ((t // row_div) % b_prime) // num_slices (row_div = 1: sequence-first rows).
+    `prepared`: workspace already filled by svlora_prepare for these (lora_a, lora_b, s_eff): no preparation launch;
+    the returned `tiles` is then empty (keep using `prepared`)."""
     _need_cuda(x, w, lora_a, lora_b, s_eff)
     T, K = x.shape
     N = w.shape[0]
@@ -59,6 +61,13 @@ def svlora_fwd(x: Tensor, w: Tensor, bias: Optional[Tensor], lora_a: Tensor, lor
     z = torch.empty((T, rp), device=x.device, dtype=torch.bfloat16)
     lib = _cabi.load()
     ws_bytes = lib.ffm_svlora_fwd_workspace_bytes(T, K, N, nS)
+    if prepared is not None:
+        if prepared.numel() < ws_bytes or not prepared.is_cuda:
+            raise _cabi.FfmError("svlora_fwd: prepared workspace too small")
+        _cabi.call("ffm_svlora_fwd", _ptr(x), _ptr(w), _ptr(bias), 0, 0, 0, _ptr(y), _ptr(y_dact) if act else 0, _ptr(h),
+                   _ptr(z), _ptr(prepared), prepared.numel(), T, K, N, r, nS, b_prime, num_slices, int(row_div),
+                   float(scaling), int(act), _stream())
+        return y, y_dact, h, z, y.new_empty((0,), dtype=torch.uint8)
     ws = torch.empty((ws_bytes,), device=x.device, dtype=torch.uint8)
     _cabi.call("ffm_svlora_fwd", _ptr(x), _ptr(w), _ptr(bias), _ptr(lora_a), _ptr(lora_b), _ptr(s_eff), _ptr(y),
                _ptr(y_dact) if act else 0, _ptr(h), _ptr(z), _ptr(ws), ws_bytes, T, K, N, r, nS, b_prime, num_slices,
@@ -66,8 +75,29 @@ def svlora_fwd(x: Tensor, w: Tensor, bias: Optional[Tensor], lora_a: Tensor, lor
     return y, y_dact, h, z, ws
 
 
+@torch.library.custom_op("ffm::svlora_prepare", mutates_args=())
+def svlora_prepare(lora_a: Tensor, lora_b: Tensor, s_eff: Tensor, scaling: float) -> Tensor:
+    """Workspace with the bf16 adapter tiles of both directions + scaled singular values (ffm_svlora_prepare).  Depends on
+    parameters and attribute rows only: issue it ahead of the layer (side stream) and pass it to svlora_fwd(prepared=)."""
+    _need_cuda(lora_a, lora_b, s_eff)
+    K, r = lora_a.shape
+    N = lora_b.shape[1]
+    nS = s_eff.shape[0]
+    lib = _cabi.load()
+    ws_bytes = lib.ffm_svlora_fwd_workspace_bytes(0, K, N, nS)
+    ws = torch.empty((ws_bytes,), device=lora_a.device, dtype=torch.uint8)
+    _cabi.call("ffm_svlora_prepare", _ptr(lora_a), _ptr(lora_b), _ptr(s_eff), _ptr(ws), ws_bytes, K, N, r, nS,
+               float(scaling), _stream())
+    return ws
+
+
+@svlora_prepare.register_fake
+def _(lora_a, lora_b, s_eff, scaling):
+    return lora_a.new_empty((1,), dtype=torch.uint8)
+
+
 @svlora_fwd.register_fake
-def _(x, w, bias, lora_a, lora_b, s_eff, scaling, b_prime, num_slices, act, row_div=1):
+def _(x, w, bias, lora_a, lora_b, s_eff, scaling, b_prime, num_slices, act, row_div=1, prepared=None):
     T, N = x.shape[0], w.shape[0]
     y = x.new_empty((T, N))
     rp = padded_rank(lora_a.shape[1])
@@ -133,6 +163,19 @@ def svlora_bwd_into(dy: Tensor, x: Tensor, w_t: Tensor, lora_a: Tensor, lora_b: 
 @svlora_bwd_into.register_fake
 def _(dy, x, w_t, lora_a, lora_b, s_eff, h, z, tiles, gelu_dact, dA, dB, scaling, b_prime, num_slices, row_div=1):
     return x.new_empty(x.shape), s_eff.new_empty(s_eff.shape)
+
+
+_PENDING_DIRECT_WRITES: list = []     # events behind in-place gradient writes that autograd does not know about
+
+
+def join_direct_grad_writes() -> None:
+    """Make the current stream wait for every in-place gradient write issued by the last backward() (call it after
+    loss.backward() and before the optimizer reads the flat gradient buffer).  A no-op without direct gradients."""
+    if _PENDING_DIRECT_WRITES:
+        cur = torch.cuda.current_stream()
+        for ev in _PENDING_DIRECT_WRITES:
+            cur.wait_event(ev)
+        _PENDING_DIRECT_WRITES.clear()
 
 
 def _direct_grad(param: Tensor) -> Optional[Tensor]:
@@ -208,6 +251,12 @@ class _SEff(torch.autograd.Function):
             nS, r = ds_eff.shape
             _cabi.call("ffm_ds", _ptr(ctx.attr), _ptr(ds_eff), _ptr(gS), _ptr(gSg) if ctx.has_global else 0, nS, ctx.G,
                        r, float(ctx.lam), _stream())
+            # No AccumulateGrad node runs for S, so the autograd engine does not join this node's stream (the forward
+            # may have run on a side stream, clip_model.Transformer._prepare_adapters) with the caller's at the end of
+            # backward(): leave an event for join_direct_grad_writes().
+            ev = torch.cuda.Event()
+            ev.record()
+            _PENDING_DIRECT_WRITES.append(ev)
             return None, None, None, None
         dS, dSg = ds_op(ctx.attr, ds_eff.contiguous(), ctx.G, ctx.lam, ctx.has_global)
         return None, dS, (dSg.reshape(ctx.sg_shape) if ctx.has_global else None), None
@@ -250,9 +299,13 @@ class _SVLoRAMLP(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, x2d, w1, w1_t, b1, a1, bb1, s1, w2, w2_t, b2, a2, bb2, s2, scaling, b_prime, num_slices,
-                row_div):
-        g, u, h1, z1, t1 = svlora_fwd(x2d, w1, b1, a1, bb1, s1, scaling, b_prime, num_slices, 1, row_div)
-        y, _, h2, z2, t2 = svlora_fwd(g, w2, b2, a2, bb2, s2, scaling, b_prime, num_slices, 0, row_div)
+                row_div, p1=None, p2=None):
+        g, u, h1, z1, t1 = svlora_fwd(x2d, w1, b1, a1, bb1, s1, scaling, b_prime, num_slices, 1, row_div, p1)
+        y, _, h2, z2, t2 = svlora_fwd(g, w2, b2, a2, bb2, s2, scaling, b_prime, num_slices, 0, row_div, p2)
+        if p1 is not None:
+            t1 = p1
+        if p2 is not None:
+            t2 = p2
         ctx.save_for_backward(x2d, g, u, h1, h2, w1_t, a1, bb1, s1, w2_t, a2, bb2, s2, z1, t1, z2, t2)
         ctx.cfg = (scaling, b_prime, num_slices, row_div)
         return y
@@ -265,12 +318,14 @@ class _SVLoRAMLP(torch.autograd.Function):
                                                  b_prime, num_slices, row_div)
         dx, dA1, dB1, ds1 = _svlora_bwd_dispatch(du, x2d, w1_t, a1, bb1, s1, h1, z1, t1, None, scaling, b_prime,
                                                  num_slices, row_div)
-        return dx, None, None, None, dA1, dB1, ds1, None, None, None, dA2, dB2, ds2, None, None, None, None
+        return dx, None, None, None, dA1, dB1, ds1, None, None, None, dA2, dB2, ds2, None, None, None, None, None, None
 
 
-def svlora_mlp(x2d, fc, proj, scaling: float, b_prime: int, num_slices: int, row_div: int = 1) -> Tensor:
-    """fc / proj = (w, w_t, bias, lora_a, lora_b, s_eff) tuples."""
-    return _SVLoRAMLP.apply(x2d, *fc, *proj, scaling, b_prime, num_slices, row_div)
+def svlora_mlp(x2d, fc, proj, scaling: float, b_prime: int, num_slices: int, row_div: int = 1,
+               prepared: Optional[Tuple[Tensor, Tensor]] = None) -> Tensor:
+    """fc / proj = (w, w_t, bias, lora_a, lora_b, s_eff) tuples; prepared = (svlora_prepare of fc, of proj) or None."""
+    p1, p2 = prepared if prepared is not None else (None, None)
+    return _SVLoRAMLP.apply(x2d, *fc, *proj, scaling, b_prime, num_slices, row_div, p1, p2)
 
 
 # =====================================================================================================

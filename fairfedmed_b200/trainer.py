@@ -140,6 +140,7 @@ class GLP_OT_SVLoRA:
         if self.sync_metrics and not bool(torch.isfinite(loss.detach())):   # detect_anomaly (engine/trainer.py:260-262)
             raise FloatingPointError("Loss is infinite or NaN!")
         loss.backward()
+        ops.join_direct_grad_writes()
         n_steps = 2 if self.cfg.TRAINER.GLP_OT_LORA.UNFREEZE_IMAGE_ENCODER else 1
         o = self.cfg.OPTIM
         ops.sgd_step_(self.flat_params, self.flat_grads, self.flat_mom, self.current_lr(), o.MOMENTUM, o.WEIGHT_DECAY,
@@ -211,6 +212,7 @@ class GLP_OT_SVLoRA:
             loss = F.cross_entropy(output, self._g_label)
             self.flat_grads.zero_()
             loss.backward()
+            ops.join_direct_grad_writes()
             n_steps = 2 if self.cfg.TRAINER.GLP_OT_LORA.UNFREEZE_IMAGE_ENCODER else 1
             o = self.cfg.OPTIM
             ops.sgd_step_(self.flat_params, self.flat_grads, self.flat_mom, self._g_lr, o.MOMENTUM, o.WEIGHT_DECAY,

@@ -60,6 +60,16 @@ size_t ffm_svlora_fwd_workspace_bytes(int T, int K, int N, int n_samples);
 size_t ffm_svlora_bwd_workspace_bytes(int T, int K, int N, int n_samples);
 
 /*
+ * ffm_svlora_prepare — the per-call operand preparation of ffm_svlora_fwd on its own: fills `workspace`
+ * (ffm_svlora_fwd_workspace_bytes(T, K, N, n_samples); T is ignored) with the bf16 adapter tiles of both directions
+ * and the scaled singular values.  It depends on the parameters and the attribute rows only, not on activations, so a
+ * host can issue it for every layer ahead of time (another stream) and then call ffm_svlora_fwd with
+ * lora_a = lora_b = NULL (s_eff ignored) and that workspace: the forward then skips its own preparation launch.
+ */
+int ffm_svlora_prepare(const float* lora_a, const float* lora_b, const float* s_eff, void* workspace,
+                       size_t workspace_bytes, int K, int N, int r, int n_samples, float scaling, ffm_stream_t stream);
+
+/*
  * Forward of FairLoRALinear / SVLoRALinear / LoRALinear
  *   replaces trainers/GLP_OT_SVLoRA.py:450-482 (FairLoRALinear.forward), :308-312, :241-242.
  *

@@ -1,7 +1,8 @@
 """GPU parity of the ViT input-side kernels (scope row f3) and of the training-step plumbing added around them:
 patchify+normalise (bit-exact vs the reference's expression order), class/positional embedding + ln_pre + ln_1
-(vs an fp32 torch restatement of clip/model.py:434-440,:354), direct adapter-gradient writes (bit-equal to the
-autograd-accumulated path) and the text tower on a side stream (bit-equal to the single-stream schedule)."""
+(vs an fp32 torch restatement of clip/model.py:434-440,:354), direct adapter-gradient writes (same result as the
+autograd-accumulated path) and the side-stream schedule (text tower, hoisted adapter preparation: same result as the
+single-stream schedule, eagerly and replayed from the captured step graph)."""
 from __future__ import annotations
 
 import pytest
@@ -63,7 +64,8 @@ def _small_trainer(direct: bool, overlap: bool):
     tr.sync_metrics = False
     tr.step_auc = False
     tr.model.check_nan = False
-    tr.model.overlap_text = overlap
+    tr.model.overlap_text = overlap                                    # text tower on a side stream
+    tr.model.image_encoder.transformer.hoist_adapter_prep = overlap    # s_eff / adapter tiles of all blocks up front
     tr.batch_idx, tr.num_batches = 0, 10 ** 9
     if not direct:
         for p in tr.model.parameters():
