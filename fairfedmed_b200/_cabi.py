@@ -40,9 +40,9 @@ SIGNATURES = {
     "ffm_seff": (_i, [_vp, _fp, _fp, _fp, _i, _i, _i, _f, _vp]),
     "ffm_ds": (_i, [_vp, _fp, _fp, _fp, _i, _i, _i, _f, _vp]),
     "ffm_ot_head_workspace_bytes": (_sz, [_i, _i, _i, _i, _i]),
-    "ffm_ot_head_fwd": (_i, [_vp, _i, _fp, _fp, _fp, _fp, _fp, _fp, _vp, _vp, _sz,
+    "ffm_ot_head_fwd": (_i, [_vp, _i, _i, _fp, _fp, _fp, _fp, _fp, _fp, _vp, _vp, _sz,
                              _i, _i, _i, _i, _i, _i, _i, _f, _f, _i, _f, _vp]),
-    "ffm_ot_head_bwd": (_i, [_vp, _i, _fp, _fp, _fp, _fp, _fp, _fp, _vp, _fp, _fp, _vp, _sz,
+    "ffm_ot_head_bwd": (_i, [_vp, _i, _i, _fp, _fp, _fp, _fp, _fp, _fp, _vp, _fp, _fp, _vp, _sz,
                              _i, _i, _i, _i, _i, _i, _i, _vp]),
     "ffm_sinkhorn_workspace_bytes": (_sz, [_i, _i, _i]),
     "ffm_sinkhorn": (_i, [_fp, _fp, _vp, _vp, _sz, _i, _i, _i, _i, _f, _f, _i, _vp]),

@@ -283,8 +283,10 @@ class ModifiedVisionTransformer(nn.Module, _Bf16Cache):
                   *self.ln_post.parameters(), *tr.resblocks[0].ln_1.parameters()]
         return not any(p.requires_grad for p in params)
 
-    def forward_patches(self, patches: torch.Tensor, attr: Optional[torch.Tensor] = None):
-        """`forward` from the im2col'ed, normalised image on (patches [B', G, 3*P*P], e.g. ops.patchify_normalize)."""
+    def forward_patches(self, patches: torch.Tensor, attr: Optional[torch.Tensor] = None, batch_first: bool = False):
+        """`forward` from the im2col'ed, normalised image on (patches [B', G, 3*P*P], e.g. ops.patchify_normalize).
+        batch_first=True returns the tokens as they are stored, [B', L, output_dim] (ops.ot_head(batch_first=True)
+        reads that layout directly); the default is the reference's sequence-first view."""
         dt = patches.dtype
         x = patches @ self._bf("conv1", self.conv1.weight, dt).flatten(1).t()                  # [B', g*g, width]
         tr = self.transformer
@@ -297,13 +299,13 @@ class ModifiedVisionTransformer(nn.Module, _Bf16Cache):
                                       ln1.bias.detach(), self.ln_pre.eps, ln1.eps)
             x = tr(x0, attr=attr, final_ln=self.ln_post, h0=h0)
             x = x @ self._bf("proj", self.proj, dt)
-            return x.transpose(0, 1)
+            return x if batch_first else x.transpose(0, 1)
         cls = self._bf("cls", self.class_embedding, dt).expand(x.shape[0], 1, -1)
         x = torch.cat([cls, x], dim=1) + self._bf("pos", self.positional_embedding, dt)
         x = self.ln_pre(x)
         x = self.transformer(x, attr=attr, final_ln=self.ln_post)
         x = x @ self._bf("proj", self.proj, dt)                                                # [B', L, output_dim]
-        return x.transpose(0, 1)                                                               # [L, B', output_dim]
+        return x if batch_first else x.transpose(0, 1)                                         # [L, B', output_dim]
 
 
 class TextEncoder(nn.Module, _Bf16Cache):
@@ -467,7 +469,7 @@ class CustomCLIP(nn.Module):
             ve = self.image_encoder
             patches = ops.patchify_normalize(image.float().contiguous(), self.pixel_mean.reshape(-1),
                                              self.pixel_std.reshape(-1), ve.patch_size, True)
-            feats = ve.forward_patches(patches, attr=attr_dev)
+            feats = ve.forward_patches(patches, attr=attr_dev, batch_first=True)       # [B', M+1, D] as stored
         else:
             x = self.preprocess(image.float())
             feats = self.image_encoder(x.to(dt), attr=attr_dev)                    # [M+1, B', D]
@@ -477,10 +479,10 @@ class CustomCLIP(nn.Module):
         else:
             prompts = self.prompt_learner()
             txt = self.text_encoder(prompts, self.prompt_learner.eot_index)       # [N*n_cls, D] fp32
-        num_slices = feats.shape[1] // b
+        num_slices = feats.shape[0 if fast_input else 1] // b
         logits, status, _ = ops.ot_head(feats, txt, self.logit_scale, n_cls=self.n_cls, num_slices=num_slices,
                                         ot=self.OT, eps=self.eps, thresh=self.thresh, max_iter=self.max_iter,
-                                        top_percent=self.top_percent)
+                                        top_percent=self.top_percent, batch_first=fast_input)
         self.last_status = status
         if self.OT != "None" and self.check_nan and int(status[1].item()) != 0:
             return None                                                            # reference :738-743

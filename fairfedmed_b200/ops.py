@@ -453,10 +453,15 @@ def _(patch_emb, cls, pos, g_pre, b_pre, g_1, b_1, eps_pre, eps_1):
 
 @torch.library.custom_op("ffm::ot_head_fwd", mutates_args=())
 def ot_head_fwd(img: Tensor, txt: Tensor, logit_scale: Tensor, num_slices: int, mode: int, eps: float, thresh: float,
-                max_iter: int, top_percent: float) -> Tuple[Tensor, Tensor, Tensor, Tensor, Tensor, Tensor]:
-    """logits, T, sim, inv_norm, status, workspace.  img [M+1, Bp, D] (bf16/f32), txt [N, n_cls, D] f32."""
+                max_iter: int, top_percent: float,
+                batch_first: bool = False) -> Tuple[Tensor, Tensor, Tensor, Tensor, Tensor, Tensor]:
+    """logits, T, sim, inv_norm, status, workspace.  img [M+1, Bp, D] (or [Bp, M+1, D] with batch_first; bf16/f32),
+    txt [N, n_cls, D] f32."""
     _need_cuda(img, txt, logit_scale)
-    Mp1, Bp, D = img.shape
+    if batch_first:
+        Bp, Mp1, D = img.shape
+    else:
+        Mp1, Bp, D = img.shape
     M = Mp1 - 1
     N, n_cls, _ = txt.shape
     P = Bp * n_cls
@@ -469,7 +474,8 @@ def ot_head_fwd(img: Tensor, txt: Tensor, logit_scale: Tensor, num_slices: int, 
     lib = _cabi.load()
     ws_bytes = lib.ffm_ot_head_workspace_bytes(M, Bp, D, N, n_cls)
     ws = torch.empty((ws_bytes,), device=dev, dtype=torch.uint8)
-    _cabi.call("ffm_ot_head_fwd", _ptr(img), int(img.dtype == torch.bfloat16), _ptr(txt), _ptr(logit_scale),
+    _cabi.call("ffm_ot_head_fwd", _ptr(img), int(img.dtype == torch.bfloat16), int(bool(batch_first)), _ptr(txt),
+               _ptr(logit_scale),
                _ptr(logits), _ptr(T) if mode else 0, _ptr(sim), _ptr(inv_norm), _ptr(status), _ptr(ws), ws_bytes, M,
                Bp, D, N, n_cls, num_slices, mode, float(eps), float(thresh), int(max_iter), float(top_percent),
                _stream())
@@ -477,8 +483,8 @@ def ot_head_fwd(img: Tensor, txt: Tensor, logit_scale: Tensor, num_slices: int, 
 
 
 @ot_head_fwd.register_fake
-def _(img, txt, logit_scale, num_slices, mode, eps, thresh, max_iter, top_percent):
-    Mp1, Bp, D = img.shape
+def _(img, txt, logit_scale, num_slices, mode, eps, thresh, max_iter, top_percent, batch_first=False):
+    Mp1, Bp, D = (img.shape[1], img.shape[0], img.shape[2]) if batch_first else img.shape
     N, n_cls, _ = txt.shape
     f = dict(device=img.device, dtype=torch.float32)
     P = Bp * n_cls
@@ -490,48 +496,54 @@ def _(img, txt, logit_scale, num_slices, mode, eps, thresh, max_iter, top_percen
 
 @torch.library.custom_op("ffm::ot_head_bwd", mutates_args=())
 def ot_head_bwd(img: Tensor, txt: Tensor, logit_scale: Tensor, d_logits: Tensor, T: Tensor, sim: Tensor,
-                inv_norm: Tensor, ws: Tensor, num_slices: int, mode: int) -> Tuple[Tensor, Tensor, Tensor]:
-    Mp1, Bp, D = img.shape
+                inv_norm: Tensor, ws: Tensor, num_slices: int, mode: int,
+                batch_first: bool = False) -> Tuple[Tensor, Tensor, Tensor]:
+    if batch_first:
+        Bp, Mp1, D = img.shape
+    else:
+        Mp1, Bp, D = img.shape
     N, n_cls, _ = txt.shape
     d_img = torch.empty_like(img)
     d_txt = torch.empty_like(txt)
     d_ls = torch.empty((), device=img.device, dtype=torch.float32)
-    _cabi.call("ffm_ot_head_bwd", _ptr(img), int(img.dtype == torch.bfloat16), _ptr(txt), _ptr(logit_scale),
+    _cabi.call("ffm_ot_head_bwd", _ptr(img), int(img.dtype == torch.bfloat16), int(bool(batch_first)), _ptr(txt),
+               _ptr(logit_scale),
                _ptr(d_logits), _ptr(T) if mode else 0, _ptr(sim), _ptr(inv_norm), _ptr(d_img), _ptr(d_txt), _ptr(d_ls),
                _ptr(ws), ws.numel(), Mp1 - 1, Bp, D, N, n_cls, num_slices, mode, _stream())
     return d_img, d_txt, d_ls
 
 
 @ot_head_bwd.register_fake
-def _(img, txt, logit_scale, d_logits, T, sim, inv_norm, ws, num_slices, mode):
+def _(img, txt, logit_scale, d_logits, T, sim, inv_norm, ws, num_slices, mode, batch_first=False):
     return torch.empty_like(img), torch.empty_like(txt), logit_scale.new_empty(())
 
 
 class _OTHead(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, img, txt, logit_scale, num_slices, mode, eps, thresh, max_iter, top_percent):
+    def forward(ctx, img, txt, logit_scale, num_slices, mode, eps, thresh, max_iter, top_percent, batch_first=False):
         logits, T, sim, inv_norm, status, ws = ot_head_fwd(img, txt, logit_scale, num_slices, mode, eps, thresh,
-                                                           max_iter, top_percent)
+                                                           max_iter, top_percent, batch_first)
         ctx.save_for_backward(img, txt, logit_scale, T, sim, inv_norm, ws)
-        ctx.cfg = (num_slices, mode)
+        ctx.cfg = (num_slices, mode, batch_first)
         ctx.mark_non_differentiable(status, T)
         return logits, status, T
 
     @staticmethod
     def backward(ctx, d_logits, _d_status, _d_T):
         img, txt, logit_scale, T, sim, inv_norm, ws = ctx.saved_tensors
-        num_slices, mode = ctx.cfg
+        num_slices, mode, batch_first = ctx.cfg
         d_img, d_txt, d_ls = ot_head_bwd(img, txt, logit_scale, d_logits.contiguous().float(), T, sim, inv_norm, ws,
-                                         num_slices, mode)
-        return d_img, d_txt, d_ls.reshape(logit_scale.shape), None, None, None, None, None, None
+                                         num_slices, mode, batch_first)
+        return d_img, d_txt, d_ls.reshape(logit_scale.shape), None, None, None, None, None, None, None
 
 
 def ot_head(image_features: Tensor, text_features: Tensor, logit_scale: Tensor, *, n_cls: int, num_slices: int = 1,
             ot: str = "Sinkhorn", eps: float = 0.1, thresh: float = 1e-3, max_iter: int = 100,
-            top_percent: float = 0.8):
+            top_percent: float = 0.8, batch_first: bool = False):
     """Head of CustomCLIP.forward (trainers/GLP_OT_SVLoRA.py:696-757).
 
-    image_features [M+1, Bp, D] (bf16 or f32), text_features [N*n_cls, D] prompt-major. Returns
+    image_features [M+1, Bp, D] like the reference (or [Bp, M+1, D] with batch_first=True; bf16 or f32),
+    text_features [N*n_cls, D] prompt-major. Returns
     (logits [Bp/num_slices, n_cls] f32, status int32[2] = {iterations, nan flag}, T)."""
     img = image_features.contiguous()
     if img.dtype not in (torch.bfloat16, torch.float32):
@@ -539,7 +551,7 @@ def ot_head(image_features: Tensor, text_features: Tensor, logit_scale: Tensor, 
     D = img.shape[-1]
     txt = text_features.float().contiguous().view(-1, n_cls, D)
     ls = logit_scale.float().reshape(1) if logit_scale.dim() == 0 else logit_scale.float()
-    return _OTHead.apply(img, txt, ls, num_slices, OT_MODES[ot], eps, thresh, max_iter, top_percent)
+    return _OTHead.apply(img, txt, ls, num_slices, OT_MODES[ot], eps, thresh, max_iter, top_percent, bool(batch_first))
 
 
 def sinkhorn(K: Tensor, *, mode: str = "Sinkhorn", v_mass: float = 1.0, thresh: float = 1e-3, max_iter: int = 100):

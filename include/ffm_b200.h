@@ -194,12 +194,15 @@ size_t ffm_ot_head_workspace_bytes(int M, int Bp, int D, int n_prompts, int n_cl
  *
  *   Outputs: logits [Bp/num_slices, n_cls] f32; T_out [Bp*n_cls, M, n_prompts] f32 (may be NULL when mode = NONE);
  *   status_out int32[2] = {iterations run, 1 if T contains NaN (reference returns None :738-743)}.
- *   img_is_bf16 selects the storage type of img.
+ *   img_is_bf16 selects the storage type of img.  img_batch_first = 1: img (and d_img of the backward) is stored
+ *   batch-first [Bp, M+1, D] (the layout fairfedmed_b200's ViT tower keeps internally) instead of the reference's
+ *   sequence-first [M+1, Bp, D] — same values, no transposition pass.  8 <= D <= 1024, D % 8 == 0.
  */
-int ffm_ot_head_fwd(const void* img, int img_is_bf16, const float* txt, const float* logit_scale, float* logits,
-                    float* T_out, float* sim_out, float* inv_norm_out, int32_t* status_out, void* workspace,
-                    size_t workspace_bytes, int M, int Bp, int D, int n_prompts, int n_cls, int num_slices, int mode,
-                    float eps, float thresh, int max_iter, float top_percent, ffm_stream_t stream);
+int ffm_ot_head_fwd(const void* img, int img_is_bf16, int img_batch_first, const float* txt, const float* logit_scale,
+                    float* logits, float* T_out, float* sim_out, float* inv_norm_out, int32_t* status_out,
+                    void* workspace, size_t workspace_bytes, int M, int Bp, int D, int n_prompts, int n_cls,
+                    int num_slices, int mode, float eps, float thresh, int max_iter, float top_percent,
+                    ffm_stream_t stream);
 
 /*
  * Backward of the head. The transport plan is a constant (computed under no_grad, :734), so gradients flow
@@ -207,7 +210,7 @@ int ffm_ot_head_fwd(const void* img, int img_is_bf16, const float* txt, const fl
  *   d_img [M+1, Bp, D] (same storage type as img; row 0 receives zeros), d_txt [n_prompts, n_cls, D] f32,
  *   d_logit_scale f32[1].
  */
-int ffm_ot_head_bwd(const void* img, int img_is_bf16, const float* txt, const float* logit_scale,
+int ffm_ot_head_bwd(const void* img, int img_is_bf16, int img_batch_first, const float* txt, const float* logit_scale,
                     const float* d_logits, const float* T_plan, const float* sim, const float* inv_norm, void* d_img,
                     float* d_txt, float* d_logit_scale, void* workspace, size_t workspace_bytes, int M, int Bp, int D,
                     int n_prompts, int n_cls, int num_slices, int mode, ffm_stream_t stream);

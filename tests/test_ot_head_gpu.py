@@ -70,7 +70,7 @@ def test_sinkhorn_nan_flag():
     assert not bool(torch.isfinite(T).all())
 
 
-def _head_case(ot, M, Bp, D, n_cls, N, slices, dtype, seed):
+def _head_case(ot, M, Bp, D, n_cls, N, slices, dtype, seed, batch_first=False):
     from fairfedmed_b200 import ops
     g = torch.Generator().manual_seed(seed)
     feats = torch.randn(M + 1, Bp, D, generator=g)
@@ -86,11 +86,15 @@ def _head_case(ot, M, Bp, D, n_cls, N, slices, dtype, seed):
     ref, T_ref, _, iters = rp.ot_head(f_o, t_o, l_o, n_cls=n_cls, batch=Bp // slices, ot=ot, return_aux=True)
     (ref * dl).sum().backward()
     # kernel
-    f_g = feats.to(DEV).to(dtype).requires_grad_(True)
+    f_g = feats.to(DEV).to(dtype)
+    if batch_first:                      # the ViT tower's own layout [Bp, M+1, D]: same values, no transposition pass
+        f_g = f_g.transpose(0, 1).contiguous()
+    f_g.requires_grad_(True)
     t_g = txt.to(DEV).requires_grad_(True)
     l_g = ls.to(DEV).requires_grad_(True)
-    logits, status, T = ops.ot_head(f_g, t_g, l_g, n_cls=n_cls, num_slices=slices, ot=ot)
+    logits, status, T = ops.ot_head(f_g, t_g, l_g, n_cls=n_cls, num_slices=slices, ot=ot, batch_first=batch_first)
     (logits * dl.to(DEV)).sum().backward()
+    f_grad = f_g.grad.transpose(0, 1) if batch_first else f_g.grad
     st = status.cpu().tolist()
     if ot != "None":
         assert st == [iters, 0]
@@ -100,8 +104,8 @@ def _head_case(ot, M, Bp, D, n_cls, N, slices, dtype, seed):
     scale = float(ref.abs().max())
     assert float((logits.cpu() - ref).abs().max()) <= tol * scale
     gscale = float(f_o.grad.abs().max())
-    assert float(f_g.grad[0].abs().max()) == 0.0                      # pooled token gets no gradient
-    assert float((f_g.grad.float().cpu() - f_o.grad).abs().max()) <= (5e-4 if dtype == torch.float32 else 2e-2) * gscale
+    assert float(f_grad[0].abs().max()) == 0.0                        # pooled token gets no gradient
+    assert float((f_grad.float().cpu() - f_o.grad).abs().max()) <= (5e-4 if dtype == torch.float32 else 2e-2) * gscale
     assert float((t_g.grad.cpu() - t_o.grad).abs().max()) <= (5e-4 if dtype == torch.float32 else 2e-2) * float(t_o.grad.abs().max())
     assert float((l_g.grad.cpu() - l_o.grad).abs()) <= tol * max(1.0, float(l_o.grad.abs()))
 
@@ -110,6 +114,20 @@ def _head_case(ot, M, Bp, D, n_cls, N, slices, dtype, seed):
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
 def test_head_forward_backward_matches_oracle(ot, dtype):
     _head_case(ot, M=196, Bp=8, D=512, n_cls=2, N=2, slices=1, dtype=dtype, seed=7)
+
+
+@pytest.mark.parametrize("ot", ["None", "Sinkhorn"])
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_head_batch_first_layout(ot, dtype):
+    _head_case(ot, M=196, Bp=8, D=512, n_cls=2, N=2, slices=1, dtype=dtype, seed=17, batch_first=True)
+    _head_case(ot, M=16, Bp=6, D=64, n_cls=2, N=2, slices=2, dtype=dtype, seed=18, batch_first=True)
+
+
+def test_head_wide_rows_and_many_text_vectors():
+    """Shapes outside the register build of the backward (D > 512 or more than 4 text vectors): shared-memory build."""
+    _head_case("Sinkhorn", M=49, Bp=6, D=1024, n_cls=2, N=2, slices=1, dtype=torch.bfloat16, seed=19, batch_first=True)
+    _head_case("Sinkhorn", M=36, Bp=4, D=256, n_cls=2, N=3, slices=1, dtype=torch.float32, seed=20)
+    _head_case("None", M=36, Bp=4, D=264, n_cls=3, N=2, slices=1, dtype=torch.float32, seed=21)
 
 
 def test_head_oct_slices_and_rn50_token_count():
