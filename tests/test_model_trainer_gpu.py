@@ -181,8 +181,12 @@ def test_trainer_step_matches_oracle_double_sgd():
         assert float((got - upd).abs().max()) <= 6e-2 * float(upd.abs().max()) + 1e-7, k
 
 
-def test_two_client_round_and_evaluation():
-    """BASELINE config 1 shape (2 clients, batch 8, 1 local epoch, 1 round) on shrunken towers: the global weights
+@pytest.mark.parametrize("dataset,attributes,attr_type", [
+    ("FairFedMed", ["race"], "race"),                              # BASELINE config 1
+    ("FedChexMimic", ["age", "gender", "race"], "age"),            # BASELINE config 5: CheXpert / MIMIC shaped, 2 groups
+])
+def test_two_client_round_and_evaluation(dataset, attributes, attr_type):
+    """BASELINE config 1 / 5 shape (2 clients, batch 8, 1 local epoch, 1 round) on shrunken towers: the global weights
     after the round equal the oracle's n_k / n_{k,g}-weighted average (+ shared half of S, EMA) of the two local
     results obtained by driving an identical trainer by hand (same seeds, same shared optimizer state, F7)."""
     import fairfedmed_b200.trainer  # noqa: F401
@@ -190,6 +194,7 @@ def test_two_client_round_and_evaluation():
     from fairfedmed_b200.federated import run_federated
     from fairfedmed_b200.registry import build_trainer
     cfg = _tiny_cfg(ot="None", users=2, batch=8, n_train=16)
+    cfg.DATASET.merge_from_dict(dict(NAME=dataset, ATTRIBUTES=attributes, ATTRIBUTE_TYPE=attr_type))
     manual = build_trainer(cfg)
     manual.step_auc = False
     start = manual.get_flat().clone()
@@ -204,7 +209,8 @@ def test_two_client_round_and_evaluation():
     _, global_flat, hist = run_federated(cfg, rounds=1, shared_half_s=True, trainer=fed)
     spec = fed.flat_spec
     n_k = [len(fed.fed_train_loader_x_dict[k].dataset) for k in range(2)]
-    n_kg = [fed.fed_train_loader_x_dict[k].dataset.count_by_attribute("race") for k in range(2)]
+    n_kg = [fed.fed_train_loader_x_dict[k].dataset.count_by_attribute(attr_type) for k in range(2)]
+    assert fed.num_groups == len(n_kg[0])
     w = [{k2: v.cpu() for k2, v in fed_utils.unpack(spec, f).items()} for f in locals_]
     w_g = {k2: v.cpu() for k2, v in fed_utils.unpack(spec, start).items()}
     ref = rp.average_weights_ema(w_g, w, [0, 1], n_k, n_kg, 0, 1, shared_half_s=True)
@@ -215,6 +221,36 @@ def test_two_client_round_and_evaluation():
         torch.testing.assert_close(got[k2].cpu(), ref[k2], rtol=1e-3, atol=1e-5)
     res = fed.test(idx=0, current_epoch=0)
     assert len(res) == 13 and 0 <= res[0] <= 100 and 0 <= res[3] <= 100
+    assert len(fed.last_results["esaucs_by_attrs"]) == len(attributes)            # one ES-AUC per attribute
+
+
+def test_trainer_runs_oct_volumes_with_four_attributes():
+    """BASELINE config 3 shape (shrunk): OCT B-scan stacks [B, 32, H, W] folded into 4 slice-images per sample, the
+    trainable slice projection in front of the tower, attribute used for the adapters = gender (2 groups), evaluation
+    over the four FairFedMed attributes the reference knows (trainers/GLP_OT_SVLoRA.py:775-790)."""
+    import fairfedmed_b200.trainer  # noqa: F401
+    from fairfedmed_b200.registry import build_trainer
+    cfg = _tiny_cfg(ot="Sinkhorn", users=1, batch=4, n_train=8)
+    cfg.MODEL_ARCH.merge_from_dict(dict(VISION_WIDTH=256))          # fused add+LayerNorm chain, autograd input side
+    cfg.DATASET.merge_from_dict(dict(MODALITY_TYPE="oct_bscans", DIM_PER_3D_SLICE=8,
+                                     ATTRIBUTES=["race", "gender", "ethnicity", "language"], ATTRIBUTE_TYPE="gender"))
+    tr = build_trainer(cfg)
+    assert tr.num_groups == 2 and any("proj_per_3d_slice" in n for n in tr.trainable_names)
+    with torch.no_grad():
+        for n_, p_ in tr.model.named_parameters():
+            if "lora_A" in n_:
+                p_.copy_(0.05 * torch.randn(p_.shape, generator=torch.Generator().manual_seed(4)).to(p_.device))
+    batch = next(iter(tr.fed_train_loader_x_dict[0]))
+    assert tuple(batch["img"].shape) == (4, 32, 64, 64) and tuple(batch["attrs"].shape) == (4, 4)
+    tr.batch_idx, tr.num_batches = 0, 2
+    out = tr.forward_backward(batch)
+    assert np.isfinite(out["loss"])
+    sd = dict(tr.model.named_parameters())
+    for frag in ("proj_per_3d_slice.weight", "lora_A", "lora_B", "lora_S", "prompt_learner.ctx"):
+        k = next(n for n in tr.trainable_names if frag in n)
+        assert float(sd[k].grad.abs().max()) > 0, k
+    res = tr.test(idx=0, current_epoch=0)
+    assert len(res) == 13 and len(tr.last_results["esaucs_by_attrs"]) == 4 and len(tr.last_results["dpds"]) == 4
 
 
 @pytest.mark.gpu

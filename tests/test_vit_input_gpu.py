@@ -55,6 +55,7 @@ def test_vit_embed_ln_matches_torch(bp, G, C):
 
 def _small_trainer(direct: bool, overlap: bool):
     import bench
+    import fairfedmed_b200.trainer  # noqa: F401  (registers GLP_OT_SVLoRA)
     from fairfedmed_b200.registry import build_trainer
     cfg = bench.make_cfg(1, 4, "Sinkhorn")
     cfg.MODEL_ARCH.VISION_LAYERS = 2
