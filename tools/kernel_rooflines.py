@@ -26,6 +26,7 @@ def measure(fn, reps=10, flush=True):
         for _ in range(reps):
             if flush:
                 flush_buf.zero_()
+                flush_buf.view(torch.int32).sum()      # read pass: the timed kernel does not pay for dirty write-backs
             fn()
         torch.cuda.synchronize()
     agg = collections.defaultdict(list)
@@ -114,6 +115,39 @@ for k, us in m.items():
         add(k, "M+1=197 B'=64 D=512 bf16", us, bytes_=197 * 64 * 512 * 2.0)
     else:
         add(k, "config 2 head (128 problems)", us, note="latency bound: 200 KB problem")
+# head forward + backward in the tower's own batch-first layout
+feats_bf = feats.transpose(0, 1).contiguous().requires_grad_(True)
+txt_g = txt.clone().requires_grad_(True)
+ls_g = ls.clone().requires_grad_(True)
+dl = torch.randn(64, 2, generator=g).to(dev)
+
+
+def head_fb():
+    lg, _, _ = ops.ot_head(feats_bf, txt_g, ls_g, n_cls=2, num_slices=1, ot="Sinkhorn", batch_first=True)
+    (lg * dl).sum().backward()
+m = measure(head_fb)
+for k, us in m.items():
+    if "head_bwd" in k:
+        add(k, "B'=64 M+1=197 D=512 bf16 (batch-first)", us, bytes_=2 * 197 * 64 * 512 * 2.0,
+            note="algorithmic bytes = read features + write their gradient")
+    elif "txt_bwd" in k:
+        add(k, "296 partials x 4 x 512", us, note="latency bound")
+
+# ---------------- ViT input side ----------------
+img = torch.randint(0, 256, (64, 1, 224, 224), generator=g).float().repeat(1, 3, 1, 1).to(dev)
+mean = torch.tensor([0.48145466, 0.4578275, 0.40821073], device=dev)
+std = torch.tensor([0.26862954, 0.26130258, 0.27577711], device=dev)
+m = measure(lambda: ops.patchify_normalize(img, mean, std, 16, True))
+for k, us in m.items():
+    add(k, "B'=64 3x224x224 fp32 -> bf16 patches", us, bytes_=64 * 3 * 224 * 224 * 6.0)
+pe = torch.randn(64, 196, 768, generator=g).bfloat16().to(dev)
+cls_e = torch.randn(768, generator=g).to(dev)
+pos_e = torch.randn(197, 768, generator=g).to(dev)
+one, zero = torch.ones(768, device=dev), torch.zeros(768, device=dev)
+m = measure(lambda: ops.vit_embed_ln(pe, cls_e, pos_e, one, zero, one, zero, 1e-5, 1e-5))
+for k, us in m.items():
+    add(k, "B'=64 G=196 C=768", us, bytes_=(64 * 196 + 2 * 64 * 197) * 768 * 2.0 + 197 * 768 * 4.0)
+
 for P in (128, 8192, 65536):
     sim = torch.rand(P, 196, 2, generator=g)
     Kmat = torch.exp(-(1 - sim) / 0.1).to(dev)
