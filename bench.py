@@ -308,12 +308,21 @@ def run_ours(args):
     # ---- e2e: host batches through the public trainer API, H2D inside, loss read back every step ----
     copy_stream = torch.cuda.Stream(device=dev)
     staged = {}
+    # three rotating device staging slots (allocated once: no allocator traffic, no cudaMalloc inside the timed region)
+    n_slots = 3
+    slots = [{k: torch.empty_like(v, device=dev) for k, v in host[0].items()} for _ in range(n_slots)]
+    slot_free = [None] * n_slots                       # event: the step that last read the slot has consumed it
 
     def stage(i):
+        sl = i % n_slots
         with torch.cuda.stream(copy_stream):
-            staged[i] = ({k: v.to(dev, non_blocking=True) for k, v in host[i % pool].items()},
-                         torch.cuda.Event())
-            staged[i][1].record(copy_stream)
+            if slot_free[sl] is not None:
+                copy_stream.wait_event(slot_free[sl])
+            for k, v in host[i % pool].items():
+                slots[sl][k].copy_(v, non_blocking=True)                # H2D from pinned memory, every step
+            ev = torch.cuda.Event()
+            ev.record(copy_stream)
+        staged[i] = (slots[sl], ev)
 
     losses = []
     loss_ring = torch.zeros(8, dtype=torch.float32).pin_memory()
@@ -335,17 +344,24 @@ def run_ours(args):
         stage(i + 1)                                   # prefetch the next batch while this one computes
         torch.cuda.current_stream().wait_event(ev)
         out = run_step(batch)
+        consumed = torch.cuda.Event()
+        consumed.record()
+        slot_free[i % n_slots] = consumed
         slot = i % 8
         loss_ring[slot:slot + 1].copy_(out["loss"].detach().reshape(1), non_blocking=True)   # D2H, every step
         done = torch.cuda.Event()
         done.record()
         in_flight.append((slot, done))
         drain(keep=1)                                  # read step i-1's loss while step i runs (no pipeline bubble)
-        for v in batch.values():
-            v.record_stream(torch.cuda.current_stream())
 
     staged.clear()
-    ms_e2e, _ = timed(step_host, args.steps, max(args.warmup, 3), finalize=lambda: drain(keep=0))
+    import gc
+    gc.collect()
+    gc.disable()                                       # a collector pause inside a 20-step region is a 1 ms/step artefact
+    try:
+        ms_e2e, _ = timed(step_host, args.steps, max(args.warmup, 3), finalize=lambda: drain(keep=0))
+    finally:
+        gc.enable()
     staged.clear()
     e2e_value = BATCH * world * args.steps / (ms_e2e / 1e3)
     if rank == 0 and len(host_ts) > args.steps:      # diagnostics only (stderr): host-side gaps between e2e steps

@@ -4,8 +4,10 @@
 //   * adapter gradients dA = x^T·dh, dB = (scaling z)^T·dy       (autograd of :477-478)
 //   * per-sample        ds_eff[b] = sum_{t in sample b} scaling·dzu ⊙ h   (segmented by sample id)
 // Reference lines are trainers/GLP_OT_SVLoRA.py in /root/reference.
+#include <stdlib.h>
+
 #include "../../include/ffm_b200.h"
-#include "ffm_common.cuh"
+#include "svlora_gemm.cuh"
 
 namespace ffm {
 
@@ -212,6 +214,114 @@ adapter_grad_kernel(const __nv_bfloat16* __restrict__ Ma, const __nv_bfloat16* _
 }
 
 // ----------------------------------------------------------------------------------------------
+// TMA build of the same contraction (default).  ncu on the cp.async build: LDGSTS writes shared memory sector by sector
+// (6-way excess wavefronts), a third of the warp stalls sit on the stage barrier, DRAM 54 % busy.  Here one elected
+// thread issues three bulk tensor copies per stage (two SW128 boxes of 64 rows x 64 columns of M, one [64 x R] box of
+// v) into a 4-stage ring guarded by mbarriers; consumers read the swizzled boxes with the same ldmatrix.trans pattern.
+// Row chunks are multiples of 16 rows, so a chunk ends on a k-step boundary and rows past the matrix are zero-filled
+// by TMA: no element-wise clipping anywhere.
+// ----------------------------------------------------------------------------------------------
+constexpr int CT_STAGES = 4;
+template <int R> struct CtCfg {
+  static constexpr int M_BYTES = CS_ROWS * CS_COLS * 2;              // 16384: two 8 KB SW128 boxes
+  static constexpr int V_BYTES = CS_ROWS * R * 2;                    // 2048 / 4096, rows of 2R bytes, no swizzle
+  static constexpr int STAGE_BYTES = ((M_BYTES + V_BYTES + 1023) / 1024) * 1024;
+  static constexpr int SMEM_BYTES = CT_STAGES * STAGE_BYTES + 1024 + 64;   // + alignment slack + barriers
+};
+
+template <int R>
+__global__ void __launch_bounds__(CS_THREADS)
+adapter_grad_tma_kernel(const __grid_constant__ CUtensorMap tm_ma, const __grid_constant__ CUtensorMap tm_va,
+                        const __grid_constant__ CUtensorMap tm_mb, const __grid_constant__ CUtensorMap tm_vb,
+                        float* __restrict__ partial_a, int Ca, int groups_a, float* __restrict__ partial_b, int Cb,
+                        int T, int rows_per_chunk) {
+  using Cfg = CtCfg<R>;
+  constexpr int NT = R / 8;
+  extern __shared__ uint8_t ct_smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(ct_smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + CT_STAGES * Cfg::STAGE_BYTES);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const bool is_a = static_cast<int>(blockIdx.y) < groups_a;
+  const CUtensorMap* tm_m = is_a ? &tm_ma : &tm_mb;
+  const CUtensorMap* tm_v = is_a ? &tm_va : &tm_vb;
+  float* __restrict__ partial = is_a ? partial_a : partial_b;
+  const int C = is_a ? Ca : Cb;
+  const int c_base = (is_a ? blockIdx.y : blockIdx.y - groups_a) * CS_COLS;
+  const int t_begin = blockIdx.x * rows_per_chunk;
+  const int t_end = min(T, t_begin + rows_per_chunk);
+  const int n_stages = (t_end - t_begin + CS_ROWS - 1) / CS_ROWS;
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(tm_m);
+    tma_prefetch_desc(tm_v);
+    for (int i = 0; i < CT_STAGES; ++i) mbar_init(&full_bar[i], 1);
+    fence_mbar_init();
+  }
+  __syncthreads();
+
+  auto issue = [&](int st_idx) {          // one thread: arm the barrier and start the three copies of a stage
+    const int buf = st_idx % CT_STAGES;
+    uint8_t* mt = smem + buf * Cfg::STAGE_BYTES;
+    const int t0 = t_begin + st_idx * CS_ROWS;
+    mbar_arrive_expect_tx(&full_bar[buf], Cfg::M_BYTES + Cfg::V_BYTES);
+    tma_load_2d(mt, tm_m, &full_bar[buf], c_base, t0);
+    tma_load_2d(mt + Cfg::M_BYTES / 2, tm_m, &full_bar[buf], c_base + 64, t0);
+    tma_load_2d(mt + Cfg::M_BYTES, tm_v, &full_bar[buf], 0, t0);
+  };
+  if (threadIdx.x == 0)
+    for (int s0 = 0; s0 < CT_STAGES && s0 < n_stages; ++s0) issue(s0);
+
+  float acc[NT][4];
+#pragma unroll
+  for (int n = 0; n < NT; ++n)
+#pragma unroll
+    for (int e = 0; e < 4; ++e) acc[n][e] = 0.f;
+
+  // ldmatrix lane roles: matrix id = lane / 8, row inside the 8x8 block = lane % 8.  A = M^T from the SW128 box of this
+  // warp (box = warp / 4, 16 columns = two 16-byte chunks of the 128-byte row, chunk index XOR (row & 7)); B = v.
+  const int mi = lane >> 3, r8 = lane & 7;
+  const uint32_t wl = warp & 3;
+  const uint32_t a_lane_off = (warp >> 2) * (Cfg::M_BYTES / 2) + (r8 + 8 * (mi >> 1)) * 128 +
+                              (((2 * wl + (mi & 1)) ^ static_cast<uint32_t>(r8)) << 4);
+  const uint32_t b_lane_off = Cfg::M_BYTES + (r8 + 8 * (mi & 1)) * (2 * R) + (8 * (mi >> 1)) * 2;
+
+  for (int st_idx = 0; st_idx < n_stages; ++st_idx) {
+    const int buf = st_idx % CT_STAGES;
+    mbar_wait(&full_bar[buf], (st_idx / CT_STAGES) & 1, 900 + buf);
+    const uint32_t st = smem_u32(smem + buf * Cfg::STAGE_BYTES);
+    const int rows_valid = min(CS_ROWS, t_end - (t_begin + st_idx * CS_ROWS));   // multiple of 16 unless it ends at T
+#pragma unroll
+    for (int ks = 0; ks < CS_ROWS / 16; ++ks) {
+      if (ks * 16 < rows_valid) {           // warp-uniform: rows past the chunk belong to the next CTA
+        uint32_t a[4];
+        ldmatrix_x4_trans(st + ks * 16 * 128 + a_lane_off, a);          // A = M^T : 16 columns x 16 rows(t)
+#pragma unroll
+        for (int g16 = 0; g16 < R / 16; ++g16) {
+          uint32_t b[4];
+          ldmatrix_x4_trans(st + ks * 16 * (2 * R) + b_lane_off + g16 * 32, b);   // B = v : 16 rows(t) x 16 ranks
+          mma_bf16_16816(acc[2 * g16], a, b[0], b[1]);
+          mma_bf16_16816(acc[2 * g16 + 1], a, b[2], b[3]);
+        }
+      }
+    }
+    __syncthreads();                        // every warp is done with this buffer: refill it
+    if (threadIdx.x == 0 && st_idx + CT_STAGES < n_stages) issue(st_idx + CT_STAGES);
+  }
+
+  const int g = lane >> 2, i2 = (lane & 3) * 2;
+#pragma unroll
+  for (int hrow = 0; hrow < 2; ++hrow) {
+    const int c = c_base + warp * 16 + g + 8 * hrow;
+    if (c < C) {
+      float* p0 = partial + (static_cast<size_t>(blockIdx.x) * C + c) * R;
+#pragma unroll
+      for (int n = 0; n < NT; ++n)
+        *reinterpret_cast<float2*>(p0 + 8 * n + i2) = make_float2(acc[n][2 * hrow], acc[n][2 * hrow + 1]);
+    }
+  }
+}
+
+// ----------------------------------------------------------------------------------------------
 // One launch that finishes the adapter gradients of a layer.  Block roles by blockIdx.x:
 //   [0, blocks_a)            dA[c*r + j]  = sum over row chunks of partial_a[chunk, c, j]
 //   [blocks_a, +blocks_b)    dB[j*N + c]  = sum over row chunks of partial_b[chunk, c, j]        (transposed store)
@@ -299,9 +409,10 @@ constexpr int CS_MAX_CHUNKS = 64;  // row chunks (partials: chunks x C x 16 fp32
 
 // three CTAs fit per SM (61 KB of smem each): fill those slots in ONE wave — a ceil() here once produced 300 CTAs for
 // 296 slots and the four stragglers doubled the kernel time (ncu: DRAM 45 % busy)
-static int pick_chunks(int T, int K, int N) {
+static int pick_chunks(int T, int K, int N, int rp) {
   const int col_groups = (K + CS_COLS - 1) / CS_COLS + (N + CS_COLS - 1) / CS_COLS;
-  int chunks = (3 * num_sms()) / col_groups;
+  const int ctas_per_sm = rp <= 16 ? 3 : 2;          // TMA build: 75 KB (rank 16) / 83 KB (rank 32) of smem per CTA
+  int chunks = (ctas_per_sm * num_sms()) / col_groups;
   if (chunks > CS_MAX_CHUNKS) chunks = CS_MAX_CHUNKS;
   const int max_chunks = (T + CS_ROWS - 1) / CS_ROWS;
   if (chunks > max_chunks) chunks = max_chunks;
@@ -310,7 +421,7 @@ static int pick_chunks(int T, int K, int N) {
 }
 
 size_t svlora_bwd_small_scratch_bytes(int T, int K, int N) {
-  return static_cast<size_t>(pick_chunks(T, K, N)) * (static_cast<size_t>(K) + N) * RPS_MAX * 4 + 256;
+  return static_cast<size_t>(pick_chunks(T, K, N, 16)) * (static_cast<size_t>(K) + N) * RPS_MAX * 4 + 256;
 }
 
 template <int R>
@@ -331,6 +442,31 @@ static int launch_adapter_grad(const __nv_bfloat16* x, const __nv_bfloat16* dh, 
   return FFM_OK;
 }
 
+template <int R>
+static int launch_adapter_grad_tma(const __nv_bfloat16* x, const __nv_bfloat16* dh, float* partial_a, int K,
+                                   int groups_a, const __nv_bfloat16* dy, const __nv_bfloat16* z, float* partial_b, int N,
+                                   int T, int rows_per_chunk, dim3 grid, cudaStream_t stream) {
+  using Cfg = CtCfg<R>;
+  CUtensorMap tm_ma, tm_va, tm_mb, tm_vb;
+  int rc;
+  if ((rc = make_map_bf16(&tm_ma, x, T, K, CS_ROWS, 64, CU_TENSOR_MAP_SWIZZLE_128B, true))) return rc;
+  if ((rc = make_map_bf16(&tm_va, dh, T, R, CS_ROWS, R, CU_TENSOR_MAP_SWIZZLE_NONE, false))) return rc;
+  if ((rc = make_map_bf16(&tm_mb, dy, T, N, CS_ROWS, 64, CU_TENSOR_MAP_SWIZZLE_128B, true))) return rc;
+  if ((rc = make_map_bf16(&tm_vb, z, T, R, CS_ROWS, R, CU_TENSOR_MAP_SWIZZLE_NONE, false))) return rc;
+  static thread_local int attr_dev = -1;
+  int dev = 0;
+  FFM_CHECK_CUDA(cudaGetDevice(&dev));
+  if (dev != attr_dev) {
+    FFM_CHECK_CUDA(cudaFuncSetAttribute(adapter_grad_tma_kernel<R>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        Cfg::SMEM_BYTES));
+    attr_dev = dev;
+  }
+  adapter_grad_tma_kernel<R><<<grid, CS_THREADS, Cfg::SMEM_BYTES, stream>>>(tm_ma, tm_va, tm_mb, tm_vb, partial_a, K,
+                                                                           groups_a, partial_b, N, T, rows_per_chunk);
+  FFM_CHECK_CUDA(cudaGetLastError());
+  return FFM_OK;
+}
+
 int launch_svlora_bwd_small(const __nv_bfloat16* x, const __nv_bfloat16* dy, const float* h, const float* dzu,
                             const __nv_bfloat16* z, const __nv_bfloat16* dh, float* dA, float* dB, float* ds_eff,
                             void* scratch, size_t scratch_bytes, int T, int K, int N, int r, int rp, int nS, int b_prime,
@@ -338,17 +474,28 @@ int launch_svlora_bwd_small(const __nv_bfloat16* x, const __nv_bfloat16* dy, con
   FFM_CHECK_ARG(row_div == 1 || row_div * b_prime == T, "svlora bwd: batch-first rows need row_div * b_prime == T");
   FFM_CHECK_ARG(T % b_prime == 0, "svlora bwd: T (%d) must be a multiple of b_prime (%d)", T, b_prime);
   FFM_CHECK_ARG(rp == 16 || rp == RPS_MAX, "svlora bwd: padded rank must be 16 or %d", RPS_MAX);
-  const int chunks = pick_chunks(T, K, N);
+  int chunks = pick_chunks(T, K, N, rp);
   FFM_CHECK_ARG(static_cast<size_t>(chunks) * (static_cast<size_t>(K) + N) * rp * 4 <= scratch_bytes,
                 "svlora bwd: scratch too small");
   float* partial_a = static_cast<float*>(scratch);
   float* partial_b = partial_a + static_cast<size_t>(chunks) * K * rp;
-  const int rows_per_chunk = (T + chunks - 1) / chunks;
   const int groups_a = (K + CS_COLS - 1) / CS_COLS, groups_b = (N + CS_COLS - 1) / CS_COLS;
-  // dA[K, r] = x^T · dh   and   dB[r, N] = z^T · dy
-  const dim3 grid(chunks, groups_a + groups_b);
-  int rc = rp == 16 ? launch_adapter_grad<16>(x, dh, partial_a, K, groups_a, dy, z, partial_b, N, T, rows_per_chunk, grid, stream)
-                    : launch_adapter_grad<32>(x, dh, partial_a, K, groups_a, dy, z, partial_b, N, T, rows_per_chunk, grid, stream);
+  static const bool use_cp_async = getenv("FFM_AG_CPASYNC") != nullptr;     // A/B timing of the two builds
+  int rc;
+  if (use_cp_async) {
+    const int rows_per_chunk = (T + chunks - 1) / chunks;
+    // dA[K, r] = x^T · dh   and   dB[r, N] = z^T · dy
+    const dim3 grid(chunks, groups_a + groups_b);
+    rc = rp == 16 ? launch_adapter_grad<16>(x, dh, partial_a, K, groups_a, dy, z, partial_b, N, T, rows_per_chunk, grid, stream)
+                  : launch_adapter_grad<32>(x, dh, partial_a, K, groups_a, dy, z, partial_b, N, T, rows_per_chunk, grid, stream);
+  } else {
+    // TMA build: chunks end on k-step (16-row) boundaries; fewer chunks than planned may remain
+    const int rows_per_chunk = (((T + chunks - 1) / chunks) + 15) & ~15;
+    chunks = (T + rows_per_chunk - 1) / rows_per_chunk;
+    const dim3 grid(chunks, groups_a + groups_b);
+    rc = rp == 16 ? launch_adapter_grad_tma<16>(x, dh, partial_a, K, groups_a, dy, z, partial_b, N, T, rows_per_chunk, grid, stream)
+                  : launch_adapter_grad_tma<32>(x, dh, partial_a, K, groups_a, dy, z, partial_b, N, T, rows_per_chunk, grid, stream);
+  }
   if (rc != FFM_OK) return rc;
   const int blocks_a = (K * rp + FIN_THREADS - 1) / FIN_THREADS, blocks_b = (N * rp + FIN_THREADS - 1) / FIN_THREADS;
   adapter_grad_finalize_kernel<<<blocks_a + blocks_b + nS, FIN_THREADS, 0, stream>>>(

@@ -83,7 +83,7 @@ for (K, N, act) in [(768, 3072, 1), (3072, 768, 0)]:
     for k, us in m.items():
         if "gemm" in k:
             add(k, f"dX T={T} K={N} N={K} gelu'={aux is not None}", us, flops=fl)
-        elif "adapter_grad_kernel" in k:
+        elif "adapter_grad_kernel" in k or "adapter_grad_tma_kernel" in k:
             add(k, f"dA+dB T={T} K={K} N={N}", us, bytes_=T * (K + N) * 2.0 + 2 * T * 16 * 2.0)
         elif "finalize" in k:
             add(k, f"K={K} N={N} nS={B}", us, note="latency bound (partials fold + segmented ds_eff)")
