@@ -313,6 +313,41 @@ class GLP_OT_SVLoRA:
         self.last_results = results
         return list(results.values())
 
+    # ------------------------------------------------------------------ checkpoints (scope row f4)
+    def save_model_with_grad(self, filename):
+        """TrainerBase.save_model_with_grad (Dassl/dassl/engine/trainer.py:177-185): trainable parameters + buffers
+        under the reference's state-dict keys — the file `federated_main.py` / the evaluation scripts expect."""
+        state = {n: p.detach().cpu().clone() for n, p in self.model.named_parameters() if p.requires_grad}
+        state.update({n: b.detach().cpu().clone() for n, b in self.model.named_buffers()})
+        torch.save(state, filename)
+
+    def load_model_with_grad(self, filename):
+        """Inverse of save_model_with_grad: copies INTO the existing parameters (they are views of the flat buffer the
+        optimizer and the aggregation work on; parameter objects must persist)."""
+        state = torch.load(filename, map_location="cpu")
+        missing, unexpected = self.model.load_state_dict(state, strict=False)
+        bad = [k for k in missing if k in self.trainable_names]
+        buffers = dict(self.model.named_buffers())        # non-persistent buffers are saved (as upstream) but constant
+        unexpected = [k for k in unexpected if k not in buffers]
+        if bad or unexpected:
+            raise KeyError(f"checkpoint does not match the model: missing trainable {bad}, unexpected {unexpected}")
+        return self
+
+    def save_flat(self, filename):
+        """Adapter-only wire format: the flat fp32 buffer exactly as the per-round all-reduce sends it, plus the key /
+        shape table that maps it back to state-dict entries (4.4 MB for ViT-B/16 instead of the reference's 500 MB
+        `global_client{idx}_final.pth`, federated_main.py:775-778)."""
+        torch.save({"flat": self.flat_params.detach().cpu().clone(), "keys": list(self.trainable_names),
+                    "shapes": [tuple(dict(self.model.named_parameters())[k].shape) for k in self.trainable_names]},
+                   filename)
+
+    def load_flat(self, filename):
+        blob = torch.load(filename, map_location="cpu")
+        if list(blob["keys"]) != list(self.trainable_names) or blob["flat"].numel() != self.flat_params.numel():
+            raise KeyError("flat checkpoint does not match this trainer's trainable tensors")
+        self.set_flat(blob["flat"].to(self.device))
+        return self
+
     # ------------------------------------------------------------------ flat-buffer access for aggregation
     def get_flat(self) -> torch.Tensor:
         return self.flat_params

@@ -318,3 +318,25 @@ def test_trainer_runs_rn50_backbone():
     for frag in ("lora_B", "lora_S", ".bn3.weight", "prompt_learner.ctx", "attnpool.c_proj.lora_A"):
         k = next(n for n in tr.trainable_names if frag in n)
         assert float(sd[k].grad.abs().max()) > 0, k
+
+
+def test_checkpoint_round_trip(tmp_path):
+    """save_model_with_grad writes the reference's filtered state dict (trainable parameters + buffers, same keys);
+    loading it or the flat wire format restores the flat buffer in place (parameter objects persist)."""
+    import fairfedmed_b200.trainer  # noqa: F401
+    from fairfedmed_b200.registry import build_trainer
+    tr = build_trainer(_tiny_cfg(ot="None"))
+    params_before = {n: p for n, p in tr.model.named_parameters()}
+    f1, f2 = tmp_path / "ckpt.pth", tmp_path / "flat.pth"
+    tr.save_model_with_grad(f1)
+    tr.save_flat(f2)
+    state = torch.load(f1)
+    want = {n for n, p in tr.model.named_parameters() if p.requires_grad} | {n for n, _ in tr.model.named_buffers()}
+    assert set(state.keys()) == want and any("lora_S" in k for k in want) and "prompt_learner.ctx" in want
+    ref = tr.get_flat().clone()
+    for loader in (lambda: tr.load_model_with_grad(f1), lambda: tr.load_flat(f2)):
+        tr.set_flat(torch.randn_like(ref))
+        loader()
+        assert torch.equal(tr.get_flat(), ref)
+        assert all(params_before[n] is p for n, p in tr.model.named_parameters())
+        assert all(p.data_ptr() >= tr.flat_params.data_ptr() for n, p in tr.model.named_parameters() if p.requires_grad)
