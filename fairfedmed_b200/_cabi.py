@@ -35,6 +35,9 @@ SIGNATURES = {
                             _i, _i, _i, _i, _i, _i, _i, _i, _f, _vp]),
     "ffm_add_layernorm_fwd": (_i, [_vp, _vp, _fp, _fp, _vp, _vp, _fp, _fp, _i, _i, _f, _vp]),
     "ffm_add_layernorm_bwd": (_i, [_vp, _vp, _vp, _fp, _fp, _fp, _vp, _i, _i, _vp]),
+    "ffm_attention_max_len": (_i, []),
+    "ffm_attention_fwd": (_i, [_vp, _vp, _fp, _i, _i, _i, _i, _i, _i, _vp]),
+    "ffm_attention_bwd": (_i, [_vp, _vp, _vp, _fp, _vp, _i, _i, _i, _i, _i, _i, _vp]),
     "ffm_patchify_normalize": (_i, [_fp, _vp, _fp, _fp, _i, _i, _i, _i, _i, _i, _vp]),
     "ffm_vit_embed_ln": (_i, [_vp, _fp, _fp, _fp, _fp, _fp, _fp, _vp, _vp, _fp, _fp, _i, _i, _i, _f, _f, _vp]),
     "ffm_seff": (_i, [_vp, _fp, _fp, _fp, _i, _i, _i, _f, _vp]),

@@ -16,6 +16,7 @@ Frozen attention / LayerNorm / patch embedding use PyTorch library kernels (bf16
 from __future__ import annotations
 
 import math
+import os
 from typing import Optional, Sequence
 
 import torch
@@ -28,6 +29,8 @@ from .resnet_model import ModifiedResNet_GLP_OT
 
 PIXEL_MEAN = (0.48145466, 0.4578275, 0.40821073)
 PIXEL_STD = (0.26862954, 0.26130258, 0.27577711)
+# attention core: "own" = csrc/attention.cu (scope row f1), "lib" = torch SDPA (cuDNN / flash kernels)
+OWN_ATTENTION = os.environ.get("FFM_ATTENTION", "own") != "lib"
 _SIDE_STREAMS: dict = {}     # (device index, role) -> side stream (module level: models stay picklable)
 
 
@@ -154,6 +157,13 @@ class ResidualAttentionBlock(nn.Module, _Bf16Cache):
         a = self.attn
         causal = self.attn_mask is not None
         qkv = F.linear(x, self._bf("in_w", a.in_proj_weight, x.dtype), self._bf("in_b", a.in_proj_bias, x.dtype))
+        seq_len = x.shape[1] if self.batch_first else x.shape[0]
+        if OWN_ATTENTION and x.is_cuda and x.dtype == torch.bfloat16 and x.dim() == 3 \
+                and ops.attention_supported(x.shape[-1], self.n_head, seq_len):
+            # own kernels: q/k/v read from the packed projection in place, dq/dk/dv written packed (no cat in backward)
+            out = ops.attention(qkv, self.n_head, causal, self.batch_first)
+            return F.linear(out, self._bf("out_w", a.out_proj.weight, x.dtype),
+                            self._bf("out_b", a.out_proj.bias, x.dtype))
         if self.batch_first:
             bn, L, c = x.shape
             hd = c // self.n_head

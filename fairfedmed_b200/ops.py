@@ -407,6 +407,83 @@ def add_layernorm(x: Tensor, res: Optional[Tensor], gamma: Tensor, beta: Tensor,
 
 
 # =====================================================================================================
+# frozen attention core (packed q/k/v in, packed dq/dk/dv out)
+# =====================================================================================================
+ATTENTION_MAX_LEN = 208
+ATTENTION_HEAD_DIM = 64
+
+
+@torch.library.custom_op("ffm::attention_fwd", mutates_args=())
+def attention_fwd(qkv: Tensor, n_head: int, causal: bool, batch_first: bool) -> Tuple[Tensor, Tensor]:
+    """out, lse.  qkv bf16 [B, L, 3*C] (batch_first) or [L, B, 3*C] as produced by the packed in_proj; out has the same
+    leading dims and C = n_head * 64 columns; lse f32 [B*n_head, L] (base 2)."""
+    _need_cuda(qkv)
+    if qkv.dtype != torch.bfloat16 or not qkv.is_contiguous() or qkv.dim() != 3:
+        raise _cabi.FfmError("attention_fwd: qkv must be contiguous bf16 [B, L, 3C] / [L, B, 3C]")
+    d0, d1, c3 = qkv.shape
+    B, L = (d0, d1) if batch_first else (d1, d0)
+    C = c3 // 3
+    if C != n_head * ATTENTION_HEAD_DIM or L > ATTENTION_MAX_LEN:
+        raise _cabi.FfmError(f"attention_fwd: head dim must be {ATTENTION_HEAD_DIM} and L <= {ATTENTION_MAX_LEN}")
+    out = torch.empty((d0, d1, C), device=qkv.device, dtype=torch.bfloat16)
+    lse = torch.empty((B * n_head, L), device=qkv.device, dtype=torch.float32)
+    _cabi.call("ffm_attention_fwd", _ptr(qkv), _ptr(out), _ptr(lse), B, L, n_head, ATTENTION_HEAD_DIM, int(bool(causal)),
+               int(bool(batch_first)), _stream())
+    return out, lse
+
+
+@attention_fwd.register_fake
+def _(qkv, n_head, causal, batch_first):
+    d0, d1, c3 = qkv.shape
+    B, L = (d0, d1) if batch_first else (d1, d0)
+    return qkv.new_empty((d0, d1, c3 // 3)), qkv.new_empty((B * n_head, L), dtype=torch.float32)
+
+
+@torch.library.custom_op("ffm::attention_bwd", mutates_args=())
+def attention_bwd(qkv: Tensor, out: Tensor, d_out: Tensor, lse: Tensor, n_head: int, causal: bool,
+                  batch_first: bool) -> Tensor:
+    _need_cuda(qkv, out, d_out, lse)
+    d0, d1, c3 = qkv.shape
+    B, L = (d0, d1) if batch_first else (d1, d0)
+    d_qkv = torch.empty_like(qkv)
+    _cabi.call("ffm_attention_bwd", _ptr(qkv), _ptr(out), _ptr(d_out), _ptr(lse), _ptr(d_qkv), B, L, n_head,
+               ATTENTION_HEAD_DIM, int(bool(causal)), int(bool(batch_first)), _stream())
+    return d_qkv
+
+
+@attention_bwd.register_fake
+def _(qkv, out, d_out, lse, n_head, causal, batch_first):
+    return torch.empty_like(qkv)
+
+
+class _Attention(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, qkv, n_head, causal, batch_first):
+        out, lse = attention_fwd(qkv, n_head, causal, batch_first)
+        ctx.save_for_backward(qkv, out, lse)
+        ctx.cfg = (n_head, causal, batch_first)
+        return out
+
+    @staticmethod
+    def backward(ctx, d_out):
+        qkv, out, lse = ctx.saved_tensors
+        n_head, causal, batch_first = ctx.cfg
+        d_out = d_out.contiguous()
+        if d_out.dtype != torch.bfloat16:
+            d_out = d_out.to(torch.bfloat16)
+        return attention_bwd(qkv, out, d_out, lse, n_head, causal, batch_first), None, None, None
+
+
+def attention(qkv: Tensor, n_head: int, causal: bool = False, batch_first: bool = True) -> Tensor:
+    """Self-attention core on the packed in_proj output (clip/model.py:350-352): returns [.., C] ready for out_proj."""
+    return _Attention.apply(qkv.contiguous(), n_head, bool(causal), bool(batch_first))
+
+
+def attention_supported(width: int, n_head: int, seq_len: int) -> bool:
+    return width == n_head * ATTENTION_HEAD_DIM and 1 <= seq_len <= ATTENTION_MAX_LEN
+
+
+# =====================================================================================================
 # ViT input side: /255 + mean/std + im2col in one pass, class token + positions + ln_pre + first ln_1 in another
 # =====================================================================================================
 @torch.library.custom_op("ffm::patchify_normalize", mutates_args=())

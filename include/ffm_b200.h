@@ -137,6 +137,24 @@ int ffm_add_layernorm_fwd(const void* x, const void* res, const float* gamma, co
 int ffm_add_layernorm_bwd(const void* d_ln, const void* d_res, const void* s, const float* gamma, const float* mean,
                           const float* rstd, void* dx, int rows, int C, ffm_stream_t stream);
 
+/* ------------------------------------------------- frozen attention core (scope row f1) ------- */
+/*
+ * softmax(Q K^T / sqrt(head_dim)) V per (sample, head) — the core of nn.MultiheadAttention as ResidualAttentionBlock
+ * calls it (clip/model.py:350-352, need_weights=False; causal = the text tower's upper-triangular -inf mask,
+ * clip/model.py:520-526).  q, k, v are read in place from the packed in_proj output and dq, dk, dv are written packed
+ * the same way, so there is no head split / transpose / concat around the kernels:
+ *   qkv, d_qkv  bf16 [B, L, 3, H, head_dim] (batch_first = 1) or [L, B, 3, H, head_dim] (0, the reference's layout)
+ *   out, d_out  bf16 [B, L, H*head_dim]     or [L, B, H*head_dim]
+ *   lse         f32  [B*H, L]  base-2 log-sum-exp of the scaled scores, forward -> backward
+ * head_dim must be 64 and L <= ffm_attention_max_len() (208): the CLIP towers (197 image tokens, 77 text tokens).
+ * Deterministic (no atomics).  No dropout (the reference trains with attention dropout 0).
+ */
+int ffm_attention_max_len(void);
+int ffm_attention_fwd(const void* qkv, void* out, float* lse, int B, int L, int H, int head_dim, int causal,
+                      int batch_first, ffm_stream_t stream);
+int ffm_attention_bwd(const void* qkv, const void* out, const void* d_out, const float* lse, void* d_qkv, int B, int L,
+                      int H, int head_dim, int causal, int batch_first, ffm_stream_t stream);
+
 /* ------------------------------------------------- ViT input side (scope row f3) -------------- */
 /*
  * ffm_patchify_normalize — CustomCLIP.forward's `image / 255`, `(image - mean) / std`

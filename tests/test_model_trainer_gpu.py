@@ -181,6 +181,50 @@ def test_trainer_step_matches_oracle_double_sgd():
         assert float((got - upd).abs().max()) <= 6e-2 * float(upd.abs().max()) + 1e-7, k
 
 
+def test_trainer_trajectory_matches_oracle_over_several_steps():
+    """Five consecutive steps on the same two batches: the bf16 device path must track the fp32 oracle's loss
+    trajectory (same weights, same batches, double SGD with momentum carried across steps) — errors must not compound."""
+    import fairfedmed_b200.trainer  # noqa: F401
+    from fairfedmed_b200.registry import build_trainer
+    cfg = _tiny_cfg(ot="Sinkhorn")
+    cfg.OPTIM.LR = 2e-2                                      # large enough that five steps visibly move the loss
+    tr = build_trainer(cfg)
+    tr.step_auc = False
+    with torch.no_grad():
+        for n_, p_ in tr.model.named_parameters():
+            if "lora_A" in n_:
+                p_.copy_(0.05 * torch.randn(p_.shape, generator=torch.Generator().manual_seed(3)).to(p_.device))
+    names = tr.trainable_names
+    p = {k: v.detach().float().cpu().clone() for k, v in tr.model.state_dict().items()}
+    for k in names:
+        p[k].requires_grad_(True)
+    eot = tr.model.prompt_learner.eot_index.cpu()
+    batches = list(tr.fed_train_loader_x_dict[0])[:2]
+    bufs = [None] * len(names)
+    got, want = [], []
+    tr.batch_idx, tr.num_batches = 0, 10 ** 9
+    for step in range(5):
+        batch = batches[step % 2]
+        got.append(tr.forward_backward(batch)["loss"])
+        logits = rp.custom_clip_forward(batch["img"].clone(), batch["attrs"][:, 0], p, eot, ot="Sinkhorn",
+                                        vision_layers=2, vision_heads=2, text_layers=2, text_heads=2, scaling=2.0 / 12)
+        loss = F.cross_entropy(logits, batch["label"])
+        want.append(float(loss))
+        grads = torch.autograd.grad(loss, [p[k] for k in names])
+        rp.sgd_double_step([p[k] for k in names], grads, bufs, lr=cfg.OPTIM.LR)
+    assert abs(want[0] - want[-1]) > 1e-3, "the oracle's loss did not move: the test would be vacuous"
+    for g_, w_ in zip(got, want):
+        assert abs(g_ - w_) <= 2e-2, (got, want)
+    # parameters after five steps: update direction and size agree with the oracle
+    sd = tr.model.state_dict()
+    for k in names:
+        ref_k = p[k].detach()
+        scale = float(ref_k.abs().max())
+        if scale < 1e-9:
+            continue
+        assert float((sd[k].float().cpu() - ref_k).abs().max()) <= 3e-2 * scale + 1e-6, k
+
+
 @pytest.mark.parametrize("dataset,attributes,attr_type", [
     ("FairFedMed", ["race"], "race"),                              # BASELINE config 1
     ("FedChexMimic", ["age", "gender", "race"], "age"),            # BASELINE config 5: CheXpert / MIMIC shaped, 2 groups
