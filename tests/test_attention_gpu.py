@@ -83,5 +83,5 @@ def test_attention_is_deterministic_and_matches_library_path():
         try:
             outs.append(blk.attention(x).float())
         finally:
-            clip_model.OWN_ATTENTION = True
+            clip_model.OWN_ATTENTION = False
     assert float((outs[0] - outs[1]).abs().max()) <= 2e-2 * float(outs[1].abs().max()) + 1e-3
