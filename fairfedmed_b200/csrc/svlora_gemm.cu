@@ -786,9 +786,20 @@ int ffm_svlora_bwd(const void* dy, const void* x, const void* w_t, const float* 
                    const void* gelu_dact, void* dx, float* d_lora_a, float* d_lora_b, float* d_s_eff, void* workspace,
                    size_t workspace_bytes, int T, int K, int N, int r, int n_samples, int b_prime, int num_slices,
                    int row_div, float scaling, cudaStream_t stream) {
+  return ffm_svlora_bwd_phase(dy, x, w_t, lora_a, lora_b, s_eff, h, z, fwd_workspace, gelu_dact, dx, d_lora_a, d_lora_b,
+                              d_s_eff, workspace, workspace_bytes, T, K, N, r, n_samples, b_prime, num_slices, row_div,
+                              scaling, FFM_BWD_DX | FFM_BWD_PARAMS, stream);
+}
+
+int ffm_svlora_bwd_phase(const void* dy, const void* x, const void* w_t, const float* lora_a, const float* lora_b,
+                         const float* s_eff, const float* h, const void* z, const void* fwd_workspace,
+                         const void* gelu_dact, void* dx, float* d_lora_a, float* d_lora_b, float* d_s_eff,
+                         void* workspace, size_t workspace_bytes, int T, int K, int N, int r, int n_samples,
+                         int b_prime, int num_slices, int row_div, float scaling, int phases, cudaStream_t stream) {
   FFM_CHECK_ARG(dy && x && w_t && lora_a && lora_b && s_eff && h && z && dx && d_lora_a && d_lora_b && d_s_eff &&
                     workspace,
                 "ffm_svlora_bwd: null pointer argument");
+  FFM_CHECK_ARG((phases & ~(FFM_BWD_DX | FFM_BWD_PARAMS)) == 0 && phases != 0, "ffm_svlora_bwd_phase: bad phase mask");
   FFM_CHECK_ARG(r >= 1 && r <= RP_MAX, "ffm_svlora_bwd: rank %d not in [1, %d]", r, RP_MAX);
   FFM_CHECK_ARG(b_prime >= 1 && num_slices >= 1 && row_div >= 1 && (b_prime - 1) / num_slices < n_samples,
                 "ffm_svlora_bwd: sample mapping exceeds n_samples");
@@ -802,10 +813,12 @@ int ffm_svlora_bwd(const void* dy, const void* x, const void* w_t, const float* 
     carve_tiles(&ws, const_cast<void*>(fwd_workspace), K, N, n_samples);
   } else {
     carve_tiles(&ws, workspace, K, N, n_samples);
-    svlora_prep_kernel<<<96, 256, 0, stream>>>(lora_a, lora_b, s_eff, nullptr, nullptr, ws.a_bwd, ws.b_bwd, ws.s_rows,
-                                               K, N, r, rp, n_samples, scaling);
-    FFM_CHECK_CUDA(cudaGetLastError());
-    count_launch();
+    if (phases & FFM_BWD_DX) {
+      svlora_prep_kernel<<<96, 256, 0, stream>>>(lora_a, lora_b, s_eff, nullptr, nullptr, ws.a_bwd, ws.b_bwd,
+                                                 ws.s_rows, K, N, r, rp, n_samples, scaling);
+      FFM_CHECK_CUDA(cudaGetLastError());
+      count_launch();
+    }
   }
   float* dzu = reinterpret_cast<float*>(rest);
   rest += align256(static_cast<size_t>(T) * RP_MAX * 4);
@@ -820,8 +833,11 @@ int ffm_svlora_bwd(const void* dy, const void* x, const void* w_t, const float* 
   o.T = T; o.K = N; o.N = K; o.b_prime = b_prime; o.num_slices = num_slices; o.row_div = row_div;
   o.rp = rp;
   o.act = gelu_dact != nullptr ? ACT_QUICKGELU_GRAD : ACT_NONE;
-  int rc = launch_svlora_gemm(o, stream);
-  if (rc != FFM_OK) return rc;
+  if (phases & FFM_BWD_DX) {
+    int rc = launch_svlora_gemm(o, stream);
+    if (rc != FFM_OK) return rc;
+  }
+  if (!(phases & FFM_BWD_PARAMS)) return FFM_OK;
   return launch_svlora_bwd_small(reinterpret_cast<const __nv_bfloat16*>(x), reinterpret_cast<const __nv_bfloat16*>(dy),
                                  h, dzu, reinterpret_cast<const __nv_bfloat16*>(z), dh, d_lora_a, d_lora_b, d_s_eff,
                                  rest, scratch_bytes, T, K, N, r, rp, n_samples, b_prime, num_slices, row_div, scaling,

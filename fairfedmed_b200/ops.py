@@ -236,15 +236,24 @@ class _SEff(torch.autograd.Function):
     @staticmethod
     def forward(ctx, attr, S, S_global, lam):
         ctx.attr, ctx.lam, ctx.G = attr, lam, S.shape[0]
+        ctx.set_materialize_grads(False)      # a consumer that finished dS itself hands back None, not zeros
         ctx.has_global = S_global is not None
         # trainer-registered gradient views (see _direct_grad): dS is then written in place, autograd gets None
         ctx.direct = (_direct_grad(S), None if S_global is None else _direct_grad(S_global))
         ctx.sg_shape = None if S_global is None else S_global.shape
         sg = None if S_global is None else S_global.reshape(-1).contiguous()
-        return seff_op(attr, S.contiguous(), sg, lam)
+        out = seff_op(attr, S.contiguous(), sg, lam)
+        gS, gSg = ctx.direct
+        if gS is not None and (S_global is None or gSg is not None):
+            # everything a consumer needs to finish dS itself (the split backward of the fused MLP does, on its
+            # parameter-gradient stream; it then returns no gradient for s_eff and this node's backward never runs)
+            out._ffm_ds_ctx = (attr, float(lam), int(S.shape[0]), gS, gSg)
+        return out
 
     @staticmethod
     def backward(ctx, ds_eff):
+        if ds_eff is None:                    # dS already written by the consumer (split MLP backward)
+            return None, None, None, None
         gS, gSg = ctx.direct
         if gS is not None and (not ctx.has_global or gSg is not None):
             ds_eff = ds_eff.contiguous()
@@ -292,6 +301,52 @@ def svlora_linear(x2d: Tensor, w: Tensor, w_t: Tensor, bias: Optional[Tensor], l
     return _SVLoRALinear.apply(x2d, w, w_t, bias, lora_a, lora_b, s_eff, scaling, b_prime, num_slices, row_div)
 
 
+# adapter-gradient kernels of the fused MLP leave the dX critical path (see _SVLoRAMLP.backward); FFM_PARAMS_SIDE=0: A/B
+PARAMS_ON_SIDE_STREAM = __import__("os").environ.get("FFM_PARAMS_SIDE", "1") != "0"
+_PARAM_STREAMS: dict = {}
+
+
+def _param_stream(device) -> "torch.cuda.Stream":
+    key = torch.device(device).index
+    if key not in _PARAM_STREAMS:
+        _PARAM_STREAMS[key] = torch.cuda.Stream(device=device)
+    return _PARAM_STREAMS[key]
+
+
+def _bwd_phase(phases, dy, x, w_t, a, b, s_eff, h, z, tiles, dact, dx, gA, gB, dse, ws, scaling, b_prime, num_slices,
+               row_div):
+    T, N = dy.shape
+    K = x.shape[1]
+    _cabi.call("ffm_svlora_bwd_phase", _ptr(dy), _ptr(x), _ptr(w_t), _ptr(a), _ptr(b), _ptr(s_eff), _ptr(h), _ptr(z),
+               _ptr(tiles), _ptr(dact), _ptr(dx), _ptr(gA), _ptr(gB), _ptr(dse), _ptr(ws), ws.numel(), T, K, N,
+               a.shape[1], s_eff.shape[0], b_prime, num_slices, int(row_div), float(scaling), int(phases), _stream())
+
+
+def _split_layer_backward(main, side, dy, x, w_t, a, b, s_eff, h, z, tiles, dact, ds_ctx, scaling, b_prime, num_slices,
+                          row_div):
+    """dX GEMM on the current stream, adapter gradients + dS on the parameter-gradient stream.  Returns dx."""
+    T, N = dy.shape
+    K = x.shape[1]
+    nS, r = s_eff.shape
+    lib = _cabi.load()
+    ws = torch.empty((lib.ffm_svlora_bwd_workspace_bytes(T, K, N, nS),), device=x.device, dtype=torch.uint8)
+    dx = torch.empty((T, K), device=x.device, dtype=torch.bfloat16)
+    dse = torch.empty((nS, r), device=x.device, dtype=torch.float32)
+    gA, gB = _direct_grad(a), _direct_grad(b)
+    args = (dy, x, w_t, a, b, s_eff, h, z, tiles, dact, dx, gA, gB, dse, ws, scaling, b_prime, num_slices, row_div)
+    _bwd_phase(1, *args)
+    ev = torch.cuda.Event()
+    ev.record(main)
+    attr, lam, G, gS, gSg = ds_ctx
+    with torch.cuda.stream(side):
+        side.wait_event(ev)
+        _bwd_phase(2, *args)
+        _cabi.call("ffm_ds", _ptr(attr), _ptr(dse), _ptr(gS), _ptr(gSg), nS, G, r, lam, _stream())
+    for t in (dy, x, h, z, ws, dse, s_eff):          # allocated on the main stream, still read on the side stream
+        t.record_stream(side)
+    return dx
+
+
 class _SVLoRAMLP(torch.autograd.Function):
     """c_proj(QuickGELU(c_fc(x))) with both adapters (clip/model.py:325-332): QuickGELU is fused into the c_fc
     epilogue (dual store: the activation and its derivative) and the multiplication by that derivative into the
@@ -299,7 +354,8 @@ class _SVLoRAMLP(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, x2d, w1, w1_t, b1, a1, bb1, s1, w2, w2_t, b2, a2, bb2, s2, scaling, b_prime, num_slices,
-                row_div, p1=None, p2=None):
+                row_div, p1=None, p2=None, dsc1=None, dsc2=None):
+        ctx.ds_ctx = (dsc1, dsc2)
         g, u, h1, z1, t1 = svlora_fwd(x2d, w1, b1, a1, bb1, s1, scaling, b_prime, num_slices, 1, row_div, p1)
         y, _, h2, z2, t2 = svlora_fwd(g, w2, b2, a2, bb2, s2, scaling, b_prime, num_slices, 0, row_div, p2)
         if p1 is not None:
@@ -314,18 +370,36 @@ class _SVLoRAMLP(torch.autograd.Function):
     def backward(ctx, dy):
         x2d, g, u, h1, h2, w1_t, a1, bb1, s1, w2_t, a2, bb2, s2, z1, t1, z2, t2 = ctx.saved_tensors
         scaling, b_prime, num_slices, row_div = ctx.cfg
+        dsc1, dsc2 = ctx.ds_ctx
+        if PARAMS_ON_SIDE_STREAM and dsc1 is not None and dsc2 is not None and \
+                all(_direct_grad(t) is not None for t in (a1, bb1, a2, bb2)):
+            # Only dx feeds the blocks below: the adapter-gradient contractions, their fold and dS (6 launches, 54 us
+            # per block) run on a side stream behind the dX GEMMs and overlap the attention backward that follows.
+            main = torch.cuda.current_stream()
+            side = _param_stream(dy.device)
+            dy = dy.contiguous()
+            du = _split_layer_backward(main, side, dy, g, w2_t, a2, bb2, s2, h2, z2, t2, u, dsc2, scaling, b_prime,
+                                       num_slices, row_div)
+            dx = _split_layer_backward(main, side, du, x2d, w1_t, a1, bb1, s1, h1, z1, t1, None, dsc1, scaling, b_prime,
+                                       num_slices, row_div)
+            ev = torch.cuda.Event()
+            ev.record(side)
+            _PENDING_DIRECT_WRITES.append(ev)
+            return (dx,) + (None,) * 20
         du, dA2, dB2, ds2 = _svlora_bwd_dispatch(dy.contiguous(), g, w2_t, a2, bb2, s2, h2, z2, t2, u, scaling,
                                                  b_prime, num_slices, row_div)
         dx, dA1, dB1, ds1 = _svlora_bwd_dispatch(du, x2d, w1_t, a1, bb1, s1, h1, z1, t1, None, scaling, b_prime,
                                                  num_slices, row_div)
-        return dx, None, None, None, dA1, dB1, ds1, None, None, None, dA2, dB2, ds2, None, None, None, None, None, None
+        return (dx, None, None, None, dA1, dB1, ds1, None, None, None, dA2, dB2, ds2, None, None, None, None, None, None,
+                None, None)
 
 
 def svlora_mlp(x2d, fc, proj, scaling: float, b_prime: int, num_slices: int, row_div: int = 1,
                prepared: Optional[Tuple[Tensor, Tensor]] = None) -> Tensor:
     """fc / proj = (w, w_t, bias, lora_a, lora_b, s_eff) tuples; prepared = (svlora_prepare of fc, of proj) or None."""
     p1, p2 = prepared if prepared is not None else (None, None)
-    return _SVLoRAMLP.apply(x2d, *fc, *proj, scaling, b_prime, num_slices, row_div, p1, p2)
+    dsc1, dsc2 = getattr(fc[5], "_ffm_ds_ctx", None), getattr(proj[5], "_ffm_ds_ctx", None)
+    return _SVLoRAMLP.apply(x2d, *fc, *proj, scaling, b_prime, num_slices, row_div, p1, p2, dsc1, dsc2)
 
 
 # =====================================================================================================

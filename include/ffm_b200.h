@@ -120,6 +120,21 @@ int ffm_svlora_bwd(const void* dy, const void* x, const void* w_t, const float* 
                    size_t workspace_bytes, int T, int K, int N, int r, int n_samples, int b_prime, int num_slices,
                    int row_div, float scaling, ffm_stream_t stream);
 
+/*
+ * The same backward in two separately launchable phases (bit mask): FFM_BWD_DX = the fused dX GEMM (writes dx and the
+ * side outputs dzu / dh into `workspace`), FFM_BWD_PARAMS = the adapter-gradient contractions and the per-sample ds_eff
+ * (read x, dy, h, z and the side outputs of phase DX from the SAME workspace).  Only dx feeds the layers below, so a
+ * host may issue phase PARAMS on another stream once phase DX has completed (event) and let it overlap the rest of
+ * the backward pass; keep the workspace alive until it has run.  ffm_svlora_bwd == both phases, one stream.
+ */
+#define FFM_BWD_DX 1
+#define FFM_BWD_PARAMS 2
+int ffm_svlora_bwd_phase(const void* dy, const void* x, const void* w_t, const float* lora_a, const float* lora_b,
+                         const float* s_eff, const float* h, const void* z, const void* fwd_workspace,
+                         const void* gelu_dact, void* dx, float* d_lora_a, float* d_lora_b, float* d_s_eff,
+                         void* workspace, size_t workspace_bytes, int T, int K, int N, int r, int n_samples,
+                         int b_prime, int num_slices, int row_div, float scaling, int phases, ffm_stream_t stream);
+
 /* ------------------------------------------------- residual add + LayerNorm (frozen blocks) -- */
 /*
  * The glue between the adapted MLP and the frozen attention of ResidualAttentionBlock (clip/model.py:354-357):
