@@ -30,8 +30,8 @@ from .resnet_model import ModifiedResNet_GLP_OT
 PIXEL_MEAN = (0.48145466, 0.4578275, 0.40821073)
 PIXEL_STD = (0.26862954, 0.26130258, 0.27577711)
 # attention core: "own" = csrc/attention.cu (scope row f1: parity-green, packed dq/dk/dv, deterministic — but at this
-# round's tuning 36 / 150 us forward / backward per image-tower block against 30 / 95 us for cuDNN's tcgen05 kernels
-# incl. their helper launches, 7.8k vs 8.35k img/s), "lib" = torch SDPA.  The faster one is the default.
+# round's tuning 57 / 146 us forward / backward per image-tower block against 36 / 114 us for torch SDPA on cuDNN's
+# tcgen05 kernels incl. their helper launches, 7.87k vs 8.36k img/s), "lib" = torch SDPA.  The faster one is the default.
 OWN_ATTENTION = os.environ.get("FFM_ATTENTION", "lib") == "own"
 _SIDE_STREAMS: dict = {}     # (device index, role) -> side stream (module level: models stay picklable)
 

@@ -109,9 +109,101 @@ __device__ __forceinline__ HeadPtrs head_ptrs(const __nv_bfloat16* qkv, int b, i
 // ------------------------------------------------------------------------------------------------------------
 // forward
 // ------------------------------------------------------------------------------------------------------------
+// One block of 64 keys for one 16-row query tile.  MASKED = false is the interior case (every key valid for every row):
+// no index arithmetic or selects at all, 4 instructions per score (max, fma, ex2, add).  The running maximum m is kept
+// in the RAW score domain (the scale is positive), so scale and subtraction fuse into one FMA in front of ex2.
+template <bool CAUSAL, bool MASKED>
+__device__ __forceinline__ void fwd_block(int kb0, int k_end, int L, int row0, int row1, uint32_t ks_, uint32_t vs,
+                                          int lane, int t4, const uint32_t (&qf)[4][4], float (&o)[8][4], float& m0,
+                                          float& m1, float& l0, float& l1, float scale_log2) {
+  float s[8][4];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) s[i][0] = s[i][1] = s[i][2] = s[i][3] = 0.f;
+  // S = Q K^T for 64 keys (8 n-tiles), two n-tiles per ldmatrix.x4
+#pragma unroll
+  for (int np = 0; np < 4; ++np) {
+    if (!MASKED || kb0 + np * 16 < k_end) {            // warp-uniform
+      const int key = kb0 + np * 16 + ((lane >> 4) << 3) + (lane & 7);
+#pragma unroll
+      for (int kk = 0; kk < 4; ++kk) {
+        uint32_t kf[4];
+        ldsm4(ks_ + sw_off(key, 2 * kk + ((lane >> 3) & 1)), kf);
+        mma16816(s[2 * np], qf[kk], kf[0], kf[1]);
+        mma16816(s[2 * np + 1], qf[kk], kf[2], kf[3]);
+      }
+    }
+  }
+  if (MASKED) {
+    // keys past the sequence, past k_end (skipped sub-blocks: they are >= L, or > every row of a causal tile) and above
+    // the diagonal
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt) {
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int key = kb0 + nt * 8 + 2 * t4 + (e & 1);
+        const int row = (e & 2) ? row1 : row0;
+        if (key >= L || (CAUSAL && key > row)) s[nt][e] = -INFINITY;
+      }
+    }
+  }
+  float bm0 = fmaxf(s[0][0], s[0][1]), bm1 = fmaxf(s[0][2], s[0][3]);
+#pragma unroll
+  for (int nt = 1; nt < 8; ++nt) {
+    bm0 = fmaxf(bm0, fmaxf(s[nt][0], s[nt][1]));
+    bm1 = fmaxf(bm1, fmaxf(s[nt][2], s[nt][3]));
+  }
+  bm0 = fmaxf(bm0, __shfl_xor_sync(0xffffffffu, bm0, 1));
+  bm0 = fmaxf(bm0, __shfl_xor_sync(0xffffffffu, bm0, 2));
+  bm1 = fmaxf(bm1, __shfl_xor_sync(0xffffffffu, bm1, 1));
+  bm1 = fmaxf(bm1, __shfl_xor_sync(0xffffffffu, bm1, 2));
+  const float mn0 = fmaxf(m0, bm0), mn1 = fmaxf(m1, bm1);
+  // every row sees key 0 in the first block (also under the causal mask), so mn is finite from block 0 on
+  const float a0 = ex2((m0 - mn0) * scale_log2), a1 = ex2((m1 - mn1) * scale_log2);
+  m0 = mn0;
+  m1 = mn1;
+  const float ms0 = -mn0 * scale_log2, ms1 = -mn1 * scale_log2;
+  float ps0 = 0.f, ps1 = 0.f;
+#pragma unroll
+  for (int nt = 0; nt < 8; ++nt) {
+    s[nt][0] = ex2(fmaf(s[nt][0], scale_log2, ms0));
+    s[nt][1] = ex2(fmaf(s[nt][1], scale_log2, ms0));
+    s[nt][2] = ex2(fmaf(s[nt][2], scale_log2, ms1));
+    s[nt][3] = ex2(fmaf(s[nt][3], scale_log2, ms1));
+    ps0 += s[nt][0] + s[nt][1];
+    ps1 += s[nt][2] + s[nt][3];
+  }
+  l0 = fmaf(l0, a0, ps0);
+  l1 = fmaf(l1, a1, ps1);
+#pragma unroll
+  for (int dn = 0; dn < 8; ++dn) {
+    o[dn][0] *= a0; o[dn][1] *= a0;
+    o[dn][2] *= a1; o[dn][3] *= a1;
+  }
+  // O += P V : P re-packed as A fragments (k = 16 keys per step), V^T fragments through ldmatrix.trans
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    if (!MASKED || kb0 + j * 16 < k_end) {
+      uint32_t pa[4];
+      pa[0] = pack_bf16x2(s[2 * j][0], s[2 * j][1]);
+      pa[1] = pack_bf16x2(s[2 * j][2], s[2 * j][3]);
+      pa[2] = pack_bf16x2(s[2 * j + 1][0], s[2 * j + 1][1]);
+      pa[3] = pack_bf16x2(s[2 * j + 1][2], s[2 * j + 1][3]);
+      const int key = kb0 + j * 16 + (lane & 7) + (((lane >> 3) & 1) << 3);
+#pragma unroll
+      for (int dp = 0; dp < 4; ++dp) {
+        uint32_t vf[4];
+        ldsm4t(vs + sw_off(key, 2 * dp + (lane >> 4)), vf);
+        mma16816(o[2 * dp], pa, vf[0], vf[1]);
+        mma16816(o[2 * dp + 1], pa, vf[2], vf[3]);
+      }
+    }
+  }
+}
+
+template <bool CAUSAL>
 __global__ void __launch_bounds__(THREADS, 2)
 attention_fwd_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restrict__ out, float* __restrict__ lse,
-                     int B, int L, int H, int causal, int batch_first, float scale_log2) {
+                     int B, int L, int H, int batch_first, float scale_log2) {
   extern __shared__ __align__(1024) uint8_t att_smem[];
   uint8_t* Qs = att_smem;
   uint8_t* Ks = Qs + TILE_BYTES;
@@ -138,86 +230,13 @@ attention_fwd_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __res
     for (int i = 0; i < 8; ++i) o[i][0] = o[i][1] = o[i][2] = o[i][3] = 0.f;
     float m0 = -INFINITY, m1 = -INFINITY, l0 = 0.f, l1 = 0.f;
     const int row0 = rt * 16 + g, row1 = row0 + 8;
-    const int k_end = causal ? min(Lk, rt * 16 + 16) : Lk;      // causal: keys beyond the tile's last row are masked
+    const int k_end = CAUSAL ? min(Lk, rt * 16 + 16) : Lk;      // causal: keys beyond the tile's last row are masked
 
     for (int kb0 = 0; kb0 < k_end; kb0 += 64) {
-      float s[8][4];
-#pragma unroll
-      for (int i = 0; i < 8; ++i) s[i][0] = s[i][1] = s[i][2] = s[i][3] = 0.f;
-      // S = Q K^T for 64 keys (8 n-tiles), two n-tiles per ldmatrix.x4
-#pragma unroll
-      for (int np = 0; np < 4; ++np) {
-        if (kb0 + np * 16 < k_end) {                    // warp-uniform
-          const int key = kb0 + np * 16 + ((lane >> 4) << 3) + (lane & 7);
-#pragma unroll
-          for (int kk = 0; kk < 4; ++kk) {
-            uint32_t kf[4];
-            ldsm4(ks_ + sw_off(key, 2 * kk + ((lane >> 3) & 1)), kf);
-            mma16816(s[2 * np], qf[kk], kf[0], kf[1]);
-            mma16816(s[2 * np + 1], qf[kk], kf[2], kf[3]);
-          }
-        }
-      }
-      // scale into the exp2 domain, mask, block row maxima
-      float bm0 = -INFINITY, bm1 = -INFINITY;
-#pragma unroll
-      for (int nt = 0; nt < 8; ++nt) {
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          const int key = kb0 + nt * 8 + 2 * t4 + (e & 1);
-          const int row = (e & 2) ? row1 : row0;
-          float v = s[nt][e] * scale_log2;
-          if (key >= L || (causal && key > row) || kb0 + (nt >> 1) * 16 >= k_end) v = -INFINITY;
-          s[nt][e] = v;
-        }
-        bm0 = fmaxf(bm0, fmaxf(s[nt][0], s[nt][1]));
-        bm1 = fmaxf(bm1, fmaxf(s[nt][2], s[nt][3]));
-      }
-      bm0 = fmaxf(bm0, __shfl_xor_sync(0xffffffffu, bm0, 1));
-      bm0 = fmaxf(bm0, __shfl_xor_sync(0xffffffffu, bm0, 2));
-      bm1 = fmaxf(bm1, __shfl_xor_sync(0xffffffffu, bm1, 1));
-      bm1 = fmaxf(bm1, __shfl_xor_sync(0xffffffffu, bm1, 2));
-      const float mn0 = fmaxf(m0, bm0), mn1 = fmaxf(m1, bm1);
-      // every row sees key 0 in the first block (also under the causal mask), so mn is finite from block 0 on
-      const float a0 = ex2(m0 - mn0), a1 = ex2(m1 - mn1);
-      m0 = mn0;
-      m1 = mn1;
-      float ps0 = 0.f, ps1 = 0.f;
-#pragma unroll
-      for (int nt = 0; nt < 8; ++nt) {
-        s[nt][0] = ex2(s[nt][0] - mn0);
-        s[nt][1] = ex2(s[nt][1] - mn0);
-        s[nt][2] = ex2(s[nt][2] - mn1);
-        s[nt][3] = ex2(s[nt][3] - mn1);
-        ps0 += s[nt][0] + s[nt][1];
-        ps1 += s[nt][2] + s[nt][3];
-      }
-      l0 = l0 * a0 + ps0;
-      l1 = l1 * a1 + ps1;
-#pragma unroll
-      for (int dn = 0; dn < 8; ++dn) {
-        o[dn][0] *= a0; o[dn][1] *= a0;
-        o[dn][2] *= a1; o[dn][3] *= a1;
-      }
-      // O += P V : P re-packed as A fragments (k = 16 keys per step), V^T fragments through ldmatrix.trans
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        if (kb0 + j * 16 < k_end) {
-          uint32_t pa[4];
-          pa[0] = pack_bf16x2(s[2 * j][0], s[2 * j][1]);
-          pa[1] = pack_bf16x2(s[2 * j][2], s[2 * j][3]);
-          pa[2] = pack_bf16x2(s[2 * j + 1][0], s[2 * j + 1][1]);
-          pa[3] = pack_bf16x2(s[2 * j + 1][2], s[2 * j + 1][3]);
-          const int key = kb0 + j * 16 + (lane & 7) + (((lane >> 3) & 1) << 3);
-#pragma unroll
-          for (int dp = 0; dp < 4; ++dp) {
-            uint32_t vf[4];
-            ldsm4t(vs + sw_off(key, 2 * dp + (lane >> 4)), vf);
-            mma16816(o[2 * dp], pa, vf[0], vf[1]);
-            mma16816(o[2 * dp + 1], pa, vf[2], vf[3]);
-          }
-        }
-      }
+      // interior block: all 64 keys exist and (causal) lie at or below the tile's first row
+      const bool interior = (kb0 + 64 <= L) && (!CAUSAL || kb0 + 63 <= rt * 16);
+      if (interior) fwd_block<CAUSAL, false>(kb0, k_end, L, row0, row1, ks_, vs, lane, t4, qf, o, m0, m1, l0, l1, scale_log2);
+      else fwd_block<CAUSAL, true>(kb0, k_end, L, row0, row1, ks_, vs, lane, t4, qf, o, m0, m1, l0, l1, scale_log2);
     }
     // finish the rows: l over the quad, normalise, stage the tile through this tile's (private) Q rows
     l0 += __shfl_xor_sync(0xffffffffu, l0, 1);
@@ -233,8 +252,8 @@ attention_fwd_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __res
     }
     if (t4 == 0) {
       float* lp = lse + static_cast<size_t>(blockIdx.x) * L;
-      if (row0 < L) lp[row0] = m0 + log2f(l0);
-      if (row1 < L) lp[row1] = m1 + log2f(l1);
+      if (row0 < L) lp[row0] = fmaf(m0, scale_log2, log2f(l0));
+      if (row1 < L) lp[row1] = fmaf(m1, scale_log2, log2f(l1));
     }
     __syncwarp();
 #pragma unroll
@@ -251,10 +270,11 @@ attention_fwd_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __res
 // ------------------------------------------------------------------------------------------------------------
 // backward
 // ------------------------------------------------------------------------------------------------------------
+template <bool causal>
 __global__ void __launch_bounds__(THREADS, 2)
 attention_bwd_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16* __restrict__ out,
                      const __nv_bfloat16* __restrict__ d_out, const float* __restrict__ lse,
-                     __nv_bfloat16* __restrict__ d_qkv, int B, int L, int H, int causal, int batch_first, float scale,
+                     __nv_bfloat16* __restrict__ d_qkv, int B, int L, int H, int batch_first, float scale,
                      float scale_log2) {
   extern __shared__ __align__(1024) uint8_t att_smem[];
   uint8_t* Qs = att_smem;
@@ -317,7 +337,7 @@ attention_bwd_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16*
     load_a_frags(qs, rt, lane, qf);
     load_a_frags(gs, rt, lane, gf);
     const int row0 = rt * 16 + g, row1 = row0 + 8;
-    const float ls0 = lse_s[row0], ls1 = lse_s[row1], de0 = del_s[row0], de1 = del_s[row1];
+    const float ls0 = -lse_s[row0], ls1 = -lse_s[row1], de0 = del_s[row0], de1 = del_s[row1];
     float dq[8][4];
 #pragma unroll
     for (int i = 0; i < 8; ++i) dq[i][0] = dq[i][1] = dq[i][2] = dq[i][3] = 0.f;
@@ -352,7 +372,7 @@ attention_bwd_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16*
         for (int e = 0; e < 4; ++e) {
           const int key = kb0 + nt * 8 + 2 * t4 + (e & 1);
           const int row = (e & 2) ? row1 : row0;
-          float p = ex2(s[nt][e] * scale_log2 - ((e & 2) ? ls1 : ls0));
+          float p = ex2(fmaf(s[nt][e], scale_log2, (e & 2) ? ls1 : ls0));
           if (causal && key > row) p = 0.f;
           s[nt][e] = p * (dp[nt][e] - ((e & 2) ? de1 : de0));
         }
@@ -477,8 +497,10 @@ static int set_smem_once() {
   int dev = 0;
   FFM_CHECK_CUDA(cudaGetDevice(&dev));
   if (dev != attr_dev) {
-    FFM_CHECK_CUDA(cudaFuncSetAttribute(attention_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FWD_SMEM));
-    FFM_CHECK_CUDA(cudaFuncSetAttribute(attention_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, BWD_SMEM));
+    FFM_CHECK_CUDA(cudaFuncSetAttribute(attention_fwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, FWD_SMEM));
+    FFM_CHECK_CUDA(cudaFuncSetAttribute(attention_fwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, FWD_SMEM));
+    FFM_CHECK_CUDA(cudaFuncSetAttribute(attention_bwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, BWD_SMEM));
+    FFM_CHECK_CUDA(cudaFuncSetAttribute(attention_bwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, BWD_SMEM));
     attr_dev = dev;
   }
   return FFM_OK;
@@ -501,9 +523,14 @@ int ffm_attention_fwd(const void* qkv, void* out, float* lse, int B, int L, int 
   int rc = att::set_smem_once();
   if (rc != FFM_OK) return rc;
   const float scale_log2 = att::LOG2E / sqrtf(static_cast<float>(att::HD));
-  att::attention_fwd_kernel<<<B * H, att::THREADS, att::FWD_SMEM, stream>>>(
-      static_cast<const __nv_bfloat16*>(qkv), static_cast<__nv_bfloat16*>(out), lse, B, L, H, causal ? 1 : 0,
-      batch_first ? 1 : 0, scale_log2);
+  if (causal)
+    att::attention_fwd_kernel<true><<<B * H, att::THREADS, att::FWD_SMEM, stream>>>(
+        static_cast<const __nv_bfloat16*>(qkv), static_cast<__nv_bfloat16*>(out), lse, B, L, H, batch_first ? 1 : 0,
+        scale_log2);
+  else
+    att::attention_fwd_kernel<false><<<B * H, att::THREADS, att::FWD_SMEM, stream>>>(
+        static_cast<const __nv_bfloat16*>(qkv), static_cast<__nv_bfloat16*>(out), lse, B, L, H, batch_first ? 1 : 0,
+        scale_log2);
   FFM_CHECK_CUDA(cudaGetLastError());
   count_launch();
   return FFM_OK;
@@ -517,10 +544,16 @@ int ffm_attention_bwd(const void* qkv, const void* out, const void* d_out, const
   int rc = att::set_smem_once();
   if (rc != FFM_OK) return rc;
   const float scale = 1.0f / sqrtf(static_cast<float>(att::HD));
-  att::attention_bwd_kernel<<<B * H, att::THREADS, att::BWD_SMEM, stream>>>(
-      static_cast<const __nv_bfloat16*>(qkv), static_cast<const __nv_bfloat16*>(out),
-      static_cast<const __nv_bfloat16*>(d_out), lse, static_cast<__nv_bfloat16*>(d_qkv), B, L, H, causal ? 1 : 0,
-      batch_first ? 1 : 0, scale, scale * att::LOG2E);
+  if (causal)
+    att::attention_bwd_kernel<true><<<B * H, att::THREADS, att::BWD_SMEM, stream>>>(
+        static_cast<const __nv_bfloat16*>(qkv), static_cast<const __nv_bfloat16*>(out),
+        static_cast<const __nv_bfloat16*>(d_out), lse, static_cast<__nv_bfloat16*>(d_qkv), B, L, H, batch_first ? 1 : 0,
+        scale, scale * att::LOG2E);
+  else
+    att::attention_bwd_kernel<false><<<B * H, att::THREADS, att::BWD_SMEM, stream>>>(
+        static_cast<const __nv_bfloat16*>(qkv), static_cast<const __nv_bfloat16*>(out),
+        static_cast<const __nv_bfloat16*>(d_out), lse, static_cast<__nv_bfloat16*>(d_qkv), B, L, H, batch_first ? 1 : 0,
+        scale, scale * att::LOG2E);
   FFM_CHECK_CUDA(cudaGetLastError());
   count_launch();
   return FFM_OK;
