@@ -27,6 +27,33 @@ def test_binding_covers_header():
     assert declared == bound, (declared - bound, bound - declared)
 
 
+def test_binding_arity_and_kinds_match_header():
+    """Every ctypes signature has the parameter count of the C declaration, pointers bind to pointers, ints to ints,
+    floats to floats (an ABI drift here is silent memory corruption at run time)."""
+    import re
+    text = _cabi.HEADER_PATH.read_text()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    decls = dict()
+    for m in re.finditer(r"\b(?:int|size_t|long long|const char\*)\s+(ffm_[a-z0-9_]+)\s*\(([^;]*?)\)\s*;", text, flags=re.S):
+        name, params = m.group(1), " ".join(m.group(2).split())
+        decls[name] = [] if params in ("", "void") else [p.strip() for p in params.split(",")]
+    assert set(decls) == set(_cabi.SIGNATURES)
+    for name, params in decls.items():
+        _, argtypes = _cabi.SIGNATURES[name]
+        assert len(argtypes) == len(params), (name, len(argtypes), params)
+        for p, t in zip(params, argtypes):
+            if "*" in p or "ffm_stream_t" in p:
+                assert t is ctypes.c_void_p, (name, p, t)
+            elif p.startswith("float"):
+                assert t is ctypes.c_float, (name, p, t)
+            elif p.startswith("size_t"):
+                assert t is ctypes.c_size_t, (name, p, t)
+            elif p.startswith("int64_t"):
+                assert t is ctypes.c_int64, (name, p, t)
+            else:
+                assert t is ctypes.c_int, (name, p, t)
+
+
 def test_no_compute_metadata_calls(lib):
     assert lib.ffm_version() >= 100
     assert lib.ffm_svlora_max_rank() == 32
@@ -36,6 +63,7 @@ def test_no_compute_metadata_calls(lib):
     assert lib.ffm_ot_head_workspace_bytes(196, 64, 512, 2, 2) > 0
     assert lib.ffm_sinkhorn_workspace_bytes(128, 196, 2) > 0
     assert lib.ffm_group_auc_workspace_bytes(5000, 6, 3) > 0
+    assert lib.ffm_attention_max_len() == 208
 
 
 def test_argument_validation_without_gpu(lib):
