@@ -6,6 +6,7 @@ a CPU tensor or a missing library raises.
 """
 from __future__ import annotations
 
+import os
 from typing import Optional, Tuple
 
 import torch
@@ -302,7 +303,7 @@ def svlora_linear(x2d: Tensor, w: Tensor, w_t: Tensor, bias: Optional[Tensor], l
 
 
 # adapter-gradient kernels of the fused MLP leave the dX critical path (see _SVLoRAMLP.backward); FFM_PARAMS_SIDE=0: A/B
-PARAMS_ON_SIDE_STREAM = __import__("os").environ.get("FFM_PARAMS_SIDE", "1") != "0"
+PARAMS_ON_SIDE_STREAM = os.environ.get("FFM_PARAMS_SIDE", "1") != "0"
 _PARAM_STREAMS: dict = {}
 
 
