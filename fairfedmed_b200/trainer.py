@@ -222,7 +222,13 @@ class GLP_OT_SVLoRA:
             return loss.detach(), acc
 
         self._g_lr = self.current_lr()
-        side = torch.cuda.Stream(device=self.device)
+        # The step's main stream is captured at HIGH priority; the side streams the model forks (text tower, adapter
+        # preparation, parameter gradients) keep the default, lower one.  Kernel nodes inherit the priority of the
+        # stream they were captured on, so whenever a main-chain kernel and side work are both ready the block
+        # scheduler serves the critical path first and the side work fills what is left.
+        import os
+        prio = -1 if os.environ.get("FFM_GRAPH_PRIO", "1") != "0" else 0
+        side = torch.cuda.Stream(device=self.device, priority=prio)
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side):
             for _ in range(warmup):
@@ -230,7 +236,7 @@ class GLP_OT_SVLoRA:
         torch.cuda.current_stream().wait_stream(side)
         self.first_step = False
         self._graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(self._graph):
+        with torch.cuda.graph(self._graph, stream=side):
             self._g_loss, self._g_acc = body()
         del static
         return self._graph
