@@ -167,3 +167,25 @@ def test_sharded_aggregation_over_gloo_matches_oracle(case):
     for r in range(world):
         np.testing.assert_allclose(outs[r], ref_flat, rtol=1e-6, atol=1e-7)
     np.testing.assert_array_equal(outs[0], outs[1])
+
+
+def test_ops_host_helpers_without_gpu():
+    """Pure host logic of the op layer: rank padding, attention support predicate, no-op join without pending writes,
+    CPU tensors are rejected (no fallback)."""
+    import pytest
+    import torch
+    from fairfedmed_b200 import _cabi, ops
+    assert [ops.padded_rank(r) for r in (1, 12, 16, 17, 32)] == [16, 16, 16, 32, 32]
+    with pytest.raises(_cabi.FfmError):
+        ops.padded_rank(33)
+    assert ops.attention_supported(768, 12, 197) and ops.attention_supported(512, 8, 77)
+    assert not ops.attention_supported(768, 8, 197) and not ops.attention_supported(768, 12, 209)
+    ops.join_direct_grad_writes()                       # nothing pending: must not touch CUDA
+    assert ops._direct_grad(torch.zeros(2)) is None
+    t = torch.zeros(2)
+    t._ffm_direct_grad = torch.ones(2)
+    assert ops._direct_grad(t) is t._ffm_direct_grad
+    with pytest.raises(_cabi.FfmError, match="no CPU fallback"):
+        ops.patchify_normalize(torch.zeros(1, 3, 16, 16), torch.zeros(3), torch.ones(3), 16, True)
+    with pytest.raises(_cabi.FfmError, match="no CPU fallback"):
+        ops.attention(torch.zeros(1, 4, 192, dtype=torch.bfloat16), 1, False, True)
