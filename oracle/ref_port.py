@@ -204,10 +204,12 @@ def _quick_gelu(x):
     return x * torch.sigmoid(1.702 * x)                                            # clip/model.py:313-315
 
 
-def _mha(x, p: Mapping[str, torch.Tensor], pre: str, n_head: int, mask=None):
-    """nn.MultiheadAttention self-attention, sequence-first — clip/model.py:350-352."""
-    L, Bn, C = x.shape
-    qkv = F.linear(x, p[pre + "in_proj_weight"], p[pre + "in_proj_bias"])
+def attention_core(qkv: torch.Tensor, n_head: int, mask=None):
+    """The part of nn.MultiheadAttention between in_proj and out_proj (torch F.multi_head_attention_forward as called
+    by clip/model.py:350-352, need_weights=False, no dropout): qkv [L, B, 3C] sequence-first, packed [q | k | v] with
+    heads contiguous inside each third -> [L, B, C].  `mask`: additive [L, L] (the text tower's causal mask)."""
+    L, Bn, c3 = qkv.shape
+    C = c3 // 3
     q, k, v = qkv.chunk(3, dim=-1)
     hd = C // n_head
 
@@ -219,7 +221,13 @@ def _mha(x, p: Mapping[str, torch.Tensor], pre: str, n_head: int, mask=None):
     if mask is not None:
         att = att + mask
     att = torch.softmax(att, dim=-1)
-    out = torch.bmm(att, v).transpose(0, 1).reshape(L, Bn, C)
+    return torch.bmm(att, v).transpose(0, 1).reshape(L, Bn, C)
+
+
+def _mha(x, p: Mapping[str, torch.Tensor], pre: str, n_head: int, mask=None):
+    """nn.MultiheadAttention self-attention, sequence-first — clip/model.py:350-352."""
+    qkv = F.linear(x, p[pre + "in_proj_weight"], p[pre + "in_proj_bias"])
+    out = attention_core(qkv, n_head, mask)
     return F.linear(out, p[pre + "out_proj.weight"], p[pre + "out_proj.bias"])
 
 

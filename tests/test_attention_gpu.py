@@ -3,8 +3,6 @@ nn.MultiheadAttention computes inside ResidualAttentionBlock (clip/model.py:350-
 head on the packed in_proj output, optional causal mask (text tower), forward and backward, both memory layouts."""
 from __future__ import annotations
 
-import math
-
 import pytest
 import torch
 
@@ -13,17 +11,14 @@ DEV = "cuda:0"
 
 
 def _reference(qkv32, n_head, causal, batch_first):
-    """qkv32 fp32 [B, L, 3C] / [L, B, 3C] -> out fp32 same leading dims, C columns."""
-    x = qkv32 if batch_first else qkv32.transpose(0, 1)
-    B, L, c3 = x.shape
-    C = c3 // 3
-    hd = C // n_head
-    q, k, v = x.reshape(B, L, 3, n_head, hd).permute(2, 0, 3, 1, 4)           # each [B, H, L, hd]
-    s = (q @ k.transpose(-1, -2)) / math.sqrt(hd)
-    if causal:
-        s = s + torch.full((L, L), float("-inf"), device=x.device).triu_(1)
-    o = (torch.softmax(s, dim=-1) @ v).permute(0, 2, 1, 3).reshape(B, L, C)
-    return o if batch_first else o.transpose(0, 1)
+    """The oracle's attention core (oracle/ref_port.attention_core, pinned to torch's nn.MultiheadAttention by
+    tests/test_oracle_golden.py) on fp32 qkv [B, L, 3C] / [L, B, 3C] -> same leading dims, C columns."""
+    from oracle import ref_port as rp
+    x = qkv32.transpose(0, 1) if batch_first else qkv32                       # the oracle speaks sequence-first
+    L = x.shape[0]
+    mask = torch.full((L, L), float("-inf"), device=x.device).triu_(1) if causal else None
+    o = rp.attention_core(x, n_head, mask)
+    return o.transpose(0, 1) if batch_first else o
 
 
 @pytest.mark.parametrize("B,L,H,causal,batch_first", [

@@ -182,3 +182,19 @@ def test_custom_clip_forward_backward_matches_reference(name):
             np.testing.assert_allclose(g.numpy().reshape(ref.shape), ref, rtol=2e-3, atol=2e-4 * scale)
             n_checked += 1
     assert n_checked >= 7
+
+
+@pytest.mark.parametrize("causal", [False, True])
+def test_attention_core_is_pinned_to_torch_multihead_attention(causal):
+    """The reference's blocks call torch's nn.MultiheadAttention (clip/model.py:350-352); the oracle's restatement of
+    its core must reproduce the real module (same packed in_proj layout, scaling, mask handling)."""
+    torch.manual_seed(3)
+    L, B, C, H = 11, 3, 64, 4
+    mha = torch.nn.MultiheadAttention(C, H)
+    x = torch.randn(L, B, C)
+    mask = torch.full((L, L), float("-inf")).triu_(1) if causal else None
+    want = mha(x, x, x, need_weights=False, attn_mask=mask)[0]
+    p = {"in_proj_weight": mha.in_proj_weight, "in_proj_bias": mha.in_proj_bias,
+         "out_proj.weight": mha.out_proj.weight, "out_proj.bias": mha.out_proj.bias}
+    got = rp._mha(x, p, "", H, mask)
+    torch.testing.assert_close(got, want, rtol=1e-5, atol=1e-6)
