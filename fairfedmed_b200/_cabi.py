@@ -56,6 +56,7 @@ SIGNATURES = {
     "ffm_group_auc_workspace_bytes": (_sz, [_i, _i, _i]),
     "ffm_group_auc": (_i, [_fp, _vp, _vp, _vp, _vp, _sz, _i, _i, _i, _vp]),
     "ffm_sgd_step": (_i, [_fp, _fp, _fp, _i64, _f, _f, _f, _i, _i, _vp]),
+    "ffm_sgd_step_dev_lr": (_i, [_fp, _fp, _fp, _i64, _fp, _f, _f, _i, _vp]),
 }
 
 
@@ -91,8 +92,28 @@ def load() -> C.CDLL:
         fn.argtypes = args
     if missing and os.environ.get("FFM_ALLOW_PARTIAL_LIB") != "1":  # bring-up escape hatch only
         raise FfmError(f"{LIB_PATH} is stale or incomplete, missing symbols: {missing}; rebuild it")
+    _check_digest()
     _LIB = lib
     return lib
+
+
+def _check_digest() -> None:
+    """A library that still exports every symbol but was built from older sources must not be loaded silently:
+    compare lib/.build_digest (written by build.py) with the digest of the sources next to it."""
+    if os.environ.get("FFM_ALLOW_STALE_LIB") == "1":
+        return
+    import importlib
+    _build = importlib.import_module(__package__ + ".build")   # the package attribute `build` is a function
+    stamp = _build.LIB_DIR / ".build_digest"
+    srcs = _build.sources()
+    if not srcs:                      # binary-only deployment: nothing to compare with
+        return
+    deps = srcs + sorted(_build.CSRC.glob("*.cuh")) + [HEADER_PATH]
+    want = _build._digest(deps)
+    have = stamp.read_text() if stamp.exists() else None
+    if have != want:
+        raise FfmError(f"{LIB_PATH} was not built from the current sources (build digest mismatch): run "
+                       "`python -m fairfedmed_b200.build` (FFM_ALLOW_STALE_LIB=1 overrides)")
 
 
 def check(rc: int, what: str) -> None:

@@ -29,10 +29,9 @@ from .resnet_model import ModifiedResNet_GLP_OT
 
 PIXEL_MEAN = (0.48145466, 0.4578275, 0.40821073)
 PIXEL_STD = (0.26862954, 0.26130258, 0.27577711)
-# attention core: "own" = csrc/attention.cu (scope row f1: parity-green, packed dq/dk/dv, deterministic — but at this
-# round's tuning 57 / 146 us forward / backward per image-tower block against 36 / 114 us for torch SDPA on cuDNN's
-# tcgen05 kernels incl. their helper launches, 7.87k vs 8.36k img/s), "lib" = torch SDPA.  The faster one is the default.
-OWN_ATTENTION = os.environ.get("FFM_ATTENTION", "lib") == "own"
+# attention core: "own" = csrc/attention.cu (scope row f1: tcgen05 / TMEM forward + backward, packed dq/dk/dv,
+# deterministic), "lib" = torch SDPA (cuDNN) kept as an A/B switch.
+OWN_ATTENTION = os.environ.get("FFM_ATTENTION", "own") == "own"
 _SIDE_STREAMS: dict = {}     # (device index, role) -> side stream (module level: models stay picklable)
 
 
@@ -150,22 +149,30 @@ class ResidualAttentionBlock(nn.Module, _Bf16Cache):
         self.attn_mask = attn_mask
         self.n_head = n_head
         self.batch_first = batch_first
+        # opt-in FairLoRA adapters on in_proj / out_proj (modules.apply_lora_to_model(adapt_attention=True)); None = the
+        # reference's configuration (MLP adapters only)
+        self.attn_in_lora = None
+        self.attn_out_lora = None
 
-    def attention(self, x: torch.Tensor):
+    def _proj(self, adapter, name, x, weight, bias, attr):
+        if adapter is not None:            # raises on CPU tensors: no silent un-adapted fallback
+            return adapter(x, attr, batch_first=self.batch_first)
+        return F.linear(x, self._bf(name + "_w", weight, x.dtype), self._bf(name + "_b", bias, x.dtype))
+
+    def attention(self, x: torch.Tensor, attr: Optional[torch.Tensor] = None):
         """Self-attention with nn.MultiheadAttention semantics (clip/model.py:350-352).
 
         batch_first: x is [B, L, C]; q/k/v are strided views of the in_proj output in "bshd" memory order, which the
         fused attention kernels consume without copies.  Otherwise x is the reference's [L, B, C]."""
         a = self.attn
         causal = self.attn_mask is not None
-        qkv = F.linear(x, self._bf("in_w", a.in_proj_weight, x.dtype), self._bf("in_b", a.in_proj_bias, x.dtype))
+        qkv = self._proj(self.attn_in_lora, "in", x, a.in_proj_weight, a.in_proj_bias, attr)
         seq_len = x.shape[1] if self.batch_first else x.shape[0]
         if OWN_ATTENTION and x.is_cuda and x.dtype == torch.bfloat16 and x.dim() == 3 \
                 and ops.attention_supported(x.shape[-1], self.n_head, seq_len):
             # own kernels: q/k/v read from the packed projection in place, dq/dk/dv written packed (no cat in backward)
             out = ops.attention(qkv, self.n_head, causal, self.batch_first)
-            return F.linear(out, self._bf("out_w", a.out_proj.weight, x.dtype),
-                            self._bf("out_b", a.out_proj.bias, x.dtype))
+            return self._proj(self.attn_out_lora, "out", out, a.out_proj.weight, a.out_proj.bias, attr)
         if self.batch_first:
             bn, L, c = x.shape
             hd = c // self.n_head
@@ -179,10 +186,10 @@ class ResidualAttentionBlock(nn.Module, _Bf16Cache):
             qkv = qkv.view(L, bn, 3, self.n_head, hd).permute(2, 1, 3, 0, 4)              # [3, B, H, L, hd]
             out = F.scaled_dot_product_attention(qkv[0], qkv[1], qkv[2], is_causal=causal)
             out = out.permute(2, 0, 1, 3).reshape(L, bn, c)
-        return F.linear(out, self._bf("out_w", a.out_proj.weight, x.dtype), self._bf("out_b", a.out_proj.bias, x.dtype))
+        return self._proj(self.attn_out_lora, "out", out, a.out_proj.weight, a.out_proj.bias, attr)
 
     def forward(self, x: torch.Tensor, attr: Optional[torch.Tensor] = None):
-        x = x + self.attention(self.ln_1(x))
+        x = x + self.attention(self.ln_1(x), attr)
         x = x + self.mlp(self.ln_2(x), attr=attr)
         return x
 
@@ -244,7 +251,7 @@ class Transformer(nn.Module):
         else:
             h = h0
         for i, blk in enumerate(blocks):
-            a = blk.attention(h)
+            a = blk.attention(h, attr)
             x, h = ops.add_layernorm(x, a, blk.ln_2.weight, blk.ln_2.bias, blk.ln_2.eps)
             if prepared is not None and prepared[i] is not None:
                 pre, ev = prepared[i]

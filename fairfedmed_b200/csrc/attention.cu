@@ -1,495 +1,616 @@
 // Frozen self-attention core of ResidualAttentionBlock (clip/model.py:350-352: nn.MultiheadAttention, need_weights=False)
-// for the shapes of the CLIP towers: head dim 64, sequences up to 208 tokens (197 image tokens, 77 text tokens).
-// Scope row f1.  softmax(Q K^T / sqrt(64)) V per (sample, head), forward and backward, reading q/k/v straight from the
-// packed in_proj output [.., 3, H, 64] and writing dq/dk/dv packed the same way (no head split / concat copies).
+// on Blackwell tensor cores for the shapes of the CLIP towers: head dim 64, sequences up to 208 tokens (197 image tokens,
+// 77 text tokens).  Scope row f1.  softmax(Q K^T / sqrt(64)) V per (sample, head), forward and backward, reading q/k/v
+// straight from the packed in_proj output [.., 3, H, 64] through 3-D TMA maps (rows past the sequence end are zero-filled
+// by the hardware) and writing dq/dk/dv packed the same way (no head split / concat copies).
 //
-// Why not tcgen05: one head is a 197 x 197 x 64 problem.  A UMMA tile is 128 rows (256 with cta_group::2), so the
-// score matrix would be padded 1.7x and the softmax between the two contractions would still run on CUDA cores out
-// of TMEM; the whole head fits one CTA's shared memory (4 x 26 KB), where warp-level mma.sync m16n8k16 on 16-row
-// tiles wastes 5 % (197 -> 208) and keeps P / dS in registers between the contractions (measured mma.sync peak on
-// this part: 540 TFLOP/s, tools/micro/mma_sync_peak.cu).
+// Both kernels are persistent (one CTA per SM, heads round-robin), warp-specialised, and keep every intermediate
+// (scores, probabilities, dS) out of shared memory: the contractions accumulate in TMEM, the softmax warps read the
+// scores with tcgen05.ld (one thread per row: no shuffles), write the bf16 probabilities back INTO TMEM with tcgen05.st,
+// and the second contraction takes them from there as its A operand (tcgen05.mma with A in TMEM).  V, dO, Q and K are
+// consumed as "MN-major" B operands in place (the [token][channel] tile as TMA delivers it), so no operand is transposed.
 //
-// One CTA (7 warps) per (sample, head), two CTAs per SM (loads of one overlap the math of the other):
-//   forward : warp w owns query tiles w and w+7 (16 rows each); for each block of 64 keys: S = Q K^T (fp32
-//             accumulators), online softmax in the exp2 domain, O += P V with P re-packed to bf16 A-fragments in
-//             registers.  Output tile staged through the (private) Q rows for 16-byte coalesced stores; the row
-//             log-sum-exp (base 2) is saved for the backward.
-//   backward: recomputes P from (Q, K, lse).  Phase A (warp owns query tiles): dQ = scale * dS K with
-//             dS = P ⊙ (dO V^T - delta).  Phase B (warp owns key tiles): dV = P^T dO and dK = scale * dS^T Q with the
-//             transposed scores S^T = K Q^T recomputed, so no cross-warp reduction or P / dS staging is needed (7
-//             contractions instead of 5, no shared-memory round trip, no atomics: deterministic).
-//             delta = rowsum(dO ⊙ O) is computed while dO is staged.
-// Shared-memory tiles are [208 rows][64 bf16] with the 16-byte chunk index XOR (row & 7): conflict-free ldmatrix.
+//   forward : 2 query tiles of 128 rows per head (rows >= L are zero / discarded), all keys at once (N = L rounded up
+//             to 16, one UMMA_N): S_t = Q_t K^T -> TMEM[256 t .. +208); softmax warpgroup t: row max, P = exp2(..) as
+//             bf16 pairs over the consumed columns, row sum; O_t = P_t V (A from TMEM, K = keys) -> TMEM[256 t + 128 ..
+//             +64); epilogue O / sum -> bf16 rows of `out`, base-2 log-sum-exp to `lse`.  Q / K / V of the next head
+//             are prefetched into the second shared-memory stage while the current head computes.
+//   backward: per key tile j (128 keys = TMEM lanes) and query half a (<= 128 query columns):
+//             S^T = K_j Q_a^T and dP^T = V_j dO_a^T (TMEM regions R0 / R1); the softmax warps form P^T = exp2(S^T c -
+//             lse[q]) and dS^T = P^T (dP^T - delta[q]) per element, store both as bf16 pairs into TMEM and dS^T also
+//             into a swizzled shared-memory tile; dV_j += P^T dO_a and dK_j += dS^T Q_a take A from TMEM, dQ_a += dS K_j
+//             takes the shared tile as an MN-major A operand.  The five accumulators (dV_j, dK_j, dQ_0, dQ_1 in 4 x 64
+//             TMEM columns + the two 128-column regions = 512) never leave the chip; delta = rowsum(dO * O) is computed
+//             while the operands land.  No atomics: deterministic.
+#include <math.h>
+
+#include <mutex>
+
 #include "../../include/ffm_b200.h"
 #include "ffm_common.cuh"
 
 namespace ffm {
+
+// implemented in svlora_gemm.cu
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+PFN_encodeTiled tensor_map_encode_fn();
+
 namespace att {
 
-constexpr int HD = 64;                     // head dimension
-constexpr int LP = 208;                    // padded sequence (13 tiles of 16 rows)
-constexpr int WARPS = 7;                   // 13 row tiles over 7 warps: tiles w and w + 7
-constexpr int THREADS = WARPS * 32;        // 224
-constexpr int TILE_BYTES = LP * HD * 2;    // 26624
-constexpr int FWD_SMEM = 3 * TILE_BYTES;                        // Q, K, V           79872
-constexpr int BWD_SMEM = 4 * TILE_BYTES + 2 * LP * 4;           // Q, K, V, dO + lse + delta   108160
+constexpr int HD = 64;                      // head dimension
+constexpr int LP = 208;                     // longest sequence (13 x 16)
 constexpr float LOG2E = 1.4426950408889634f;
+constexpr int ROW_BYTES = HD * 2;           // 128 B = one SW128 swizzle row
+constexpr int Q2_BYTES = 256 * ROW_BYTES;   // two 128-row tiles           32768
+constexpr int KV_BYTES = LP * ROW_BYTES;    // all keys                    26624
 
-__device__ __forceinline__ uint32_t sw_off(int r, int c) { return static_cast<uint32_t>(r * 128 + ((c ^ (r & 7)) << 4)); }
+__device__ __forceinline__ uint32_t pack2(float a, float b) { return pack_bf16x2(a, b); }
 
-__device__ __forceinline__ void cp16(void* smem_dst, const void* gmem_src) {
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem_dst)), "l"(gmem_src) : "memory");
-}
-__device__ __forceinline__ void cp_commit_wait_all() {
-  asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
-}
-__device__ __forceinline__ void ldsm4(uint32_t addr, uint32_t (&r)[4]) {
-  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0, %1, %2, %3}, [%4];"
-               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
-               : "r"(addr));
-}
-__device__ __forceinline__ void ldsm4t(uint32_t addr, uint32_t (&r)[4]) {
-  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0, %1, %2, %3}, [%4];"
-               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
-               : "r"(addr));
-}
-__device__ __forceinline__ void mma16816(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
-  asm volatile(
-      "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, "
-      "{%0, %1, %2, %3};"
-      : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
-      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
-}
-__device__ __forceinline__ float ex2(float x) {
-  float y;
-  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
-  return y;
-}
+// ---------------------------------------------------------------------------------------------------------------
+// forward
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int FWD_THREADS = 320;            // warp 0: TMA, warp 1: MMA (+ TMEM alloc), warps 2-5 / 6-9: softmax of tile 0 / 1
+constexpr int FWD_STAGE = Q2_BYTES + 2 * KV_BYTES;                 // 86016
+constexpr int FWD_SMEM = 2 * FWD_STAGE + 256 + 1024;
 
-// Stage one [L x 64] head slice (row pitch `pitch` elements) into a swizzled tile; rows >= L are zero-filled.
-__device__ __forceinline__ void stage_tile(uint8_t* tile, const __nv_bfloat16* src, size_t pitch, int L) {
-  for (int idx = threadIdx.x; idx < LP * 8; idx += THREADS) {
-    const int r = idx >> 3, c = idx & 7;
-    uint8_t* dst = tile + sw_off(r, c);
-    if (r < L) cp16(dst, src + static_cast<size_t>(r) * pitch + c * 8);
-    else *reinterpret_cast<uint4*>(dst) = make_uint4(0u, 0u, 0u, 0u);
-  }
-}
-
-// A-operand fragments (16 rows x 64 columns = 4 k-steps) of row tile `rt` from a swizzled tile.
-__device__ __forceinline__ void load_a_frags(uint32_t tile, int rt, int lane, uint32_t (&f)[4][4]) {
-  const int row = rt * 16 + (lane & 15);
-#pragma unroll
-  for (int ks = 0; ks < 4; ++ks) ldsm4(tile + sw_off(row, 2 * ks + (lane >> 4)), f[ks]);
-}
-
-struct HeadPtrs {
-  const __nv_bfloat16 *q, *k, *v;   // first row of this (sample, head)
-  size_t pitch;                     // elements between consecutive tokens of the same sample in qkv
-  size_t opitch;                    // same for the [.., H*64] tensors (out, d_out)
-  size_t ooff;                      // element offset of this (sample, head) in those tensors
+struct FwdParams {
+  __nv_bfloat16* out;
+  float* lse;
+  int B, L, H, C, batch_first;
+  int lk_pad;        // L rounded up to 16: UMMA N of the scores, K extent of P V
+  int n_tiles;       // query tiles of 128 rows (1 or 2)
+  int total;         // B * H
+  float scale_log2;  // log2(e) / sqrt(head_dim)
 };
 
-__device__ __forceinline__ HeadPtrs head_ptrs(const __nv_bfloat16* qkv, int b, int h, int B, int L, int H,
-                                              int batch_first) {
-  HeadPtrs p;
-  const size_t C = static_cast<size_t>(H) * HD;
-  const size_t tok = batch_first ? 1 : static_cast<size_t>(B);          // rows between consecutive tokens
-  const size_t row0 = batch_first ? static_cast<size_t>(b) * L : static_cast<size_t>(b);
-  p.pitch = tok * 3 * C;
-  p.opitch = tok * C;
-  const __nv_bfloat16* base = qkv + row0 * 3 * C + static_cast<size_t>(h) * HD;
-  p.q = base;
-  p.k = base + C;
-  p.v = base + 2 * C;
-  p.ooff = row0 * C + static_cast<size_t>(h) * HD;
-  return p;
+template <bool CAUSAL>
+__global__ void __launch_bounds__(FWD_THREADS, 1)
+attention_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_kv,
+                        const FwdParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 2 * FWD_STAGE);
+  uint64_t* full = bars;            // [2] operands of a head landed
+  uint64_t* empty = bars + 2;       // [2] all MMAs reading the stage completed
+  uint64_t* s_full = bars + 4;      // [2] scores of tile t in TMEM
+  uint64_t* p_full = bars + 6;      // [2] probabilities of tile t in TMEM
+  uint64_t* o_full = bars + 8;      // [2] P V of tile t complete
+  uint64_t* t_free = bars + 10;     // [2] epilogue drained tile t
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 12);
+
+  const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
+  const int nt = p.n_tiles;
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tm_q);
+    tma_prefetch_desc(&tm_kv);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&full[i], 1);
+      mbar_init(&empty[i], 1);
+      mbar_init(&s_full[i], 1);
+      mbar_init(&p_full[i], 4);
+      mbar_init(&o_full[i], 1);
+      mbar_init(&t_free[i], 4);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_ptr, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  if (warp == 0) {
+    // ============================== TMA producer ==============================
+    const uint32_t q_bytes = static_cast<uint32_t>(128 * nt) * ROW_BYTES, kv_bytes = static_cast<uint32_t>(p.lk_pad) * ROW_BYTES;
+    int it = 0;
+    for (int u = blockIdx.x; u < p.total; u += gridDim.x, ++it) {
+      const int s = it & 1;
+      mbar_wait_uniform(&empty[s], ((it >> 1) & 1) ^ 1);
+      if (elect_one()) {
+        const int b = u / p.H, h = u - b * p.H;
+        uint8_t* st = smem + s * FWD_STAGE;
+        mbar_arrive_expect_tx(&full[s], q_bytes + 2 * kv_bytes);
+        tma_load_3d(st, &tm_q, &full[s], h * HD, 0, b);
+        tma_load_3d(st + Q2_BYTES, &tm_kv, &full[s], p.C + h * HD, 0, b);
+        tma_load_3d(st + Q2_BYTES + KV_BYTES, &tm_kv, &full[s], 2 * p.C + h * HD, 0, b);
+      }
+      __syncwarp();
+    }
+  } else if (warp == 1) {
+    // ============================== MMA issuer ==============================
+    const uint32_t idesc_s = umma_idesc_bf16(128, p.lk_pad);
+    const uint32_t idesc_pv = umma_idesc_bf16(128, HD) | UMMA_IDESC_B_MN;
+    const int pv_steps = p.lk_pad / 16;
+    int it = 0;
+    for (int u = blockIdx.x; u < p.total; u += gridDim.x, ++it) {
+      const int s = it & 1;
+      const uint32_t st = smem_u32(smem + s * FWD_STAGE);
+      mbar_wait_uniform(&full[s], (it >> 1) & 1);
+      tc_fence_after();
+      for (int t = 0; t < nt; ++t) {
+        mbar_wait_uniform(&t_free[t], (it & 1) ^ 1);      // epilogue of the previous head drained this TMEM tile
+        tc_fence_after();
+        if (elect_one()) {
+          const uint64_t ad = umma_desc_sw128(st + t * (128 * ROW_BYTES));
+          const uint64_t bd = umma_desc_sw128(st + Q2_BYTES);
+#pragma unroll
+          for (int k = 0; k < HD / 16; ++k)
+            umma_bf16(tmem_base + t * 256, ad + 2u * k, bd + 2u * k, idesc_s, k != 0 ? 1u : 0u);
+          umma_commit(&s_full[t]);
+        }
+        __syncwarp();
+      }
+      for (int t = 0; t < nt; ++t) {
+        mbar_wait_uniform(&p_full[t], it & 1);
+        tc_fence_after();
+        if (elect_one()) {
+          const uint32_t vb = st + Q2_BYTES + KV_BYTES;
+          for (int k = 0; k < pv_steps; ++k)
+            umma_bf16_ts(tmem_base + t * 256 + 128, tmem_base + t * 256 + 8 * k,
+                         umma_desc_sw128_mn(vb + k * 2048, 16), idesc_pv, k != 0 ? 1u : 0u);
+          umma_commit(&o_full[t]);
+          if (t == nt - 1) umma_commit(&empty[s]);
+        }
+        __syncwarp();
+      }
+    }
+  } else {
+    // ============================== softmax + epilogue (one thread per query row) ==============================
+    const int t = static_cast<int>(warp - 2) >> 2;           // query tile of this warpgroup
+    const uint32_t quarter = warp & 3u;                      // TMEM lane quarter this warp may touch
+    const int row = static_cast<int>(quarter * 32u + lane);
+    if (t < nt) {
+      const uint32_t taddr = tmem_base + ((quarter * 32u) << 16) + static_cast<uint32_t>(t) * 256u;
+      const int qi = t * 128 + row;
+      const int ncol = CAUSAL ? (qi + 1 < p.L ? qi + 1 : p.L) : p.L;      // valid key columns of this row
+      int it = 0;
+      for (int u = blockIdx.x; u < p.total; u += gridDim.x, ++it) {
+        const int b = u / p.H, h = u - b * p.H;
+        mbar_wait(&s_full[t], it & 1, 100 + t);
+        tc_fence_after();
+        // pass 1: row maximum of the raw scores
+        float m = -3.0e38f;
+        for (int c0 = 0; c0 < p.lk_pad; c0 += 16) {
+          uint32_t v[16];
+          tmem_ld16(taddr + c0, v);
+          tmem_ld_wait();
+          if (c0 + 16 <= ncol) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) m = fmaxf(m, __uint_as_float(v[j]));
+          } else {
+#pragma unroll
+            for (int j = 0; j < 16; ++j)
+              if (c0 + j < ncol) m = fmaxf(m, __uint_as_float(v[j]));
+          }
+        }
+        // pass 2: P = exp2(s c - m c) as bf16 pairs over the columns already consumed; fp32 row sum
+        const float mc = m * p.scale_log2;
+        float sum = 0.f;
+        for (int c0 = 0; c0 < p.lk_pad; c0 += 16) {
+          uint32_t v[16];
+          tmem_ld16(taddr + c0, v);
+          tmem_ld_wait();
+          float e[16];
+          if (c0 + 16 <= ncol) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) e[j] = fast_exp2(fmaf(__uint_as_float(v[j]), p.scale_log2, -mc));
+          } else {
+#pragma unroll
+            for (int j = 0; j < 16; ++j)
+              e[j] = (c0 + j < ncol) ? fast_exp2(fmaf(__uint_as_float(v[j]), p.scale_log2, -mc)) : 0.f;
+          }
+          uint32_t pk[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            sum += e[2 * j] + e[2 * j + 1];
+            pk[j] = pack2(e[2 * j], e[2 * j + 1]);
+          }
+          tmem_st8(taddr + (c0 >> 1), pk);
+        }
+        tmem_st_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&p_full[t]);
+
+        // epilogue: O / sum -> bf16 row of `out`
+        mbar_wait(&o_full[t], it & 1, 200 + t);
+        tc_fence_after();
+        const float inv = 1.0f / sum;
+        const bool valid = qi < p.L;
+        const size_t tok = p.batch_first ? (static_cast<size_t>(b) * p.L + qi) : (static_cast<size_t>(qi) * p.B + b);
+        uint4* orow = reinterpret_cast<uint4*>(p.out + (valid ? tok : 0) * p.C + h * HD);
+#pragma unroll
+        for (int c0 = 0; c0 < HD; c0 += 16) {
+          uint32_t v[16];
+          tmem_ld16(taddr + 128 + c0, v);
+          tmem_ld_wait();
+          if (valid) {
+            uint4 o0, o1;
+            o0.x = pack2(__uint_as_float(v[0]) * inv, __uint_as_float(v[1]) * inv);
+            o0.y = pack2(__uint_as_float(v[2]) * inv, __uint_as_float(v[3]) * inv);
+            o0.z = pack2(__uint_as_float(v[4]) * inv, __uint_as_float(v[5]) * inv);
+            o0.w = pack2(__uint_as_float(v[6]) * inv, __uint_as_float(v[7]) * inv);
+            o1.x = pack2(__uint_as_float(v[8]) * inv, __uint_as_float(v[9]) * inv);
+            o1.y = pack2(__uint_as_float(v[10]) * inv, __uint_as_float(v[11]) * inv);
+            o1.z = pack2(__uint_as_float(v[12]) * inv, __uint_as_float(v[13]) * inv);
+            o1.w = pack2(__uint_as_float(v[14]) * inv, __uint_as_float(v[15]) * inv);
+            orow[c0 / 8] = o0;
+            orow[c0 / 8 + 1] = o1;
+          }
+        }
+        if (valid) p.lse[static_cast<size_t>(u) * p.L + qi] = mc + log2f(sum);
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&t_free[t]);
+      }
+    }
+  }
+  __syncwarp();
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, 512);
 }
 
-// ------------------------------------------------------------------------------------------------------------
-// forward
-// ------------------------------------------------------------------------------------------------------------
-// One block of 64 keys for one 16-row query tile.  MASKED = false is the interior case (every key valid for every row):
-// no index arithmetic or selects at all, 4 instructions per score (max, fma, ex2, add).  The running maximum m is kept
-// in the RAW score domain (the scale is positive), so scale and subtraction fuse into one FMA in front of ex2.
-template <bool CAUSAL, bool MASKED>
-__device__ __forceinline__ void fwd_block(int kb0, int k_end, int L, int row0, int row1, uint32_t ks_, uint32_t vs,
-                                          int lane, int t4, const uint32_t (&qf)[4][4], float (&o)[8][4], float& m0,
-                                          float& m1, float& l0, float& l1, float scale_log2) {
-  float s[8][4];
-#pragma unroll
-  for (int i = 0; i < 8; ++i) s[i][0] = s[i][1] = s[i][2] = s[i][3] = 0.f;
-  // S = Q K^T for 64 keys (8 n-tiles), two n-tiles per ldmatrix.x4
-#pragma unroll
-  for (int np = 0; np < 4; ++np) {
-    if (!MASKED || kb0 + np * 16 < k_end) {            // warp-uniform
-      const int key = kb0 + np * 16 + ((lane >> 4) << 3) + (lane & 7);
-#pragma unroll
-      for (int kk = 0; kk < 4; ++kk) {
-        uint32_t kf[4];
-        ldsm4(ks_ + sw_off(key, 2 * kk + ((lane >> 3) & 1)), kf);
-        mma16816(s[2 * np], qf[kk], kf[0], kf[1]);
-        mma16816(s[2 * np + 1], qf[kk], kf[2], kf[3]);
-      }
-    }
-  }
-  if (MASKED) {
-    // keys past the sequence, past k_end (skipped sub-blocks: they are >= L, or > every row of a causal tile) and above
-    // the diagonal
-#pragma unroll
-    for (int nt = 0; nt < 8; ++nt) {
-#pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        const int key = kb0 + nt * 8 + 2 * t4 + (e & 1);
-        const int row = (e & 2) ? row1 : row0;
-        if (key >= L || (CAUSAL && key > row)) s[nt][e] = -INFINITY;
-      }
-    }
-  }
-  float bm0 = fmaxf(s[0][0], s[0][1]), bm1 = fmaxf(s[0][2], s[0][3]);
-#pragma unroll
-  for (int nt = 1; nt < 8; ++nt) {
-    bm0 = fmaxf(bm0, fmaxf(s[nt][0], s[nt][1]));
-    bm1 = fmaxf(bm1, fmaxf(s[nt][2], s[nt][3]));
-  }
-  bm0 = fmaxf(bm0, __shfl_xor_sync(0xffffffffu, bm0, 1));
-  bm0 = fmaxf(bm0, __shfl_xor_sync(0xffffffffu, bm0, 2));
-  bm1 = fmaxf(bm1, __shfl_xor_sync(0xffffffffu, bm1, 1));
-  bm1 = fmaxf(bm1, __shfl_xor_sync(0xffffffffu, bm1, 2));
-  const float mn0 = fmaxf(m0, bm0), mn1 = fmaxf(m1, bm1);
-  // every row sees key 0 in the first block (also under the causal mask), so mn is finite from block 0 on
-  const float a0 = ex2((m0 - mn0) * scale_log2), a1 = ex2((m1 - mn1) * scale_log2);
-  m0 = mn0;
-  m1 = mn1;
-  const float ms0 = -mn0 * scale_log2, ms1 = -mn1 * scale_log2;
-  float ps0 = 0.f, ps1 = 0.f;
-#pragma unroll
-  for (int nt = 0; nt < 8; ++nt) {
-    s[nt][0] = ex2(fmaf(s[nt][0], scale_log2, ms0));
-    s[nt][1] = ex2(fmaf(s[nt][1], scale_log2, ms0));
-    s[nt][2] = ex2(fmaf(s[nt][2], scale_log2, ms1));
-    s[nt][3] = ex2(fmaf(s[nt][3], scale_log2, ms1));
-    ps0 += s[nt][0] + s[nt][1];
-    ps1 += s[nt][2] + s[nt][3];
-  }
-  l0 = fmaf(l0, a0, ps0);
-  l1 = fmaf(l1, a1, ps1);
-#pragma unroll
-  for (int dn = 0; dn < 8; ++dn) {
-    o[dn][0] *= a0; o[dn][1] *= a0;
-    o[dn][2] *= a1; o[dn][3] *= a1;
-  }
-  // O += P V : P re-packed as A fragments (k = 16 keys per step), V^T fragments through ldmatrix.trans
-#pragma unroll
-  for (int j = 0; j < 4; ++j) {
-    if (!MASKED || kb0 + j * 16 < k_end) {
-      uint32_t pa[4];
-      pa[0] = pack_bf16x2(s[2 * j][0], s[2 * j][1]);
-      pa[1] = pack_bf16x2(s[2 * j][2], s[2 * j][3]);
-      pa[2] = pack_bf16x2(s[2 * j + 1][0], s[2 * j + 1][1]);
-      pa[3] = pack_bf16x2(s[2 * j + 1][2], s[2 * j + 1][3]);
-      const int key = kb0 + j * 16 + (lane & 7) + (((lane >> 3) & 1) << 3);
-#pragma unroll
-      for (int dp = 0; dp < 4; ++dp) {
-        uint32_t vf[4];
-        ldsm4t(vs + sw_off(key, 2 * dp + (lane >> 4)), vf);
-        mma16816(o[2 * dp], pa, vf[0], vf[1]);
-        mma16816(o[2 * dp + 1], pa, vf[2], vf[3]);
-      }
-    }
-  }
-}
+// ---------------------------------------------------------------------------------------------------------------
+// backward
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int BWD_THREADS = 320;            // warp 0: TMA, warp 1: MMA (+ TMEM alloc), warps 2-9: element-wise + epilogues
+constexpr int OFF_Q = 0;
+constexpr int OFF_DO = OFF_Q + KV_BYTES;             //  26624
+constexpr int OFF_K = OFF_DO + KV_BYTES;             //  53248
+constexpr int OFF_V = OFF_K + Q2_BYTES;              //  86016
+constexpr int OFF_DS = OFF_V + Q2_BYTES;             // 118784: two dS tiles [128 keys][128 queries] bf16, MN-major SW128
+constexpr int DS_TILE = 128 * 128 * 2;               //  32768
+constexpr int OFF_VEC = OFF_DS + 2 * DS_TILE;        // 184320: lse2[208], delta[208]
+constexpr int OFF_BAR = OFF_VEC + 2 * LP * 4;        // 185984
+constexpr int BWD_SMEM = OFF_BAR + 128 + 1024;
+constexpr uint32_t R0 = 0, R1 = 128, ACC_DV = 256, ACC_DK = 320, ACC_DQ = 384;   // TMEM columns
+
+struct BwdParams {
+  const __nv_bfloat16* out;
+  const float* lse;
+  __nv_bfloat16* d_qkv;
+  int B, L, H, C, batch_first;
+  int l_pad;        // L rounded up to 16
+  int nj;           // key tiles (1 or 2) = query halves
+  int total;
+  float scale, scale_log2;
+};
+
+// first query column handled by the second warp of a pair / first packed column of its output (multiple of 16)
+__device__ __forceinline__ int split_point(int n) { return 16 * ((n / 16 + 1) / 2); }
 
 template <bool CAUSAL>
-__global__ void __launch_bounds__(THREADS, 2)
-attention_fwd_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restrict__ out, float* __restrict__ lse,
-                     int B, int L, int H, int batch_first, float scale_log2) {
-  extern __shared__ __align__(1024) uint8_t att_smem[];
-  uint8_t* Qs = att_smem;
-  uint8_t* Ks = Qs + TILE_BYTES;
-  uint8_t* Vs = Ks + TILE_BYTES;
-  const int b = blockIdx.x / H, h = blockIdx.x - b * H;
-  const HeadPtrs hp = head_ptrs(qkv, b, h, B, L, H, batch_first);
-  stage_tile(Qs, hp.q, hp.pitch, L);
-  stage_tile(Ks, hp.k, hp.pitch, L);
-  stage_tile(Vs, hp.v, hp.pitch, L);
-  cp_commit_wait_all();
+__global__ void __launch_bounds__(BWD_THREADS, 1)
+attention_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_kv,
+                        const __grid_constant__ CUtensorMap tm_do, const BwdParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  float* lse2_s = reinterpret_cast<float*>(smem + OFF_VEC);
+  float* delta_s = lse2_s + LP;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + OFF_BAR);
+  uint64_t* ld_full = bars;          // operands of a head landed
+  uint64_t* ld_free = bars + 1;      // every MMA of the head completed: operands may be overwritten
+  uint64_t* sdp_full = bars + 2;     // S^T and dP^T of a unit in TMEM
+  uint64_t* pds_full = bars + 3;     // P^T / dS^T written (TMEM + shared tile)
+  uint64_t* stage_free = bars + 4;   // [2] dQ MMAs reading the shared dS tile completed
+  uint64_t* dvk_full = bars + 6;     // [2] dV_j / dK_j complete
+  uint64_t* dq_full = bars + 8;      // [2] dQ_a complete
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 10);
+
+  const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
+  const int nj = p.nj;
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tm_q);
+    tma_prefetch_desc(&tm_kv);
+    tma_prefetch_desc(&tm_do);
+    mbar_init(ld_full, 1);
+    mbar_init(ld_free, 1);
+    mbar_init(sdp_full, 1);
+    mbar_init(pds_full, 8);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&stage_free[i], 1);
+      mbar_init(&dvk_full[i], 1);
+      mbar_init(&dq_full[i], 1);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_ptr, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
   __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int g = lane >> 2, t4 = lane & 3;
-  const int n_tiles = (L + 15) >> 4;
-  const int Lk = n_tiles * 16;                          // keys actually visited (multiple of 16)
-  const uint32_t qs = smem_u32(Qs), ks_ = smem_u32(Ks), vs = smem_u32(Vs);
+  if (warp == 0) {
+    // ============================== TMA producer ==============================
+    const uint32_t q_bytes = static_cast<uint32_t>(p.l_pad) * ROW_BYTES, k_bytes = static_cast<uint32_t>(128 * nj) * ROW_BYTES;
+    int it = 0;
+    for (int u = blockIdx.x; u < p.total; u += gridDim.x, ++it) {
+      mbar_wait_uniform(ld_free, (it & 1) ^ 1);
+      if (elect_one()) {
+        const int b = u / p.H, h = u - b * p.H;
+        mbar_arrive_expect_tx(ld_full, 2 * q_bytes + 2 * k_bytes);
+        tma_load_3d(smem + OFF_Q, &tm_q, ld_full, h * HD, 0, b);
+        tma_load_3d(smem + OFF_DO, &tm_do, ld_full, h * HD, 0, b);
+        tma_load_3d(smem + OFF_K, &tm_kv, ld_full, p.C + h * HD, 0, b);
+        tma_load_3d(smem + OFF_V, &tm_kv, ld_full, 2 * p.C + h * HD, 0, b);
+      }
+      __syncwarp();
+    }
+  } else if (warp == 1) {
+    // ============================== MMA issuer ==============================
+    const uint32_t sb = smem_u32(smem);
+    const uint32_t idesc_acc = umma_idesc_bf16(128, HD) | UMMA_IDESC_B_MN;                      // A in TMEM
+    const uint32_t idesc_dq = umma_idesc_bf16(128, HD) | UMMA_IDESC_A_MN | UMMA_IDESC_B_MN;     // A = shared dS tile
+    int it = 0;
+    uint32_t n = 0;                                         // running unit counter
+    for (int u = blockIdx.x; u < p.total; u += gridDim.x, ++it) {
+      mbar_wait_uniform(ld_full, it & 1);
+      tc_fence_after();
+      for (int j = 0; j < nj; ++j) {
+        const int kk = ((p.L - 128 * j < 128 ? p.L - 128 * j : 128) + 15) / 16;   // K steps over the valid keys of tile j
+        for (int a = 0; a < nj; ++a, ++n) {
+          const int na = (a == 0) ? (p.l_pad < 128 ? p.l_pad : 128) : p.l_pad - 128;  // query columns of this unit
+          const uint32_t idesc_sn = umma_idesc_bf16(128, na);
+          if (elect_one()) {
+            const uint64_t kd = umma_desc_sw128(sb + OFF_K + j * (128 * ROW_BYTES));
+            const uint64_t vd = umma_desc_sw128(sb + OFF_V + j * (128 * ROW_BYTES));
+            const uint64_t qd = umma_desc_sw128(sb + OFF_Q + a * (128 * ROW_BYTES));
+            const uint64_t dd = umma_desc_sw128(sb + OFF_DO + a * (128 * ROW_BYTES));
+#pragma unroll
+            for (int k = 0; k < HD / 16; ++k) umma_bf16(tmem_base + R0, kd + 2u * k, qd + 2u * k, idesc_sn, k != 0 ? 1u : 0u);
+#pragma unroll
+            for (int k = 0; k < HD / 16; ++k) umma_bf16(tmem_base + R1, vd + 2u * k, dd + 2u * k, idesc_sn, k != 0 ? 1u : 0u);
+            umma_commit(sdp_full);
+          }
+          __syncwarp();
+          mbar_wait_uniform(pds_full, n & 1u);
+          tc_fence_after();
+          if (elect_one()) {
+            const int sp = split_point(na);
+            const int ks = na / 16;
+            for (int k = 0; k < ks; ++k) {                   // dV_j += P^T dO_a
+              const uint32_t col = (16 * k < sp) ? 8u * k : static_cast<uint32_t>(sp + 8 * (k - sp / 16));
+              umma_bf16_ts(tmem_base + ACC_DV, tmem_base + R0 + col,
+                           umma_desc_sw128_mn(sb + OFF_DO + (128 * a + 16 * k) * ROW_BYTES, 16), idesc_acc,
+                           (a | k) != 0 ? 1u : 0u);
+            }
+            for (int k = 0; k < ks; ++k) {                   // dK_j += dS^T Q_a
+              const uint32_t col = (16 * k < sp) ? 8u * k : static_cast<uint32_t>(sp + 8 * (k - sp / 16));
+              umma_bf16_ts(tmem_base + ACC_DK, tmem_base + R1 + col,
+                           umma_desc_sw128_mn(sb + OFF_Q + (128 * a + 16 * k) * ROW_BYTES, 16), idesc_acc,
+                           (a | k) != 0 ? 1u : 0u);
+            }
+            const uint32_t ds = sb + OFF_DS + (n & 1u) * DS_TILE;
+            for (int k = 0; k < kk; ++k)                     // dQ_a += dS K_j
+              umma_bf16(tmem_base + ACC_DQ + 64 * a, umma_desc_sw128_mn(ds + k * 2048, 128 * ROW_BYTES),
+                        umma_desc_sw128_mn(sb + OFF_K + (128 * j + 16 * k) * ROW_BYTES, 16), idesc_dq,
+                        (j | k) != 0 ? 1u : 0u);
+            umma_commit(&stage_free[n & 1u]);
+            if (a == nj - 1) umma_commit(&dvk_full[j]);
+            if (j == nj - 1) umma_commit(&dq_full[a]);
+            if (j == nj - 1 && a == nj - 1) umma_commit(ld_free);
+          }
+          __syncwarp();
+        }
+      }
+    }
+  } else {
+    // ============================== element-wise warps ==============================
+    const uint32_t quarter = warp & 3u;
+    const int half = static_cast<int>(warp - 2) >> 2;        // which column half of a unit / which accumulator
+    const int row = static_cast<int>(quarter * 32u + lane);  // key row inside tile j, query row inside half a
+    const int tid_s = static_cast<int>(threadIdx.x) - 64;    // 0..255
+    const uint32_t lane_addr = (quarter * 32u) << 16;
+    const size_t row_stride = static_cast<size_t>(3) * p.C;
+    int it = 0;
+    uint32_t n = 0;
+    for (int u = blockIdx.x; u < p.total; u += gridDim.x, ++it) {
+      const int b = u / p.H, h = u - b * p.H;
+      mbar_wait(ld_full, it & 1, 300);
+      // delta[q] = sum_d dO[q][d] O[q][d] (O from global, dO from the swizzled tile), lse2[q]; +inf masks padded queries
+      if (tid_s < LP) {
+        float d = 0.f, l2 = __int_as_float(0x7f800000);
+        if (tid_s < p.L) {
+          const size_t tok = p.batch_first ? (static_cast<size_t>(b) * p.L + tid_s) : (static_cast<size_t>(tid_s) * p.B + b);
+          const uint4* orow = reinterpret_cast<const uint4*>(p.out + tok * p.C + h * HD);
+          const uint8_t* drow = smem + OFF_DO + tid_s * ROW_BYTES;
+#pragma unroll
+          for (int c = 0; c < 8; ++c) {
+            const uint4 ov = __ldg(orow + c);
+            const uint4 dv = *reinterpret_cast<const uint4*>(drow + ((c ^ (tid_s & 7)) << 4));
+            const __nv_bfloat162* o2 = reinterpret_cast<const __nv_bfloat162*>(&ov);
+            const __nv_bfloat162* d2 = reinterpret_cast<const __nv_bfloat162*>(&dv);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const float2 of = __bfloat1622float2(o2[e]), df = __bfloat1622float2(d2[e]);
+              d = fmaf(of.x, df.x, d);
+              d = fmaf(of.y, df.y, d);
+            }
+          }
+          l2 = p.lse[static_cast<size_t>(u) * p.L + tid_s];
+        }
+        delta_s[tid_s] = d;
+        lse2_s[tid_s] = l2;
+      }
+      named_bar_sync(1, 256);
 
-  for (int rt = warp; rt < n_tiles; rt += WARPS) {
-    uint32_t qf[4][4];
-    load_a_frags(qs, rt, lane, qf);
-    float o[8][4];
+      for (int j = 0; j < nj; ++j) {
+        const int key = 128 * j + row;
+        const bool kvalid = key < p.L;
+        for (int a = 0; a < nj; ++a, ++n) {
+          const int na = (a == 0) ? (p.l_pad < 128 ? p.l_pad : 128) : p.l_pad - 128;
+          const int sp = split_point(na);
+          const int c_lo = half == 0 ? 0 : sp, c_hi = half == 0 ? sp : na;
+          mbar_wait(sdp_full, n & 1u, 400);
+          tc_fence_after();
+          if (a == 0 && j > 0) {
+            // dV_{j-1} / dK_{j-1} are complete (their commit precedes this unit's scores): drain them before this unit's
+            // first dV / dK MMA overwrites the accumulators
+            mbar_wait(&dvk_full[j - 1], it & 1, 500);
+            tc_fence_after();
+            const int kr = 128 * (j - 1) + row;
+            const uint32_t acc = tmem_base + lane_addr + (half == 0 ? ACC_DV : ACC_DK);
+            const float sc = half == 0 ? 1.0f : p.scale;
+            const size_t tok = p.batch_first ? (static_cast<size_t>(b) * p.L + kr) : (static_cast<size_t>(kr) * p.B + b);
+            uint4* dst = reinterpret_cast<uint4*>(p.d_qkv + tok * row_stride + (half == 0 ? 2 : 1) * p.C + h * HD);
 #pragma unroll
-    for (int i = 0; i < 8; ++i) o[i][0] = o[i][1] = o[i][2] = o[i][3] = 0.f;
-    float m0 = -INFINITY, m1 = -INFINITY, l0 = 0.f, l1 = 0.f;
-    const int row0 = rt * 16 + g, row1 = row0 + 8;
-    const int k_end = CAUSAL ? min(Lk, rt * 16 + 16) : Lk;      // causal: keys beyond the tile's last row are masked
-
-    for (int kb0 = 0; kb0 < k_end; kb0 += 64) {
-      // interior block: all 64 keys exist and (causal) lie at or below the tile's first row
-      const bool interior = (kb0 + 64 <= L) && (!CAUSAL || kb0 + 63 <= rt * 16);
-      if (interior) fwd_block<CAUSAL, false>(kb0, k_end, L, row0, row1, ks_, vs, lane, t4, qf, o, m0, m1, l0, l1, scale_log2);
-      else fwd_block<CAUSAL, true>(kb0, k_end, L, row0, row1, ks_, vs, lane, t4, qf, o, m0, m1, l0, l1, scale_log2);
-    }
-    // finish the rows: l over the quad, normalise, stage the tile through this tile's (private) Q rows
-    l0 += __shfl_xor_sync(0xffffffffu, l0, 1);
-    l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
-    l1 += __shfl_xor_sync(0xffffffffu, l1, 1);
-    l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
-    const float i0 = 1.0f / l0, i1 = 1.0f / l1;
-    __syncwarp();
+            for (int c0 = 0; c0 < HD; c0 += 16) {
+              uint32_t v[16];
+              tmem_ld16(acc + c0, v);
+              tmem_ld_wait();
+              uint4 o0, o1;
+              o0.x = pack2(__uint_as_float(v[0]) * sc, __uint_as_float(v[1]) * sc);
+              o0.y = pack2(__uint_as_float(v[2]) * sc, __uint_as_float(v[3]) * sc);
+              o0.z = pack2(__uint_as_float(v[4]) * sc, __uint_as_float(v[5]) * sc);
+              o0.w = pack2(__uint_as_float(v[6]) * sc, __uint_as_float(v[7]) * sc);
+              o1.x = pack2(__uint_as_float(v[8]) * sc, __uint_as_float(v[9]) * sc);
+              o1.y = pack2(__uint_as_float(v[10]) * sc, __uint_as_float(v[11]) * sc);
+              o1.z = pack2(__uint_as_float(v[12]) * sc, __uint_as_float(v[13]) * sc);
+              o1.w = pack2(__uint_as_float(v[14]) * sc, __uint_as_float(v[15]) * sc);
+              dst[c0 / 8] = o0;          // kr < L always holds for tile j-1 < nj-1
+              dst[c0 / 8 + 1] = o1;
+            }
+          }
+          mbar_wait(&stage_free[n & 1u], ((n >> 1) & 1u) ^ 1u, 600);
+          uint8_t* ds_tile = smem + OFF_DS + (n & 1u) * DS_TILE;
+          for (int c0 = c_lo; c0 < c_hi; c0 += 16) {
+            uint32_t sv[16], dv[16];
+            tmem_ld16(tmem_base + lane_addr + R0 + c0, sv);
+            tmem_ld16(tmem_base + lane_addr + R1 + c0, dv);
+            tmem_ld_wait();
+            const int q0 = 128 * a + c0;
+            uint32_t pp[8], dd[8];
 #pragma unroll
-    for (int dn = 0; dn < 8; ++dn) {
-      *reinterpret_cast<uint32_t*>(Qs + sw_off(row0, dn) + t4 * 4) = pack_bf16x2(o[dn][0] * i0, o[dn][1] * i0);
-      *reinterpret_cast<uint32_t*>(Qs + sw_off(row1, dn) + t4 * 4) = pack_bf16x2(o[dn][2] * i1, o[dn][3] * i1);
-    }
-    if (t4 == 0) {
-      float* lp = lse + static_cast<size_t>(blockIdx.x) * L;
-      if (row0 < L) lp[row0] = fmaf(m0, scale_log2, log2f(l0));
-      if (row1 < L) lp[row1] = fmaf(m1, scale_log2, log2f(l1));
-    }
-    __syncwarp();
+            for (int e = 0; e < 8; ++e) {
+              float pv[2], gv[2];
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const int idx = lane + 32 * i;
-      const int r = rt * 16 + (idx >> 3), c = idx & 7;
-      if (r < L)
-        *reinterpret_cast<uint4*>(out + hp.ooff + static_cast<size_t>(r) * hp.opitch + c * 8) =
-            *reinterpret_cast<const uint4*>(Qs + sw_off(r, c));
+              for (int w = 0; w < 2; ++w) {
+                const int q = q0 + 2 * e + w;
+                const bool on = kvalid && (!CAUSAL || q >= key);
+                const float x = fmaf(__uint_as_float(sv[2 * e + w]), p.scale_log2, -lse2_s[q]);
+                pv[w] = on ? fast_exp2(x) : 0.f;
+                gv[w] = pv[w] * (__uint_as_float(dv[2 * e + w]) - delta_s[q]);
+              }
+              pp[e] = pack2(pv[0], pv[1]);
+              dd[e] = pack2(gv[0], gv[1]);
+            }
+            const uint32_t pcol = static_cast<uint32_t>(half == 0 ? (c0 >> 1) : sp + ((c0 - sp) >> 1));
+            tmem_st8(tmem_base + lane_addr + R0 + pcol, pp);
+            tmem_st8(tmem_base + lane_addr + R1 + pcol, dd);
+            // dS (not transposed) for dQ: [key row][query contiguous], 64-query blocks of 128 rows x 128 B, SW128
+            uint8_t* blk = ds_tile + (c0 >> 6) * (128 * ROW_BYTES) + row * ROW_BYTES;
+            const int ch = (c0 & 63) >> 3;
+            *reinterpret_cast<uint4*>(blk + (((ch) ^ (row & 7)) << 4)) = make_uint4(dd[0], dd[1], dd[2], dd[3]);
+            *reinterpret_cast<uint4*>(blk + (((ch + 1) ^ (row & 7)) << 4)) = make_uint4(dd[4], dd[5], dd[6], dd[7]);
+          }
+          tmem_st_wait();
+          fence_proxy_async_smem();
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(pds_full);
+        }
+      }
+      // ---- epilogues of the head: dV / dK of the last key tile, dQ of both query halves ----
+      {
+        mbar_wait(&dvk_full[nj - 1], it & 1, 700);
+        tc_fence_after();
+        const int kr = 128 * (nj - 1) + row;
+        const uint32_t acc = tmem_base + lane_addr + (half == 0 ? ACC_DV : ACC_DK);
+        const float sc = half == 0 ? 1.0f : p.scale;
+        const bool valid = kr < p.L;
+        const size_t tok = p.batch_first ? (static_cast<size_t>(b) * p.L + kr) : (static_cast<size_t>(kr) * p.B + b);
+        uint4* dst = reinterpret_cast<uint4*>(p.d_qkv + (valid ? tok : 0) * row_stride + (half == 0 ? 2 : 1) * p.C + h * HD);
+#pragma unroll
+        for (int c0 = 0; c0 < HD; c0 += 16) {
+          uint32_t v[16];
+          tmem_ld16(acc + c0, v);
+          tmem_ld_wait();
+          if (valid) {
+            uint4 o0, o1;
+            o0.x = pack2(__uint_as_float(v[0]) * sc, __uint_as_float(v[1]) * sc);
+            o0.y = pack2(__uint_as_float(v[2]) * sc, __uint_as_float(v[3]) * sc);
+            o0.z = pack2(__uint_as_float(v[4]) * sc, __uint_as_float(v[5]) * sc);
+            o0.w = pack2(__uint_as_float(v[6]) * sc, __uint_as_float(v[7]) * sc);
+            o1.x = pack2(__uint_as_float(v[8]) * sc, __uint_as_float(v[9]) * sc);
+            o1.y = pack2(__uint_as_float(v[10]) * sc, __uint_as_float(v[11]) * sc);
+            o1.z = pack2(__uint_as_float(v[12]) * sc, __uint_as_float(v[13]) * sc);
+            o1.w = pack2(__uint_as_float(v[14]) * sc, __uint_as_float(v[15]) * sc);
+            dst[c0 / 8] = o0;
+            dst[c0 / 8 + 1] = o1;
+          }
+        }
+      }
+      for (int a = 0; a < nj; ++a) {
+        mbar_wait(&dq_full[a], it & 1, 800 + a);
+        tc_fence_after();
+        const int qr = 128 * a + row;
+        const bool valid = qr < p.L;
+        const size_t tok = p.batch_first ? (static_cast<size_t>(b) * p.L + qr) : (static_cast<size_t>(qr) * p.B + b);
+        uint4* dst = reinterpret_cast<uint4*>(p.d_qkv + (valid ? tok : 0) * row_stride + h * HD + half * 32);
+        const uint32_t acc = tmem_base + lane_addr + ACC_DQ + 64 * a + half * 32;
+#pragma unroll
+        for (int c0 = 0; c0 < 32; c0 += 16) {
+          uint32_t v[16];
+          tmem_ld16(acc + c0, v);
+          tmem_ld_wait();
+          if (valid) {
+            const float sc = p.scale;
+            uint4 o0, o1;
+            o0.x = pack2(__uint_as_float(v[0]) * sc, __uint_as_float(v[1]) * sc);
+            o0.y = pack2(__uint_as_float(v[2]) * sc, __uint_as_float(v[3]) * sc);
+            o0.z = pack2(__uint_as_float(v[4]) * sc, __uint_as_float(v[5]) * sc);
+            o0.w = pack2(__uint_as_float(v[6]) * sc, __uint_as_float(v[7]) * sc);
+            o1.x = pack2(__uint_as_float(v[8]) * sc, __uint_as_float(v[9]) * sc);
+            o1.y = pack2(__uint_as_float(v[10]) * sc, __uint_as_float(v[11]) * sc);
+            o1.z = pack2(__uint_as_float(v[12]) * sc, __uint_as_float(v[13]) * sc);
+            o1.w = pack2(__uint_as_float(v[14]) * sc, __uint_as_float(v[15]) * sc);
+            dst[c0 / 8] = o0;
+            dst[c0 / 8 + 1] = o1;
+          }
+        }
+      }
+      tc_fence_before();
+      named_bar_sync(1, 256);        // delta / lse2 of this head are dead: the next head may overwrite them
     }
   }
+  __syncwarp();
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, 512);
 }
 
-// ------------------------------------------------------------------------------------------------------------
-// backward
-// ------------------------------------------------------------------------------------------------------------
-template <bool causal>
-__global__ void __launch_bounds__(THREADS, 2)
-attention_bwd_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16* __restrict__ out,
-                     const __nv_bfloat16* __restrict__ d_out, const float* __restrict__ lse,
-                     __nv_bfloat16* __restrict__ d_qkv, int B, int L, int H, int batch_first, float scale,
-                     float scale_log2) {
-  extern __shared__ __align__(1024) uint8_t att_smem[];
-  uint8_t* Qs = att_smem;
-  uint8_t* Ks = Qs + TILE_BYTES;
-  uint8_t* Vs = Ks + TILE_BYTES;
-  uint8_t* Gs = Vs + TILE_BYTES;                                  // dO
-  float* lse_s = reinterpret_cast<float*>(Gs + TILE_BYTES);
-  float* del_s = lse_s + LP;
-  const int b = blockIdx.x / H, h = blockIdx.x - b * H;
-  const HeadPtrs hp = head_ptrs(qkv, b, h, B, L, H, batch_first);
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int g = lane >> 2, t4 = lane & 3;
-
-  stage_tile(Qs, hp.q, hp.pitch, L);
-  stage_tile(Ks, hp.k, hp.pitch, L);
-  stage_tile(Vs, hp.v, hp.pitch, L);
-  // dO through registers: delta[r] = sum_d dO[r, d] * O[r, d] on the way (8 lanes share a row)
-  for (int base = 0; base < LP * 8; base += THREADS) {
-    const int idx = base + threadIdx.x;
-    const int r = idx >> 3, c = idx & 7;
-    float part = 0.f;
-    if (r < LP) {
-      uint4 gv = make_uint4(0u, 0u, 0u, 0u);
-      if (r < L) {
-        const size_t off = hp.ooff + static_cast<size_t>(r) * hp.opitch + c * 8;
-        gv = __ldg(reinterpret_cast<const uint4*>(d_out + off));
-        const uint4 ov = __ldg(reinterpret_cast<const uint4*>(out + off));
-        const __nv_bfloat162* g2 = reinterpret_cast<const __nv_bfloat162*>(&gv);
-        const __nv_bfloat162* o2 = reinterpret_cast<const __nv_bfloat162*>(&ov);
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          const float2 a = __bfloat1622float2(g2[e]), c2 = __bfloat1622float2(o2[e]);
-          part = fmaf(a.x, c2.x, part);
-          part = fmaf(a.y, c2.y, part);
-        }
-      }
-      *reinterpret_cast<uint4*>(Gs + sw_off(r, c)) = gv;
-    }
-    part += __shfl_xor_sync(0xffffffffu, part, 1);
-    part += __shfl_xor_sync(0xffffffffu, part, 2);
-    part += __shfl_xor_sync(0xffffffffu, part, 4);
-    if (c == 0 && r < LP) del_s[r] = part;
+// ---------------------------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------------------------
+// [batch][token][channel] view of a packed bf16 activation: box = {64 channels, box_rows tokens, 1 sample}
+static int make_map_tokens(CUtensorMap* out, const void* ptr, int B, int L, int width, int batch_first, int box_rows) {
+  PFN_encodeTiled enc = tensor_map_encode_fn();
+  if (enc == nullptr) {
+    set_last_error("cuTensorMapEncodeTiled driver entry point not available");
+    return FFM_ERR_CUDA;
   }
-  for (int r = threadIdx.x; r < LP; r += THREADS)
-    lse_s[r] = r < L ? lse[static_cast<size_t>(blockIdx.x) * L + r] : INFINITY;     // padded rows: P = exp2(-inf) = 0
-  cp_commit_wait_all();
-  __syncthreads();
-
-  const int n_tiles = (L + 15) >> 4;
-  const int Lk = n_tiles * 16;
-  const uint32_t qs = smem_u32(Qs), ks_ = smem_u32(Ks), vs = smem_u32(Vs), gs = smem_u32(Gs);
-  const size_t C = static_cast<size_t>(H) * HD;
-  __nv_bfloat16* dq_base = d_qkv + (hp.q - qkv);
-  __nv_bfloat16* dk_base = dq_base + C;
-  __nv_bfloat16* dv_base = dq_base + 2 * C;
-
-  // ---------------- phase A: dQ (warp owns query tiles) ----------------
-  for (int rt = warp; rt < n_tiles; rt += WARPS) {
-    uint32_t qf[4][4], gf[4][4];
-    load_a_frags(qs, rt, lane, qf);
-    load_a_frags(gs, rt, lane, gf);
-    const int row0 = rt * 16 + g, row1 = row0 + 8;
-    const float ls0 = -lse_s[row0], ls1 = -lse_s[row1], de0 = del_s[row0], de1 = del_s[row1];
-    float dq[8][4];
-#pragma unroll
-    for (int i = 0; i < 8; ++i) dq[i][0] = dq[i][1] = dq[i][2] = dq[i][3] = 0.f;
-    const int k_end = causal ? min(Lk, rt * 16 + 16) : Lk;
-    for (int kb0 = 0; kb0 < k_end; kb0 += 32) {
-      float s[4][4], dp[4][4];
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        s[i][0] = s[i][1] = s[i][2] = s[i][3] = 0.f;
-        dp[i][0] = dp[i][1] = dp[i][2] = dp[i][3] = 0.f;
-      }
-#pragma unroll
-      for (int np = 0; np < 2; ++np) {
-        if (kb0 + np * 16 < k_end) {
-          const int key = kb0 + np * 16 + ((lane >> 4) << 3) + (lane & 7);
-#pragma unroll
-          for (int kk = 0; kk < 4; ++kk) {
-            uint32_t f[4];
-            ldsm4(ks_ + sw_off(key, 2 * kk + ((lane >> 3) & 1)), f);
-            mma16816(s[2 * np], qf[kk], f[0], f[1]);
-            mma16816(s[2 * np + 1], qf[kk], f[2], f[3]);
-            ldsm4(vs + sw_off(key, 2 * kk + ((lane >> 3) & 1)), f);
-            mma16816(dp[2 * np], gf[kk], f[0], f[1]);
-            mma16816(dp[2 * np + 1], gf[kk], f[2], f[3]);
-          }
-        }
-      }
-      // dS = P ⊙ (dP - delta); padded keys have K = V = 0, so whatever P they get meets a zero K row below
-#pragma unroll
-      for (int nt = 0; nt < 4; ++nt) {
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          const int key = kb0 + nt * 8 + 2 * t4 + (e & 1);
-          const int row = (e & 2) ? row1 : row0;
-          float p = ex2(fmaf(s[nt][e], scale_log2, (e & 2) ? ls1 : ls0));
-          if (causal && key > row) p = 0.f;
-          s[nt][e] = p * (dp[nt][e] - ((e & 2) ? de1 : de0));
-        }
-      }
-#pragma unroll
-      for (int j = 0; j < 2; ++j) {
-        if (kb0 + j * 16 < k_end) {
-          uint32_t da[4];
-          da[0] = pack_bf16x2(s[2 * j][0], s[2 * j][1]);
-          da[1] = pack_bf16x2(s[2 * j][2], s[2 * j][3]);
-          da[2] = pack_bf16x2(s[2 * j + 1][0], s[2 * j + 1][1]);
-          da[3] = pack_bf16x2(s[2 * j + 1][2], s[2 * j + 1][3]);
-          const int key = kb0 + j * 16 + (lane & 7) + (((lane >> 3) & 1) << 3);
-#pragma unroll
-          for (int dpi = 0; dpi < 4; ++dpi) {
-            uint32_t f[4];
-            ldsm4t(ks_ + sw_off(key, 2 * dpi + (lane >> 4)), f);
-            mma16816(dq[2 * dpi], da, f[0], f[1]);
-            mma16816(dq[2 * dpi + 1], da, f[2], f[3]);
-          }
-        }
-      }
-    }
-#pragma unroll
-    for (int dn = 0; dn < 8; ++dn) {
-      if (row0 < L)
-        *reinterpret_cast<uint32_t*>(dq_base + static_cast<size_t>(row0) * hp.pitch + dn * 8 + 2 * t4) =
-            pack_bf16x2(dq[dn][0] * scale, dq[dn][1] * scale);
-      if (row1 < L)
-        *reinterpret_cast<uint32_t*>(dq_base + static_cast<size_t>(row1) * hp.pitch + dn * 8 + 2 * t4) =
-            pack_bf16x2(dq[dn][2] * scale, dq[dn][3] * scale);
-    }
+  const cuuint64_t row = static_cast<cuuint64_t>(width) * 2;
+  cuuint64_t dims[3] = {static_cast<cuuint64_t>(width), static_cast<cuuint64_t>(L), static_cast<cuuint64_t>(B)};
+  cuuint64_t strides[2] = {batch_first ? row : row * B, batch_first ? row * L : row};
+  cuuint32_t box[3] = {HD, static_cast<cuuint32_t>(box_rows), 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(ptr), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_last_error("cuTensorMapEncodeTiled (attention, %d x %d x %d, box %d rows) failed: %d", B, L, width, box_rows, (int)r);
+    return FFM_ERR_CUDA;
   }
-
-  // ---------------- phase B: dK, dV (warp owns key tiles; transposed scores) ----------------
-  for (int kt = warp; kt < n_tiles; kt += WARPS) {
-    uint32_t kf[4][4];
-    load_a_frags(ks_, kt, lane, kf);
-    const int key0 = kt * 16 + g, key1 = key0 + 8;
-    float dk[8][4], dv[8][4];
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      dk[i][0] = dk[i][1] = dk[i][2] = dk[i][3] = 0.f;
-      dv[i][0] = dv[i][1] = dv[i][2] = dv[i][3] = 0.f;
-    }
-    const int q_begin = causal ? kt * 16 : 0;             // causal: queries before this key tile never see it
-    for (int qb0 = q_begin; qb0 < Lk; qb0 += 16) {
-      float st[2][4], dpt[2][4];
-#pragma unroll
-      for (int i = 0; i < 2; ++i) {
-        st[i][0] = st[i][1] = st[i][2] = st[i][3] = 0.f;
-        dpt[i][0] = dpt[i][1] = dpt[i][2] = dpt[i][3] = 0.f;
-      }
-      {
-        const int qrow = qb0 + ((lane >> 4) << 3) + (lane & 7);
-#pragma unroll
-        for (int kk = 0; kk < 4; ++kk) {
-          uint32_t f[4], vfrag[4];
-          ldsm4(qs + sw_off(qrow, 2 * kk + ((lane >> 3) & 1)), f);             // B = Q rows of this query block
-          mma16816(st[0], kf[kk], f[0], f[1]);
-          mma16816(st[1], kf[kk], f[2], f[3]);
-          ldsm4(vs + sw_off(kt * 16 + (lane & 15), 2 * kk + (lane >> 4)), vfrag); // A = V rows of this key tile
-          ldsm4(gs + sw_off(qrow, 2 * kk + ((lane >> 3) & 1)), f);             // B = dO rows of this query block
-          mma16816(dpt[0], vfrag, f[0], f[1]);
-          mma16816(dpt[1], vfrag, f[2], f[3]);
-        }
-      }
-      // P^T and dS^T: rows = keys (key0 / key1), columns = queries
-#pragma unroll
-      for (int nt = 0; nt < 2; ++nt) {
-        const int q0 = qb0 + nt * 8 + 2 * t4;
-        const float2 lq = *reinterpret_cast<const float2*>(lse_s + q0);
-        const float2 dq2 = *reinterpret_cast<const float2*>(del_s + q0);
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          const int qi = q0 + (e & 1);
-          const int key = (e & 2) ? key1 : key0;
-          float p = ex2(st[nt][e] * scale_log2 - ((e & 1) ? lq.y : lq.x));
-          if (causal && key > qi) p = 0.f;
-          st[nt][e] = p;
-          dpt[nt][e] = p * (dpt[nt][e] - ((e & 1) ? dq2.y : dq2.x));
-        }
-      }
-      uint32_t pa[4], da[4];
-      pa[0] = pack_bf16x2(st[0][0], st[0][1]);   pa[1] = pack_bf16x2(st[0][2], st[0][3]);
-      pa[2] = pack_bf16x2(st[1][0], st[1][1]);   pa[3] = pack_bf16x2(st[1][2], st[1][3]);
-      da[0] = pack_bf16x2(dpt[0][0], dpt[0][1]); da[1] = pack_bf16x2(dpt[0][2], dpt[0][3]);
-      da[2] = pack_bf16x2(dpt[1][0], dpt[1][1]); da[3] = pack_bf16x2(dpt[1][2], dpt[1][3]);
-      const int qrow_t = qb0 + (lane & 7) + (((lane >> 3) & 1) << 3);
-#pragma unroll
-      for (int dpi = 0; dpi < 4; ++dpi) {
-        uint32_t f[4];
-        ldsm4t(gs + sw_off(qrow_t, 2 * dpi + (lane >> 4)), f);                  // B[k = query][n = d] = dO
-        mma16816(dv[2 * dpi], pa, f[0], f[1]);
-        mma16816(dv[2 * dpi + 1], pa, f[2], f[3]);
-        ldsm4t(qs + sw_off(qrow_t, 2 * dpi + (lane >> 4)), f);                  // B[k = query][n = d] = Q
-        mma16816(dk[2 * dpi], da, f[0], f[1]);
-        mma16816(dk[2 * dpi + 1], da, f[2], f[3]);
-      }
-    }
-#pragma unroll
-    for (int dn = 0; dn < 8; ++dn) {
-      const size_t c0 = dn * 8 + 2 * t4;
-      if (key0 < L) {
-        *reinterpret_cast<uint32_t*>(dk_base + static_cast<size_t>(key0) * hp.pitch + c0) =
-            pack_bf16x2(dk[dn][0] * scale, dk[dn][1] * scale);
-        *reinterpret_cast<uint32_t*>(dv_base + static_cast<size_t>(key0) * hp.pitch + c0) =
-            pack_bf16x2(dv[dn][0], dv[dn][1]);
-      }
-      if (key1 < L) {
-        *reinterpret_cast<uint32_t*>(dk_base + static_cast<size_t>(key1) * hp.pitch + c0) =
-            pack_bf16x2(dk[dn][2] * scale, dk[dn][3] * scale);
-        *reinterpret_cast<uint32_t*>(dv_base + static_cast<size_t>(key1) * hp.pitch + c0) =
-            pack_bf16x2(dv[dn][2], dv[dn][3]);
-      }
-    }
-  }
+  return FFM_OK;
 }
 
 static int set_smem_once() {
@@ -497,10 +618,10 @@ static int set_smem_once() {
   int dev = 0;
   FFM_CHECK_CUDA(cudaGetDevice(&dev));
   if (dev != attr_dev) {
-    FFM_CHECK_CUDA(cudaFuncSetAttribute(attention_fwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, FWD_SMEM));
-    FFM_CHECK_CUDA(cudaFuncSetAttribute(attention_fwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, FWD_SMEM));
-    FFM_CHECK_CUDA(cudaFuncSetAttribute(attention_bwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, BWD_SMEM));
-    FFM_CHECK_CUDA(cudaFuncSetAttribute(attention_bwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, BWD_SMEM));
+    FFM_CHECK_CUDA(cudaFuncSetAttribute(attention_fwd_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, FWD_SMEM));
+    FFM_CHECK_CUDA(cudaFuncSetAttribute(attention_fwd_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, FWD_SMEM));
+    FFM_CHECK_CUDA(cudaFuncSetAttribute(attention_bwd_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, BWD_SMEM));
+    FFM_CHECK_CUDA(cudaFuncSetAttribute(attention_bwd_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, BWD_SMEM));
     attr_dev = dev;
   }
   return FFM_OK;
@@ -520,17 +641,26 @@ int ffm_attention_fwd(const void* qkv, void* out, float* lse, int B, int L, int 
   FFM_CHECK_ARG(qkv && out && lse, "ffm_attention_fwd: null pointer argument");
   FFM_CHECK_ARG(head_dim == att::HD, "ffm_attention_fwd: head dimension must be %d", att::HD);
   FFM_CHECK_ARG(B >= 1 && H >= 1 && L >= 1 && L <= att::LP, "ffm_attention_fwd: 1 <= L <= %d", att::LP);
+  FFM_CHECK_ARG((reinterpret_cast<uintptr_t>(qkv) & 15u) == 0 && (reinterpret_cast<uintptr_t>(out) & 15u) == 0,
+                "ffm_attention_fwd: qkv / out must be 16-byte aligned");
   int rc = att::set_smem_once();
   if (rc != FFM_OK) return rc;
-  const float scale_log2 = att::LOG2E / sqrtf(static_cast<float>(att::HD));
+  att::FwdParams p;
+  p.out = static_cast<__nv_bfloat16*>(out);
+  p.lse = lse;
+  p.B = B; p.L = L; p.H = H; p.C = H * att::HD; p.batch_first = batch_first ? 1 : 0;
+  p.lk_pad = (L + 15) / 16 * 16;
+  p.n_tiles = L > 128 ? 2 : 1;
+  p.total = B * H;
+  p.scale_log2 = att::LOG2E / sqrtf(static_cast<float>(att::HD));
+  CUtensorMap tm_q, tm_kv;
+  if ((rc = att::make_map_tokens(&tm_q, qkv, B, L, 3 * p.C, p.batch_first, 128 * p.n_tiles))) return rc;
+  if ((rc = att::make_map_tokens(&tm_kv, qkv, B, L, 3 * p.C, p.batch_first, p.lk_pad))) return rc;
+  const int grid = p.total < num_sms() ? p.total : num_sms();
   if (causal)
-    att::attention_fwd_kernel<true><<<B * H, att::THREADS, att::FWD_SMEM, stream>>>(
-        static_cast<const __nv_bfloat16*>(qkv), static_cast<__nv_bfloat16*>(out), lse, B, L, H, batch_first ? 1 : 0,
-        scale_log2);
+    att::attention_fwd_tc_kernel<true><<<grid, att::FWD_THREADS, att::FWD_SMEM, stream>>>(tm_q, tm_kv, p);
   else
-    att::attention_fwd_kernel<false><<<B * H, att::THREADS, att::FWD_SMEM, stream>>>(
-        static_cast<const __nv_bfloat16*>(qkv), static_cast<__nv_bfloat16*>(out), lse, B, L, H, batch_first ? 1 : 0,
-        scale_log2);
+    att::attention_fwd_tc_kernel<false><<<grid, att::FWD_THREADS, att::FWD_SMEM, stream>>>(tm_q, tm_kv, p);
   FFM_CHECK_CUDA(cudaGetLastError());
   count_launch();
   return FFM_OK;
@@ -541,19 +671,30 @@ int ffm_attention_bwd(const void* qkv, const void* out, const void* d_out, const
   FFM_CHECK_ARG(qkv && out && d_out && lse && d_qkv, "ffm_attention_bwd: null pointer argument");
   FFM_CHECK_ARG(head_dim == att::HD, "ffm_attention_bwd: head dimension must be %d", att::HD);
   FFM_CHECK_ARG(B >= 1 && H >= 1 && L >= 1 && L <= att::LP, "ffm_attention_bwd: 1 <= L <= %d", att::LP);
+  FFM_CHECK_ARG(((reinterpret_cast<uintptr_t>(qkv) | reinterpret_cast<uintptr_t>(out) | reinterpret_cast<uintptr_t>(d_out) |
+                  reinterpret_cast<uintptr_t>(d_qkv)) & 15u) == 0,
+                "ffm_attention_bwd: device pointers must be 16-byte aligned");
   int rc = att::set_smem_once();
   if (rc != FFM_OK) return rc;
-  const float scale = 1.0f / sqrtf(static_cast<float>(att::HD));
+  att::BwdParams p;
+  p.out = static_cast<const __nv_bfloat16*>(out);
+  p.lse = lse;
+  p.d_qkv = static_cast<__nv_bfloat16*>(d_qkv);
+  p.B = B; p.L = L; p.H = H; p.C = H * att::HD; p.batch_first = batch_first ? 1 : 0;
+  p.l_pad = (L + 15) / 16 * 16;
+  p.nj = L > 128 ? 2 : 1;
+  p.total = B * H;
+  p.scale = 1.0f / sqrtf(static_cast<float>(att::HD));
+  p.scale_log2 = p.scale * att::LOG2E;
+  CUtensorMap tm_q, tm_kv, tm_do;
+  if ((rc = att::make_map_tokens(&tm_q, qkv, B, L, 3 * p.C, p.batch_first, p.l_pad))) return rc;
+  if ((rc = att::make_map_tokens(&tm_kv, qkv, B, L, 3 * p.C, p.batch_first, 128 * p.nj))) return rc;
+  if ((rc = att::make_map_tokens(&tm_do, d_out, B, L, p.C, p.batch_first, p.l_pad))) return rc;
+  const int grid = p.total < num_sms() ? p.total : num_sms();
   if (causal)
-    att::attention_bwd_kernel<true><<<B * H, att::THREADS, att::BWD_SMEM, stream>>>(
-        static_cast<const __nv_bfloat16*>(qkv), static_cast<const __nv_bfloat16*>(out),
-        static_cast<const __nv_bfloat16*>(d_out), lse, static_cast<__nv_bfloat16*>(d_qkv), B, L, H, batch_first ? 1 : 0,
-        scale, scale * att::LOG2E);
+    att::attention_bwd_tc_kernel<true><<<grid, att::BWD_THREADS, att::BWD_SMEM, stream>>>(tm_q, tm_kv, tm_do, p);
   else
-    att::attention_bwd_kernel<false><<<B * H, att::THREADS, att::BWD_SMEM, stream>>>(
-        static_cast<const __nv_bfloat16*>(qkv), static_cast<const __nv_bfloat16*>(out),
-        static_cast<const __nv_bfloat16*>(d_out), lse, static_cast<__nv_bfloat16*>(d_qkv), B, L, H, batch_first ? 1 : 0,
-        scale, scale * att::LOG2E);
+    att::attention_bwd_tc_kernel<false><<<grid, att::BWD_THREADS, att::BWD_SMEM, stream>>>(tm_q, tm_kv, tm_do, p);
   FFM_CHECK_CUDA(cudaGetLastError());
   count_launch();
   return FFM_OK;

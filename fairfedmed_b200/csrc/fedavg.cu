@@ -94,6 +94,27 @@ sgd_kernel(float* __restrict__ param, const float* __restrict__ grad, float* __r
   }
 }
 
+// Same update with the learning rate read from device memory: a captured CUDA graph of the training step stays valid
+// when the StepLR schedule changes the rate (the host rewrites one float instead of re-capturing).
+__global__ void __launch_bounds__(FA_THREADS)
+sgd_dev_lr_kernel(float* __restrict__ param, const float* __restrict__ grad, float* __restrict__ mom, int64_t n,
+                  const float* __restrict__ lr_dev, float momentum, float wd, int n_steps) {
+  const float lr = __ldg(lr_dev);
+  const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride) {
+    float w = param[i];
+    const float g = grad[i];
+    float b = mom[i];
+    for (int k = 0; k < n_steps; ++k) {
+      const float d = fmaf(wd, w, g);
+      b = fmaf(momentum, b, d);
+      w = fmaf(-lr, b, w);
+    }
+    param[i] = w;
+    mom[i] = b;
+  }
+}
+
 static int grid_for(int64_t n) {
   int64_t blocks = (n + FA_THREADS - 1) / FA_THREADS;
   const int64_t cap = static_cast<int64_t>(num_sms()) * 4;
@@ -143,6 +164,17 @@ int ffm_sgd_step(float* param, const float* grad, float* momentum_buf, int64_t n
   FFM_CHECK_ARG(n >= 1 && n_steps >= 1, "ffm_sgd_step: bad sizes");
   sgd_kernel<<<grid_for(n), FA_THREADS, 0, stream>>>(param, grad, momentum_buf, n, lr, momentum, weight_decay,
                                                      n_steps, first_step);
+  FFM_CHECK_CUDA(cudaGetLastError());
+  count_launch();
+  return FFM_OK;
+}
+
+int ffm_sgd_step_dev_lr(float* param, const float* grad, float* momentum_buf, int64_t n, const float* lr_dev,
+                        float momentum, float weight_decay, int n_steps, cudaStream_t stream) {
+  FFM_CHECK_ARG(param && grad && momentum_buf && lr_dev, "ffm_sgd_step_dev_lr: null pointer argument");
+  FFM_CHECK_ARG(n >= 1 && n_steps >= 1, "ffm_sgd_step_dev_lr: bad sizes");
+  sgd_dev_lr_kernel<<<grid_for(n), FA_THREADS, 0, stream>>>(param, grad, momentum_buf, n, lr_dev, momentum,
+                                                            weight_decay, n_steps);
   FFM_CHECK_CUDA(cudaGetLastError());
   count_launch();
   return FFM_OK;

@@ -493,6 +493,8 @@ static PFN_encodeTiled get_encode_fn() {
   return fn;
 }
 
+PFN_encodeTiled tensor_map_encode_fn() { return get_encode_fn(); }   // shared with attention.cu
+
 int make_map_bf16(CUtensorMap* out, const void* ptr, uint64_t rows, uint64_t cols, uint32_t box_rows,
                          uint32_t box_cols, CUtensorMapSwizzle swz, bool promote) {
   PFN_encodeTiled enc = get_encode_fn();

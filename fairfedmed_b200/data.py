@@ -83,6 +83,22 @@ class SyntheticLoader:
             yield batch
 
 
+class CachedLoader:
+    """Replays a fixed list of (pinned-host) batches: the loader a throughput run uses so that batch SYNTHESIS (uint8 ->
+    fp32, channel replication on the host) is not what gets measured; the H2D copy of every batch still happens per
+    step in the trainer.  `dataset` is forwarded for len() / count_by_attribute()."""
+
+    def __init__(self, batches, n_batches: int, dataset=None):
+        self.batches, self.n, self.dataset = list(batches), int(n_batches), dataset
+
+    def __len__(self):
+        return self.n
+
+    def __iter__(self):
+        for i in range(self.n):
+            yield self.batches[i % len(self.batches)]
+
+
 class _DatasetInfo:
     classnames = ["NOT Glaucoma", "Glaucoma"]   # an explicit LIST (upstream iterates a set: hash-order hazard)
     lab2cname = {0: "NOT Glaucoma", 1: "Glaucoma"}

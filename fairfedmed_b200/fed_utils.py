@@ -41,13 +41,14 @@ class FlatSpec:
 
 def build_spec(reference: Dict[str, torch.Tensor], keys: Optional[Sequence[str]] = None,
                num_groups: Optional[int] = None) -> FlatSpec:
-    """Describe `keys` of `reference` (default: every floating-point tensor, in dict order).
+    """Describe `keys` of `reference` (default: every tensor, in dict order; integer tensors such as BatchNorm's
+    `num_batches_tracked` travel as floats, which is what the reference's `w * freq` arithmetic turns them into).
 
     A key is weighted per group when it contains 'lora_S', group counts are supplied and its leading dimension
     equals the number of groups (utils/fed_utils.py:77) — restricted here to 2-D tensors, the only case in which
     the reference's `[:, None]` broadcast is well formed."""
     if keys is None:
-        keys = [k for k, v in reference.items() if torch.is_tensor(v) and v.is_floating_point()]
+        keys = [k for k, v in reference.items() if torch.is_tensor(v)]
     shapes, offsets, kinds = [], [], []
     pos, r = 0, 1
     for k in keys:
@@ -68,7 +69,7 @@ def pack(spec: FlatSpec, sd: Dict[str, torch.Tensor], device, out: Optional[torc
     flat = torch.empty(spec.numel, device=device, dtype=torch.float32) if out is None else out
     for k, off, shp in zip(spec.keys, spec.offsets, spec.shapes):
         n = torch.Size(shp).numel()
-        flat[off:off + n].copy_(sd[k].detach().reshape(-1), non_blocking=True)
+        flat[off:off + n].copy_(sd[k].detach().reshape(-1), non_blocking=True)      # casts integer tensors to fp32
     return flat
 
 
@@ -77,7 +78,8 @@ def unpack(spec: FlatSpec, flat: torch.Tensor, like: Optional[Dict[str, torch.Te
     for k, off, shp in zip(spec.keys, spec.offsets, spec.shapes):
         t = flat[off:off + torch.Size(shp).numel()].view(shp)
         if like is not None:
-            t = t.to(device=like[k].device, dtype=like[k].dtype)
+            # an averaged integer tensor stays a float tensor, as upstream (int64 * python float -> float32)
+            t = t.to(device=like[k].device, dtype=like[k].dtype if like[k].is_floating_point() else torch.float32)
         out[k] = t
     return out
 
@@ -94,8 +96,8 @@ def _device_for(tensors) -> torch.device:
 
 def average_weights_EMA(w_g, w, idxs_users, datanumber_client, datanumber_client_by_attr, epoch, max_epoch,
                         beta=0.999, islist=False, shared_half_s=False):
-    """Drop-in for utils/fed_utils.py:42-100 (dict branch). Tensors not of floating type are taken from the first
-    selected client unchanged."""
+    """Drop-in for utils/fed_utils.py:42-100 (dict branch): every tensor of the state dict is averaged, BatchNorm
+    running statistics and batch counters included."""
     if islist:
         raise NotImplementedError("list-of-tensors aggregation is not on the FairLoRA path")
     first = w[idxs_users[0]]

@@ -23,18 +23,35 @@ LAMBDA_GROUP = 0.7  # trainers/GLP_OT_SVLoRA.py:459
 
 
 def _attr_on(device, attr: Optional[torch.Tensor]) -> Optional[torch.Tensor]:
-    """The reference hands every layer the same CPU int64 tensor (never moved, :988-994). Copy it once per step."""
+    """The reference hands every layer the same CPU int64 tensor (never moved, :988-994).  The device copy is cached
+    under the tensor's CONTENT (a few dozen group ids), so all layers of a step share one copy and an in-place edit
+    of the host tensor can never return stale ids."""
     if attr is None:
         return None
     if attr.device == device and attr.dtype == torch.int64:
         return attr
+    if attr.is_cuda:
+        return attr.to(device=device, dtype=torch.int64).contiguous()
+    key = (str(device), tuple(attr.shape), tuple(attr.reshape(-1).tolist()))
     cache = getattr(_attr_on, "_cache", None)
-    key = (attr.data_ptr(), attr._version, tuple(attr.shape), str(device))
     if cache is not None and cache[0] == key:
         return cache[1]
     dev_attr = attr.to(device=device, dtype=torch.int64, non_blocking=False).contiguous()
-    _attr_on._cache = (key, dev_attr, attr)   # keep `attr` alive so the data_ptr key cannot be recycled
+    _attr_on._cache = (key, dev_attr)
     return dev_attr
+
+
+class FrozenLinearView:
+    """A frozen projection that lives as bare parameters of another module (nn.MultiheadAttention's packed
+    `in_proj_weight` / `in_proj_bias`, or its `out_proj`), presented with the nn.Linear attributes the adapters read.
+    Deliberately NOT an nn.Module: wrapping it must not register the frozen tensors under a second state-dict key."""
+
+    def __init__(self, weight: torch.Tensor, bias: Optional[torch.Tensor]):
+        self.weight, self.bias = weight, bias
+        self.out_features, self.in_features = weight.shape
+
+    def parameters(self):
+        return [p for p in (self.weight, self.bias) if p is not None]
 
 
 class _AdapterBase(nn.Module):
@@ -103,18 +120,32 @@ class _AdapterBase(nn.Module):
             x2d = x2d.to(torch.bfloat16)
         return x2d.contiguous(), restore, bp
 
-    def _run(self, x, s_eff):
+    def _run(self, x, s_eff, batch_first: bool = False):
+        """batch_first: x is [B', L, C] (the layout inside this package's ViT tower) instead of the reference's
+        sequence-first [L, B', C]; the kernel is told through row_div which sample a row belongs to."""
         if not x.is_cuda:
             raise RuntimeError("fairfedmed_b200 adapters need CUDA tensors: there is no CPU fallback "
                                "(the CPU oracle lives under oracle/ and is test infrastructure only)")
         w, w_t, bias = self._operands()
-        x2d, restore, bp = self._tokens_in(x)
+        row_div = 1
+        if batch_first:
+            if self.is_1x1_conv or x.dim() != 3:
+                raise ValueError("batch_first adapters take [B', L, C] token tensors")
+            bp, row_div = x.shape[0], x.shape[1]
+            lead = x.shape[:-1]
+            x2d = x.reshape(-1, x.shape[-1])
+            x2d = (x2d if x2d.dtype == torch.bfloat16 else x2d.to(torch.bfloat16)).contiguous()
+
+            def restore(y2d):
+                return y2d.reshape(*lead, -1)
+        else:
+            x2d, restore, bp = self._tokens_in(x)
         n_samples = s_eff.shape[0]
         if bp % n_samples != 0:
             raise ValueError(f"batch columns {bp} not divisible by the number of attribute rows {n_samples}")
         num_slices = bp // n_samples                                   # OCT slices per sample (:473-475)
         y2d = ops.svlora_linear(x2d, w, w_t, bias, self.lora_A.weight, self.lora_B.weight, s_eff, self.scaling, bp,
-                                num_slices)
+                                num_slices, row_div)
         y = restore(y2d)
         return y if y.dtype == x.dtype else y.to(x.dtype)
 
@@ -164,8 +195,8 @@ class FairLoRALinear(_AdapterBase):
         sg = self.lora_S_global.weight if self.global_s else None
         return ops.effective_singular_values(a, self.lora_S.weight, sg, lam)
 
-    def forward(self, x, attr=None):
-        return self._run(x, self._s_eff(attr, x.device))
+    def forward(self, x, attr=None, batch_first: bool = False):
+        return self._run(x, self._s_eff(attr, x.device), batch_first)
 
     def weight(self, x, attr=None):
         """Per-sample merged weight [B', out, in] with a HARD one-hot mixture (:425-445). RN50 attention pool only."""
@@ -236,11 +267,27 @@ class LoRALinear(_AdapterBase):
 
 
 def apply_lora_to_model(model, unfreeze_image_encoder, rank=4, alpha=0.04, lora_type="loRA", global_s=False,
-                        num_attrs=1):
+                        num_attrs=1, adapt_attention=False):
     """Module surgery with the reference's selection rules (:503-573): ViT -> the `.mlp.` linears of
     `image_encoder.*`; ResNet -> 1x1 convs named conv* under layer1-4 (FairLoRA) and the attention-pool
-    linears (plain LoRA)."""
+    linears (plain LoRA).
+
+    adapt_attention (opt-in, OFF for parity with the reference, which adapts the MLP only — SURVEY F2): additionally puts
+    a FairLoRA adapter on the packed in_proj (C -> 3C) and on out_proj of every image-tower attention block, as the
+    north-star's "every attention and MLP linear" words it.  New state-dict keys:
+    `image_encoder.transformer.resblocks.{i}.attn_in_lora.{lora_A,lora_S,lora_B}.weight`, `...attn_out_lora...`."""
     named = dict(model.named_modules())
+    if adapt_attention and unfreeze_image_encoder:
+        if lora_type != "FairLoRA":
+            raise NotImplementedError("adapt_attention is built for FairLoRA adapters")
+        for name, module in named.items():
+            if name.startswith("image_encoder.") and hasattr(module, "attn") and hasattr(module, "attn_in_lora") \
+                    and isinstance(module.attn, nn.MultiheadAttention):
+                a = module.attn
+                module.attn_in_lora = FairLoRALinear(FrozenLinearView(a.in_proj_weight, a.in_proj_bias), rank=rank,
+                                                     alpha=alpha, global_s=global_s, num_attrs=num_attrs)
+                module.attn_out_lora = FairLoRALinear(FrozenLinearView(a.out_proj.weight, a.out_proj.bias), rank=rank,
+                                                      alpha=alpha, global_s=global_s, num_attrs=num_attrs)
     for name, module in named.items():
         if not (unfreeze_image_encoder and name.startswith("image_encoder.")):
             continue

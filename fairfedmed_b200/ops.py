@@ -750,6 +750,14 @@ def sgd_step_(param: Tensor, grad: Tensor, momentum_buf: Tensor, lr: float, mome
                float(weight_decay), int(n_steps), int(bool(first_step)), _stream())
 
 
+def sgd_step_dev_lr_(param: Tensor, grad: Tensor, momentum_buf: Tensor, lr_dev: Tensor, momentum: float,
+                     weight_decay: float, n_steps: int) -> None:
+    """sgd_step_ with the learning rate in device memory (graph-replayable; momentum buffer zero-initialised)."""
+    _need_cuda(param, grad, momentum_buf, lr_dev)
+    _cabi.call("ffm_sgd_step_dev_lr", _ptr(param), _ptr(grad), _ptr(momentum_buf), param.numel(), _ptr(lr_dev),
+               float(momentum), float(weight_decay), int(n_steps), _stream())
+
+
 def group_auc_counts(prob: Tensor, label: Tensor, attrs: Optional[Tensor], max_groups: int) -> Tensor:
     """uint64-as-int64 counts [n_slots, 8] = {gt0, eq0, gt1, eq1, tp, fp, tn, fn}; see include/ffm_b200.h."""
     _need_cuda(prob, label, attrs)

@@ -309,6 +309,15 @@ int ffm_group_auc(const float* prob, const int32_t* label, const int32_t* attrs,
 int ffm_sgd_step(float* param, const float* grad, float* momentum_buf, int64_t n, float lr, float momentum,
                  float weight_decay, int n_steps, int first_step, ffm_stream_t stream);
 
+/*
+ * ffm_sgd_step with the learning rate read from DEVICE memory (`lr_dev`, one float) and a zero-initialised momentum
+ * buffer standing in for torch's lazily created one (momentum * 0 + d == d, so no first-step flag): the form a captured
+ * CUDA graph of the training step uses — the StepLR schedule (Dassl/dassl/optim/lr_scheduler.py) then only rewrites
+ * that float.
+ */
+int ffm_sgd_step_dev_lr(float* param, const float* grad, float* momentum_buf, int64_t n, const float* lr_dev,
+                        float momentum, float weight_decay, int n_steps, ffm_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

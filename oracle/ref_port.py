@@ -38,7 +38,7 @@ def group_mixture(attr: Optional[torch.Tensor], num_groups: int, dtype=torch.flo
 
 def effective_singular_values(attr, S: torch.Tensor, S_global: Optional[torch.Tensor] = None, hard=False):
     """s_eff [B or 1, r] = pi @ S (+ S_global) — :464-467."""
-    pi = group_mixture(attr, S.shape[0], S.dtype, hard=hard)
+    pi = group_mixture(attr, S.shape[0], S.dtype, hard=hard).to(S.device)   # (device-agnostic: the GPU-eager baseline)
     s_eff = pi @ S
     if S_global is not None:
         s_eff = s_eff + S_global.reshape(1, -1)
@@ -168,13 +168,13 @@ def ot_head(image_features: torch.Tensor, text_features: torch.Tensor, logit_sca
     else:
         with torch.no_grad():
             KK = torch.exp(-(1.0 - sim) / eps)
-            xx = torch.full((sim.shape[0], M), 1.0 / M, dtype=sim.dtype)
+            xx = torch.full((sim.shape[0], M), 1.0 / M, dtype=sim.dtype, device=sim.device)
             if ot == "Sinkhorn":
-                yy = torch.full((sim.shape[0], N), 1.0 / N, dtype=sim.dtype)
+                yy = torch.full((sim.shape[0], N), 1.0 / N, dtype=sim.dtype, device=sim.device)
                 T, iters = sinkhorn(KK, xx, yy, thresh, max_iter)
             elif ot == "COT":
                 tp = min(float(xx.sum().item()), top_percent)     # :727
-                yy = torch.full((sim.shape[0], N), 1.0 / N, dtype=sim.dtype) * tp
+                yy = torch.full((sim.shape[0], N), 1.0 / N, dtype=sim.dtype, device=sim.device) * tp
                 T, iters = entropic_cot(xx, yy, KK, thresh, max_iter)
             else:
                 raise NotImplementedError(ot)
@@ -285,10 +285,10 @@ def text_encoder(prompts, eot_index, p, *, n_layers=12, n_head=8, pre="text_enco
     """TextEncoder.forward — :55-66 (causal mask from clip/model.py:562-568)."""
     x = prompts + p[pre + "positional_embedding"].to(prompts.dtype)
     L = x.shape[1]
-    mask = torch.full((L, L), float("-inf"), dtype=x.dtype).triu_(1)
+    mask = torch.full((L, L), float("-inf"), dtype=x.dtype, device=x.device).triu_(1)
     x = transformer(x.transpose(0, 1), p, pre + "transformer.", n_layers, n_head, mask=mask).transpose(0, 1)
     x = _ln(x, p[pre + "ln_final.weight"], p[pre + "ln_final.bias"])
-    return x[torch.arange(x.shape[0]), eot_index] @ p[pre + "text_projection"]
+    return x[torch.arange(x.shape[0], device=x.device), eot_index.to(x.device)] @ p[pre + "text_projection"]
 
 
 def _bn_train(x, p, pre, eps=1e-5):
@@ -358,8 +358,8 @@ def custom_clip_forward(image, attr, p, eot_index, *, n_prompts=2, n_cls=2, ot="
         lo = image.amin(dim=(1, 2, 3), keepdim=True)
         hi = image.amax(dim=(1, 2, 3), keepdim=True)
         image = (image - lo) / (hi - lo + 1e-5)
-    mean = torch.tensor(PIXEL_MEAN, dtype=image.dtype).reshape(1, -1, 1, 1)
-    std = torch.tensor(PIXEL_STD, dtype=image.dtype).reshape(1, -1, 1, 1)
+    mean = torch.tensor(PIXEL_MEAN, dtype=image.dtype, device=image.device).reshape(1, -1, 1, 1)
+    std = torch.tensor(PIXEL_STD, dtype=image.dtype, device=image.device).reshape(1, -1, 1, 1)
     image = (image - mean) / std
     if isinstance(vision_layers, (tuple, list)):       # CLIP ResNet backbone: vision_heads = width * 32 // 64
         feats = resnet_image_encoder(image, p, attr, layers=tuple(vision_layers), n_head=vision_heads, scaling=scaling)

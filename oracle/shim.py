@@ -16,12 +16,40 @@ import sys
 import types
 
 REF_ROOT = os.environ.get("FFM_REFERENCE_ROOT", "/root/reference")
+STAGED_ZIP = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ref", "reference.zip")
 
 _installed = False
 
 
-def available() -> bool:
+def _unpack_staged() -> bool:
+    """No reference tree (GPU box): unpack oracle/_ref/reference.zip (oracle/stage_ref.py) into a scratch directory."""
+    global REF_ROOT
+    if not os.path.isfile(STAGED_ZIP):
+        return False
+    import hashlib
+    import tempfile
+    import zipfile
+    tag = hashlib.sha1(f"{os.path.getsize(STAGED_ZIP)}-{os.path.getmtime(STAGED_ZIP)}".encode()).hexdigest()[:12]
+    dst = os.path.join(tempfile.gettempdir(), f"ffm_reference_{tag}")
+    if not os.path.isdir(os.path.join(dst, "trainers")):
+        tmp = dst + f".{os.getpid()}"
+        with zipfile.ZipFile(STAGED_ZIP) as z:
+            z.extractall(tmp)
+        try:
+            os.replace(tmp, dst)
+        except OSError:                      # another process won the race
+            pass
+    REF_ROOT = dst
     return os.path.isdir(os.path.join(REF_ROOT, "trainers"))
+
+
+def available() -> bool:
+    return os.path.isdir(os.path.join(REF_ROOT, "trainers")) or _unpack_staged()
+
+
+def kind() -> str:
+    """'reference' when the real reference modules can be imported (tree or staged archive), else 'port'."""
+    return "reference" if available() else "port"
 
 
 def _module(name: str, **attrs):
@@ -32,7 +60,15 @@ def _module(name: str, **attrs):
 
 
 class _AttrDict(dict):
-    """Smallest possible stand-in for yacs.config.CfgNode."""
+    """Stand-in for yacs.config.CfgNode (yacs is not installed here): attribute access, clone, and the subset of the
+    yacs API `federated_main.setup_cfg` uses — merge_from_file (yaml, string values literal_eval'ed like yacs does),
+    merge_from_list, freeze / defrost."""
+
+    def __init__(self, init_dict=None, key_list=None, new_allowed=False):
+        super().__init__()
+        dict.__setattr__(self, "_frozen", False)
+        for k, v in (init_dict or {}).items():
+            self[k] = _AttrDict(v) if isinstance(v, dict) and not isinstance(v, _AttrDict) else v
 
     def __getattr__(self, key):
         try:
@@ -41,11 +77,64 @@ class _AttrDict(dict):
             raise AttributeError(key) from e
 
     def __setattr__(self, key, value):
+        if dict.__getattribute__(self, "__dict__").get("_frozen", False):
+            raise AttributeError(f"Attempted to set {key} to {value}, but CfgNode is immutable")
         self[key] = value
 
     def clone(self):
         import copy
         return copy.deepcopy(self)
+
+    @staticmethod
+    def _decode(v):
+        if isinstance(v, str):
+            import ast
+            try:
+                return ast.literal_eval(v)
+            except (ValueError, SyntaxError):
+                return v
+        return v
+
+    def _merge(self, other):
+        for k, v in other.items():
+            if isinstance(v, dict):
+                node = self.get(k)
+                if not isinstance(node, _AttrDict):
+                    node = _AttrDict()
+                    dict.__setitem__(self, k, node)
+                node._merge(v)
+            else:
+                dict.__setitem__(self, k, self._decode(v))
+
+    def merge_from_file(self, path):
+        import yaml
+        with open(path) as f:
+            self._merge(yaml.safe_load(f) or {})
+
+    def merge_from_list(self, opts):
+        opts = list(opts or [])
+        assert len(opts) % 2 == 0
+        for full_key, v in zip(opts[0::2], opts[1::2]):
+            node = self
+            parts = full_key.split(".")
+            for part in parts[:-1]:
+                node = node[part]
+            dict.__setitem__(node, parts[-1], self._decode(v))
+
+    def freeze(self):
+        dict.__getattribute__(self, "__dict__")["_frozen"] = True
+        for v in self.values():
+            if isinstance(v, _AttrDict):
+                v.freeze()
+
+    def defrost(self):
+        dict.__getattribute__(self, "__dict__")["_frozen"] = False
+        for v in self.values():
+            if isinstance(v, _AttrDict):
+                v.defrost()
+
+    def is_frozen(self):
+        return dict.__getattribute__(self, "__dict__").get("_frozen", False)
 
 
 def install() -> None:

@@ -91,6 +91,10 @@ FEDAVG_CASES = {
                  n_k=[100, 50, 75, 20], n_kg=[[40, 30, 30], [10, 20, 20], [25, 25, 25], [5, 5, 10]]),
     "no_shared": dict(n_clients=3, idxs=[0, 1, 2], groups=2, rank=12, epoch=0, max_epoch=50, shared_half_s=False,
                       seed=33, n_k=[7, 9, 11], n_kg=[[3, 4], [4, 5], [6, 5]]),
+    # ResNet trunk: the reference averages the WHOLE state dict, i.e. also BatchNorm running statistics and the int64
+    # batch counter (which comes back as a float tensor), utils/fed_utils.py:63-98
+    "rn50_bn": dict(n_clients=3, idxs=[0, 2], groups=3, rank=32, epoch=7, max_epoch=50, shared_half_s=True, seed=34,
+                    n_k=[64, 32, 96], n_kg=[[20, 20, 24], [10, 12, 10], [40, 30, 26]], batchnorm=True),
 }
 
 
@@ -99,6 +103,19 @@ def fedavg_inputs(rc):
     G, r = rc["groups"], rc["rank"]
 
     def one():
+        if rc.get("batchnorm"):
+            p = "image_encoder.layer1.0."
+            return {
+                "prompt_learner.ctx": torch.randn(2, 4, 16, generator=g),
+                p + "conv1.lora_A.weight": torch.randn(16, r, generator=g),
+                p + "conv1.lora_S.weight": torch.rand(G, r, generator=g),
+                p + "conv1.lora_B.weight": torch.randn(r, 8, generator=g),
+                p + "bn1.weight": torch.randn(8, generator=g),
+                p + "bn1.bias": torch.randn(8, generator=g),
+                p + "bn1.running_mean": torch.randn(8, generator=g),
+                p + "bn1.running_var": torch.rand(8, generator=g) + 0.5,
+                p + "bn1.num_batches_tracked": torch.randint(1, 50, (), generator=g),
+            }
         return {
             "prompt_learner.ctx": torch.randn(2, 4, 16, generator=g),
             "image_encoder.transformer.resblocks.0.mlp.c_fc.lora_A.weight": torch.randn(24, r, generator=g),

@@ -189,3 +189,31 @@ def test_ops_host_helpers_without_gpu():
         ops.patchify_normalize(torch.zeros(1, 3, 16, 16), torch.zeros(3), torch.ones(3), 16, True)
     with pytest.raises(_cabi.FfmError, match="no CPU fallback"):
         ops.attention(torch.zeros(1, 4, 192, dtype=torch.bfloat16), 1, False, True)
+
+
+def test_adapt_attention_opt_in_adds_adapters_without_touching_reference_keys():
+    """North-star wording "every attention and MLP linear": opt-in FairLoRA on in_proj / out_proj of the image tower.
+    Off by default (the reference adapts the MLP only): then the state-dict keys are the reference's; on, only
+    adapter tensors are added and the frozen attention parameters keep their single key."""
+    def build(flag):
+        m = CustomCLIP(vision_layers=2, vision_width=128, text_layers=1, text_width=64, text_heads=2, embed_dim=64,
+                       image_resolution=32)
+        for n, p in m.named_parameters():
+            p.requires_grad_("prompt_learner" in n)
+        modules.apply_lora_to_model(m, True, rank=12, alpha=2, lora_type="FairLoRA", num_attrs=3, adapt_attention=flag)
+        return m
+    off, on = build(False), build(True)
+    k_off, k_on = set(off.state_dict()), set(on.state_dict())
+    assert not any("attn_in_lora" in k or "attn_out_lora" in k for k in k_off)
+    extra = k_on - k_off
+    assert extra == {f"image_encoder.transformer.resblocks.{i}.{a}.{w}.weight" for i in range(2)
+                     for a in ("attn_in_lora", "attn_out_lora") for w in ("lora_A", "lora_S", "lora_B")}
+    sd = on.state_dict()
+    assert sd["image_encoder.transformer.resblocks.0.attn_in_lora.lora_A.weight"].shape == (128, 12)
+    assert sd["image_encoder.transformer.resblocks.0.attn_in_lora.lora_B.weight"].shape == (12, 384)
+    assert sd["image_encoder.transformer.resblocks.1.attn_out_lora.lora_B.weight"].shape == (12, 128)
+    trainable = [n for n, p in on.named_parameters() if p.requires_grad]
+    assert len(trainable) == 1 + 2 * 4 * 3                       # ctx + 2 blocks x (c_fc, c_proj, in, out) x (A, S, B)
+    assert not any(p.requires_grad for n, p in on.named_parameters() if ".attn.in_proj" in n or ".attn.out_proj" in n)
+    with pytest.raises(NotImplementedError):
+        modules.apply_lora_to_model(build(False), True, rank=4, lora_type="LoRA", adapt_attention=True)

@@ -3,6 +3,7 @@ same seeded weights), one trainer step vs the oracle's double-SGD step, and a 2-
 shape, shrunk towers) checked against a manual aggregation."""
 from __future__ import annotations
 
+import os
 from pathlib import Path
 
 import numpy as np
@@ -384,3 +385,112 @@ def test_checkpoint_round_trip(tmp_path):
         assert torch.equal(tr.get_flat(), ref)
         assert all(params_before[n] is p for n, p in tr.model.named_parameters())
         assert all(p.data_ptr() >= tr.flat_params.data_ptr() for n, p in tr.model.named_parameters() if p.requires_grad)
+
+
+def test_full_size_vit_b16_step_matches_oracle():
+    """The shape the bench times — ViT-B/16, 12 layers, width 768, 224x224, rank 12, 3 groups, Sinkhorn head — at batch 8
+    (configs[0] size) end to end against the fp32 oracle with the same weights: logits, loss and sampled adapter /
+    prompt gradients from the first, a middle and the last block."""
+    import fairfedmed_b200.trainer  # noqa: F401
+    from fairfedmed_b200.config import get_cfg_default
+    from fairfedmed_b200.registry import build_trainer
+    cfg = get_cfg_default()
+    cfg.DATASET.merge_from_dict(dict(USERS=1, NUM_TRAIN_PER_CLIENT=8, NUM_TEST_PER_CLIENT=8))
+    cfg.DATALOADER.TRAIN_X.BATCH_SIZE = 8
+    cfg.TRAINER.GLP_OT.OT = "Sinkhorn"
+    tr = build_trainer(cfg)
+    assert tr.flat_params.numel() == 1_110_880
+    g = torch.Generator().manual_seed(11)
+    with torch.no_grad():
+        for n_, p_ in tr.model.named_parameters():
+            if "lora_A" in n_:
+                p_.copy_((0.02 * torch.randn(p_.shape, generator=g)).to(p_.device))
+    batch = next(iter(tr.fed_train_loader_x_dict[0]))
+    image, label, attr = batch["img"], batch["label"], batch["attrs"][:, 0].contiguous()
+    tr.model.train()
+    logits = tr.model(image.to(DEV), attr)
+    loss = F.cross_entropy(logits.float(), label.to(DEV))
+    tr.flat_grads.zero_()
+    loss.backward()
+    from fairfedmed_b200 import ops
+    ops.join_direct_grad_writes()
+    torch.cuda.synchronize()
+    got = {n: p_.grad.detach().float().cpu().clone() for n, p_ in tr.model.named_parameters() if p_.requires_grad}
+
+    torch.set_num_threads(max(1, (os.cpu_count() or 2)))
+    p = {k: v.detach().float().cpu().clone() for k, v in tr.model.state_dict().items()}
+    sample = ["prompt_learner.ctx"] + [f"image_encoder.transformer.resblocks.{i}.mlp.{l}.{w}.weight"
+                                       for i, l in ((0, "c_fc"), (6, "c_proj"), (11, "c_fc"))
+                                       for w in ("lora_A", "lora_B", "lora_S")]
+    for k in sample:
+        p[k].requires_grad_(True)
+    eot = tr.model.prompt_learner.eot_index.cpu()
+    ref_logits = rp.custom_clip_forward(image.clone(), attr, p, eot, ot="Sinkhorn", scaling=2.0 / 12)
+    ref_loss = F.cross_entropy(ref_logits, label)
+    ref_g = torch.autograd.grad(ref_loss, [p[k] for k in sample])
+    ref = ref_logits.detach()
+    # bf16 activations through 12 blocks vs fp32: logits within 3e-2 * max|logit| (+0.02), loss within 2e-2
+    assert float((logits.detach().float().cpu() - ref).abs().max()) <= 3e-2 * float(ref.abs().max()) + 0.02
+    assert abs(float(loss) - float(ref_loss)) <= 2e-2
+    for k, r in zip(sample, ref_g):
+        gk, r = got[k].reshape(-1), r.reshape(-1)
+        assert float(r.abs().max()) > 0, k
+        cos = float(F.cosine_similarity(gk, r, dim=0))
+        rel = float((gk - r).abs().max() / r.abs().max())
+        assert cos >= 0.99 and rel <= 8e-2, f"{k}: cos {cos:.4f} rel {rel:.3e}"
+
+
+def test_rn50_round_aggregates_and_resets_batchnorm_statistics():
+    """Config 4 (shrunk): the reference averages the WHOLE state dict every round, BatchNorm running_mean / running_var /
+    num_batches_tracked included (utils/fed_utils.py:63-98), and every client starts a round from the global copy
+    (federated_main.py:616-623).  The flat buffer therefore carries those statistics: after a 2-client round the
+    aggregated buffer — adapters, BatchNorm affine AND running statistics — equals the oracle's average of the two
+    clients' state dicts, and the second client did not inherit the first one's statistics."""
+    import fairfedmed_b200.trainer  # noqa: F401
+    from fairfedmed_b200 import fed_utils
+    from fairfedmed_b200.federated import run_federated
+    from fairfedmed_b200.registry import build_trainer
+    cfg = _tiny_cfg(ot="None", users=2, batch=8, n_train=16)
+    cfg.MODEL.BACKBONE.NAME = "RN50"
+    cfg.MODEL_ARCH.merge_from_dict(dict(VISION_LAYERS=(1, 1, 1, 1), VISION_WIDTH=16, EMBED=64))
+    cfg.TRAINER.GLP_OT_LORA.merge_from_dict(dict(RANK=32, ALPHA=8.0))
+
+    def fresh():
+        tr = build_trainer(cfg)
+        tr.step_auc = False
+        with torch.no_grad():
+            for n_, p_ in tr.model.named_parameters():
+                if ".bn3.weight" in n_:
+                    p_.fill_(1.0)
+        return tr
+
+    fed = fresh()
+    spec = fed.flat_spec
+    stat_keys = [k for k in spec.keys if "running_" in k or "num_batches_tracked" in k]
+    assert len(stat_keys) == 3 * sum(isinstance(m_, torch.nn.BatchNorm2d) for m_ in fed.model.modules()) > 0
+    assert fed.get_flat().numel() > fed.flat_params.numel()
+    start = fed.get_flat().clone()
+    # the SAME run supplies the per-client buffers (a second trainer would differ by the run-to-run noise of the library
+    # convolution / BatchNorm kernels, which a random-init ResNet amplifies)
+    _, global_flat, hist = run_federated(cfg, rounds=1, shared_half_s=True, trainer=fed, evaluate=False,
+                                         keep_locals=True)
+    locals_ = [hist[0]["locals"][k] for k in range(2)]
+    i_mean = spec.keys.index(next(k for k in stat_keys if k.endswith("bn1.running_mean")))
+    sl = slice(spec.offsets[i_mean], spec.offsets[i_mean] + int(torch.Size(spec.shapes[i_mean]).numel()))
+    assert float((locals_[0][sl] - start[sl]).abs().max()) > 0            # training moved the statistics ...
+    assert float((locals_[0][sl] - locals_[1][sl]).abs().max()) > 0       # ... differently per client
+    i_cnt = spec.keys.index(next(k for k in stat_keys if k.endswith("bn1.num_batches_tracked")))
+    assert float(locals_[1][spec.offsets[i_cnt]]) == float(locals_[0][spec.offsets[i_cnt]]) == 2.0   # reset per client
+    n_k = [len(fed.fed_train_loader_x_dict[k].dataset) for k in range(2)]
+    n_kg = [fed.fed_train_loader_x_dict[k].dataset.count_by_attribute("race") for k in range(2)]
+    w = [{k2: v.cpu() for k2, v in fed_utils.unpack(spec, f).items()} for f in locals_]
+    w_g = {k2: v.cpu() for k2, v in fed_utils.unpack(spec, start).items()}
+    ref = rp.average_weights_ema(w_g, w, [0, 1], n_k, n_kg, 0, 1, shared_half_s=True)
+    got = fed_utils.unpack(spec, global_flat)
+    for k2 in spec.keys:
+        torch.testing.assert_close(got[k2].cpu().float(), ref[k2].float(), rtol=1e-5, atol=1e-6, msg=k2)
+    # evaluation runs model.eval() on the AGGREGATED statistics
+    bn = next(m_ for m_ in fed.model.modules() if isinstance(m_, torch.nn.BatchNorm2d))
+    assert bn.running_mean.data_ptr() >= fed.flat_all.data_ptr()
+    res = fed.test(idx=0, current_epoch=0)
+    assert len(res) == 13 and np.isfinite(res[3])

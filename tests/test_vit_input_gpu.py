@@ -57,7 +57,7 @@ def _small_trainer(direct: bool, overlap: bool):
     import bench
     import fairfedmed_b200.trainer  # noqa: F401  (registers GLP_OT_SVLoRA)
     from fairfedmed_b200.registry import build_trainer
-    cfg = bench.make_cfg(1, 4, "Sinkhorn")
+    cfg = bench.make_cfg(1, 4, "Sinkhorn", bench.CONFIGS[2])
     cfg.MODEL_ARCH.VISION_LAYERS = 2
     cfg.MODEL_ARCH.TEXT_LAYERS = 2
     cfg.INPUT.SIZE = (64, 64)
@@ -128,18 +128,49 @@ def test_direct_gradients_and_side_stream_do_not_change_the_step():
 
 
 def test_graphed_step_with_side_stream_matches_eager():
-    """The captured step (fork/join of the text stream inside the graph) reproduces the eager losses."""
+    """The captured step (fork/join of the text stream inside the graph) reproduces the eager losses; the capture's
+    warm-up steps are rolled back (parameters, momentum), so step k of both trainers sees the same state."""
     tr_e, batch = _small_trainer(True, True)
     tr_g, _ = _small_trainer(True, True)
-    eager = [tr_e.forward_backward(batch)["loss"].item() for _ in range(4)]
-    first = tr_g.forward_backward(batch)["loss"].item()          # first step eagerly (momentum initialisation)
+    eager = [tr_e.forward_backward(batch)["loss"].item() for _ in range(3)]
+    first = tr_g.forward_backward(batch)["loss"].item()          # first step eagerly
     dev_batch = {k: v.to(DEV) for k, v in batch.items()}
-    # capture runs `warmup` real steps before recording
-    tr_g.capture_step_graph(dev_batch, warmup=1)
+    before = tr_g.get_flat().clone()
+    tr_g.capture_step_graph(dev_batch, warmup=2)
+    assert torch.equal(tr_g.get_flat(), before), "capture must not move the parameters"
     graphed = [tr_g.forward_backward_graphed(dev_batch)["loss"].item() for _ in range(2)]
     assert first == pytest.approx(eager[0], abs=1e-5)
-    # steps 3 and 4 of the eager run correspond to the two replays (step 2 was the capture warm-up; the capture pass
-    # itself only records)
-    assert graphed[0] == pytest.approx(eager[2], abs=1e-4)
-    assert graphed[1] == pytest.approx(eager[3], abs=1e-4)
+    assert graphed[0] == pytest.approx(eager[1], abs=1e-4)
+    assert graphed[1] == pytest.approx(eager[2], abs=1e-4)
     assert float((tr_g.flat_params - tr_e.flat_params).abs().max()) <= 1e-5
+
+
+def test_train_replays_the_graph_and_matches_the_eager_epoch():
+    """The PUBLIC train(idx=...) path: `step_metrics = "epoch"` (captured graph, staged batches, deferred read-back) and
+    `"step"` (eager, python floats per step like the reference) give the same per-step losses / accuracies / training
+    AUCs and the same parameters over two client-epochs — including a StepLR change between them, which the graph
+    picks up from device memory without re-capture, and a graph captured from the very first step (zero momentum)."""
+    import fairfedmed_b200.trainer  # noqa: F401
+    from fairfedmed_b200.data import CachedLoader
+    trs = []
+    for mode in ("step", "epoch"):
+        tr, _ = _small_trainer(True, True)
+        tr.cfg.OPTIM.STEPSIZE = (2,)                 # StepLR(step_size=2): the rate drops after the first client-epoch
+        tr.cfg.OPTIM.GAMMA = 0.5
+        tr.step_metrics, tr.sync_metrics, tr.step_auc = mode, True, True
+        batches = list(tr.fed_train_loader_x_dict[0])
+        assert len(batches) >= 2
+        tr.fed_train_loader_x_dict[0] = CachedLoader(batches, len(batches), tr.fed_train_loader_x_dict[0].dataset)
+        logs = []
+        for ep in range(2):
+            last = tr.train(idx=0, global_epoch=ep, is_fed=True, is_last_client=True)
+            logs.append(tr.last_epoch_summaries if mode == "epoch" else [last])
+        trs.append((tr, logs))
+    (te, le), (tg, lg) = trs
+    assert tg._graph is not None and te._graph is None
+    assert te.sched_steps == tg.sched_steps == 4 and te.current_lr() == pytest.approx(0.25 * te.base_lr)
+    for ep in range(2):
+        assert lg[ep][-1]["loss"] == pytest.approx(le[ep][-1]["loss"], abs=2e-4)
+        assert lg[ep][-1]["acc"] == pytest.approx(le[ep][-1]["acc"], abs=1e-4)
+        assert lg[ep][-1]["auc"] == pytest.approx(le[ep][-1]["auc"], abs=1e-6)
+    assert float((tg.flat_params - te.flat_params).abs().max()) <= 2e-5
