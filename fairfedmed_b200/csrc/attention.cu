@@ -23,6 +23,8 @@
 //             TMEM columns + the two 128-column regions = 512) never leave the chip; delta = rowsum(dO * O) is computed
 //             while the operands land.  No atomics: deterministic.
 #include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
 
 #include <mutex>
 
@@ -259,17 +261,22 @@ attention_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_c
 // ---------------------------------------------------------------------------------------------------------------
 // backward
 // ---------------------------------------------------------------------------------------------------------------
-constexpr int BWD_THREADS = 320;            // warp 0: TMA, warp 1: MMA (+ TMEM alloc), warps 2-9: element-wise + epilogues
+// A unit = (key tile j of 128 keys, query chunk a of <= 64 queries).  Two TMEM buffers of 128 columns (S^T | dP^T, 64
+// columns each) ping-pong, so the contractions of unit n + 1 run while the element-wise warps work on unit n; two groups
+// of four warps (one warp per TMEM lane quarter) alternate units, each thread owning one key row of its unit.
+constexpr int BWD_THREADS = 320;            // warp 0: TMA, warp 1: MMA (+ TMEM alloc), warps 2-5 / 6-9: element-wise group 0 / 1
 constexpr int OFF_Q = 0;
 constexpr int OFF_DO = OFF_Q + KV_BYTES;             //  26624
 constexpr int OFF_K = OFF_DO + KV_BYTES;             //  53248
 constexpr int OFF_V = OFF_K + Q2_BYTES;              //  86016
-constexpr int OFF_DS = OFF_V + Q2_BYTES;             // 118784: two dS tiles [128 keys][128 queries] bf16, MN-major SW128
-constexpr int DS_TILE = 128 * 128 * 2;               //  32768
-constexpr int OFF_VEC = OFF_DS + 2 * DS_TILE;        // 184320: lse2[208], delta[208]
-constexpr int OFF_BAR = OFF_VEC + 2 * LP * 4;        // 185984
+constexpr int OFF_DS = OFF_V + Q2_BYTES;             // 118784: dS [128 keys][256 queries] bf16 = 4 column blocks, MN-major SW128
+constexpr int DS_BLOCK = 128 * ROW_BYTES;            //  16384: 64 queries x 128 key rows
+constexpr int OFF_ST = OFF_DS + 4 * DS_BLOCK;        // 184320: two output staging tiles [128 rows][64] bf16 (one per group)
+constexpr int ST_TILE = 128 * ROW_BYTES;             //  16384
+constexpr int OFF_VEC = OFF_ST + 2 * ST_TILE;        // 217088: lse2[208], delta[208]
+constexpr int OFF_BAR = OFF_VEC + 2 * LP * 4;        // 218752
 constexpr int BWD_SMEM = OFF_BAR + 128 + 1024;
-constexpr uint32_t R0 = 0, R1 = 128, ACC_DV = 256, ACC_DK = 320, ACC_DQ = 384;   // TMEM columns
+constexpr uint32_t ACC_DV = 256, ACC_DK = 320, ACC_DQ = 384;   // TMEM columns; buffers: S^T at 128 b, dP^T at 128 b + 64
 
 struct BwdParams {
   const __nv_bfloat16* out;
@@ -277,18 +284,63 @@ struct BwdParams {
   __nv_bfloat16* d_qkv;
   int B, L, H, C, batch_first;
   int l_pad;        // L rounded up to 16
-  int nj;           // key tiles (1 or 2) = query halves
+  int nj;           // key tiles of 128 (1 or 2)
+  int nq;           // query chunks of 64 (1..4)
   int total;
   float scale, scale_log2;
+  int prof;         // debug: accumulate per-role wait / work cycles into g_bwd_prof (ffm_attention_bwd_profile)
 };
 
-// first query column handled by the second warp of a pair / first packed column of its output (multiple of 16)
-__device__ __forceinline__ int split_point(int n) { return 16 * ((n / 16 + 1) / 2); }
+// debug counters, 16 per CTA: see ffm_attention_bwd_profile
+__device__ long long g_bwd_prof[160 * 16];
+#define ATT_TIMED(acc, stmt)                          \
+  do {                                                \
+    if (p.prof) {                                     \
+      const long long _t = clock64();                 \
+      stmt;                                           \
+      acc += clock64() - _t;                          \
+    } else {                                          \
+      stmt;                                           \
+    }                                                 \
+  } while (0)
+
+__device__ __forceinline__ float4 lds128(uint32_t addr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+  return v;
+}
+
+// TMEM columns of K step k (16 queries) of a chunk: bf16 pairs are packed over the columns their fp32 source occupied
+__device__ __forceinline__ uint32_t packed_col(int k) { return static_cast<uint32_t>(8 * k); }
+
+// accumulator row (fp32, 64 columns from `acc`) x `sc` -> 64 bf16 into row `row` of a SW128 staging tile
+__device__ __forceinline__ void stage_row64(uint32_t acc, float sc, uint8_t* tile, int row) {
+  uint8_t* line = tile + row * ROW_BYTES;
+#pragma unroll
+  for (int c0 = 0; c0 < HD; c0 += 16) {
+    uint32_t v[16];
+    tmem_ld16(acc + c0, v);
+    tmem_ld_wait();
+    uint4 o0, o1;
+    o0.x = pack2(__uint_as_float(v[0]) * sc, __uint_as_float(v[1]) * sc);
+    o0.y = pack2(__uint_as_float(v[2]) * sc, __uint_as_float(v[3]) * sc);
+    o0.z = pack2(__uint_as_float(v[4]) * sc, __uint_as_float(v[5]) * sc);
+    o0.w = pack2(__uint_as_float(v[6]) * sc, __uint_as_float(v[7]) * sc);
+    o1.x = pack2(__uint_as_float(v[8]) * sc, __uint_as_float(v[9]) * sc);
+    o1.y = pack2(__uint_as_float(v[10]) * sc, __uint_as_float(v[11]) * sc);
+    o1.z = pack2(__uint_as_float(v[12]) * sc, __uint_as_float(v[13]) * sc);
+    o1.w = pack2(__uint_as_float(v[14]) * sc, __uint_as_float(v[15]) * sc);
+    const int ch = c0 >> 3;
+    *reinterpret_cast<uint4*>(line + (((ch) ^ (row & 7)) << 4)) = o0;
+    *reinterpret_cast<uint4*>(line + (((ch + 1) ^ (row & 7)) << 4)) = o1;
+  }
+}
 
 template <bool CAUSAL>
 __global__ void __launch_bounds__(BWD_THREADS, 1)
 attention_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_kv,
-                        const __grid_constant__ CUtensorMap tm_do, const BwdParams p) {
+                        const __grid_constant__ CUtensorMap tm_do, const __grid_constant__ CUtensorMap tm_dqkv,
+                        const BwdParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   float* lse2_s = reinterpret_cast<float*>(smem + OFF_VEC);
@@ -296,26 +348,28 @@ attention_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_c
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + OFF_BAR);
   uint64_t* ld_full = bars;          // operands of a head landed
   uint64_t* ld_free = bars + 1;      // every MMA of the head completed: operands may be overwritten
-  uint64_t* sdp_full = bars + 2;     // S^T and dP^T of a unit in TMEM
-  uint64_t* pds_full = bars + 3;     // P^T / dS^T written (TMEM + shared tile)
-  uint64_t* stage_free = bars + 4;   // [2] dQ MMAs reading the shared dS tile completed
-  uint64_t* dvk_full = bars + 6;     // [2] dV_j / dK_j complete
-  uint64_t* dq_full = bars + 8;      // [2] dQ_a complete
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 10);
+  uint64_t* sdp_full = bars + 2;     // [2] S^T and dP^T of a unit in TMEM buffer b
+  uint64_t* pds_full = bars + 4;     // [2] P^T / dS^T of buffer b written (TMEM + shared dS block)
+  uint64_t* stage_free = bars + 6;   // [2] dQ MMAs of query half h completed: its shared dS blocks may be rewritten
+  uint64_t* dvk_full = bars + 8;     //     dV_j / dK_j complete
+  uint64_t* dq_full = bars + 9;      // [2] dQ of query half h complete
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 11);
 
   const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
-  const int nj = p.nj;
+  const int nj = p.nj, nq = p.nq;
+  const int units = nj * nq;
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tm_q);
     tma_prefetch_desc(&tm_kv);
     tma_prefetch_desc(&tm_do);
+    tma_prefetch_desc(&tm_dqkv);
     mbar_init(ld_full, 1);
     mbar_init(ld_free, 1);
-    mbar_init(sdp_full, 1);
-    mbar_init(pds_full, 8);
+    mbar_init(dvk_full, 1);
     for (int i = 0; i < 2; ++i) {
+      mbar_init(&sdp_full[i], 1);
+      mbar_init(&pds_full[i], 4);
       mbar_init(&stage_free[i], 1);
-      mbar_init(&dvk_full[i], 1);
       mbar_init(&dq_full[i], 1);
     }
     fence_mbar_init();
@@ -333,8 +387,9 @@ attention_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_c
     // ============================== TMA producer ==============================
     const uint32_t q_bytes = static_cast<uint32_t>(p.l_pad) * ROW_BYTES, k_bytes = static_cast<uint32_t>(128 * nj) * ROW_BYTES;
     int it = 0;
+    long long w_free = 0;
     for (int u = blockIdx.x; u < p.total; u += gridDim.x, ++it) {
-      mbar_wait_uniform(ld_free, (it & 1) ^ 1);
+      ATT_TIMED(w_free, mbar_wait_uniform(ld_free, (it & 1) ^ 1));
       if (elect_one()) {
         const int b = u / p.H, h = u - b * p.H;
         mbar_arrive_expect_tx(ld_full, 2 * q_bytes + 2 * k_bytes);
@@ -342,80 +397,121 @@ attention_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_c
         tma_load_3d(smem + OFF_DO, &tm_do, ld_full, h * HD, 0, b);
         tma_load_3d(smem + OFF_K, &tm_kv, ld_full, p.C + h * HD, 0, b);
         tma_load_3d(smem + OFF_V, &tm_kv, ld_full, 2 * p.C + h * HD, 0, b);
+        const int un = u + static_cast<int>(gridDim.x);      // the operand tiles are single-buffered: at least pull the
+        if (un < p.total) {                                  // next head's tiles into L2 while this one computes
+          const int bn = un / p.H, hn = un - bn * p.H;
+          tma_prefetch_3d(&tm_q, hn * HD, 0, bn);
+          tma_prefetch_3d(&tm_do, hn * HD, 0, bn);
+          tma_prefetch_3d(&tm_kv, p.C + hn * HD, 0, bn);
+          tma_prefetch_3d(&tm_kv, 2 * p.C + hn * HD, 0, bn);
+        }
       }
       __syncwarp();
     }
+    if (p.prof && lane == 0) g_bwd_prof[blockIdx.x * 16 + 3] = w_free;
   } else if (warp == 1) {
     // ============================== MMA issuer ==============================
     const uint32_t sb = smem_u32(smem);
+    const long long t_begin = clock64();
+    long long w_ld = 0, w_pds = 0;
     const uint32_t idesc_acc = umma_idesc_bf16(128, HD) | UMMA_IDESC_B_MN;                      // A in TMEM
-    const uint32_t idesc_dq = umma_idesc_bf16(128, HD) | UMMA_IDESC_A_MN | UMMA_IDESC_B_MN;     // A = shared dS tile
+    const uint32_t idesc_dq = umma_idesc_bf16(128, HD) | UMMA_IDESC_A_MN | UMMA_IDESC_B_MN;     // A = shared dS blocks
+
+    // S^T = K_j Q_a^T and dP^T = V_j dO_a^T of unit w into buffer (n & 1)
+    auto issue_sdp = [&](int w, uint32_t n) {
+      const int j = w / nq, a = w - j * nq;
+      const int na = (p.l_pad - 64 * a) < 64 ? (p.l_pad - 64 * a) : 64;
+      const uint32_t idesc_sn = umma_idesc_bf16(128, na);
+      const uint32_t buf = tmem_base + 128u * (n & 1u);
+      if (elect_one()) {
+        const uint64_t kd = umma_desc_sw128(sb + OFF_K + j * (128 * ROW_BYTES));
+        const uint64_t vd = umma_desc_sw128(sb + OFF_V + j * (128 * ROW_BYTES));
+        const uint64_t qd = umma_desc_sw128(sb + OFF_Q + a * (64 * ROW_BYTES));
+        const uint64_t dd = umma_desc_sw128(sb + OFF_DO + a * (64 * ROW_BYTES));
+#pragma unroll
+        for (int k = 0; k < HD / 16; ++k) umma_bf16(buf, kd + 2u * k, qd + 2u * k, idesc_sn, k != 0 ? 1u : 0u);
+#pragma unroll
+        for (int k = 0; k < HD / 16; ++k) umma_bf16(buf + 64, vd + 2u * k, dd + 2u * k, idesc_sn, k != 0 ? 1u : 0u);
+        umma_commit(&sdp_full[n & 1u]);
+      }
+      __syncwarp();
+    };
+
     int it = 0;
-    uint32_t n = 0;                                         // running unit counter
+    uint32_t n = 0;                                         // running unit counter (same enumeration in every role)
     for (int u = blockIdx.x; u < p.total; u += gridDim.x, ++it) {
-      mbar_wait_uniform(ld_full, it & 1);
+      ATT_TIMED(w_ld, mbar_wait_uniform(ld_full, it & 1));
       tc_fence_after();
-      for (int j = 0; j < nj; ++j) {
-        const int kk = ((p.L - 128 * j < 128 ? p.L - 128 * j : 128) + 15) / 16;   // K steps over the valid keys of tile j
-        for (int a = 0; a < nj; ++a, ++n) {
-          const int na = (a == 0) ? (p.l_pad < 128 ? p.l_pad : 128) : p.l_pad - 128;  // query columns of this unit
-          const uint32_t idesc_sn = umma_idesc_bf16(128, na);
-          if (elect_one()) {
-            const uint64_t kd = umma_desc_sw128(sb + OFF_K + j * (128 * ROW_BYTES));
-            const uint64_t vd = umma_desc_sw128(sb + OFF_V + j * (128 * ROW_BYTES));
-            const uint64_t qd = umma_desc_sw128(sb + OFF_Q + a * (128 * ROW_BYTES));
-            const uint64_t dd = umma_desc_sw128(sb + OFF_DO + a * (128 * ROW_BYTES));
-#pragma unroll
-            for (int k = 0; k < HD / 16; ++k) umma_bf16(tmem_base + R0, kd + 2u * k, qd + 2u * k, idesc_sn, k != 0 ? 1u : 0u);
-#pragma unroll
-            for (int k = 0; k < HD / 16; ++k) umma_bf16(tmem_base + R1, vd + 2u * k, dd + 2u * k, idesc_sn, k != 0 ? 1u : 0u);
-            umma_commit(sdp_full);
-          }
-          __syncwarp();
-          mbar_wait_uniform(pds_full, n & 1u);
-          tc_fence_after();
-          if (elect_one()) {
-            const int sp = split_point(na);
-            const int ks = na / 16;
-            for (int k = 0; k < ks; ++k) {                   // dV_j += P^T dO_a
-              const uint32_t col = (16 * k < sp) ? 8u * k : static_cast<uint32_t>(sp + 8 * (k - sp / 16));
-              umma_bf16_ts(tmem_base + ACC_DV, tmem_base + R0 + col,
-                           umma_desc_sw128_mn(sb + OFF_DO + (128 * a + 16 * k) * ROW_BYTES, 16), idesc_acc,
-                           (a | k) != 0 ? 1u : 0u);
-            }
-            for (int k = 0; k < ks; ++k) {                   // dK_j += dS^T Q_a
-              const uint32_t col = (16 * k < sp) ? 8u * k : static_cast<uint32_t>(sp + 8 * (k - sp / 16));
-              umma_bf16_ts(tmem_base + ACC_DK, tmem_base + R1 + col,
-                           umma_desc_sw128_mn(sb + OFF_Q + (128 * a + 16 * k) * ROW_BYTES, 16), idesc_acc,
-                           (a | k) != 0 ? 1u : 0u);
-            }
-            const uint32_t ds = sb + OFF_DS + (n & 1u) * DS_TILE;
-            for (int k = 0; k < kk; ++k)                     // dQ_a += dS K_j
-              umma_bf16(tmem_base + ACC_DQ + 64 * a, umma_desc_sw128_mn(ds + k * 2048, 128 * ROW_BYTES),
+      issue_sdp(0, n);
+      for (int w = 0; w < units; ++w, ++n) {
+        const int j = w / nq, a = w - j * nq;
+        if (w + 1 < units) issue_sdp(w + 1, n + 1);          // runs under the element-wise work of unit w
+        ATT_TIMED(w_pds, mbar_wait_uniform(&pds_full[n & 1u], (n >> 1) & 1u));
+        tc_fence_after();
+        if (elect_one()) {
+          const int na = (p.l_pad - 64 * a) < 64 ? (p.l_pad - 64 * a) : 64;
+          const uint32_t buf = tmem_base + 128u * (n & 1u);
+          const int ks = na / 16;
+          for (int k = 0; k < ks; ++k)                       // dV_j += P^T dO_a
+            umma_bf16_ts(tmem_base + ACC_DV, buf + packed_col(k),
+                         umma_desc_sw128_mn(sb + OFF_DO + (64 * a + 16 * k) * ROW_BYTES, 16), idesc_acc,
+                         (a | k) != 0 ? 1u : 0u);
+          for (int k = 0; k < ks; ++k)                       // dK_j += dS^T Q_a
+            umma_bf16_ts(tmem_base + ACC_DK, buf + 64 + packed_col(k),
+                         umma_desc_sw128_mn(sb + OFF_Q + (64 * a + 16 * k) * ROW_BYTES, 16), idesc_acc,
+                         (a | k) != 0 ? 1u : 0u);
+          if ((a & 1) == 1 || a == nq - 1) {                 // both chunks of query half h are staged: dQ_h += dS K_j
+            const int h = a >> 1;
+            const int kk = ((p.L - 128 * j < 128 ? p.L - 128 * j : 128) + 15) / 16;
+            for (int k = 0; k < kk; ++k)
+              umma_bf16(tmem_base + ACC_DQ + 64 * h, umma_desc_sw128_mn(sb + OFF_DS + 2 * h * DS_BLOCK + k * 2048, DS_BLOCK),
                         umma_desc_sw128_mn(sb + OFF_K + (128 * j + 16 * k) * ROW_BYTES, 16), idesc_dq,
                         (j | k) != 0 ? 1u : 0u);
-            umma_commit(&stage_free[n & 1u]);
-            if (a == nj - 1) umma_commit(&dvk_full[j]);
-            if (j == nj - 1) umma_commit(&dq_full[a]);
-            if (j == nj - 1 && a == nj - 1) umma_commit(ld_free);
+            umma_commit(&stage_free[h]);
+            if (j == nj - 1) umma_commit(&dq_full[h]);
           }
-          __syncwarp();
+          if (a == nq - 1) umma_commit(dvk_full);
+          if (w == units - 1) umma_commit(ld_free);
         }
+        __syncwarp();
       }
+    }
+    if (p.prof && lane == 0) {
+      g_bwd_prof[blockIdx.x * 16 + 0] = clock64() - t_begin;
+      g_bwd_prof[blockIdx.x * 16 + 1] = w_ld;
+      g_bwd_prof[blockIdx.x * 16 + 2] = w_pds;
     }
   } else {
     // ============================== element-wise warps ==============================
+    long long c_ld = 0, c_pre = 0, c_sdp = 0, c_stage = 0, c_epw = 0, c_work = 0, c_drain = 0, c_end = 0;
     const uint32_t quarter = warp & 3u;
-    const int half = static_cast<int>(warp - 2) >> 2;        // which column half of a unit / which accumulator
-    const int row = static_cast<int>(quarter * 32u + lane);  // key row inside tile j, query row inside half a
+    const uint32_t grp = (warp - 2u) >> 2;                    // handles units with (n & 1) == grp, i.e. TMEM buffer grp
+    const int row = static_cast<int>(quarter * 32u + lane);  // key row inside tile j / query row inside a half
     const int tid_s = static_cast<int>(threadIdx.x) - 64;    // 0..255
     const uint32_t lane_addr = (quarter * 32u) << 16;
-    const size_t row_stride = static_cast<size_t>(3) * p.C;
+    const uint32_t buf = tmem_base + lane_addr + 128u * grp;
+    const uint32_t lse_addr = smem_u32(lse2_s), delta_addr = smem_u32(delta_s);
+    uint8_t* stage = smem + OFF_ST + grp * ST_TILE;          // this group's output staging tile
+    const bool storer = quarter == 0 && lane == 0;           // issues the group's TMA stores
+    // accumulator tile (128 rows x 64 fp32 at TMEM column `acc_col`) x sc -> bf16 -> staging tile -> one TMA store to
+    // d_qkv[b, row0 .. row0 + 127, col0 .. col0 + 63]; rows past the sequence end are clipped by the hardware
+    auto drain_tile = [&](uint32_t acc_col, float sc, int col0, int row0, int b) {
+      if (storer) tma_store_wait_read<0>();                  // the previous store has finished reading the tile
+      named_bar_sync(2 + grp, 128);
+      stage_row64(tmem_base + lane_addr + acc_col, sc, stage, row);
+      fence_proxy_async_smem();
+      named_bar_sync(2 + grp, 128);
+      if (storer) {
+        tma_store_3d(&tm_dqkv, stage, col0, row0, b);
+        tma_store_commit();
+      }
+    };
     int it = 0;
     uint32_t n = 0;
     for (int u = blockIdx.x; u < p.total; u += gridDim.x, ++it) {
       const int b = u / p.H, h = u - b * p.H;
-      mbar_wait(ld_full, it & 1, 300);
+      ATT_TIMED(c_ld, mbar_wait(ld_full, it & 1, 300));
+      const long long t_pre = clock64();
       // delta[q] = sum_d dO[q][d] O[q][d] (O from global, dO from the swizzled tile), lse2[q]; +inf masks padded queries
       if (tid_s < LP) {
         float d = 0.f, l2 = __int_as_float(0x7f800000);
@@ -442,144 +538,98 @@ attention_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_c
         lse2_s[tid_s] = l2;
       }
       named_bar_sync(1, 256);
+      c_pre += clock64() - t_pre;
 
-      for (int j = 0; j < nj; ++j) {
+      for (int w = 0; w < units; ++w, ++n) {
+        if ((n & 1u) != grp) continue;
+        const int j = w / nq, a = w - j * nq;
+        const int na = (p.l_pad - 64 * a) < 64 ? (p.l_pad - 64 * a) : 64;
         const int key = 128 * j + row;
         const bool kvalid = key < p.L;
-        for (int a = 0; a < nj; ++a, ++n) {
-          const int na = (a == 0) ? (p.l_pad < 128 ? p.l_pad : 128) : p.l_pad - 128;
-          const int sp = split_point(na);
-          const int c_lo = half == 0 ? 0 : sp, c_hi = half == 0 ? sp : na;
-          mbar_wait(sdp_full, n & 1u, 400);
+        ATT_TIMED(c_sdp, mbar_wait(&sdp_full[grp], (n >> 1) & 1u, 400));
+        tc_fence_after();
+        if (a == 0 && j > 0) {
+          // dV_{j-1} / dK_{j-1} are complete: drain them before this unit's first dV / dK MMA overwrites the accumulators
+          ATT_TIMED(c_epw, mbar_wait(dvk_full, static_cast<uint32_t>(it * nj + j - 1) & 1u, 500));
           tc_fence_after();
-          if (a == 0 && j > 0) {
-            // dV_{j-1} / dK_{j-1} are complete (their commit precedes this unit's scores): drain them before this unit's
-            // first dV / dK MMA overwrites the accumulators
-            mbar_wait(&dvk_full[j - 1], it & 1, 500);
-            tc_fence_after();
-            const int kr = 128 * (j - 1) + row;
-            const uint32_t acc = tmem_base + lane_addr + (half == 0 ? ACC_DV : ACC_DK);
-            const float sc = half == 0 ? 1.0f : p.scale;
-            const size_t tok = p.batch_first ? (static_cast<size_t>(b) * p.L + kr) : (static_cast<size_t>(kr) * p.B + b);
-            uint4* dst = reinterpret_cast<uint4*>(p.d_qkv + tok * row_stride + (half == 0 ? 2 : 1) * p.C + h * HD);
-#pragma unroll
-            for (int c0 = 0; c0 < HD; c0 += 16) {
-              uint32_t v[16];
-              tmem_ld16(acc + c0, v);
-              tmem_ld_wait();
-              uint4 o0, o1;
-              o0.x = pack2(__uint_as_float(v[0]) * sc, __uint_as_float(v[1]) * sc);
-              o0.y = pack2(__uint_as_float(v[2]) * sc, __uint_as_float(v[3]) * sc);
-              o0.z = pack2(__uint_as_float(v[4]) * sc, __uint_as_float(v[5]) * sc);
-              o0.w = pack2(__uint_as_float(v[6]) * sc, __uint_as_float(v[7]) * sc);
-              o1.x = pack2(__uint_as_float(v[8]) * sc, __uint_as_float(v[9]) * sc);
-              o1.y = pack2(__uint_as_float(v[10]) * sc, __uint_as_float(v[11]) * sc);
-              o1.z = pack2(__uint_as_float(v[12]) * sc, __uint_as_float(v[13]) * sc);
-              o1.w = pack2(__uint_as_float(v[14]) * sc, __uint_as_float(v[15]) * sc);
-              dst[c0 / 8] = o0;          // kr < L always holds for tile j-1 < nj-1
-              dst[c0 / 8 + 1] = o1;
-            }
-          }
-          mbar_wait(&stage_free[n & 1u], ((n >> 1) & 1u) ^ 1u, 600);
-          uint8_t* ds_tile = smem + OFF_DS + (n & 1u) * DS_TILE;
-          for (int c0 = c_lo; c0 < c_hi; c0 += 16) {
-            uint32_t sv[16], dv[16];
-            tmem_ld16(tmem_base + lane_addr + R0 + c0, sv);
-            tmem_ld16(tmem_base + lane_addr + R1 + c0, dv);
-            tmem_ld_wait();
-            const int q0 = 128 * a + c0;
-            uint32_t pp[8], dd[8];
-#pragma unroll
-            for (int e = 0; e < 8; ++e) {
-              float pv[2], gv[2];
-#pragma unroll
-              for (int w = 0; w < 2; ++w) {
-                const int q = q0 + 2 * e + w;
-                const bool on = kvalid && (!CAUSAL || q >= key);
-                const float x = fmaf(__uint_as_float(sv[2 * e + w]), p.scale_log2, -lse2_s[q]);
-                pv[w] = on ? fast_exp2(x) : 0.f;
-                gv[w] = pv[w] * (__uint_as_float(dv[2 * e + w]) - delta_s[q]);
-              }
-              pp[e] = pack2(pv[0], pv[1]);
-              dd[e] = pack2(gv[0], gv[1]);
-            }
-            const uint32_t pcol = static_cast<uint32_t>(half == 0 ? (c0 >> 1) : sp + ((c0 - sp) >> 1));
-            tmem_st8(tmem_base + lane_addr + R0 + pcol, pp);
-            tmem_st8(tmem_base + lane_addr + R1 + pcol, dd);
-            // dS (not transposed) for dQ: [key row][query contiguous], 64-query blocks of 128 rows x 128 B, SW128
-            uint8_t* blk = ds_tile + (c0 >> 6) * (128 * ROW_BYTES) + row * ROW_BYTES;
-            const int ch = (c0 & 63) >> 3;
-            *reinterpret_cast<uint4*>(blk + (((ch) ^ (row & 7)) << 4)) = make_uint4(dd[0], dd[1], dd[2], dd[3]);
-            *reinterpret_cast<uint4*>(blk + (((ch + 1) ^ (row & 7)) << 4)) = make_uint4(dd[4], dd[5], dd[6], dd[7]);
-          }
-          tmem_st_wait();
-          fence_proxy_async_smem();
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(pds_full);
+          const long long t_dr = clock64();
+          drain_tile(ACC_DV, 1.0f, 2 * p.C + h * HD, 128 * (j - 1), b);
+          drain_tile(ACC_DK, p.scale, p.C + h * HD, 128 * (j - 1), b);
+          c_drain += clock64() - t_dr;
         }
-      }
-      // ---- epilogues of the head: dV / dK of the last key tile, dQ of both query halves ----
-      {
-        mbar_wait(&dvk_full[nj - 1], it & 1, 700);
-        tc_fence_after();
-        const int kr = 128 * (nj - 1) + row;
-        const uint32_t acc = tmem_base + lane_addr + (half == 0 ? ACC_DV : ACC_DK);
-        const float sc = half == 0 ? 1.0f : p.scale;
-        const bool valid = kr < p.L;
-        const size_t tok = p.batch_first ? (static_cast<size_t>(b) * p.L + kr) : (static_cast<size_t>(kr) * p.B + b);
-        uint4* dst = reinterpret_cast<uint4*>(p.d_qkv + (valid ? tok : 0) * row_stride + (half == 0 ? 2 : 1) * p.C + h * HD);
-#pragma unroll
-        for (int c0 = 0; c0 < HD; c0 += 16) {
-          uint32_t v[16];
-          tmem_ld16(acc + c0, v);
-          tmem_ld_wait();
-          if (valid) {
-            uint4 o0, o1;
-            o0.x = pack2(__uint_as_float(v[0]) * sc, __uint_as_float(v[1]) * sc);
-            o0.y = pack2(__uint_as_float(v[2]) * sc, __uint_as_float(v[3]) * sc);
-            o0.z = pack2(__uint_as_float(v[4]) * sc, __uint_as_float(v[5]) * sc);
-            o0.w = pack2(__uint_as_float(v[6]) * sc, __uint_as_float(v[7]) * sc);
-            o1.x = pack2(__uint_as_float(v[8]) * sc, __uint_as_float(v[9]) * sc);
-            o1.y = pack2(__uint_as_float(v[10]) * sc, __uint_as_float(v[11]) * sc);
-            o1.z = pack2(__uint_as_float(v[12]) * sc, __uint_as_float(v[13]) * sc);
-            o1.w = pack2(__uint_as_float(v[14]) * sc, __uint_as_float(v[15]) * sc);
-            dst[c0 / 8] = o0;
-            dst[c0 / 8 + 1] = o1;
-          }
+        // the shared dS blocks of this query half were last read by the dQ MMAs of the previous key tile (or head)
+        {
+          const int done = it * nj + j - 1;
+          if (done >= 0) ATT_TIMED(c_stage, mbar_wait(&stage_free[a >> 1], static_cast<uint32_t>(done) & 1u, 600));
         }
-      }
-      for (int a = 0; a < nj; ++a) {
-        mbar_wait(&dq_full[a], it & 1, 800 + a);
-        tc_fence_after();
-        const int qr = 128 * a + row;
-        const bool valid = qr < p.L;
-        const size_t tok = p.batch_first ? (static_cast<size_t>(b) * p.L + qr) : (static_cast<size_t>(qr) * p.B + b);
-        uint4* dst = reinterpret_cast<uint4*>(p.d_qkv + (valid ? tok : 0) * row_stride + h * HD + half * 32);
-        const uint32_t acc = tmem_base + lane_addr + ACC_DQ + 64 * a + half * 32;
+        const long long t_work = clock64();
+        uint8_t* blk = smem + OFF_DS + a * DS_BLOCK + row * ROW_BYTES;
+        for (int c0 = 0; c0 < na; c0 += 16) {
+          uint32_t sv[16], dv[16];
+          tmem_ld16(buf + c0, sv);
+          tmem_ld16(buf + 64 + c0, dv);
+          const int q0 = 64 * a + c0;
+          float l2[16], dl[16];
 #pragma unroll
-        for (int c0 = 0; c0 < 32; c0 += 16) {
-          uint32_t v[16];
-          tmem_ld16(acc + c0, v);
-          tmem_ld_wait();
-          if (valid) {
-            const float sc = p.scale;
-            uint4 o0, o1;
-            o0.x = pack2(__uint_as_float(v[0]) * sc, __uint_as_float(v[1]) * sc);
-            o0.y = pack2(__uint_as_float(v[2]) * sc, __uint_as_float(v[3]) * sc);
-            o0.z = pack2(__uint_as_float(v[4]) * sc, __uint_as_float(v[5]) * sc);
-            o0.w = pack2(__uint_as_float(v[6]) * sc, __uint_as_float(v[7]) * sc);
-            o1.x = pack2(__uint_as_float(v[8]) * sc, __uint_as_float(v[9]) * sc);
-            o1.y = pack2(__uint_as_float(v[10]) * sc, __uint_as_float(v[11]) * sc);
-            o1.z = pack2(__uint_as_float(v[12]) * sc, __uint_as_float(v[13]) * sc);
-            o1.w = pack2(__uint_as_float(v[14]) * sc, __uint_as_float(v[15]) * sc);
-            dst[c0 / 8] = o0;
-            dst[c0 / 8 + 1] = o1;
+          for (int e = 0; e < 4; ++e) {
+            const float4 x = lds128(lse_addr + (q0 + 4 * e) * 4), y = lds128(delta_addr + (q0 + 4 * e) * 4);
+            l2[4 * e] = x.x; l2[4 * e + 1] = x.y; l2[4 * e + 2] = x.z; l2[4 * e + 3] = x.w;
+            dl[4 * e] = y.x; dl[4 * e + 1] = y.y; dl[4 * e + 2] = y.z; dl[4 * e + 3] = y.w;
           }
+          tmem_ld_wait();
+          uint32_t pp[8], dd[8];
+#pragma unroll
+          for (int e = 0; e < 8; ++e) {
+            float pv[2], gv[2];
+#pragma unroll
+            for (int t = 0; t < 2; ++t) {
+              const int i = 2 * e + t;
+              float pr = fast_exp2(fmaf(__uint_as_float(sv[i]), p.scale_log2, -l2[i]));
+              if (CAUSAL) pr = (q0 + i >= key) ? pr : 0.f;
+              pv[t] = pr;
+              gv[t] = pr * (__uint_as_float(dv[i]) - dl[i]);
+            }
+            pp[e] = kvalid ? pack2(pv[0], pv[1]) : 0u;
+            dd[e] = kvalid ? pack2(gv[0], gv[1]) : 0u;
+          }
+          tmem_st8(buf + (c0 >> 1), pp);
+          tmem_st8(buf + 64 + (c0 >> 1), dd);
+          // dS (not transposed) for dQ: [key row][query contiguous]: two 16-byte chunks of this row's 128-byte line
+          const int ch = c0 >> 3;
+          *reinterpret_cast<uint4*>(blk + (((ch) ^ (row & 7)) << 4)) = make_uint4(dd[0], dd[1], dd[2], dd[3]);
+          *reinterpret_cast<uint4*>(blk + (((ch + 1) ^ (row & 7)) << 4)) = make_uint4(dd[4], dd[5], dd[6], dd[7]);
+        }
+        tmem_st_wait();
+        fence_proxy_async_smem();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&pds_full[grp]);
+        c_work += clock64() - t_work;
+      }
+      // ---- epilogues of the head: group 0 drains dV / dK of the last key tile, group 1 both query halves of dQ ----
+      if (grp == 0) {
+        ATT_TIMED(c_epw, mbar_wait(dvk_full, static_cast<uint32_t>(it * nj + nj - 1) & 1u, 700));
+        tc_fence_after();
+        const long long t_dr = clock64();
+        drain_tile(ACC_DV, 1.0f, 2 * p.C + h * HD, 128 * (nj - 1), b);
+        drain_tile(ACC_DK, p.scale, p.C + h * HD, 128 * (nj - 1), b);
+        c_drain += clock64() - t_dr;
+      } else {
+        for (int hq = 0; hq < (nq + 1) / 2; ++hq) {
+          ATT_TIMED(c_epw, mbar_wait(&dq_full[hq], it & 1, 800 + hq));
+          tc_fence_after();
+          const long long t_dr = clock64();
+          drain_tile(ACC_DQ + 64 * hq, p.scale, h * HD, 128 * hq, b);
+          c_drain += clock64() - t_dr;
         }
       }
       tc_fence_before();
-      named_bar_sync(1, 256);        // delta / lse2 of this head are dead: the next head may overwrite them
+      ATT_TIMED(c_end, named_bar_sync(1, 256));   // accumulators drained, delta / lse2 dead: the next head may proceed
+    }
+    if (storer) tma_store_wait_all<0>();
+    if (p.prof && lane == 0 && quarter == 0) {      // one warp per group reports: slots 4.. (group 0), 10.. (group 1)
+      long long* o = g_bwd_prof + blockIdx.x * 16 + (grp == 0 ? 4 : 10);
+      o[0] = c_ld + c_pre; o[1] = c_sdp; o[2] = c_stage + c_epw; o[3] = c_work; o[4] = c_drain; o[5] = c_end;
     }
   }
   __syncwarp();
@@ -683,20 +733,39 @@ int ffm_attention_bwd(const void* qkv, const void* out, const void* d_out, const
   p.B = B; p.L = L; p.H = H; p.C = H * att::HD; p.batch_first = batch_first ? 1 : 0;
   p.l_pad = (L + 15) / 16 * 16;
   p.nj = L > 128 ? 2 : 1;
+  p.nq = (p.l_pad + 63) / 64;
   p.total = B * H;
   p.scale = 1.0f / sqrtf(static_cast<float>(att::HD));
   p.scale_log2 = p.scale * att::LOG2E;
-  CUtensorMap tm_q, tm_kv, tm_do;
+  {
+    static int prof = -1;
+    if (prof < 0) { const char* e = getenv("FFM_ATT_PROF"); prof = (e != nullptr && e[0] == '1') ? 1 : 0; }
+    p.prof = prof;
+  }
+  CUtensorMap tm_q, tm_kv, tm_do, tm_dqkv;
   if ((rc = att::make_map_tokens(&tm_q, qkv, B, L, 3 * p.C, p.batch_first, p.l_pad))) return rc;
   if ((rc = att::make_map_tokens(&tm_kv, qkv, B, L, 3 * p.C, p.batch_first, 128 * p.nj))) return rc;
   if ((rc = att::make_map_tokens(&tm_do, d_out, B, L, p.C, p.batch_first, p.l_pad))) return rc;
+  if ((rc = att::make_map_tokens(&tm_dqkv, d_qkv, B, L, 3 * p.C, p.batch_first, 128))) return rc;
   const int grid = p.total < num_sms() ? p.total : num_sms();
   if (causal)
-    att::attention_bwd_tc_kernel<true><<<grid, att::BWD_THREADS, att::BWD_SMEM, stream>>>(tm_q, tm_kv, tm_do, p);
+    att::attention_bwd_tc_kernel<true><<<grid, att::BWD_THREADS, att::BWD_SMEM, stream>>>(tm_q, tm_kv, tm_do, tm_dqkv, p);
   else
-    att::attention_bwd_tc_kernel<false><<<grid, att::BWD_THREADS, att::BWD_SMEM, stream>>>(tm_q, tm_kv, tm_do, p);
+    att::attention_bwd_tc_kernel<false><<<grid, att::BWD_THREADS, att::BWD_SMEM, stream>>>(tm_q, tm_kv, tm_do, tm_dqkv, p);
   FFM_CHECK_CUDA(cudaGetLastError());
   count_launch();
+  if (p.prof) {      // debug only: per-role cycle counters of this launch, averaged over the CTAs
+    static long long h[160 * 16];
+    FFM_CHECK_CUDA(cudaStreamSynchronize(stream));
+    FFM_CHECK_CUDA(cudaMemcpyFromSymbol(h, att::g_bwd_prof, sizeof(h)));
+    double avg[16] = {0};
+    for (int c = 0; c < grid; ++c)
+      for (int k = 0; k < 16; ++k) avg[k] += static_cast<double>(h[c * 16 + k]) / grid;
+    fprintf(stderr, "[att bwd prof] total %.0f | mma: wait ld %.0f pds %.0f | tma: wait free %.0f | g0: ld+pre %.0f sdp %.0f "
+            "stage+ep-wait %.0f work %.0f drain %.0f end %.0f | g1: ld+pre %.0f sdp %.0f stage+ep-wait %.0f work %.0f drain "
+            "%.0f end %.0f\n", avg[0], avg[1], avg[2], avg[3], avg[4], avg[5], avg[6], avg[7], avg[8], avg[9], avg[10], avg[11],
+            avg[12], avg[13], avg[14], avg[15]);
+  }
   return FFM_OK;
 }
 

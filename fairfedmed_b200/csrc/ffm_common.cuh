@@ -480,6 +480,21 @@ __device__ __forceinline__ void tma_load_3d(void* smem_dst, const CUtensorMap* m
       : "memory");
 }
 
+// 3-D tile store shared -> global (bulk-group completion); rows / columns outside the tensor are clipped by the hardware
+__device__ __forceinline__ void tma_store_3d(const CUtensorMap* m, const void* smem_src, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"(
+                   reinterpret_cast<uint64_t>(m)),
+               "r"(smem_u32(smem_src)), "r"(c0), "r"(c1), "r"(c2)
+               : "memory");
+}
+
+// warm L2 with a tile that a later tma_load_3d will fetch
+__device__ __forceinline__ void tma_prefetch_3d(const CUtensorMap* m, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.prefetch.tensor.3d.L2.global [%0, {%1, %2, %3}];" ::"l"(reinterpret_cast<uint64_t>(m)),
+               "r"(c0), "r"(c1), "r"(c2)
+               : "memory");
+}
+
 // SW128 operand whose CONTIGUOUS dimension is M / N ("MN-major"): rows of 128 B = 64 consecutive M/N elements for one
 // k, 8 k-rows per 1024-B swizzle atom (SBO), further 64-element column blocks `lbo_bytes` apart.  A K = 16 step is 16
 // rows = 2048 B.  Needs bit 15 (A) / bit 16 (B) of the instruction descriptor.
