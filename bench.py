@@ -159,6 +159,16 @@ def reference_step_fn(batch: int, ot: str, c: dict, device: str = "cpu", seed: i
     image, label, attr = b["img"].to(device), b["label"].to(device), b["attrs"][:, 0].contiguous()
     is_oct = c["modality"] == "oct_bscans"
     if shim.available():
+        import contextlib
+        with contextlib.redirect_stdout(sys.stderr):     # the reference prints while it builds: keep stdout to ONE JSON line
+            return _reference_modules_step(batch, ot, c, device, seed, G, g, image, label, attr), "reference"
+    return _port_step(batch, ot, c, device, seed, G, g, image, label, attr, is_oct), "port"
+
+
+def _reference_modules_step(batch, ot, c, device, seed, G, g, image, label, attr):
+    import torch.nn.functional as F
+    from oracle import shim
+    if True:
         T, CM, _, _ = shim.modules()
         cfg = shim.make_cfg(modality=c["modality"], ot=ot, dataset=c["dataset"], dim_per_3d_slice=8)
         torch.manual_seed(seed)
@@ -188,11 +198,14 @@ def reference_step_fn(batch: int, ot: str, c: dict, device: str = "cpu", seed: i
             optim.zero_grad()
             loss.backward()
             optim.step(); optim.step()                     # one optimizer registered under two names (F6)
-            return float(loss)
+            return float(loss.detach())
 
-        return step, "reference"
+        return step
 
-    # restated port (no reference tree, no staged archive)
+
+def _port_step(batch, ot, c, device, seed, G, g, image, label, attr, is_oct):
+    """restated port (no reference tree, no staged archive)"""
+    import torch.nn.functional as F
     from fairfedmed_b200.clip_model import CustomCLIP
     from fairfedmed_b200.modules import apply_lora_to_model
     from oracle import ref_port as rp
@@ -219,9 +232,9 @@ def reference_step_fn(batch: int, ot: str, c: dict, device: str = "cpu", seed: i
         loss = F.cross_entropy(logits, label)
         grads = torch.autograd.grad(loss, [params[k] for k in names])
         rp.sgd_double_step([params[k] for k in names], grads, bufs, lr=1e-3)
-        return float(loss)
+        return float(loss.detach())
 
-    return step, "port"
+    return step
 
 
 def time_reference(steps: int, warmup: int, batch: int, ot: str, c: dict, budget_s: float, device: str = "cpu"):

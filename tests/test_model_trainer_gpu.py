@@ -89,7 +89,7 @@ def test_rn50_wiring_is_exact_with_reference_math(monkeypatch):
     rc = recipes.MODEL_CASES[name]
     gold = np.load(GOLD / "model.npz")
 
-    def run_ref(self, x, s_eff):
+    def run_ref(self, x, s_eff, batch_first=False):
         W = self.original_linear.weight.reshape(self.out_features, self.in_features).float()
         b = self.original_linear.bias
         if self.is_1x1_conv:
