@@ -53,12 +53,19 @@ __device__ __forceinline__ uint32_t pack2(float a, float b) { return pack_bf16x2
 // ---------------------------------------------------------------------------------------------------------------
 // forward
 // ---------------------------------------------------------------------------------------------------------------
-constexpr int FWD_THREADS = 320;            // warp 0: TMA, warp 1: MMA (+ TMEM alloc), warps 2-5 / 6-9: softmax of tile 0 / 1
-constexpr int FWD_STAGE = Q2_BYTES + 2 * KV_BYTES;                 // 86016
-constexpr int FWD_SMEM = 2 * FWD_STAGE + 256 + 1024;
+// A unit = (head, query tile of 128 rows).  Two score buffers in TMEM ping-pong ([0, 208) and [208, 416)), the output
+// accumulator has its own 64 columns, so the tensor pipe works on S of unit n + 1 and P V of unit n - 1 while the softmax
+// warps are on unit n; two softmax groups alternate units and four separate warps drain O, so a softmax group never waits
+// for its own P V or epilogue.
+constexpr int FWD_THREADS = 448;            // warp 0: TMA, 1: MMA (+ TMEM alloc), 2-5 / 6-9: softmax groups, 10-13: epilogue
+constexpr int FWD_STAGE = Q2_BYTES + 2 * KV_BYTES;                 // 86016: Q (2 tiles), K, V of one head
+constexpr int FWD_OFF_OUT = 2 * FWD_STAGE;                          // 172032: output staging tile [128][64] bf16, SW128
+constexpr int FWD_OFF_STAT = FWD_OFF_OUT + 128 * ROW_BYTES;         // 188416: [2 buffers][128 rows] {1 / sum, lse2}
+constexpr int FWD_OFF_BAR = FWD_OFF_STAT + 2 * 128 * 8;
+constexpr int FWD_SMEM = FWD_OFF_BAR + 256 + 1024;
+constexpr uint32_t FWD_O_COL = 416;
 
 struct FwdParams {
-  __nv_bfloat16* out;
   float* lse;
   int B, L, H, C, batch_first;
   int lk_pad;        // L rounded up to 16: UMMA N of the scores, K extent of P V
@@ -70,30 +77,32 @@ struct FwdParams {
 template <bool CAUSAL>
 __global__ void __launch_bounds__(FWD_THREADS, 1)
 attention_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_kv,
-                        const FwdParams p) {
+                        const __grid_constant__ CUtensorMap tm_out, const FwdParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 2 * FWD_STAGE);
+  float2* stat = reinterpret_cast<float2*>(smem + FWD_OFF_STAT);       // [2][128]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + FWD_OFF_BAR);
   uint64_t* full = bars;            // [2] operands of a head landed
   uint64_t* empty = bars + 2;       // [2] all MMAs reading the stage completed
-  uint64_t* s_full = bars + 4;      // [2] scores of tile t in TMEM
-  uint64_t* p_full = bars + 6;      // [2] probabilities of tile t in TMEM
-  uint64_t* o_full = bars + 8;      // [2] P V of tile t complete
-  uint64_t* t_free = bars + 10;     // [2] epilogue drained tile t
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 12);
+  uint64_t* s_full = bars + 4;      // [2] scores of a unit in TMEM buffer b
+  uint64_t* p_full = bars + 6;      // [2] probabilities (and row statistics) of buffer b written
+  uint64_t* o_full = bars + 8;      //     P V of a unit complete
+  uint64_t* e_done = bars + 9;      // [2] epilogue of a unit with parity b finished (O drained, statistics read)
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 11);
 
   const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
   const int nt = p.n_tiles;
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tm_q);
     tma_prefetch_desc(&tm_kv);
+    tma_prefetch_desc(&tm_out);
+    mbar_init(o_full, 1);
     for (int i = 0; i < 2; ++i) {
       mbar_init(&full[i], 1);
       mbar_init(&empty[i], 1);
       mbar_init(&s_full[i], 1);
       mbar_init(&p_full[i], 4);
-      mbar_init(&o_full[i], 1);
-      mbar_init(&t_free[i], 4);
+      mbar_init(&e_done[i], 4);
     }
     fence_mbar_init();
   }
@@ -128,129 +137,182 @@ attention_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_c
     const uint32_t idesc_s = umma_idesc_bf16(128, p.lk_pad);
     const uint32_t idesc_pv = umma_idesc_bf16(128, HD) | UMMA_IDESC_B_MN;
     const int pv_steps = p.lk_pad / 16;
+    const uint32_t sb = smem_u32(smem);
+    // O = P V of unit m (its head sits in stage `stage`); `last` releases the stage to the producer
+    auto issue_pv = [&](uint32_t m, int stage, bool last) {
+      mbar_wait_uniform(&p_full[m & 1u], (m >> 1) & 1u);
+      if (m > 0) mbar_wait_uniform(&e_done[(m - 1) & 1u], ((m - 1) >> 1) & 1u);   // O of unit m - 1 drained
+      tc_fence_after();
+      if (elect_one()) {
+        const uint32_t vb = sb + stage * FWD_STAGE + Q2_BYTES + KV_BYTES;
+        const uint32_t pa = tmem_base + 208u * (m & 1u);
+        for (int k = 0; k < pv_steps; ++k)
+          umma_bf16_ts(tmem_base + FWD_O_COL, pa + 8 * k, umma_desc_sw128_mn(vb + k * 2048, 16), idesc_pv,
+                       k != 0 ? 1u : 0u);
+        umma_commit(o_full);
+        if (last) umma_commit(&empty[stage]);
+      }
+      __syncwarp();
+    };
     int it = 0;
+    uint32_t n = 0;                                           // running unit counter
+    int prev_stage = 0;
+    bool prev_last = false;
     for (int u = blockIdx.x; u < p.total; u += gridDim.x, ++it) {
       const int s = it & 1;
-      const uint32_t st = smem_u32(smem + s * FWD_STAGE);
+      const uint32_t st = sb + s * FWD_STAGE;
       mbar_wait_uniform(&full[s], (it >> 1) & 1);
       tc_fence_after();
-      for (int t = 0; t < nt; ++t) {
-        mbar_wait_uniform(&t_free[t], (it & 1) ^ 1);      // epilogue of the previous head drained this TMEM tile
-        tc_fence_after();
+      for (int t = 0; t < nt; ++t, ++n) {
+        // S of unit n into buffer n & 1 (its previous tenant's probabilities were consumed by P V of unit n - 2, issued
+        // before this point and executed in order)
         if (elect_one()) {
           const uint64_t ad = umma_desc_sw128(st + t * (128 * ROW_BYTES));
           const uint64_t bd = umma_desc_sw128(st + Q2_BYTES);
 #pragma unroll
           for (int k = 0; k < HD / 16; ++k)
-            umma_bf16(tmem_base + t * 256, ad + 2u * k, bd + 2u * k, idesc_s, k != 0 ? 1u : 0u);
-          umma_commit(&s_full[t]);
+            umma_bf16(tmem_base + 208u * (n & 1u), ad + 2u * k, bd + 2u * k, idesc_s, k != 0 ? 1u : 0u);
+          umma_commit(&s_full[n & 1u]);
         }
         __syncwarp();
-      }
-      for (int t = 0; t < nt; ++t) {
-        mbar_wait_uniform(&p_full[t], it & 1);
-        tc_fence_after();
-        if (elect_one()) {
-          const uint32_t vb = st + Q2_BYTES + KV_BYTES;
-          for (int k = 0; k < pv_steps; ++k)
-            umma_bf16_ts(tmem_base + t * 256 + 128, tmem_base + t * 256 + 8 * k,
-                         umma_desc_sw128_mn(vb + k * 2048, 16), idesc_pv, k != 0 ? 1u : 0u);
-          umma_commit(&o_full[t]);
-          if (t == nt - 1) umma_commit(&empty[s]);
-        }
-        __syncwarp();
+        if (n > 0) issue_pv(n - 1, prev_stage, prev_last);   // runs under the softmax of unit n
+        prev_stage = s;
+        prev_last = t == nt - 1;
       }
     }
-  } else {
-    // ============================== softmax + epilogue (one thread per query row) ==============================
-    const int t = static_cast<int>(warp - 2) >> 2;           // query tile of this warpgroup
+    if (n > 0) issue_pv(n - 1, prev_stage, prev_last);
+  } else if (warp < 10) {
+    // ============================== softmax (one thread per query row) ==============================
+    const uint32_t grp = (warp - 2u) >> 2;                   // handles units with (n & 1) == grp
     const uint32_t quarter = warp & 3u;                      // TMEM lane quarter this warp may touch
     const int row = static_cast<int>(quarter * 32u + lane);
-    if (t < nt) {
-      const uint32_t taddr = tmem_base + ((quarter * 32u) << 16) + static_cast<uint32_t>(t) * 256u;
-      const int qi = t * 128 + row;
-      const int ncol = CAUSAL ? (qi + 1 < p.L ? qi + 1 : p.L) : p.L;      // valid key columns of this row
-      int it = 0;
-      for (int u = blockIdx.x; u < p.total; u += gridDim.x, ++it) {
-        const int b = u / p.H, h = u - b * p.H;
-        mbar_wait(&s_full[t], it & 1, 100 + t);
+    const uint32_t taddr = tmem_base + ((quarter * 32u) << 16) + 208u * grp;
+    uint32_t n = 0;
+    for (int u = blockIdx.x; u < p.total; u += gridDim.x) {
+      for (int t = 0; t < nt; ++t, ++n) {
+        if ((n & 1u) != grp) continue;
+        const int qi = t * 128 + row;
+        const int ncol = CAUSAL ? (qi + 1 < p.L ? qi + 1 : p.L) : p.L;      // valid key columns of this row
+        const bool warp_live = t * 128 + static_cast<int>(quarter) * 32 < p.L;   // any valid query row in this warp?
+        mbar_wait(&s_full[grp], (n >> 1) & 1u, 100 + grp);
         tc_fence_after();
-        // pass 1: row maximum of the raw scores
-        float m = -3.0e38f;
-        for (int c0 = 0; c0 < p.lk_pad; c0 += 16) {
-          uint32_t v[16];
-          tmem_ld16(taddr + c0, v);
-          tmem_ld_wait();
-          if (c0 + 16 <= ncol) {
+        float m = -3.0e38f, sum = 0.f, mc = 0.f;
+        if (warp_live) {
+          // pass 1: row maximum of the raw scores (the next chunk's TMEM read is in flight under the current one)
+          uint32_t va[16], vb[16];
+          tmem_ld16(taddr, va);
+          for (int c0 = 0; c0 < p.lk_pad; c0 += 32) {
+            tmem_ld_wait();
+            const bool has_b = c0 + 16 < p.lk_pad;
+            if (has_b) tmem_ld16(taddr + c0 + 16, vb);
+            if (c0 + 16 <= ncol) {
 #pragma unroll
-            for (int j = 0; j < 16; ++j) m = fmaxf(m, __uint_as_float(v[j]));
-          } else {
+              for (int j = 0; j < 16; ++j) m = fmaxf(m, __uint_as_float(va[j]));
+            } else {
 #pragma unroll
-            for (int j = 0; j < 16; ++j)
-              if (c0 + j < ncol) m = fmaxf(m, __uint_as_float(v[j]));
+              for (int j = 0; j < 16; ++j)
+                if (c0 + j < ncol) m = fmaxf(m, __uint_as_float(va[j]));
+            }
+            if (has_b) {
+              tmem_ld_wait();
+              if (c0 + 32 < p.lk_pad) tmem_ld16(taddr + c0 + 32, va);
+              if (c0 + 32 <= ncol) {
+#pragma unroll
+                for (int j = 0; j < 16; ++j) m = fmaxf(m, __uint_as_float(vb[j]));
+              } else {
+#pragma unroll
+                for (int j = 0; j < 16; ++j)
+                  if (c0 + 16 + j < ncol) m = fmaxf(m, __uint_as_float(vb[j]));
+              }
+            }
+          }
+          // pass 2: P = exp2(s c - m c) as bf16 pairs over the columns already consumed; fp32 row sum
+          mc = m * p.scale_log2;
+          uint32_t v[16], w[16];
+          tmem_ld16(taddr, v);
+          for (int c0 = 0; c0 < p.lk_pad; c0 += 16) {
+            tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 16; ++j) w[j] = v[j];
+            if (c0 + 16 < p.lk_pad) tmem_ld16(taddr + c0 + 16, v);
+            float e[16];
+            if (c0 + 16 <= ncol) {
+#pragma unroll
+              for (int j = 0; j < 16; ++j) e[j] = fast_exp2(fmaf(__uint_as_float(w[j]), p.scale_log2, -mc));
+            } else {
+#pragma unroll
+              for (int j = 0; j < 16; ++j)
+                e[j] = (c0 + j < ncol) ? fast_exp2(fmaf(__uint_as_float(w[j]), p.scale_log2, -mc)) : 0.f;
+            }
+            uint32_t pk[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              sum += e[2 * j] + e[2 * j + 1];
+              pk[j] = pack2(e[2 * j], e[2 * j + 1]);
+            }
+            tmem_st8(taddr + (c0 >> 1), pk);
           }
         }
-        // pass 2: P = exp2(s c - m c) as bf16 pairs over the columns already consumed; fp32 row sum
-        const float mc = m * p.scale_log2;
-        float sum = 0.f;
-        for (int c0 = 0; c0 < p.lk_pad; c0 += 16) {
-          uint32_t v[16];
-          tmem_ld16(taddr + c0, v);
-          tmem_ld_wait();
-          float e[16];
-          if (c0 + 16 <= ncol) {
-#pragma unroll
-            for (int j = 0; j < 16; ++j) e[j] = fast_exp2(fmaf(__uint_as_float(v[j]), p.scale_log2, -mc));
-          } else {
-#pragma unroll
-            for (int j = 0; j < 16; ++j)
-              e[j] = (c0 + j < ncol) ? fast_exp2(fmaf(__uint_as_float(v[j]), p.scale_log2, -mc)) : 0.f;
-          }
-          uint32_t pk[8];
-#pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            sum += e[2 * j] + e[2 * j + 1];
-            pk[j] = pack2(e[2 * j], e[2 * j + 1]);
-          }
-          tmem_st8(taddr + (c0 >> 1), pk);
-        }
+        // row statistics for the epilogue warps (their previous reader, the epilogue of unit n - 2, must be done)
+        if (n >= 2) mbar_wait(&e_done[grp], ((n - 2) >> 1) & 1u, 150 + grp);
+        stat[grp * 128 + row] = make_float2(warp_live ? 1.0f / sum : 0.f, mc + log2f(sum));
         tmem_st_wait();
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(&p_full[t]);
-
-        // epilogue: O / sum -> bf16 row of `out`
-        mbar_wait(&o_full[t], it & 1, 200 + t);
+        if (lane == 0) mbar_arrive(&p_full[grp]);
+      }
+    }
+  } else {
+    // ============================== epilogue: O / sum -> bf16 tile -> TMA store; log-sum-exp ==============================
+    const uint32_t quarter = warp & 3u;
+    const int row = static_cast<int>(quarter * 32u + lane);
+    const uint32_t oaddr = tmem_base + ((quarter * 32u) << 16) + FWD_O_COL;
+    uint8_t* tile = smem + FWD_OFF_OUT;
+    uint8_t* line = tile + row * ROW_BYTES;
+    const bool storer = warp == 10 && lane == 0;
+    uint32_t n = 0;
+    for (int u = blockIdx.x; u < p.total; u += gridDim.x) {
+      const int b = u / p.H, h = u - b * p.H;
+      for (int t = 0; t < nt; ++t, ++n) {
+        mbar_wait(o_full, n & 1u, 200);
         tc_fence_after();
-        const float inv = 1.0f / sum;
-        const bool valid = qi < p.L;
-        const size_t tok = p.batch_first ? (static_cast<size_t>(b) * p.L + qi) : (static_cast<size_t>(qi) * p.B + b);
-        uint4* orow = reinterpret_cast<uint4*>(p.out + (valid ? tok : 0) * p.C + h * HD);
+        const float2 st2 = stat[(n & 1u) * 128 + row];
+        const int qi = t * 128 + row;
+        if (storer) tma_store_wait_read<0>();                // the previous store has finished reading the tile
+        named_bar_sync(2, 128);
 #pragma unroll
         for (int c0 = 0; c0 < HD; c0 += 16) {
           uint32_t v[16];
-          tmem_ld16(taddr + 128 + c0, v);
+          tmem_ld16(oaddr + c0, v);
           tmem_ld_wait();
-          if (valid) {
-            uint4 o0, o1;
-            o0.x = pack2(__uint_as_float(v[0]) * inv, __uint_as_float(v[1]) * inv);
-            o0.y = pack2(__uint_as_float(v[2]) * inv, __uint_as_float(v[3]) * inv);
-            o0.z = pack2(__uint_as_float(v[4]) * inv, __uint_as_float(v[5]) * inv);
-            o0.w = pack2(__uint_as_float(v[6]) * inv, __uint_as_float(v[7]) * inv);
-            o1.x = pack2(__uint_as_float(v[8]) * inv, __uint_as_float(v[9]) * inv);
-            o1.y = pack2(__uint_as_float(v[10]) * inv, __uint_as_float(v[11]) * inv);
-            o1.z = pack2(__uint_as_float(v[12]) * inv, __uint_as_float(v[13]) * inv);
-            o1.w = pack2(__uint_as_float(v[14]) * inv, __uint_as_float(v[15]) * inv);
-            orow[c0 / 8] = o0;
-            orow[c0 / 8 + 1] = o1;
-          }
+          const float inv = st2.x;
+          uint4 o0, o1;
+          o0.x = pack2(__uint_as_float(v[0]) * inv, __uint_as_float(v[1]) * inv);
+          o0.y = pack2(__uint_as_float(v[2]) * inv, __uint_as_float(v[3]) * inv);
+          o0.z = pack2(__uint_as_float(v[4]) * inv, __uint_as_float(v[5]) * inv);
+          o0.w = pack2(__uint_as_float(v[6]) * inv, __uint_as_float(v[7]) * inv);
+          o1.x = pack2(__uint_as_float(v[8]) * inv, __uint_as_float(v[9]) * inv);
+          o1.y = pack2(__uint_as_float(v[10]) * inv, __uint_as_float(v[11]) * inv);
+          o1.z = pack2(__uint_as_float(v[12]) * inv, __uint_as_float(v[13]) * inv);
+          o1.w = pack2(__uint_as_float(v[14]) * inv, __uint_as_float(v[15]) * inv);
+          const int ch = c0 >> 3;
+          *reinterpret_cast<uint4*>(line + (((ch) ^ (row & 7)) << 4)) = o0;
+          *reinterpret_cast<uint4*>(line + (((ch + 1) ^ (row & 7)) << 4)) = o1;
         }
-        if (valid) p.lse[static_cast<size_t>(u) * p.L + qi] = mc + log2f(sum);
+        // O and the statistics of this unit are consumed: the next P V / the next softmax of this parity may proceed
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(&t_free[t]);
+        if (lane == 0) mbar_arrive(&e_done[n & 1u]);
+        if (qi < p.L) p.lse[static_cast<size_t>(u) * p.L + qi] = st2.y;
+        fence_proxy_async_smem();
+        named_bar_sync(2, 128);
+        if (storer) {
+          tma_store_3d(&tm_out, tile, h * HD, t * 128, b);   // rows past the sequence end are clipped
+          tma_store_commit();
+        }
       }
     }
+    if (storer) tma_store_wait_all<0>();
   }
   __syncwarp();
   tc_fence_before();
@@ -696,21 +758,21 @@ int ffm_attention_fwd(const void* qkv, void* out, float* lse, int B, int L, int 
   int rc = att::set_smem_once();
   if (rc != FFM_OK) return rc;
   att::FwdParams p;
-  p.out = static_cast<__nv_bfloat16*>(out);
   p.lse = lse;
   p.B = B; p.L = L; p.H = H; p.C = H * att::HD; p.batch_first = batch_first ? 1 : 0;
   p.lk_pad = (L + 15) / 16 * 16;
   p.n_tiles = L > 128 ? 2 : 1;
   p.total = B * H;
   p.scale_log2 = att::LOG2E / sqrtf(static_cast<float>(att::HD));
-  CUtensorMap tm_q, tm_kv;
+  CUtensorMap tm_q, tm_kv, tm_out;
   if ((rc = att::make_map_tokens(&tm_q, qkv, B, L, 3 * p.C, p.batch_first, 128 * p.n_tiles))) return rc;
   if ((rc = att::make_map_tokens(&tm_kv, qkv, B, L, 3 * p.C, p.batch_first, p.lk_pad))) return rc;
+  if ((rc = att::make_map_tokens(&tm_out, out, B, L, p.C, p.batch_first, 128))) return rc;
   const int grid = p.total < num_sms() ? p.total : num_sms();
   if (causal)
-    att::attention_fwd_tc_kernel<true><<<grid, att::FWD_THREADS, att::FWD_SMEM, stream>>>(tm_q, tm_kv, p);
+    att::attention_fwd_tc_kernel<true><<<grid, att::FWD_THREADS, att::FWD_SMEM, stream>>>(tm_q, tm_kv, tm_out, p);
   else
-    att::attention_fwd_tc_kernel<false><<<grid, att::FWD_THREADS, att::FWD_SMEM, stream>>>(tm_q, tm_kv, p);
+    att::attention_fwd_tc_kernel<false><<<grid, att::FWD_THREADS, att::FWD_SMEM, stream>>>(tm_q, tm_kv, tm_out, p);
   FFM_CHECK_CUDA(cudaGetLastError());
   count_launch();
   return FFM_OK;

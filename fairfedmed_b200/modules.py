@@ -128,7 +128,20 @@ class _AdapterBase(nn.Module):
                                "(the CPU oracle lives under oracle/ and is test infrastructure only)")
         w, w_t, bias = self._operands()
         row_div = 1
-        if batch_first:
+        if self.is_1x1_conv and x.dim() == 4:
+            # a 1x1 convolution is a linear layer over the B*H*W pixels.  The reference walks them as [hw, b, c]
+            # (:469-471, a permute copy each way); in channels-last memory the pixels of one image are already rows of
+            # a [b, hw, c] matrix, so the kernel reads / writes the activations in place and is told through row_div
+            # which sample a row belongs to: no layout copies around the 32 adapted convolutions of the ResNet trunk.
+            b, c, h, wd = x.shape
+            xc = x.contiguous(memory_format=torch.channels_last)
+            x2d = xc.permute(0, 2, 3, 1).reshape(b * h * wd, c)
+            x2d = (x2d if x2d.dtype == torch.bfloat16 else x2d.to(torch.bfloat16)).contiguous()
+            bp, row_div = b, h * wd
+
+            def restore(y2d):
+                return y2d.view(b, h, wd, -1).permute(0, 3, 1, 2)      # logical NCHW, channels-last memory
+        elif batch_first:
             if self.is_1x1_conv or x.dim() != 3:
                 raise ValueError("batch_first adapters take [B', L, C] token tensors")
             bp, row_div = x.shape[0], x.shape[1]
