@@ -35,6 +35,7 @@ SIGNATURES = {
                             _i, _i, _i, _i, _i, _i, _i, _i, _f, _vp]),
     "ffm_svlora_bwd_phase": (_i, [_vp, _vp, _vp, _fp, _fp, _fp, _fp, _vp, _vp, _vp, _vp, _fp, _fp, _fp, _vp, _sz,
                                   _i, _i, _i, _i, _i, _i, _i, _i, _f, _i, _vp]),
+    "ffm_frozen_linear": (_i, [_vp, _vp, _fp, _vp, _i, _i, _i, _vp]),
     "ffm_add_layernorm_fwd": (_i, [_vp, _vp, _fp, _fp, _vp, _vp, _fp, _fp, _i, _i, _f, _vp]),
     "ffm_add_layernorm_bwd": (_i, [_vp, _vp, _vp, _fp, _fp, _fp, _vp, _i, _i, _vp]),
     "ffm_attention_max_len": (_i, []),

@@ -32,6 +32,9 @@ PIXEL_STD = (0.26862954, 0.26130258, 0.27577711)
 # attention core: "own" = csrc/attention.cu (scope row f1: tcgen05 / TMEM forward + backward, packed dq/dk/dv,
 # deterministic), "lib" = torch SDPA (cuDNN) kept as an A/B switch.
 OWN_ATTENTION = os.environ.get("FFM_ATTENTION", "own") == "own"
+# in_proj / out_proj of the image tower: "own" = ffm_frozen_linear (the fused GEMM built without the adapter side product),
+# "lib" = cuBLAS through F.linear
+OWN_PROJ = os.environ.get("FFM_PROJ", "own") == "own"
 _SIDE_STREAMS: dict = {}     # (device index, role) -> side stream (module level: models stay picklable)
 
 
@@ -53,6 +56,17 @@ class _Bf16Cache:
         hit = store.get(name)
         if hit is None or hit[0] != key:
             store[name] = (key, tensor.detach().to(dtype).contiguous())
+            hit = store[name]
+        return hit[1]
+
+
+    def _bf_t(self, name: str, tensor: torch.Tensor):
+        """bf16 copy of the TRANSPOSE of a frozen 2-D weight (the dX operand of ops.frozen_linear)."""
+        store = self.__dict__.setdefault("_bf_store", {})
+        key = (tensor.data_ptr(), tensor._version, tensor.device, "t")
+        hit = store.get(name)
+        if hit is None or hit[0] != key:
+            store[name] = (key, tensor.detach().t().to(torch.bfloat16).contiguous())
             hit = store[name]
         return hit[1]
 
@@ -157,6 +171,12 @@ class ResidualAttentionBlock(nn.Module, _Bf16Cache):
     def _proj(self, adapter, name, x, weight, bias, attr):
         if adapter is not None:            # raises on CPU tensors: no silent un-adapted fallback
             return adapter(x, attr, batch_first=self.batch_first)
+        if OWN_PROJ and x.is_cuda and x.dtype == torch.bfloat16 and self.attn_mask is None \
+                and weight.shape[0] % 8 == 0 and weight.shape[1] % 8 == 0 and not weight.requires_grad:
+            # image tower (no causal mask): frozen projections on the package's own tcgen05 GEMM
+            w = self._bf(name + "_w", weight, torch.bfloat16)
+            w_t = self._bf_t(name + "_wt", weight)
+            return ops.frozen_linear(x, w, w_t, None if bias is None else self._bf(name + "_bf", bias, torch.float32))
         return F.linear(x, self._bf(name + "_w", weight, x.dtype), self._bf(name + "_b", bias, x.dtype))
 
     def attention(self, x: torch.Tensor, attr: Optional[torch.Tensor] = None):

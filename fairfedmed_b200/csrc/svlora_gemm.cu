@@ -139,7 +139,9 @@ constexpr int EPI_THREADS = 256;
 constexpr int Z_THREADS = 128;     // epilogue threads that write the Z tile (one per tile row)
 
 
-template <int ACT, int R>
+// ADAPT = false: the same pipeline for a FROZEN linear without an adapter (in_proj / out_proj of the attention blocks):
+// no Aside k-slices, UMMA N = 192, no H -> Z -> fix-up chain — the epilogue starts as soon as the mainloop commits.
+template <int ACT, int R, bool ADAPT = true>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 svlora_gemm_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_w,
                    const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b,
@@ -147,7 +149,9 @@ svlora_gemm_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_consta
                    const GemmParams p) {
   using C = GemmCfg<R>;
   constexpr int STAGES = C::STAGES, STAGE_BYTES = C::STAGE_BYTES, Z_TILE_BYTES = C::Z_TILE_BYTES;
-  constexpr int BS_TILE_BYTES = C::BS_TILE_BYTES, NUM_BARS = C::NUM_BARS, UMMA_N_MAIN = C::UMMA_N_MAIN;
+  constexpr int BS_TILE_BYTES = C::BS_TILE_BYTES, NUM_BARS = C::NUM_BARS;
+  constexpr int UMMA_N_MAIN = ADAPT ? C::UMMA_N_MAIN : BN;
+  constexpr int LOAD_BYTES = ADAPT ? STAGE_BYTES : (X_TILE_BYTES + W_TILE_BYTES);
   constexpr int OFF_STAGES = C::OFF_STAGES, OFF_OUT = C::OFF_OUT, OFF_Z = C::OFF_Z, OFF_BS = C::OFF_BS;
   constexpr int OFF_BIAS = C::OFF_BIAS, OFF_BAR = C::OFF_BAR;
   extern __shared__ uint8_t smem_raw[];
@@ -170,8 +174,10 @@ svlora_gemm_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_consta
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tm_x);
     tma_prefetch_desc(&tm_w);
-    tma_prefetch_desc(&tm_a);
-    tma_prefetch_desc(&tm_b);
+    if (ADAPT) {
+      tma_prefetch_desc(&tm_a);
+      tma_prefetch_desc(&tm_b);
+    }
     tma_prefetch_desc(&tm_y);
     if (p.has_pre) tma_prefetch_desc(&tm_y2);
   }
@@ -211,10 +217,10 @@ svlora_gemm_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_consta
           if (p.dbg & 2) {
             mbar_arrive(&full_bar[stage]);
           } else {
-            mbar_arrive_expect_tx(&full_bar[stage], STAGE_BYTES);
+            mbar_arrive_expect_tx(&full_bar[stage], LOAD_BYTES);
             tma_load_2d(st, &tm_x, &full_bar[stage], kb * BK, m_blk * BM);
             tma_load_2d(st + X_TILE_BYTES, &tm_w, &full_bar[stage], kb * BK, n_blk * BN);
-            tma_load_2d(st + X_TILE_BYTES + W_TILE_BYTES, &tm_a, &full_bar[stage], kb * BK, 0);
+            if (ADAPT) tma_load_2d(st + X_TILE_BYTES + W_TILE_BYTES, &tm_a, &full_bar[stage], kb * BK, 0);
           }
         }
         __syncwarp();
@@ -257,15 +263,17 @@ svlora_gemm_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_consta
       const uint32_t aph = (it >> 1) & 1u;
       mbar_wait_uniform(&tmem_empty[s], aph ^ 1u);   // epilogue drained tile it-2 (=> Bside[s], Z[s] free)
       tc_fence_after();
-      if (elect_one()) {
-        mbar_arrive_expect_tx(&bs_full[s], BS_TILE_BYTES);
-        tma_load_2d(smem + OFF_BS + s * BS_TILE_BYTES, &tm_b, &bs_full[s], 0, n_blk * BN);
+      if (ADAPT) {
+        if (elect_one()) {
+          mbar_arrive_expect_tx(&bs_full[s], BS_TILE_BYTES);
+          tma_load_2d(smem + OFF_BS + s * BS_TILE_BYTES, &tm_b, &bs_full[s], 0, n_blk * BN);
+        }
+        __syncwarp();
       }
-      __syncwarp();
 
       const uint32_t d_tmem = tmem_base + s * ACC_COLS;
       for (int kb = 0; kb < p.k_blocks; ++kb) {
-        if (pend >= 0) {
+        if (ADAPT && pend >= 0) {
           // Z of the previous tile ready?  (vote keeps the decision warp-uniform for the compiler)
           if (__all_sync(0xffffffffu, mbar_test_wait(&z_full[pend], pend_phase))) {
             fixup(pend, pend_phase);
@@ -290,6 +298,11 @@ svlora_gemm_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_consta
         __syncwarp();
         if (++stage == STAGES) { stage = 0; phase ^= 1u; }
       }
+      if (!ADAPT) {
+        if (elect_one()) umma_commit(&d_full[s]);     // no fix-up: the accumulator is final
+        __syncwarp();
+        continue;
+      }
       if (elect_one()) umma_commit(&h_full[s]);
       __syncwarp();
       if (pend >= 0) {
@@ -299,7 +312,7 @@ svlora_gemm_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_consta
       pend = s;
       pend_phase = aph;
     }
-    if (pend >= 0) {
+    if (ADAPT && pend >= 0) {
       mbar_wait_uniform(&z_full[pend], pend_phase);
       fixup(pend, pend_phase);
     }
@@ -334,7 +347,7 @@ svlora_gemm_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_consta
         bias_w[pc * EPI_PIECE_COLS + lane] = (p.bias != nullptr && col < p.N) ? __ldg(p.bias + col) : 0.0f;
       }
 
-      if (half == 0) {
+      if (ADAPT && half == 0) {
         // ---- H -> Z (SW32 K-major A operand of the fix-up UMMA) ----
         // this row's scaled singular values first: their global-load latency hides behind the wait for H
         const int grow_c = grow < p.T ? grow : (p.T - 1);
@@ -543,17 +556,22 @@ int gemm_debug_mask() {
   return v;
 }
 
-template <int R>
+template <int R, bool ADAPT = true>
 static int launch_single(const GemmOperands& o, const GemmParams& p0, cudaStream_t stream) {
   using C = GemmCfg<R>;
   CUtensorMap tm_x, tm_w, tm_a, tm_b, tm_y, tm_y2;
   int rc;
   if ((rc = make_map_bf16(&tm_x, o.x, o.T, o.K, BM, BK, CU_TENSOR_MAP_SWIZZLE_128B, true))) return rc;
   if ((rc = make_map_bf16(&tm_w, o.wmat, o.N, o.K, BN, BK, CU_TENSOR_MAP_SWIZZLE_128B, true))) return rc;
-  if ((rc = make_map_bf16(&tm_a, o.a_side, R, o.K, R, BK, CU_TENSOR_MAP_SWIZZLE_128B, true))) return rc;
-  if ((rc = make_map_bf16(&tm_b, o.b_side, o.N, R, BN, R, R == 16 ? CU_TENSOR_MAP_SWIZZLE_32B : CU_TENSOR_MAP_SWIZZLE_64B,
-                          false)))
-    return rc;
+  if (ADAPT) {
+    if ((rc = make_map_bf16(&tm_a, o.a_side, R, o.K, R, BK, CU_TENSOR_MAP_SWIZZLE_128B, true))) return rc;
+    if ((rc = make_map_bf16(&tm_b, o.b_side, o.N, R, BN, R,
+                            R == 16 ? CU_TENSOR_MAP_SWIZZLE_32B : CU_TENSOR_MAP_SWIZZLE_64B, false)))
+      return rc;
+  } else {
+    tm_a = tm_w;      // never dereferenced by the ADAPT = false build
+    tm_b = tm_w;
+  }
   if ((rc = make_map_bf16(&tm_y, o.out, o.T, o.N, 32, EPI_PIECE_COLS, CU_TENSOR_MAP_SWIZZLE_64B, false))) return rc;
   const bool has_pre = p0.has_pre != 0;
   if ((rc = make_map_bf16(&tm_y2, has_pre ? o.out_pre : o.out, o.T, o.N, 32, EPI_PIECE_COLS, CU_TENSOR_MAP_SWIZZLE_64B,
@@ -570,12 +588,14 @@ static int launch_single(const GemmOperands& o, const GemmParams& p0, cudaStream
     int dev = 0;
     FFM_CHECK_CUDA(cudaGetDevice(&dev));
     if (dev != attr_dev) {
-      FFM_CHECK_CUDA(cudaFuncSetAttribute(svlora_gemm_kernel<ACT_NONE, R>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                          C::SMEM_BYTES));
-      FFM_CHECK_CUDA(cudaFuncSetAttribute(svlora_gemm_kernel<ACT_QUICKGELU, R>,
+      FFM_CHECK_CUDA(cudaFuncSetAttribute(svlora_gemm_kernel<ACT_NONE, R, ADAPT>,
                                           cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
-      FFM_CHECK_CUDA(cudaFuncSetAttribute(svlora_gemm_kernel<ACT_QUICKGELU_GRAD, R>,
-                                          cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
+      if (ADAPT) {
+        FFM_CHECK_CUDA(cudaFuncSetAttribute(svlora_gemm_kernel<ACT_QUICKGELU, R, true>,
+                                            cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
+        FFM_CHECK_CUDA(cudaFuncSetAttribute(svlora_gemm_kernel<ACT_QUICKGELU_GRAD, R, true>,
+                                            cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
+      }
       attr_dev = dev;
     }
   }
@@ -583,6 +603,13 @@ static int launch_single(const GemmOperands& o, const GemmParams& p0, cudaStream
   const int grid = tiles < num_sms() ? tiles : num_sms();
   GemmProfileScope prof;
   if ((rc = gemm_profile_begin(&prof, stream))) return rc;
+  if constexpr (!ADAPT) {
+    svlora_gemm_kernel<ACT_NONE, R, false><<<grid, NUM_THREADS, C::SMEM_BYTES, stream>>>(tm_x, tm_w, tm_a, tm_b, tm_y,
+                                                                                         tm_y2, p);
+    FFM_CHECK_CUDA(cudaGetLastError());
+    count_launch();
+    return gemm_profile_end(&prof, o.T, o.K, o.N, stream);
+  }
   switch (p.act) {
     case ACT_QUICKGELU:
       svlora_gemm_kernel<ACT_QUICKGELU, R><<<grid, NUM_THREADS, C::SMEM_BYTES, stream>>>(tm_x, tm_w, tm_a, tm_b, tm_y,
@@ -781,6 +808,24 @@ int ffm_svlora_fwd(const void* x, const void* w, const float* bias, const float*
   o.T = T; o.K = K; o.N = N; o.b_prime = b_prime; o.num_slices = num_slices; o.row_div = row_div; o.act = act;
   o.rp = rp;
   return launch_svlora_gemm(o, stream);
+}
+
+int ffm_frozen_linear(const void* x, const void* w, const float* bias, void* y, int T, int K, int N, cudaStream_t stream) {
+  FFM_CHECK_ARG(x && w && y, "ffm_frozen_linear: null pointer argument");
+  FFM_CHECK_ARG(T > 0 && K > 0 && N > 0 && K % 8 == 0 && N % 8 == 0,
+                "ffm_frozen_linear: T, K, N must be positive and K (%d), N (%d) multiples of 8", K, N);
+  const uintptr_t align_or = reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(w) | reinterpret_cast<uintptr_t>(y);
+  FFM_CHECK_ARG((align_or & 15u) == 0, "ffm_frozen_linear: device pointers must be 16-byte aligned");
+  GemmOperands o;
+  o.x = x; o.wmat = w; o.a_side = nullptr; o.b_side = nullptr; o.s_rows = nullptr; o.bias = bias;
+  o.out = y; o.out_pre = nullptr; o.h_out = nullptr; o.z_out = nullptr; o.aux = nullptr;
+  o.T = T; o.K = K; o.N = N; o.b_prime = 1; o.num_slices = 1; o.row_div = 1; o.act = ACT_NONE; o.rp = RP;
+  GemmParams p;
+  p.bias = bias; p.s_rows = nullptr; p.h_out = nullptr; p.z_out = nullptr; p.aux = nullptr;
+  p.T = T; p.K = K; p.N = N; p.rp = RP; p.b_prime = 1; p.num_slices = 1; p.row_div = 1; p.act = ACT_NONE; p.has_pre = 0;
+  p.m_tiles = p.n_tiles = p.k_blocks = 0;
+  p.dbg = gemm_debug_mask();
+  return launch_single<RP, false>(o, p, stream);
 }
 
 int ffm_svlora_bwd(const void* dy, const void* x, const void* w_t, const float* lora_a, const float* lora_b,

@@ -302,6 +302,46 @@ def svlora_linear(x2d: Tensor, w: Tensor, w_t: Tensor, bias: Optional[Tensor], l
     return _SVLoRALinear.apply(x2d, w, w_t, bias, lora_a, lora_b, s_eff, scaling, b_prime, num_slices, row_div)
 
 
+@torch.library.custom_op("ffm::frozen_linear", mutates_args=())
+def frozen_linear_op(x2d: Tensor, w: Tensor, bias: Optional[Tensor]) -> Tensor:
+    """y [T, N] = x2d [T, K] · w [N, K]^T + bias (bf16 in / out, fp32 bias): ffm_frozen_linear."""
+    _need_cuda(x2d, w, bias)
+    T, K = x2d.shape
+    N = w.shape[0]
+    y = torch.empty((T, N), device=x2d.device, dtype=torch.bfloat16)
+    _cabi.call("ffm_frozen_linear", _ptr(x2d), _ptr(w), _ptr(bias), _ptr(y), T, K, N, _stream())
+    return y
+
+
+@frozen_linear_op.register_fake
+def _(x2d, w, bias):
+    return x2d.new_empty((x2d.shape[0], w.shape[0]))
+
+
+class _FrozenLinear(torch.autograd.Function):
+    """A frozen projection on the library's own GEMM: forward x W^T + b, backward dx = dy W (the same kernel on W^T)."""
+
+    @staticmethod
+    def forward(ctx, x2d, w, w_t, bias):
+        ctx.save_for_backward(w_t)
+        return frozen_linear_op(x2d, w, bias)
+
+    @staticmethod
+    def backward(ctx, dy):
+        (w_t,) = ctx.saved_tensors
+        dy = dy.contiguous()
+        if dy.dtype != torch.bfloat16:
+            dy = dy.to(torch.bfloat16)
+        return frozen_linear_op(dy, w_t, None), None, None, None
+
+
+def frozen_linear(x: Tensor, w: Tensor, w_t: Tensor, bias: Optional[Tensor]) -> Tensor:
+    """x [..., K] bf16, w [N, K] / w_t [K, N] bf16 copies of a frozen weight, bias fp32 or None -> [..., N] bf16."""
+    lead = x.shape[:-1]
+    y = _FrozenLinear.apply(x.reshape(-1, x.shape[-1]).contiguous(), w, w_t, bias)
+    return y.reshape(*lead, -1)
+
+
 # adapter-gradient kernels of the fused MLP leave the dX critical path (see _SVLoRAMLP.backward); FFM_PARAMS_SIDE=0: A/B
 PARAMS_ON_SIDE_STREAM = os.environ.get("FFM_PARAMS_SIDE", "1") != "0"
 _PARAM_STREAMS: dict = {}

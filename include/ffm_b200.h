@@ -152,6 +152,15 @@ int ffm_add_layernorm_fwd(const void* x, const void* res, const float* gamma, co
 int ffm_add_layernorm_bwd(const void* d_ln, const void* d_res, const void* s, const float* gamma, const float* mean,
                           const float* rstd, void* dx, int rows, int C, ffm_stream_t stream);
 
+/* ------------------------------------------------- frozen projections (scope row f1) ---------- */
+/*
+ * y[T, N] = x[T, K] · w[N, K]^T + bias — the in_proj / out_proj of nn.MultiheadAttention inside
+ * ResidualAttentionBlock (clip/model.py:350-352) on the same tcgen05 / TMA pipeline as ffm_svlora_fwd, built without the
+ * adapter side product (UMMA N = 192, no fix-up).  The backward of a frozen projection is the same call on the
+ * transposed weight: dx[T, K] = dy[T, N] · w_t[K, N]^T.  bf16 operands, fp32 bias (or NULL), bf16 result.
+ */
+int ffm_frozen_linear(const void* x, const void* w, const float* bias, void* y, int T, int K, int N, ffm_stream_t stream);
+
 /* ------------------------------------------------- frozen attention core (scope row f1) ------- */
 /*
  * softmax(Q K^T / sqrt(head_dim)) V per (sample, head) — the core of nn.MultiheadAttention as ResidualAttentionBlock

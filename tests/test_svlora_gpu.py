@@ -27,6 +27,9 @@ def _dev():
     return torch.device("cuda:0")
 
 
+DEV = "cuda:0"
+
+
 def _close_bf16(got, ref, what):
     ref = torch.as_tensor(ref).float().to(got.device)
     got = got.float()
@@ -236,3 +239,81 @@ def test_invalid_arguments_raise():
         ops.svlora_fwd(x, W, None, A, Bm, s[:2].contiguous(), 0.1, 8, 1, 0)
     with pytest.raises(_cabi.FfmError, match="CUDA tensors only"):
         ops.svlora_fwd(x.cpu(), W, None, A, Bm, s, 0.1, 8, 1, 0)
+
+
+def test_adapt_attention_opt_in_matches_oracle():
+    """North-star opt-in: FairLoRA on in_proj (C -> 3C) and out_proj of an image-tower block, batch-first
+    rows as inside the tower.  The block's attention branch must equal the oracle's composition
+    fairlora_linear -> attention_core -> fairlora_linear (trainers/GLP_OT_SVLoRA.py:450-482 applied to the two projections of
+    clip/model.py:350-352), forward and adapter / input gradients, within the bf16 budget of the fused linear."""
+    from fairfedmed_b200 import clip_model, modules
+    from oracle import ref_port as rp
+    g = torch.Generator().manual_seed(21)
+    C, H, L, B, G, r = 256, 4, 37, 6, 3, 12
+    blk = clip_model.ResidualAttentionBlock(C, H, batch_first=True)
+    holder = torch.nn.Module()
+    holder.image_encoder = torch.nn.Module()
+    holder.image_encoder.blk = blk
+    with torch.no_grad():
+        for p_ in blk.parameters():
+            p_.copy_(p_.bfloat16().float())
+            p_.requires_grad_(False)
+    modules.apply_lora_to_model(holder, True, rank=r, alpha=2.0, lora_type="FairLoRA", num_attrs=G, adapt_attention=True)
+    assert isinstance(blk.attn_in_lora, modules.FairLoRALinear) and isinstance(blk.attn_out_lora, modules.FairLoRALinear)
+    blk.to(DEV)
+    with torch.no_grad():
+        for ad in (blk.attn_in_lora, blk.attn_out_lora):
+            ad.lora_A.weight.copy_((0.05 * torch.randn(ad.lora_A.weight.shape, generator=g)).bfloat16().float())
+            ad.lora_B.weight.copy_((0.3 * torch.randn(ad.lora_B.weight.shape, generator=g)).bfloat16().float())
+    x = torch.randn(B, L, C, generator=g).bfloat16()
+    attr = torch.randint(0, G, (B,), generator=g)
+    d_out = torch.randn(B, L, C, generator=g)
+    xg = x.to(DEV).requires_grad_(True)
+    y = blk.attention(xg, attr)                                           # [B, L, C]
+    (y.float() * d_out.to(DEV)).sum().backward()
+
+    # oracle, sequence-first fp32
+    xo = x.float().transpose(0, 1).contiguous().requires_grad_(True)      # [L, B, C]
+    a = blk.attn
+    P = {}
+    for name, ad in (("in", blk.attn_in_lora), ("out", blk.attn_out_lora)):
+        for k in ("lora_A", "lora_S", "lora_B"):
+            P[name + k] = getattr(ad, k).weight.detach().cpu().clone().requires_grad_(True)
+    qkv = rp.fairlora_linear(xo, a.in_proj_weight.detach().cpu(), a.in_proj_bias.detach().cpu(), P["inlora_A"],
+                             P["inlora_S"], P["inlora_B"], attr, 2.0 / r)
+    core = rp.attention_core(qkv, H, None)
+    yo = rp.fairlora_linear(core, a.out_proj.weight.detach().cpu(), a.out_proj.bias.detach().cpu(), P["outlora_A"],
+                            P["outlora_S"], P["outlora_B"], attr, 2.0 / r)
+    (yo * d_out.transpose(0, 1)).sum().backward()
+
+    def close(got, ref, tol, what):
+        err = float((got.float().cpu() - ref).abs().max())
+        assert err <= tol * float(ref.abs().max()) + 1e-6, f"{what}: {err:.3e} vs max {float(ref.abs().max()):.3e}"
+
+    close(y.detach().transpose(0, 1), yo.detach(), 3e-2, "attention branch output")
+    close(xg.grad.transpose(0, 1), xo.grad, 4e-2, "dx")
+    for name, ad in (("in", blk.attn_in_lora), ("out", blk.attn_out_lora)):
+        close(ad.lora_A.weight.grad, P[name + "lora_A"].grad, 4e-2, name + " dA")
+        close(ad.lora_B.weight.grad, P[name + "lora_B"].grad, 4e-2, name + " dB")
+        close(ad.lora_S.weight.grad, P[name + "lora_S"].grad, 5e-2, name + " dS")
+
+
+@pytest.mark.parametrize("T,K,N", [(197 * 8, 768, 2304), (197 * 8, 768, 768), (333, 256, 384), (77, 512, 1536)])
+def test_frozen_linear_matches_fp32(T, K, N):
+    """ffm_frozen_linear (in_proj / out_proj of clip/model.py:350-352 without adapters): y = x W^T + b and dx = dy W against
+    fp32 torch on the same bf16-rounded operands; ragged row / column tiles included."""
+    from fairfedmed_b200 import ops
+    g = torch.Generator().manual_seed(T + N)
+    x = torch.randn(T, K, generator=g).bfloat16()
+    W = (torch.randn(N, K, generator=g) * K ** -0.5).bfloat16()
+    b = torch.randn(N, generator=g)
+    dy = torch.randn(T, N, generator=g).bfloat16()
+    xg = x.to(DEV).requires_grad_(True)
+    y = ops.frozen_linear(xg, W.to(DEV), W.t().contiguous().to(DEV), b.to(DEV))
+    y.backward(dy.to(DEV))
+    ref = x.float() @ W.float().t() + b
+    dref = dy.float() @ W.float()
+    lim = 2.0 ** -7 * ref.abs() + 2e-3 * float(ref.abs().max())
+    assert bool(((y.float().cpu() - ref).abs() <= lim).all())
+    lim = 2.0 ** -7 * dref.abs() + 2e-3 * float(dref.abs().max())
+    assert bool(((xg.grad.float().cpu() - dref).abs() <= lim).all())
