@@ -503,6 +503,15 @@ class CustomCLIP(nn.Module):
             # conv trunk with training-mode BatchNorm over small batches: keep fp32 activations (bf16 only inside the
             # fused adapter kernels), batch statistics amplify bf16 rounding
             feats = self.image_encoder(self.preprocess(image.float()), attr=attr_dev)
+        elif (image.is_cuda and self.is_3d_input and isinstance(ve, ModifiedVisionTransformer) and ve.patch_size % 8 == 0
+              and image.shape[2] % ve.patch_size == 0 and image.shape[3] % ve.patch_size == 0 and image.shape[3] % 4 == 0):
+            # OCT volumes (:681-693): the trainable slice projection with the /255 folded into its weights (a library
+            # convolution), then min-max scaling + mean/std + bf16 cast + im2col as two fused passes (own backward)
+            fast_input = True
+            slices = image.float().reshape(-1, self.dim_per_3d_slice, image.shape[2], image.shape[3])
+            y = F.conv2d(slices, self.proj_per_3d_slice.weight / 255.0, self.proj_per_3d_slice.bias, padding=2)
+            patches = ops.oct_minmax_patchify(y, self.pixel_mean.reshape(-1), self.pixel_std.reshape(-1), ve.patch_size)
+            feats = ve.forward_patches(patches, attr=attr_dev, batch_first=True)
         elif fast_input:
             # /255, mean/std, bf16 cast and im2col in one pass over the raw image
             ve = self.image_encoder

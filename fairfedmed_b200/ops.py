@@ -621,6 +621,65 @@ def _(image, mean, std, patch, div255):
     return image.new_empty((bp, (h // patch) * (w // patch), c * patch * patch), dtype=torch.bfloat16)
 
 
+@torch.library.custom_op("ffm::oct_minmax_patchify", mutates_args=())
+def oct_minmax_patchify_op(y: Tensor, mean: Tensor, std: Tensor, patch: int) -> Tuple[Tensor, Tensor, Tensor]:
+    """patches, lo, hi: per-slice min-max scaling + mean/std + bf16 im2col of y f32 [B', C, H, W] (ffm_oct_minmax_patchify)."""
+    _need_cuda(y, mean, std)
+    if y.dtype != torch.float32 or not y.is_contiguous():
+        raise _cabi.FfmError("oct_minmax_patchify: y must be contiguous fp32 [B', C, H, W]")
+    bp, c, h, w = y.shape
+    out = torch.empty((bp, (h // patch) * (w // patch), c * patch * patch), device=y.device, dtype=torch.bfloat16)
+    lo = torch.empty((bp,), device=y.device, dtype=torch.float32)
+    hi = torch.empty((bp,), device=y.device, dtype=torch.float32)
+    _cabi.call("ffm_oct_minmax_patchify", _ptr(y), _ptr(lo), _ptr(hi), _ptr(out), _ptr(mean), _ptr(std), bp, c, h, w,
+               int(patch), _stream())
+    return out, lo, hi
+
+
+@oct_minmax_patchify_op.register_fake
+def _(y, mean, std, patch):
+    bp, c, h, w = y.shape
+    return (y.new_empty((bp, (h // patch) * (w // patch), c * patch * patch), dtype=torch.bfloat16), y.new_empty((bp,)),
+            y.new_empty((bp,)))
+
+
+@torch.library.custom_op("ffm::oct_input_bwd", mutates_args=())
+def oct_input_bwd_op(d_patches: Tensor, y: Tensor, lo: Tensor, hi: Tensor, std: Tensor, patch: int) -> Tensor:
+    bp, c, h, w = y.shape
+    d_y = torch.empty_like(y)
+    _cabi.call("ffm_oct_input_bwd", _ptr(d_patches), _ptr(y), _ptr(lo), _ptr(hi), _ptr(std), _ptr(d_y), bp, c, h, w,
+               int(patch), _stream())
+    return d_y
+
+
+@oct_input_bwd_op.register_fake
+def _(d_patches, y, lo, hi, std, patch):
+    return torch.empty_like(y)
+
+
+class _OctMinMaxPatchify(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, y, mean, std, patch):
+        patches, lo, hi = oct_minmax_patchify_op(y, mean, std, patch)
+        ctx.save_for_backward(y, lo, hi, std)
+        ctx.patch = patch
+        return patches
+
+    @staticmethod
+    def backward(ctx, d_patches):
+        y, lo, hi, std = ctx.saved_tensors
+        d_patches = d_patches.contiguous()
+        if d_patches.dtype != torch.bfloat16:
+            d_patches = d_patches.to(torch.bfloat16)
+        return oct_input_bwd_op(d_patches, y, lo, hi, std, ctx.patch), None, None, None
+
+
+def oct_minmax_patchify(y: Tensor, mean: Tensor, std: Tensor, patch: int) -> Tensor:
+    """OCT input side after the slice projection (trainers/GLP_OT_SVLoRA.py:686-693): per-slice min-max scaling, CLIP
+    mean/std, bf16 cast and im2col in two passes over y, with the matching fused backward (differentiable in y)."""
+    return _OctMinMaxPatchify.apply(y.contiguous(), mean.float().contiguous(), std.float().contiguous(), int(patch))
+
+
 @torch.library.custom_op("ffm::vit_embed_ln", mutates_args=())
 def vit_embed_ln(patch_emb: Tensor, cls: Tensor, pos: Tensor, g_pre: Tensor, b_pre: Tensor, g_1: Tensor, b_1: Tensor,
                  eps_pre: float, eps_1: float) -> Tuple[Tensor, Tensor]:

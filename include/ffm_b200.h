@@ -205,6 +205,20 @@ int ffm_vit_embed_ln(const void* patch_emb, const float* class_embedding, const 
                      ffm_stream_t stream);
 
 /*
+ * OCT input side — trainers/GLP_OT_SVLoRA.py:686-693 after the trainable slice projection y = proj_per_3d_slice(slices / 255):
+ *   z = (y - amin(y)) / (amax(y) - amin(y) + 1e-5) per slice-image over (C, H, W), then (z - mean[c]) / std[c], cast and
+ *   im2col for the stride-`patch` convolution.
+ * ffm_oct_minmax_patchify: y f32 [Bp, C, H, W] -> lo / hi f32 [Bp] and patches bf16 [Bp*G, C*patch*patch]
+ *   (two launches: one reduction pass, one conversion pass).
+ * ffm_oct_input_bwd: d_patches bf16 (gradient of `patches`) -> d_y f32 [Bp, C, H, W], including the min / max terms
+ *   (torch.amin / amax split the gradient evenly among the pixels attaining the extremum); deterministic.
+ */
+int ffm_oct_minmax_patchify(const float* y, float* lo, float* hi, void* patches, const float* mean, const float* stdv,
+                            int Bp, int C, int H, int W, int patch, ffm_stream_t stream);
+int ffm_oct_input_bwd(const void* d_patches, const float* y, const float* lo, const float* hi, const float* stdv,
+                      float* d_y, int Bp, int C, int H, int W, int patch, ffm_stream_t stream);
+
+/*
  * Group mixing of singular values — trainers/GLP_OT_SVLoRA.py:453-467.
  *   attr != NULL: pi[b,g] = lambda (0.7 in the reference) if attr[b]==g else (1-lambda)/(G-1)
  *   attr == NULL: n_samples must be 1 and pi = 1/G

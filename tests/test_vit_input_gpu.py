@@ -174,3 +174,40 @@ def test_train_replays_the_graph_and_matches_the_eager_epoch():
         assert lg[ep][-1]["acc"] == pytest.approx(le[ep][-1]["acc"], abs=1e-4)
         assert lg[ep][-1]["auc"] == pytest.approx(le[ep][-1]["auc"], abs=1e-6)
     assert float((tg.flat_params - te.flat_params).abs().max()) <= 2e-5
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("shape,patch", [((6, 3, 32, 32), 8), ((5, 3, 224, 224), 16)])
+def test_oct_minmax_patchify_forward_and_backward_match_autograd(shape, patch):
+    """OCT input side after the slice projection (trainers/GLP_OT_SVLoRA.py:686-693): per-slice min-max scaling, mean / std,
+    cast, im2col — fused forward and backward against autograd over the reference's own expressions (fp32)."""
+    from fairfedmed_b200 import ops
+    torch.manual_seed(5)
+    bp, c, h, w = shape
+    y = torch.randn(shape, device="cuda:0") * 3.0
+    y[0, 0, 0, :4] = y[0].max() + 1.0           # ties at the maximum: amax splits the gradient evenly
+    y[1, 2, 3, 5:7] = y[1].min() - 1.0          # ties at the minimum
+    mean = torch.tensor([0.48, 0.46, 0.41], device="cuda:0")
+    std = torch.tensor([0.27, 0.26, 0.28], device="cuda:0")
+    w_out = torch.randn(bp, (h // patch) * (w // patch), c * patch * patch, device="cuda:0")
+
+    y1 = y.clone().requires_grad_(True)
+    got = ops.oct_minmax_patchify(y1, mean, std, patch)
+    (got.float() * w_out).sum().backward()
+
+    y2 = y.clone().requires_grad_(True)
+    lo = y2.amin(dim=(1, 2, 3), keepdim=True)
+    hi = y2.amax(dim=(1, 2, 3), keepdim=True)
+    z = (y2 - lo) / (hi - lo + 1e-5)
+    z = (z - mean.view(1, 3, 1, 1)) / std.view(1, 3, 1, 1)
+    ref = z.reshape(bp, c, h // patch, patch, w // patch, patch).permute(0, 2, 4, 1, 3, 5).reshape(got.shape)
+    # the fused backward sees the bf16-rounded upstream gradient, so hand the reference the same one
+    (ref * w_out.to(torch.bfloat16).float()).sum().backward()
+
+    assert torch.equal(got, ref.to(torch.bfloat16))
+    scale = float(y2.grad.abs().max())
+    assert float((y1.grad - y2.grad).abs().max()) <= 2e-4 * scale
+    # deterministic: same bits on a second run
+    y3 = y.clone().requires_grad_(True)
+    (ops.oct_minmax_patchify(y3, mean, std, patch).float() * w_out).sum().backward()
+    assert torch.equal(y1.grad, y3.grad)
