@@ -272,7 +272,12 @@ class LoRALinear(_AdapterBase):
         nn.init.normal_(self.lora_B.weight)
 
     def weight(self, x=None, attr=None):
-        return self.original_linear.weight + self.scaling * (self.lora_A.weight @ self.lora_B.weight).t()
+        """Merged weight W + scaling (A B)^T (:236-240): one fused pass with its own backward on the GPU."""
+        w = self.original_linear.weight
+        if not w.is_cuda:
+            raise RuntimeError("fairfedmed_b200 adapters need CUDA tensors: there is no CPU fallback")
+        return ops.lora_merged_weight(w.reshape(self.out_features, self.in_features), self.lora_A.weight,
+                                      self.lora_B.weight, self.scaling)
 
     def forward(self, x, attr=None):
         ones = torch.ones((1, self.rank), device=x.device, dtype=torch.float32)

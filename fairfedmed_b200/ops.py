@@ -444,8 +444,65 @@ def svlora_mlp(x2d, fc, proj, scaling: float, b_prime: int, num_slices: int, row
 
 
 # =====================================================================================================
-# GLP_OT head
+# merged weight of a plain LoRA projection (RN50 attention pool)
 # =====================================================================================================
+@torch.library.custom_op("ffm::lora_merged_weight", mutates_args=())
+def lora_merged_weight_op(w: Tensor, a: Tensor, b: Tensor, scaling: float) -> Tensor:
+    _need_cuda(w, a, b)
+    out_f, in_f = w.shape
+    out = torch.empty_like(w)
+    _cabi.call("ffm_lora_merged_weight", _ptr(w), _ptr(a), _ptr(b), _ptr(out), out_f, in_f, int(a.shape[1]),
+               float(scaling), _stream())
+    return out
+
+
+@lora_merged_weight_op.register_fake
+def _(w, a, b, scaling):
+    return torch.empty_like(w)
+
+
+@torch.library.custom_op("ffm::lora_merged_weight_bwd", mutates_args=())
+def lora_merged_weight_bwd_op(d_wm: Tensor, a: Tensor, b: Tensor, scaling: float) -> Tuple[Tensor, Tensor]:
+    _need_cuda(d_wm, a, b)
+    out_f, in_f = d_wm.shape
+    nbytes = int(_cabi.load().ffm_lora_merged_weight_ws_bytes(in_f))
+    ws = torch.empty((nbytes // 4,), device=d_wm.device, dtype=torch.float32)
+    d_a, d_b = torch.empty_like(a), torch.empty_like(b)
+    _cabi.call("ffm_lora_merged_weight_bwd", _ptr(d_wm), _ptr(a), _ptr(b), _ptr(d_a), _ptr(d_b), _ptr(ws), nbytes, out_f,
+               in_f, int(a.shape[1]), float(scaling), _stream())
+    return d_a, d_b
+
+
+@lora_merged_weight_bwd_op.register_fake
+def _(d_wm, a, b, scaling):
+    return torch.empty_like(a), torch.empty_like(b)
+
+
+class _LoraMergedWeight(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, w, a, b, scaling):
+        ctx.save_for_backward(a, b)
+        ctx.scaling = scaling
+        return lora_merged_weight_op(w, a, b, scaling)
+
+    @staticmethod
+    def backward(ctx, d_wm):
+        a, b = ctx.saved_tensors
+        d_a, d_b = lora_merged_weight_bwd_op(d_wm.float().contiguous(), a, b, ctx.scaling)
+        return None, d_a, d_b, None
+
+
+def lora_merged_weight(w: Tensor, a: Tensor, b: Tensor, scaling: float) -> Tensor:
+    """W + scaling * (A @ B)^T in one pass, with its own deterministic backward for A and B (the frozen W gets no gradient).
+    w f32 [out, in] frozen, a = lora_A.weight f32 [in, r], b = lora_B.weight f32 [r, out]
+    (LoRALinear.weight, trainers/GLP_OT_SVLoRA.py:236-240)."""
+    if w.requires_grad:
+        raise _cabi.FfmError("lora_merged_weight: the base weight must be frozen")
+    if w.dtype != torch.float32 or a.dtype != torch.float32 or b.dtype != torch.float32:
+        raise _cabi.FfmError("lora_merged_weight: fp32 operands expected")
+    return _LoraMergedWeight.apply(w.detach().contiguous(), a.contiguous(), b.contiguous(), float(scaling))
+
+
 # =====================================================================================================
 # residual add + LayerNorm (frozen glue between the adapted MLP and attention)
 # =====================================================================================================

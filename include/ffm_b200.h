@@ -219,6 +219,19 @@ int ffm_oct_input_bwd(const void* d_patches, const float* y, const float* lo, co
                       float* d_y, int Bp, int C, int H, int W, int patch, ffm_stream_t stream);
 
 /*
+ * Merged weight of a plain LoRA projection — LoRALinear.weight(x, attr), trainers/GLP_OT_SVLoRA.py:236-240, consumed by the
+ * RN50 attention pool (clip/model.py:88-97):  out[o, i] = W[o, i] + scaling * sum_j A[i, j] * B[j, o]
+ *   W, out f32 [out_f, in_f]; A = lora_A.weight f32 [in_f, r]; B = lora_B.weight f32 [r, out_f]; r <= 32.
+ * ffm_lora_merged_weight_bwd: dWm f32 [out_f, in_f] -> dA [in_f, r], dB [r, out_f] (deterministic; `ws` of at least
+ * ffm_lora_merged_weight_ws_bytes(in_f) bytes).
+ */
+size_t ffm_lora_merged_weight_ws_bytes(int in_f);
+int ffm_lora_merged_weight(const float* W, const float* A, const float* B, float* out, int out_f, int in_f, int r,
+                           float scaling, ffm_stream_t stream);
+int ffm_lora_merged_weight_bwd(const float* dWm, const float* A, const float* B, float* dA, float* dB, float* ws,
+                               size_t ws_bytes, int out_f, int in_f, int r, float scaling, ffm_stream_t stream);
+
+/*
  * Group mixing of singular values — trainers/GLP_OT_SVLoRA.py:453-467.
  *   attr != NULL: pi[b,g] = lambda (0.7 in the reference) if attr[b]==g else (1-lambda)/(G-1)
  *   attr == NULL: n_samples must be 1 and pi = 1/G

@@ -317,3 +317,28 @@ def test_frozen_linear_matches_fp32(T, K, N):
     assert bool(((y.float().cpu() - ref).abs() <= lim).all())
     lim = 2.0 ** -7 * dref.abs() + 2e-3 * float(dref.abs().max())
     assert bool(((xg.grad.float().cpu() - dref).abs() <= lim).all())
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("out_f,in_f,r", [(1024, 2048, 32), (2048, 2048, 32), (96, 200, 4), (33, 130, 12)])
+def test_lora_merged_weight_matches_reference_expression(out_f, in_f, r):
+    """LoRALinear.weight (trainers/GLP_OT_SVLoRA.py:236-240): W + scaling (A B)^T and its gradients for A and B, fused kernels
+    against autograd over the reference's expression in fp64."""
+    from fairfedmed_b200 import ops
+    torch.manual_seed(3)
+    w = torch.randn(out_f, in_f, device=DEV)
+    a = (0.1 * torch.randn(in_f, r, device=DEV)).requires_grad_(True)
+    b = torch.randn(r, out_f, device=DEV).requires_grad_(True)
+    g = torch.randn(out_f, in_f, device=DEV)
+    scaling = 0.25
+    got = ops.lora_merged_weight(w, a, b, scaling)
+    got.backward(g)
+    a64, b64 = a.detach().double().requires_grad_(True), b.detach().double().requires_grad_(True)
+    ref = w.double() + scaling * (a64 @ b64).t()
+    ref.backward(g.double())
+    torch.testing.assert_close(got.detach().double(), ref.detach(), rtol=1e-5, atol=1e-5)
+    torch.testing.assert_close(a.grad.double(), a64.grad, rtol=1e-4, atol=1e-4 * float(a64.grad.abs().max()))
+    torch.testing.assert_close(b.grad.double(), b64.grad, rtol=1e-4, atol=1e-4 * float(b64.grad.abs().max()))
+    a2, b2 = a.detach().clone().requires_grad_(True), b.detach().clone().requires_grad_(True)
+    ops.lora_merged_weight(w, a2, b2, scaling).backward(g)
+    assert torch.equal(a.grad, a2.grad) and torch.equal(b.grad, b2.grad)      # deterministic reductions
