@@ -44,8 +44,9 @@ SIGNATURES = {
     "ffm_patchify_normalize": (_i, [_fp, _vp, _fp, _fp, _i, _i, _i, _i, _i, _i, _vp]),
     "ffm_vit_embed_ln": (_i, [_vp, _fp, _fp, _fp, _fp, _fp, _fp, _vp, _vp, _fp, _fp, _i, _i, _i, _f, _f, _vp]),
     "ffm_oct_minmax_patchify": (_i, [_fp, _fp, _fp, _vp, _fp, _fp, _i, _i, _i, _i, _i, _vp]),
-    "ffm_oct_input_bwd": (_i, [_vp, _fp, _fp, _fp, _fp, _fp, _i, _i, _i, _i, _i, _vp]),
-    "ffm_lora_merged_weight_ws_bytes": (_sz, [_i]),
+    "ffm_oct_input_bwd_ws_bytes": (_sz, [_i]),
+    "ffm_oct_input_bwd": (_i, [_vp, _fp, _fp, _fp, _fp, _fp, _vp, _sz, _i, _i, _i, _i, _i, _vp]),
+    "ffm_lora_merged_weight_ws_bytes": (_sz, [_i, _i]),
     "ffm_lora_merged_weight": (_i, [_fp, _fp, _fp, _fp, _i, _i, _i, _f, _vp]),
     "ffm_lora_merged_weight_bwd": (_i, [_fp, _fp, _fp, _fp, _fp, _fp, _sz, _i, _i, _i, _f, _vp]),
     "ffm_seff": (_i, [_vp, _fp, _fp, _fp, _i, _i, _i, _f, _vp]),

@@ -10,11 +10,12 @@
 //   expand   : each sample is replicated per (attribute slot a', column c) into a 64-bit key
 //                [ a' : 8 | group+1 : 8 | c : 1 | order-preserving f32 score : 32 | is_positive : 1 ]
 //              (a' = 0 is the "overall" slot; is_positive = (label == c)),
-//   sort     : LSD radix sort, 8-bit digits, 7 passes (stable; per-block digit histograms -> exclusive scan ->
-//              ranked scatter with warp match_any), keys only,
+//   sort     : LSD radix sort, 8-bit digits, 7 passes (stable; per-block digit histograms -> one scan block per digit
+//              -> ranked scatter with warp match_any, digit bases scanned in shared memory), keys only,
 //   prefix   : exclusive prefix count of positives over the sorted keys,
-//   rank     : every positive binary-searches the start of its tie run and of its segment; negatives strictly
-//              below and tied negatives accumulate into 64-bit counters per slot,
+//   rank     : every positive finds the start of its tie run by galloping back from its own position (segment starts
+//              come from a small table); negatives strictly below and tied negatives accumulate into 64-bit counters
+//              per slot,
 //   confusion: tp / fp / tn / fn of pred = argmax(prob) per slot.
 #include <algorithm>
 
@@ -99,12 +100,59 @@ exclusive_scan_kernel(uint32_t* __restrict__ data, int n) {
   }
 }
 
+// block-wide exclusive scan of one value per thread (RS_THREADS threads); returns the exclusive prefix, *total = block sum
+__device__ __forceinline__ uint32_t block_exclusive_scan(uint32_t v, uint32_t* warp_tot, uint32_t* total) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  uint32_t inc = v;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const uint32_t u = __shfl_up_sync(0xffffffffu, inc, o);
+    if (lane >= o) inc += u;
+  }
+  __syncthreads();                    // warp_tot may still be read by the previous call
+  if (lane == 31) warp_tot[warp] = inc;
+  __syncthreads();
+  uint32_t woff = 0, tot = 0;
+#pragma unroll
+  for (int w = 0; w < RS_THREADS / 32; ++w) {
+    const uint32_t t = warp_tot[w];
+    if (w < warp) woff += t;
+    tot += t;
+  }
+  *total = tot;
+  return woff + inc - v;
+}
+
+// one block per digit: exclusive scan of the digit's per-block counts in place (coalesced chunks of RS_THREADS), the
+// digit's total to totals[digit].  256 blocks instead of one: the table scan no longer serialises a pass.
+__global__ void __launch_bounds__(RS_THREADS)
+digit_row_scan_kernel(uint32_t* __restrict__ counts, uint32_t* __restrict__ totals, int nblocks) {
+  __shared__ uint32_t warp_tot[RS_THREADS / 32];
+  uint32_t* row = counts + static_cast<size_t>(blockIdx.x) * nblocks;
+  uint32_t carry = 0;
+  for (int base = 0; base < nblocks; base += RS_THREADS) {
+    const int i = base + threadIdx.x;
+    const uint32_t v = i < nblocks ? row[i] : 0u;
+    uint32_t tot;
+    const uint32_t ex = block_exclusive_scan(v, warp_tot, &tot);
+    if (i < nblocks) row[i] = carry + ex;
+    carry += tot;
+  }
+  if (threadIdx.x == 0) totals[blockIdx.x] = carry;
+}
+
 __global__ void __launch_bounds__(RS_THREADS)
 radix_scatter_kernel(const unsigned long long* __restrict__ keys_in, unsigned long long* __restrict__ keys_out,
-                     const uint32_t* __restrict__ offsets, int shift, int nblocks) {
+                     const uint32_t* __restrict__ offsets, const uint32_t* __restrict__ totals, int shift, int nblocks) {
   __shared__ uint16_t row_cnt[RS_ROWS][256];    // keys of digit d in row r, then exclusive prefix over rows
+  __shared__ uint32_t digit_base[256];          // keys with a smaller digit, over the whole array
+  __shared__ uint32_t warp_tot[RS_THREADS / 32];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   for (int i = threadIdx.x; i < RS_ROWS * 256; i += RS_THREADS) (&row_cnt[0][0])[i] = 0;
+  {
+    uint32_t tot;
+    digit_base[threadIdx.x] = block_exclusive_scan(totals[threadIdx.x], warp_tot, &tot);
+  }
   __syncthreads();
   const size_t base = static_cast<size_t>(blockIdx.x) * RS_CHUNK;
   constexpr int ROWS_PER_WARP = RS_ROWS / (RS_THREADS / 32);
@@ -136,7 +184,8 @@ radix_scatter_kernel(const unsigned long long* __restrict__ keys_in, unsigned lo
   for (int k = 0; k < ROWS_PER_WARP; ++k) {
     const int row = warp * ROWS_PER_WARP + k;
     const uint32_t d = static_cast<uint32_t>(key[k] >> shift) & 0xFF;
-    const uint32_t dst = offsets[static_cast<size_t>(d) * nblocks + blockIdx.x] + row_cnt[row][d] + rank_in_row[k];
+    const uint32_t dst = digit_base[d] + offsets[static_cast<size_t>(d) * nblocks + blockIdx.x] + row_cnt[row][d] +
+                         rank_in_row[k];
     keys_out[dst] = key[k];
   }
 }
@@ -197,23 +246,46 @@ pos_prefix_kernel(const unsigned long long* __restrict__ keys, const uint32_t* _
 }
 
 // ---- rank counts ------------------------------------------------------------------------------------
-__device__ __forceinline__ long long lower_bound_key(const unsigned long long* __restrict__ keys, long long n,
-                                                     unsigned long long target) {
-  long long lo = 0, hi = n;
-  while (lo < hi) {
-    const long long mid = (lo + hi) >> 1;
-    if (keys[mid] < target) lo = mid + 1; else hi = mid;
-  }
-  return lo;
-}
-
 __device__ __forceinline__ int slot_of(int a, int g1, int max_groups) {
   return a == 0 ? 0 : 1 + (a - 1) * (max_groups + 1) + g1;
 }
 
+// first index of every (attribute slot, group, column) segment of the sorted keys: seg_start[slot * 2 + c]
 __global__ void __launch_bounds__(RS_THREADS)
-rank_count_kernel(const unsigned long long* __restrict__ keys, const uint32_t* __restrict__ pos_before, long long E,
-                  unsigned long long* __restrict__ counts, int n_slots, int max_groups) {
+segment_start_kernel(const unsigned long long* __restrict__ keys, long long E, uint32_t* __restrict__ seg_start,
+                     int max_groups) {
+  const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < E; i += stride) {
+    const unsigned long long k = keys[i];
+    if (i > 0 && (keys[i - 1] >> 33) == (k >> 33)) continue;
+    const int g1 = static_cast<int>((k >> 34) & 0xFF);
+    if (g1 > max_groups) continue;
+    seg_start[slot_of(static_cast<int>((k >> 42) & 0xFF), g1, max_groups) * 2 + static_cast<int>((k >> 33) & 1ull)] =
+        static_cast<uint32_t>(i);
+  }
+}
+
+// lower bound of `target` in keys[lo, hi] known to satisfy keys[hi] >= target: gallop back from hi (tie runs are short
+// for real-valued scores: typically one or two probes), then bisect the bracket
+__device__ __forceinline__ long long lower_bound_back(const unsigned long long* __restrict__ keys, long long lo,
+                                                      long long hi, unsigned long long target) {
+  long long step = 1;
+  while (hi - step >= lo && keys[hi - step] >= target) {
+    hi -= step;
+    step <<= 1;
+  }
+  long long l = (hi - step >= lo) ? hi - step + 1 : lo;     // keys[l - 1] < target (or l == lo), keys[hi] >= target
+  while (l < hi) {
+    const long long mid = (l + hi) >> 1;
+    if (keys[mid] < target) l = mid + 1; else hi = mid;
+  }
+  return l;
+}
+
+__global__ void __launch_bounds__(RS_THREADS)
+rank_count_kernel(const unsigned long long* __restrict__ keys, const uint32_t* __restrict__ pos_before,
+                  const uint32_t* __restrict__ seg_start, long long E, unsigned long long* __restrict__ counts,
+                  int n_slots, int max_groups) {
   extern __shared__ unsigned long long cnt_s[];   // [n_slots, 4] : gt0, eq0, gt1, eq1
   for (int i = threadIdx.x; i < n_slots * 4; i += blockDim.x) cnt_s[i] = 0ull;
   __syncthreads();
@@ -225,13 +297,13 @@ rank_count_kernel(const unsigned long long* __restrict__ keys, const uint32_t* _
     const int a = static_cast<int>((k >> 42) & 0xFF);
     if (g1 > max_groups) continue;                          // group id outside the requested range
     const int c = static_cast<int>((k >> 33) & 1ull);
-    const long long seg_lo = lower_bound_key(keys, E, (k >> 33) << 33);
-    const long long run_lo = lower_bound_key(keys, E, k & ~1ull);     // first negative tied with this score
-    const long long run_pos = lower_bound_key(keys, E, k);            // first positive tied with this score
+    const int slot = slot_of(a, g1, max_groups);
+    const long long seg_lo = seg_start[slot * 2 + c];
+    const long long run_pos = lower_bound_back(keys, seg_lo, i, k);              // first positive tied with this score
+    const long long run_lo = lower_bound_back(keys, seg_lo, run_pos, k & ~1ull); // first negative tied with this score
     const unsigned long long pos_between = pos_before[run_lo] - pos_before[seg_lo];
     const unsigned long long gt = static_cast<unsigned long long>(run_lo - seg_lo) - pos_between;
     const unsigned long long eq = static_cast<unsigned long long>(run_pos - run_lo);
-    const int slot = slot_of(a, g1, max_groups);
     atomicAdd(&cnt_s[slot * 4 + c * 2 + 0], gt);
     atomicAdd(&cnt_s[slot * 4 + c * 2 + 1], eq);
   }
@@ -289,12 +361,13 @@ using namespace ffm;
 extern "C" {
 
 size_t ffm_group_auc_workspace_bytes(int N, int n_attr, int max_groups) {
-  (void)max_groups;
   long long E, E_pad;
   int nb;
   auc_sizes(N, n_attr, &E, &E_pad, &nb);
+  const size_t n_slots = 1 + static_cast<size_t>(n_attr) * (max_groups + 1);
   return 2 * a256(static_cast<size_t>(E_pad) * 8) + a256(static_cast<size_t>(256) * nb * 4) +
-         a256(static_cast<size_t>(nb) * 4 + 4) + a256(static_cast<size_t>(E_pad + 1) * 4);
+         a256(static_cast<size_t>(nb) * 4 + 4) + a256(static_cast<size_t>(E_pad + 1) * 4) + a256(256 * 4) +
+         a256(n_slots * 2 * 4);
 }
 
 int ffm_group_auc(const float* prob, const int32_t* label, const int32_t* attrs, uint64_t* counts_out,
@@ -314,7 +387,9 @@ int ffm_group_auc(const float* prob, const int32_t* label, const int32_t* attrs,
   unsigned long long* keys_b = reinterpret_cast<unsigned long long*>(w); w += a256(static_cast<size_t>(E_pad) * 8);
   uint32_t* hist = reinterpret_cast<uint32_t*>(w); w += a256(static_cast<size_t>(256) * nb * 4);
   uint32_t* block_sums = reinterpret_cast<uint32_t*>(w); w += a256(static_cast<size_t>(nb) * 4 + 4);
-  uint32_t* pos_before = reinterpret_cast<uint32_t*>(w);
+  uint32_t* pos_before = reinterpret_cast<uint32_t*>(w); w += a256(static_cast<size_t>(E_pad + 1) * 4);
+  uint32_t* totals = reinterpret_cast<uint32_t*>(w); w += a256(256 * 4);
+  uint32_t* seg_start = reinterpret_cast<uint32_t*>(w);
 
   const int n_slots = 1 + n_attr * (max_groups + 1);
   FFM_CHECK_ARG(static_cast<size_t>(n_slots) * 32 <= 48 * 1024, "ffm_group_auc: too many (attribute, group) slots");
@@ -326,8 +401,8 @@ int ffm_group_auc(const float* prob, const int32_t* label, const int32_t* attrs,
   for (int pass = 0; pass < RS_PASSES; ++pass) {
     const int shift = pass * 8;
     radix_hist_kernel<<<nb, RS_THREADS, 0, stream>>>(src, hist, shift, nb);
-    exclusive_scan_kernel<<<1, 1024, 0, stream>>>(hist, 256 * nb);
-    radix_scatter_kernel<<<nb, RS_THREADS, 0, stream>>>(src, dst, hist, shift, nb);
+    digit_row_scan_kernel<<<256, RS_THREADS, 0, stream>>>(hist, totals, nb);
+    radix_scatter_kernel<<<nb, RS_THREADS, 0, stream>>>(src, dst, hist, totals, shift, nb);
     unsigned long long* t = src; src = dst; dst = t;
   }
   // the padding keys (all ones) also carry digit 0xFF in the 8th byte, so 7 passes keep them at the end
@@ -335,13 +410,14 @@ int ffm_group_auc(const float* prob, const int32_t* label, const int32_t* attrs,
   exclusive_scan_kernel<<<1, 1024, 0, stream>>>(block_sums, nb);
   pos_prefix_kernel<<<nb, RS_THREADS, 0, stream>>>(src, block_sums, pos_before);
   const int rgrid = static_cast<int>(std::min<long long>((E + 255) / 256, 8ll * num_sms()));
+  segment_start_kernel<<<rgrid, RS_THREADS, 0, stream>>>(src, E, seg_start, max_groups);
   rank_count_kernel<<<rgrid, RS_THREADS, static_cast<size_t>(n_slots) * 32, stream>>>(
-      src, pos_before, E, reinterpret_cast<unsigned long long*>(counts_out), n_slots, max_groups);
+      src, pos_before, seg_start, E, reinterpret_cast<unsigned long long*>(counts_out), n_slots, max_groups);
   const int cgrid = std::min((N + 255) / 256, 4 * num_sms());
   confusion_kernel<<<cgrid, RS_THREADS, static_cast<size_t>(n_slots) * 32, stream>>>(
       prob, label, attrs, reinterpret_cast<unsigned long long*>(counts_out), N, n_attr, n_slots, max_groups);
   FFM_CHECK_CUDA(cudaGetLastError());
-  count_launch(1 + 3 * RS_PASSES + 5);
+  count_launch(1 + 3 * RS_PASSES + 6);
   return FFM_OK;
 }
 

@@ -30,11 +30,16 @@ lora_merge_fwd_kernel(const float* __restrict__ W, const float* __restrict__ A, 
     const int j = e / MW_TO, o = e - j * MW_TO;
     B_s[j][o] = (j < r && o0 + o < out_f) ? scaling * __ldg(B + static_cast<size_t>(j) * out_f + o0 + o) : 0.f;
   }
-  __syncthreads();
   const int i = threadIdx.x & (MW_TI - 1), ob = (threadIdx.x >> 7) * 16;
   float acc[16];
+  // the frozen weight first (in flight while the tiles are staged and contracted); the low-rank term accumulates on top
 #pragma unroll
-  for (int k = 0; k < 16; ++k) acc[k] = 0.f;
+  for (int k = 0; k < 16; ++k) {
+    const int o = o0 + ob + k;
+    acc[k] = (i0 + i < in_f && o < out_f) ? __ldg(W + static_cast<size_t>(o) * in_f + i0 + i) : 0.f;
+  }
+  __syncthreads();
+#pragma unroll 4
   for (int j = 0; j < r; ++j) {
     const float a = A_s[i][j];
 #pragma unroll
@@ -51,8 +56,7 @@ lora_merge_fwd_kernel(const float* __restrict__ W, const float* __restrict__ A, 
     for (int k = 0; k < 16; ++k) {
       const int o = o0 + ob + k;
       if (o < out_f) {
-        const size_t idx = static_cast<size_t>(o) * in_f + i0 + i;
-        out[idx] = __ldg(W + idx) + acc[k];
+        out[static_cast<size_t>(o) * in_f + i0 + i] = acc[k];
       }
     }
   }
@@ -79,75 +83,81 @@ lora_merge_da_kernel(const float* __restrict__ dWm, const float* __restrict__ B,
     __syncthreads();
     if (i0 + i < in_f) {
       const int n = min(MW_TO, o_end - ot);
-      for (int o = 0; o < n; ++o) {
-        const float d = __ldg(dWm + static_cast<size_t>(ot + o) * in_f + i0 + i);
+      for (int ob = 0; ob < MW_TO; ob += 8) {
+        float d[8];
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          const float4 b = *reinterpret_cast<const float4*>(&Bt_s[o][jb + 4 * q]);
-          acc[4 * q + 0] = fmaf(d, b.x, acc[4 * q + 0]);
-          acc[4 * q + 1] = fmaf(d, b.y, acc[4 * q + 1]);
-          acc[4 * q + 2] = fmaf(d, b.z, acc[4 * q + 2]);
-          acc[4 * q + 3] = fmaf(d, b.w, acc[4 * q + 3]);
+        for (int u = 0; u < 8; ++u)       // eight independent loads in flight (rows past the range contribute zero)
+          d[u] = (ob + u < n) ? __ldg(dWm + static_cast<size_t>(ot + ob + u) * in_f + i0 + i) : 0.f;
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const float4 b = *reinterpret_cast<const float4*>(&Bt_s[ob + u][jb + 4 * q]);
+            acc[4 * q + 0] = fmaf(d[u], b.x, acc[4 * q + 0]);
+            acc[4 * q + 1] = fmaf(d[u], b.y, acc[4 * q + 1]);
+            acc[4 * q + 2] = fmaf(d[u], b.z, acc[4 * q + 2]);
+            acc[4 * q + 3] = fmaf(d[u], b.w, acc[4 * q + 3]);
+          }
         }
       }
     }
   }
   if (i0 + i < in_f) {
-    float* dst = part + (static_cast<size_t>(blockIdx.y) * in_f + i0 + i) * MW_RMAX + jb;
+    float* dst = part + (static_cast<size_t>(blockIdx.y) * in_f + i0 + i) * r;
 #pragma unroll
-    for (int k = 0; k < 16; ++k) dst[k] = scaling * acc[k];
+    for (int k = 0; k < 16; ++k)
+      if (jb + k < r) dst[jb + k] = scaling * acc[k];
   }
 }
 
-__global__ void lora_merge_da_fold_kernel(const float* __restrict__ part, float* __restrict__ dA, int in_f, int r) {
+// dst[e] = sum over `splits` partials of n elements each, in index order (deterministic)
+__global__ void lora_merge_fold_kernel(const float* __restrict__ part, float* __restrict__ dst, int n, int splits) {
   const int e = blockIdx.x * blockDim.x + threadIdx.x;
-  if (e >= in_f * r) return;
-  const int i = e / r, j = e - i * r;
+  if (e >= n) return;
   float s = 0.f;
-#pragma unroll
-  for (int k = 0; k < MW_SPLIT; ++k) s += part[(static_cast<size_t>(k) * in_f + i) * MW_RMAX + j];
-  dA[e] = s;
+  for (int k = 0; k < splits; ++k) s += part[static_cast<size_t>(k) * n + e];
+  dst[e] = s;
 }
 
-// dB: one warp per output row o; lanes stride over i, 32 accumulators (one per j), butterfly at the end
+// dB partials: block (16 output rows, split of the input features); dWm rows and the A rows of a 128-feature chunk are
+// staged in shared memory, thread (o, j pair) accumulates two outputs
+constexpr int MW_DB_O = 16;
+constexpr int MW_DB_I = 128;
+constexpr int MW_DB_SPLIT = 4;
+
 __global__ void __launch_bounds__(256)
-lora_merge_db_kernel(const float* __restrict__ dWm, const float* __restrict__ A, float* __restrict__ dB, int out_f, int in_f,
-                     int r, float scaling) {
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int o = blockIdx.x * 8 + warp;
-  if (o >= out_f) return;
-  float acc[MW_RMAX];
-#pragma unroll
-  for (int j = 0; j < MW_RMAX; ++j) acc[j] = 0.f;
-  const float* drow = dWm + static_cast<size_t>(o) * in_f;
-  if (r == MW_RMAX) {
-    for (int i = lane; i < in_f; i += 32) {
-      const float d = __ldg(drow + i);
-      const float4* ar = reinterpret_cast<const float4*>(A + static_cast<size_t>(i) * MW_RMAX);
-#pragma unroll
-      for (int q = 0; q < MW_RMAX / 4; ++q) {
-        const float4 a = __ldg(ar + q);
-        acc[4 * q + 0] = fmaf(d, a.x, acc[4 * q + 0]);
-        acc[4 * q + 1] = fmaf(d, a.y, acc[4 * q + 1]);
-        acc[4 * q + 2] = fmaf(d, a.z, acc[4 * q + 2]);
-        acc[4 * q + 3] = fmaf(d, a.w, acc[4 * q + 3]);
-      }
+lora_merge_db_kernel(const float* __restrict__ dWm, const float* __restrict__ A, float* __restrict__ part, int out_f,
+                     int in_f, int r, float scaling) {
+  __shared__ __align__(16) float dW_s[MW_DB_O][MW_DB_I];
+  __shared__ __align__(16) float A_s[MW_DB_I][MW_RMAX];
+  const int o0 = blockIdx.x * MW_DB_O;
+  const int chunk = ((in_f + MW_DB_SPLIT - 1) / MW_DB_SPLIT + MW_DB_I - 1) / MW_DB_I * MW_DB_I;
+  const int i_beg = blockIdx.y * chunk, i_end = min(in_f, i_beg + chunk);
+  const int o = threadIdx.x >> 4, j = (threadIdx.x & 15) * 2;
+  float acc0 = 0.f, acc1 = 0.f;
+  for (int it = i_beg; it < i_end; it += MW_DB_I) {
+    __syncthreads();
+    for (int e = threadIdx.x; e < MW_DB_O * MW_DB_I; e += 256) {
+      const int oo = e / MW_DB_I, ii = e - oo * MW_DB_I;
+      dW_s[oo][ii] = (o0 + oo < out_f && it + ii < i_end) ? __ldg(dWm + static_cast<size_t>(o0 + oo) * in_f + it + ii) : 0.f;
     }
-  } else {
-    for (int i = lane; i < in_f; i += 32) {
-      const float d = __ldg(drow + i);
-      const float* ar = A + static_cast<size_t>(i) * r;
-#pragma unroll
-      for (int j = 0; j < MW_RMAX; ++j)
-        if (j < r) acc[j] = fmaf(d, __ldg(ar + j), acc[j]);
+    for (int e = threadIdx.x; e < MW_DB_I * MW_RMAX; e += 256) {
+      const int ii = e / MW_RMAX, jj = e - ii * MW_RMAX;
+      A_s[ii][jj] = (jj < r && it + ii < i_end) ? __ldg(A + static_cast<size_t>(it + ii) * r + jj) : 0.f;
+    }
+    __syncthreads();
+#pragma unroll 8
+    for (int ii = 0; ii < MW_DB_I; ++ii) {
+      const float d = dW_s[o][ii];
+      const float2 a = *reinterpret_cast<const float2*>(&A_s[ii][j]);
+      acc0 = fmaf(d, a.x, acc0);
+      acc1 = fmaf(d, a.y, acc1);
     }
   }
-#pragma unroll
-  for (int j = 0; j < MW_RMAX; ++j) {
-    float v = acc[j];
-#pragma unroll
-    for (int s = 16; s > 0; s >>= 1) v += __shfl_xor_sync(0xffffffffu, v, s);
-    if (lane == 0 && j < r) dB[static_cast<size_t>(j) * out_f + o] = scaling * v;
+  if (o0 + o < out_f) {
+    float* dst = part + static_cast<size_t>(blockIdx.y) * r * out_f;
+    if (j < r) dst[static_cast<size_t>(j) * out_f + o0 + o] = scaling * acc0;
+    if (j + 1 < r) dst[static_cast<size_t>(j + 1) * out_f + o0 + o] = scaling * acc1;
   }
 }
 
@@ -157,8 +167,10 @@ using namespace ffm;
 
 extern "C" {
 
-size_t ffm_lora_merged_weight_ws_bytes(int in_f) {
-  return static_cast<size_t>(MW_SPLIT) * static_cast<size_t>(in_f > 0 ? in_f : 0) * MW_RMAX * sizeof(float);
+size_t ffm_lora_merged_weight_ws_bytes(int out_f, int in_f) {
+  const size_t a = static_cast<size_t>(MW_SPLIT) * static_cast<size_t>(in_f > 0 ? in_f : 0) * MW_RMAX;
+  const size_t b = static_cast<size_t>(MW_DB_SPLIT) * static_cast<size_t>(out_f > 0 ? out_f : 0) * MW_RMAX;
+  return (a + b) * sizeof(float);
 }
 
 int ffm_lora_merged_weight(const float* W, const float* A, const float* B, float* out, int out_f, int in_f, int r,
@@ -176,16 +188,21 @@ int ffm_lora_merged_weight_bwd(const float* dWm, const float* A, const float* B,
                                size_t ws_bytes, int out_f, int in_f, int r, float scaling, cudaStream_t stream) {
   FFM_CHECK_ARG(dWm && A && B && dA && dB && ws, "ffm_lora_merged_weight_bwd: null pointer argument");
   FFM_CHECK_ARG(out_f >= 1 && in_f >= 1 && r >= 1 && r <= MW_RMAX, "ffm_lora_merged_weight_bwd: rank must be 1..32");
-  FFM_CHECK_ARG(ws_bytes >= ffm_lora_merged_weight_ws_bytes(in_f), "ffm_lora_merged_weight_bwd: workspace too small");
-  FFM_CHECK_ARG(r != MW_RMAX || (reinterpret_cast<uintptr_t>(A) & 15u) == 0, "ffm_lora_merged_weight_bwd: A must be 16-byte aligned");
+  FFM_CHECK_ARG(ws_bytes >= ffm_lora_merged_weight_ws_bytes(out_f, in_f),
+                "ffm_lora_merged_weight_bwd: workspace too small");
+  float* part_a = ws;
+  float* part_b = ws + static_cast<size_t>(MW_SPLIT) * in_f * MW_RMAX;
   dim3 grid_a((in_f + MW_TI - 1) / MW_TI, MW_SPLIT);
-  lora_merge_da_kernel<<<grid_a, 256, 0, stream>>>(dWm, B, ws, out_f, in_f, r, scaling);
+  lora_merge_da_kernel<<<grid_a, 256, 0, stream>>>(dWm, B, part_a, out_f, in_f, r, scaling);
   FFM_CHECK_CUDA(cudaGetLastError());
-  lora_merge_da_fold_kernel<<<(in_f * r + 255) / 256, 256, 0, stream>>>(ws, dA, in_f, r);
+  lora_merge_fold_kernel<<<(in_f * r + 255) / 256, 256, 0, stream>>>(part_a, dA, in_f * r, MW_SPLIT);
   FFM_CHECK_CUDA(cudaGetLastError());
-  lora_merge_db_kernel<<<(out_f + 7) / 8, 256, 0, stream>>>(dWm, A, dB, out_f, in_f, r, scaling);
+  dim3 grid_b((out_f + MW_DB_O - 1) / MW_DB_O, MW_DB_SPLIT);
+  lora_merge_db_kernel<<<grid_b, 256, 0, stream>>>(dWm, A, part_b, out_f, in_f, r, scaling);
   FFM_CHECK_CUDA(cudaGetLastError());
-  count_launch(3);
+  lora_merge_fold_kernel<<<(out_f * r + 255) / 256, 256, 0, stream>>>(part_b, dB, out_f * r, MW_DB_SPLIT);
+  FFM_CHECK_CUDA(cudaGetLastError());
+  count_launch(4);
   return FFM_OK;
 }
 

@@ -4,8 +4,8 @@
 // normalised with the CLIP mean / std and handed to the stride-P patch convolution.  The reference spends two reductions and
 // six element-wise passes (plus their autograd mirrors) on [B', 3, H, W] fp32 tensors; here:
 //   forward : oct_minmax_kernel (one read of y) + oct_patchify_kernel (one read of y, bf16 im2col rows written once)
-//   backward: oct_input_bwd_kernel — one block per slice-image: pass 1 reduces S1 = sum g, S2 = sum g (y - lo) and the
-//             number of pixels attaining lo / hi in a fixed order (deterministic), pass 2 writes
+//   backward: oct_bwd_reduce_kernel reduces S1 = sum g, S2 = sum g (y - lo) and the number of pixels attaining lo / hi per
+//             slice-image in a fixed order (deterministic), oct_bwd_apply_kernel writes
 //             d_y = g / R + [y == lo] d_lo / n_lo + [y == hi] d_hi / n_hi   with g = d_patch / std, R = hi - lo + 1e-5,
 //             d_lo = -S1 / R + S2 / R^2, d_hi = -S2 / R^2  (torch.amin / amax split the gradient evenly among ties).
 // The gradient of the projection's weights is then the library's convolution weight-gradient on d_y (the projection itself
@@ -90,51 +90,112 @@ oct_patchify_kernel(const float* __restrict__ y, const float* __restrict__ lo, c
   reinterpret_cast<uint4*>(out)[i] = pk;
 }
 
-// one block per slice-image; pixel index i -> (c, h, w) and its position in the bf16 patch rows
-__global__ void __launch_bounds__(OCT_THREADS)
-oct_input_bwd_kernel(const __nv_bfloat16* __restrict__ d_patches, const float* __restrict__ y,
-                     const float* __restrict__ lo, const float* __restrict__ hi, const float* __restrict__ stdv,
-                     float* __restrict__ d_y, int C, int H, int W, int P, int gw, int G) {
+// ---- backward ----
+// Work item = 8 consecutive pixels of one patch row (the forward's mapping): d_patches is read as one 16-byte load, y as two.
+constexpr int OCT_SPLIT = 8;       // blocks per slice-image in the reduction pass
+
+struct OctChunk {
+  const float* y;       // 8 pixels of the slice-image
+  size_t pix;           // their offset inside the [C, H, W] image
+  int c;
+};
+
+__device__ __forceinline__ OctChunk oct_chunk(int k, int C, int H, int W, int P, int gw) {
+  // k enumerates the 16-byte chunks of one image's patch rows: [g][c][py][px8]
+  const int p8 = P >> 3, pp8 = (P * P) >> 3, row_chunks = C * pp8;
+  const int g = k / row_chunks, k8 = k - g * row_chunks;
+  const int c = k8 / pp8, rem = k8 - c * pp8;
+  const int py = rem / p8, px = (rem - py * p8) << 3;
+  const int gy = g / gw, gx = g - gy * gw;
+  OctChunk o;
+  o.c = c;
+  o.pix = (static_cast<size_t>(c) * H + static_cast<size_t>(gy) * P + py) * W + static_cast<size_t>(gx) * P + px;
+  o.y = nullptr;
+  return o;
+}
+
+__device__ __forceinline__ void unpack_bf16x8(const uint4& raw, float (&g)[8]) {
+  const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&raw);
+#pragma unroll
+  for (int e = 0; e < 4; ++e) { const float2 f = __bfloat1622float2(h2[e]); g[2 * e] = f.x; g[2 * e + 1] = f.y; }
+}
+
+// pass 1: block (split, image) -> partial S1 = sum g, S2 = sum g (y - lo), n_lo, n_hi  (g = d_patch / std[c])
+__global__ void __launch_bounds__(256)
+oct_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ d_patches, const float* __restrict__ y,
+                      const float* __restrict__ lo, const float* __restrict__ hi, const float* __restrict__ stdv,
+                      float4* __restrict__ part, int C, int H, int W, int P, int gw, int chunks_per_image) {
   __shared__ float red[33];
-  const int b = blockIdx.x;
-  const int n = C * H * W;
-  const float l = lo[b], h = hi[b], R = (h - l) + 1e-5f;
-  const float* yb = y + static_cast<size_t>(b) * n;
-  float* dyb = d_y + static_cast<size_t>(b) * n;
-  const __nv_bfloat16* dpb = d_patches + static_cast<size_t>(b) * G * C * P * P;
-  const int row_len = C * P * P;
-
-  auto grad_at = [&](int i) -> float {      // g = d_out / std at pixel i of this slice-image
-    const int c = i / (H * W);
-    const int r = i - c * H * W;
-    const int hh = r / W, ww = r - hh * W;
-    const int g = (hh / P) * gw + ww / P;
-    const int k = c * P * P + (hh % P) * P + (ww % P);
-    return __bfloat162float(dpb[static_cast<size_t>(g) * row_len + k]) / __ldg(stdv + c);
-  };
-
+  const int b = blockIdx.y;
+  const float l = __ldg(lo + b), h = __ldg(hi + b);
+  const uint4* dp = reinterpret_cast<const uint4*>(d_patches) + static_cast<size_t>(b) * chunks_per_image;
+  const float* yb = y + static_cast<size_t>(b) * C * H * W;
+  const int per = (chunks_per_image + OCT_SPLIT - 1) / OCT_SPLIT;
+  const int k_end = min(chunks_per_image, (static_cast<int>(blockIdx.x) + 1) * per);
   float s1 = 0.f, s2 = 0.f, n_lo = 0.f, n_hi = 0.f;
-  for (int i = threadIdx.x; i < n; i += OCT_THREADS) {
-    const float g = grad_at(i), yv = yb[i];
-    s1 += g;
-    s2 = fmaf(g, yv - l, s2);
-    n_lo += (yv == l) ? 1.f : 0.f;
-    n_hi += (yv == h) ? 1.f : 0.f;
+  for (int k = blockIdx.x * per + threadIdx.x; k < k_end; k += 256) {
+    const OctChunk ch = oct_chunk(k, C, H, W, P, gw);
+    const uint4 raw = __ldg(dp + k);
+    const float4 y0 = __ldg(reinterpret_cast<const float4*>(yb + ch.pix));
+    const float4 y1 = __ldg(reinterpret_cast<const float4*>(yb + ch.pix) + 1);
+    const float yv[8] = {y0.x, y0.y, y0.z, y0.w, y1.x, y1.y, y1.z, y1.w};
+    float g[8];
+    unpack_bf16x8(raw, g);
+    const float inv_s = 1.0f / __ldg(stdv + ch.c);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const float ge = g[e] * inv_s;
+      s1 += ge;
+      s2 = fmaf(ge, yv[e] - l, s2);
+      n_lo += (yv[e] == l) ? 1.f : 0.f;
+      n_hi += (yv[e] == h) ? 1.f : 0.f;
+    }
   }
   s1 = block_reduce(s1, red, false, false);
   s2 = block_reduce(s2, red, false, false);
   n_lo = block_reduce(n_lo, red, false, false);
   n_hi = block_reduce(n_hi, red, false, false);
-  const float inv_r = 1.0f / R;
+  if (threadIdx.x == 0) part[static_cast<size_t>(b) * OCT_SPLIT + blockIdx.x] = make_float4(s1, s2, n_lo, n_hi);
+}
+
+// pass 2: coefficients per slice-image (partials folded in a fixed order), then
+//   d_y = g / R + [y == lo] d_lo / n_lo + [y == hi] d_hi / n_hi
+__global__ void __launch_bounds__(256)
+oct_bwd_apply_kernel(const __nv_bfloat16* __restrict__ d_patches, const float* __restrict__ y,
+                     const float* __restrict__ lo, const float* __restrict__ hi, const float* __restrict__ stdv,
+                     const float4* __restrict__ part, float* __restrict__ d_y, int C, int H, int W, int P, int gw,
+                     int chunks_per_image) {
+  const int b = blockIdx.y;
+  const int k = blockIdx.x * 256 + threadIdx.x;
+  if (k >= chunks_per_image) return;
+  const float l = __ldg(lo + b), h = __ldg(hi + b);
+  float s1 = 0.f, s2 = 0.f, n_lo = 0.f, n_hi = 0.f;
+#pragma unroll
+  for (int q = 0; q < OCT_SPLIT; ++q) {
+    const float4 v = __ldg(part + static_cast<size_t>(b) * OCT_SPLIT + q);
+    s1 += v.x; s2 += v.y; n_lo += v.z; n_hi += v.w;
+  }
+  const float inv_r = 1.0f / ((h - l) + 1e-5f);
   const float d_lo = (-s1 * inv_r + s2 * inv_r * inv_r) / fmaxf(n_lo, 1.f);
   const float d_hi = (-s2 * inv_r * inv_r) / fmaxf(n_hi, 1.f);
-  for (int i = threadIdx.x; i < n; i += OCT_THREADS) {
-    const float yv = yb[i];
-    float d = grad_at(i) * inv_r;
-    if (yv == l) d += d_lo;
-    if (yv == h) d += d_hi;
-    dyb[i] = d;
+  const OctChunk ch = oct_chunk(k, C, H, W, P, gw);
+  const size_t base = static_cast<size_t>(b) * C * H * W + ch.pix;
+  const uint4 raw = __ldg(reinterpret_cast<const uint4*>(d_patches) + static_cast<size_t>(b) * chunks_per_image + k);
+  const float4 y0 = __ldg(reinterpret_cast<const float4*>(y + base));
+  const float4 y1 = __ldg(reinterpret_cast<const float4*>(y + base) + 1);
+  const float yv[8] = {y0.x, y0.y, y0.z, y0.w, y1.x, y1.y, y1.z, y1.w};
+  float g[8], o[8];
+  unpack_bf16x8(raw, g);
+  const float sc = inv_r / __ldg(stdv + ch.c);
+#pragma unroll
+  for (int e = 0; e < 8; ++e) {
+    float d = g[e] * sc;
+    if (yv[e] == l) d += d_lo;
+    if (yv[e] == h) d += d_hi;
+    o[e] = d;
   }
+  reinterpret_cast<float4*>(d_y + base)[0] = make_float4(o[0], o[1], o[2], o[3]);
+  reinterpret_cast<float4*>(d_y + base)[1] = make_float4(o[4], o[5], o[6], o[7]);
 }
 
 }  // namespace ffm
@@ -162,15 +223,29 @@ int ffm_oct_minmax_patchify(const float* y, float* lo, float* hi, void* patches,
   return FFM_OK;
 }
 
+size_t ffm_oct_input_bwd_ws_bytes(int Bp) {
+  return static_cast<size_t>(Bp > 0 ? Bp : 0) * OCT_SPLIT * sizeof(float4);
+}
+
 int ffm_oct_input_bwd(const void* d_patches, const float* y, const float* lo, const float* hi, const float* stdv,
-                      float* d_y, int Bp, int C, int H, int W, int patch, cudaStream_t stream) {
-  FFM_CHECK_ARG(d_patches && y && lo && hi && stdv && d_y, "ffm_oct_input_bwd: null pointer argument");
-  FFM_CHECK_ARG(Bp >= 1 && C >= 1 && patch >= 1 && H % patch == 0 && W % patch == 0, "ffm_oct_input_bwd: bad sizes");
-  const int gw = W / patch, G = (H / patch) * gw;
-  oct_input_bwd_kernel<<<Bp, OCT_THREADS, 0, stream>>>(static_cast<const __nv_bfloat16*>(d_patches), y, lo, hi, stdv, d_y,
-                                                       C, H, W, patch, gw, G);
+                      float* d_y, void* ws, size_t ws_bytes, int Bp, int C, int H, int W, int patch,
+                      cudaStream_t stream) {
+  FFM_CHECK_ARG(d_patches && y && lo && hi && stdv && d_y && ws, "ffm_oct_input_bwd: null pointer argument");
+  FFM_CHECK_ARG(Bp >= 1 && Bp <= 65535 && C >= 1 && patch >= 8 && patch % 8 == 0 && H % patch == 0 && W % patch == 0 &&
+                    W % 4 == 0,
+                "ffm_oct_input_bwd: patch must be a multiple of 8 dividing H and W, W a multiple of 4, Bp <= 65535");
+  FFM_CHECK_ARG(ws_bytes >= ffm_oct_input_bwd_ws_bytes(Bp), "ffm_oct_input_bwd: workspace too small");
+  const int gw = W / patch;
+  const int chunks = C * H * W / 8;
+  float4* part = static_cast<float4*>(ws);
+  oct_bwd_reduce_kernel<<<dim3(OCT_SPLIT, Bp), 256, 0, stream>>>(static_cast<const __nv_bfloat16*>(d_patches), y, lo, hi,
+                                                                  stdv, part, C, H, W, patch, gw, chunks);
   FFM_CHECK_CUDA(cudaGetLastError());
-  count_launch();
+  oct_bwd_apply_kernel<<<dim3((chunks + 255) / 256, Bp), 256, 0, stream>>>(static_cast<const __nv_bfloat16*>(d_patches), y,
+                                                                           lo, hi, stdv, part, d_y, C, H, W, patch, gw,
+                                                                           chunks);
+  FFM_CHECK_CUDA(cudaGetLastError());
+  count_launch(2);
   return FFM_OK;
 }
 

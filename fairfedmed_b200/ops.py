@@ -465,7 +465,7 @@ def _(w, a, b, scaling):
 def lora_merged_weight_bwd_op(d_wm: Tensor, a: Tensor, b: Tensor, scaling: float) -> Tuple[Tensor, Tensor]:
     _need_cuda(d_wm, a, b)
     out_f, in_f = d_wm.shape
-    nbytes = int(_cabi.load().ffm_lora_merged_weight_ws_bytes(in_f))
+    nbytes = int(_cabi.load().ffm_lora_merged_weight_ws_bytes(out_f, in_f))
     ws = torch.empty((nbytes // 4,), device=d_wm.device, dtype=torch.float32)
     d_a, d_b = torch.empty_like(a), torch.empty_like(b)
     _cabi.call("ffm_lora_merged_weight_bwd", _ptr(d_wm), _ptr(a), _ptr(b), _ptr(d_a), _ptr(d_b), _ptr(ws), nbytes, out_f,
@@ -704,8 +704,10 @@ def _(y, mean, std, patch):
 def oct_input_bwd_op(d_patches: Tensor, y: Tensor, lo: Tensor, hi: Tensor, std: Tensor, patch: int) -> Tensor:
     bp, c, h, w = y.shape
     d_y = torch.empty_like(y)
-    _cabi.call("ffm_oct_input_bwd", _ptr(d_patches), _ptr(y), _ptr(lo), _ptr(hi), _ptr(std), _ptr(d_y), bp, c, h, w,
-               int(patch), _stream())
+    nbytes = int(_cabi.load().ffm_oct_input_bwd_ws_bytes(bp))
+    ws = torch.empty((nbytes // 4,), device=y.device, dtype=torch.float32)
+    _cabi.call("ffm_oct_input_bwd", _ptr(d_patches), _ptr(y), _ptr(lo), _ptr(hi), _ptr(std), _ptr(d_y), _ptr(ws), nbytes,
+               bp, c, h, w, int(patch), _stream())
     return d_y
 
 

@@ -211,21 +211,23 @@ int ffm_vit_embed_ln(const void* patch_emb, const float* class_embedding, const 
  * ffm_oct_minmax_patchify: y f32 [Bp, C, H, W] -> lo / hi f32 [Bp] and patches bf16 [Bp*G, C*patch*patch]
  *   (two launches: one reduction pass, one conversion pass).
  * ffm_oct_input_bwd: d_patches bf16 (gradient of `patches`) -> d_y f32 [Bp, C, H, W], including the min / max terms
- *   (torch.amin / amax split the gradient evenly among the pixels attaining the extremum); deterministic.
+ *   (torch.amin / amax split the gradient evenly among the pixels attaining the extremum); deterministic; `ws` of at
+ *   least ffm_oct_input_bwd_ws_bytes(Bp) bytes.
  */
 int ffm_oct_minmax_patchify(const float* y, float* lo, float* hi, void* patches, const float* mean, const float* stdv,
                             int Bp, int C, int H, int W, int patch, ffm_stream_t stream);
+size_t ffm_oct_input_bwd_ws_bytes(int Bp);
 int ffm_oct_input_bwd(const void* d_patches, const float* y, const float* lo, const float* hi, const float* stdv,
-                      float* d_y, int Bp, int C, int H, int W, int patch, ffm_stream_t stream);
+                      float* d_y, void* ws, size_t ws_bytes, int Bp, int C, int H, int W, int patch, ffm_stream_t stream);
 
 /*
  * Merged weight of a plain LoRA projection — LoRALinear.weight(x, attr), trainers/GLP_OT_SVLoRA.py:236-240, consumed by the
  * RN50 attention pool (clip/model.py:88-97):  out[o, i] = W[o, i] + scaling * sum_j A[i, j] * B[j, o]
  *   W, out f32 [out_f, in_f]; A = lora_A.weight f32 [in_f, r]; B = lora_B.weight f32 [r, out_f]; r <= 32.
  * ffm_lora_merged_weight_bwd: dWm f32 [out_f, in_f] -> dA [in_f, r], dB [r, out_f] (deterministic; `ws` of at least
- * ffm_lora_merged_weight_ws_bytes(in_f) bytes).
+ * ffm_lora_merged_weight_ws_bytes(out_f, in_f) bytes).
  */
-size_t ffm_lora_merged_weight_ws_bytes(int in_f);
+size_t ffm_lora_merged_weight_ws_bytes(int out_f, int in_f);
 int ffm_lora_merged_weight(const float* W, const float* A, const float* B, float* out, int out_f, int in_f, int r,
                            float scaling, ffm_stream_t stream);
 int ffm_lora_merged_weight_bwd(const float* dWm, const float* A, const float* B, float* dA, float* dB, float* ws,

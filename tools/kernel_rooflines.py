@@ -88,6 +88,62 @@ for (K, N, act) in [(768, 3072, 1), (3072, 768, 0)]:
         elif "finalize" in k:
             add(k, f"K={K} N={N} nS={B}", us, note="latency bound (partials fold + segmented ds_eff)")
 
+# ---------------- frozen in_proj / out_proj of the image tower (adapter-free build of the fused GEMM) ----------------
+for (K, N) in [(768, 2304), (768, 768), (2304, 768)]:
+    x = torch.randn(T, K, generator=g).bfloat16().to(dev)
+    W = (torch.randn(N, K, generator=g) * K ** -0.5).bfloat16().to(dev)
+    bias = torch.randn(N, generator=g).to(dev)
+    m = measure(lambda: ops.frozen_linear_op(x, W, bias))
+    for k, us in m.items():
+        add(k, f"frozen linear T={T} K={K} N={N}", us, flops=2.0 * T * K * N)
+
+# ---------------- attention core (tcgen05): image tower B'=64, L=197, 12 heads x 64 ----------------
+qkv = torch.randn(64, 197, 2304, generator=g).bfloat16().to(dev)
+do = (0.1 * torch.randn(64, 197, 768, generator=g)).bfloat16().to(dev)
+st = {}
+
+
+def att_f():
+    st["o"] = ops.attention_fwd(qkv, 12, False, True)
+m = measure(att_f)
+att_fl = 4.0 * 64 * 12 * 197 * 197 * 64
+for k, us in m.items():
+    add(k, "fwd B'=64 L=197 H=12 d=64", us, flops=att_fl,
+        note=f"HBM floor (qkv + out = {64 * 197 * 3072 * 2 / 1e6:.0f} MB) {64 * 197 * 3072 * 2 / HBM / 1e3:.1f} us")
+o_, lse_ = st["o"]
+m = measure(lambda: ops.attention_bwd(qkv, o_, do, lse_, 12, False, True))
+for k, us in m.items():
+    add(k, "bwd B'=64 L=197 H=12 d=64", us, flops=2.5 * att_fl,
+        note=f"HBM floor (qkv + out + d_out + d_qkv = {64 * 197 * 6144 * 2 / 1e6:.0f} MB) {64 * 197 * 6144 * 2 / HBM / 1e3:.1f} us")
+
+# ---------------- OCT input side (config 3: 256 slice-images) and merged LoRA weight (RN50 attention pool) ----------------
+yo = (3.0 * torch.randn(256, 3, 224, 224, generator=g)).to(dev)
+mean3 = torch.tensor([0.48145466, 0.4578275, 0.40821073], device=dev)
+std3 = torch.tensor([0.26862954, 0.26130258, 0.27577711], device=dev)
+st = {}
+
+
+def oct_f():
+    st["o"] = ops.oct_minmax_patchify_op(yo, mean3, std3, 16)
+m = measure(oct_f)
+npx = 256 * 3 * 224 * 224
+for k, us in m.items():
+    add(k, "B'=256 3x224x224 fp32", us, bytes_=npx * (4.0 if "minmax" in k else 6.0))
+pt, lo_, hi_ = st["o"]
+dpt = torch.randn(pt.shape, generator=g).bfloat16().to(dev)
+m = measure(lambda: ops.oct_input_bwd_op(dpt, yo, lo_, hi_, std3, 16))
+for k, us in m.items():
+    add(k, "B'=256 3x224x224", us, bytes_=npx * 10.0, note="algorithmic bytes = d_patches + y in, d_y out (second pass served by L2)")
+Wm = torch.randn(2048, 2048, generator=g).to(dev)
+Am = (0.1 * torch.randn(2048, 32, generator=g)).to(dev)
+Bmm = torch.randn(32, 2048, generator=g).to(dev)
+m = measure(lambda: ops.lora_merged_weight_op(Wm, Am, Bmm, 0.25))
+for k, us in m.items():
+    add(k, "out=2048 in=2048 r=32 fp32", us, bytes_=2.0 * 2048 * 2048 * 4)
+m = measure(lambda: ops.lora_merged_weight_bwd_op(Wm, Am, Bmm, 0.25))
+for k, us in m.items():
+    add(k, "out=2048 in=2048 r=32 fp32", us, bytes_=2048 * 2048 * 4.0)
+
 # ---------------- residual add + LayerNorm ----------------
 xa = torch.randn(T, 768, generator=g).bfloat16().to(dev)
 xb = torch.randn(T, 768, generator=g).bfloat16().to(dev)
@@ -171,6 +227,21 @@ grad = torch.randn(Pn, generator=g).to(dev)
 m = measure(lambda: ops.sgd_step_(flat, grad, mom, 1e-3, 0.9, 5e-4, 2, False))
 for k, us in m.items():
     add(k, f"P={Pn} fp32, double step", us, bytes_=5.0 * Pn * 4)
+# FedAvg over the flat buffer: scale (per-client weights) and EMA epilogue
+from fairfedmed_b200.fed_utils import FlatSpec  # noqa: E402,F401
+kinds = torch.zeros(1, dtype=torch.int32, device=dev)
+offs = torch.zeros(1, dtype=torch.int64, device=dev)
+lens = torch.full((1,), Pn, dtype=torch.int64, device=dev)
+wg = torch.ones(3, device=dev) / 3
+try:
+    m = measure(lambda: ops.fedavg_scale(flat, kinds, offs, lens, 0.5, wg, 3, 12))
+    for k, us in m.items():
+        add(k, f"P={Pn} fp32", us, bytes_=2.0 * Pn * 4)
+    m = measure(lambda: ops.fedavg_epilogue(flat, grad, kinds, offs, lens, 0.06, True, 3, 12))
+    for k, us in m.items():
+        add(k, f"P={Pn} fp32", us, bytes_=3.0 * Pn * 4)
+except Exception as e:      # argument layout of the aggregation entry points changed: keep the rest of the table
+    rows.append({"kernel": "fedavg", "note": f"not measured: {type(e).__name__}: {e}"[:200]})
 N = 200000
 prob = torch.softmax(torch.randn(N, 2, generator=g), 1).to(dev)
 lab = torch.randint(0, 2, (N,), generator=g).to(dev)
