@@ -1,4 +1,4 @@
-// Merged weight of a plain LoRA projection (scope row a4): LoRALinear.weight(x, attr) of trainers/GLP_OT_SVLoRA.py:236-240,
+// Merged weight of a plain LoRA projection (scope row a4): LoRALinear.weight(x, attr) of trainers/GLP_OT_SVLoRA.py:235-239,
 //     Wm[o, i] = W[o, i] + scaling * sum_j A[i, j] B[j, o]          A = lora_A.weight [in, r], B = lora_B.weight [r, out]
 // which the RN50 attention pool hands to F.multi_head_attention_forward (clip/model.py:88-97) for its q / k / v / c
 // projections, and its backward  dA[i, j] = scaling sum_o dWm[o, i] B[j, o],  dB[j, o] = scaling sum_i dWm[o, i] A[i, j].

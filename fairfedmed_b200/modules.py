@@ -272,7 +272,7 @@ class LoRALinear(_AdapterBase):
         nn.init.normal_(self.lora_B.weight)
 
     def weight(self, x=None, attr=None):
-        """Merged weight W + scaling (A B)^T (:236-240): one fused pass with its own backward on the GPU."""
+        """Merged weight W + scaling (A B)^T (:235-239): one fused pass with its own backward on the GPU."""
         w = self.original_linear.weight
         if not w.is_cuda:
             raise RuntimeError("fairfedmed_b200 adapters need CUDA tensors: there is no CPU fallback")

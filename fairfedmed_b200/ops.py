@@ -495,7 +495,7 @@ class _LoraMergedWeight(torch.autograd.Function):
 def lora_merged_weight(w: Tensor, a: Tensor, b: Tensor, scaling: float) -> Tensor:
     """W + scaling * (A @ B)^T in one pass, with its own deterministic backward for A and B (the frozen W gets no gradient).
     w f32 [out, in] frozen, a = lora_A.weight f32 [in, r], b = lora_B.weight f32 [r, out]
-    (LoRALinear.weight, trainers/GLP_OT_SVLoRA.py:236-240)."""
+    (LoRALinear.weight, trainers/GLP_OT_SVLoRA.py:235-239)."""
     if w.requires_grad:
         raise _cabi.FfmError("lora_merged_weight: the base weight must be frozen")
     if w.dtype != torch.float32 or a.dtype != torch.float32 or b.dtype != torch.float32:

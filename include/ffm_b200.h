@@ -221,7 +221,7 @@ int ffm_oct_input_bwd(const void* d_patches, const float* y, const float* lo, co
                       float* d_y, void* ws, size_t ws_bytes, int Bp, int C, int H, int W, int patch, ffm_stream_t stream);
 
 /*
- * Merged weight of a plain LoRA projection — LoRALinear.weight(x, attr), trainers/GLP_OT_SVLoRA.py:236-240, consumed by the
+ * Merged weight of a plain LoRA projection — LoRALinear.weight(x, attr), trainers/GLP_OT_SVLoRA.py:235-239, consumed by the
  * RN50 attention pool (clip/model.py:88-97):  out[o, i] = W[o, i] + scaling * sum_j A[i, j] * B[j, o]
  *   W, out f32 [out_f, in_f]; A = lora_A.weight f32 [in_f, r]; B = lora_B.weight f32 [r, out_f]; r <= 32.
  * ffm_lora_merged_weight_bwd: dWm f32 [out_f, in_f] -> dA [in_f, r], dB [r, out_f] (deterministic; `ws` of at least

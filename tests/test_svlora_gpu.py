@@ -322,7 +322,7 @@ def test_frozen_linear_matches_fp32(T, K, N):
 @pytest.mark.gpu
 @pytest.mark.parametrize("out_f,in_f,r", [(1024, 2048, 32), (2048, 2048, 32), (96, 200, 4), (33, 130, 12)])
 def test_lora_merged_weight_matches_reference_expression(out_f, in_f, r):
-    """LoRALinear.weight (trainers/GLP_OT_SVLoRA.py:236-240): W + scaling (A B)^T and its gradients for A and B, fused kernels
+    """LoRALinear.weight (trainers/GLP_OT_SVLoRA.py:235-239): W + scaling (A B)^T and its gradients for A and B, fused kernels
     against autograd over the reference's expression in fp64."""
     from fairfedmed_b200 import ops
     torch.manual_seed(3)
