@@ -325,7 +325,9 @@ attention_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_c
 // ---------------------------------------------------------------------------------------------------------------
 // A unit = (key tile j of 128 keys, query chunk a of <= 64 queries).  Two TMEM buffers of 128 columns (S^T | dP^T, 64
 // columns each) ping-pong, so the contractions of unit n + 1 run while the element-wise warps work on unit n; two groups
-// of four warps (one warp per TMEM lane quarter) alternate units, each thread owning one key row of its unit.
+// of four warps (one warp per TMEM lane quarter) share every unit — group g owns query columns [32g, 32g + 32), each
+// thread one key row — which halves the S^T / dP^T -> P^T / dS^T turn-around the MMA warp waits for (93.4 -> 89.9 us
+// against whole units alternating between the groups).
 constexpr int BWD_THREADS = 320;            // warp 0: TMA, warp 1: MMA (+ TMEM alloc), warps 2-5 / 6-9: element-wise group 0 / 1
 constexpr int OFF_Q = 0;
 constexpr int OFF_DO = OFF_Q + KV_BYTES;             //  26624
@@ -373,7 +375,9 @@ __device__ __forceinline__ float4 lds128(uint32_t addr) {
 }
 
 // TMEM columns of K step k (16 queries) of a chunk: bf16 pairs are packed over the columns their fp32 source occupied
-__device__ __forceinline__ uint32_t packed_col(int k) { return static_cast<uint32_t>(8 * k); }
+// TMEM column of the packed bf16 block for query columns [16k, 16k + 16) of a unit: each element-wise group writes its
+// two blocks over score columns it has itself already read ([0, 16) for group 0, [32, 48) for group 1)
+__device__ __forceinline__ uint32_t packed_col(int k) { return static_cast<uint32_t>(8 * k + (k >= 2 ? 16 : 0)); }
 
 // accumulator row (fp32, 64 columns from `acc`) x `sc` -> 64 bf16 into row `row` of a SW128 staging tile
 __device__ __forceinline__ void stage_row64(uint32_t acc, float sc, uint8_t* tile, int row) {
@@ -430,7 +434,7 @@ attention_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_c
     mbar_init(dvk_full, 1);
     for (int i = 0; i < 2; ++i) {
       mbar_init(&sdp_full[i], 1);
-      mbar_init(&pds_full[i], 4);
+      mbar_init(&pds_full[i], 8);
       mbar_init(&stage_free[i], 1);
       mbar_init(&dq_full[i], 1);
     }
@@ -547,11 +551,10 @@ attention_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_c
     // ============================== element-wise warps ==============================
     long long c_ld = 0, c_pre = 0, c_sdp = 0, c_stage = 0, c_epw = 0, c_work = 0, c_drain = 0, c_end = 0;
     const uint32_t quarter = warp & 3u;
-    const uint32_t grp = (warp - 2u) >> 2;                    // handles units with (n & 1) == grp, i.e. TMEM buffer grp
+    const uint32_t grp = (warp - 2u) >> 2;                    // handles query columns [32 grp, 32 grp + 32) of every unit
     const int row = static_cast<int>(quarter * 32u + lane);  // key row inside tile j / query row inside a half
     const int tid_s = static_cast<int>(threadIdx.x) - 64;    // 0..255
     const uint32_t lane_addr = (quarter * 32u) << 16;
-    const uint32_t buf = tmem_base + lane_addr + 128u * grp;
     const uint32_t lse_addr = smem_u32(lse2_s), delta_addr = smem_u32(delta_s);
     uint8_t* stage = smem + OFF_ST + grp * ST_TILE;          // this group's output staging tile
     const bool storer = quarter == 0 && lane == 0;           // issues the group's TMA stores
@@ -603,20 +606,22 @@ attention_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_c
       c_pre += clock64() - t_pre;
 
       for (int w = 0; w < units; ++w, ++n) {
-        if ((n & 1u) != grp) continue;
+        // BOTH groups work on every unit (half of its query columns each): the S^T / dP^T -> P^T / dS^T turn-around that
+        // the MMA warp waits for is half as long as with whole units alternating between the groups
         const int j = w / nq, a = w - j * nq;
         const int na = (p.l_pad - 64 * a) < 64 ? (p.l_pad - 64 * a) : 64;
         const int key = 128 * j + row;
         const bool kvalid = key < p.L;
-        ATT_TIMED(c_sdp, mbar_wait(&sdp_full[grp], (n >> 1) & 1u, 400));
+        const uint32_t buf = tmem_base + lane_addr + 128u * (n & 1u);
+        ATT_TIMED(c_sdp, mbar_wait(&sdp_full[n & 1u], (n >> 1) & 1u, 400));
         tc_fence_after();
         if (a == 0 && j > 0) {
           // dV_{j-1} / dK_{j-1} are complete: drain them before this unit's first dV / dK MMA overwrites the accumulators
           ATT_TIMED(c_epw, mbar_wait(dvk_full, static_cast<uint32_t>(it * nj + j - 1) & 1u, 500));
           tc_fence_after();
           const long long t_dr = clock64();
-          drain_tile(ACC_DV, 1.0f, 2 * p.C + h * HD, 128 * (j - 1), b);
-          drain_tile(ACC_DK, p.scale, p.C + h * HD, 128 * (j - 1), b);
+          if (grp == 0) drain_tile(ACC_DV, 1.0f, 2 * p.C + h * HD, 128 * (j - 1), b);
+          else drain_tile(ACC_DK, p.scale, p.C + h * HD, 128 * (j - 1), b);
           c_drain += clock64() - t_dr;
         }
         // the shared dS blocks of this query half were last read by the dQ MMAs of the previous key tile (or head)
@@ -626,7 +631,8 @@ attention_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_c
         }
         const long long t_work = clock64();
         uint8_t* blk = smem + OFF_DS + a * DS_BLOCK + row * ROW_BYTES;
-        for (int c0 = 0; c0 < na; c0 += 16) {
+        const int c_end_col = na < 32 * static_cast<int>(grp) + 32 ? na : 32 * static_cast<int>(grp) + 32;
+        for (int c0 = 32 * static_cast<int>(grp); c0 < c_end_col; c0 += 16) {
           uint32_t sv[16], dv[16];
           tmem_ld16(buf + c0, sv);
           tmem_ld16(buf + 64 + c0, dv);
@@ -654,8 +660,8 @@ attention_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_c
             pp[e] = kvalid ? pack2(pv[0], pv[1]) : 0u;
             dd[e] = kvalid ? pack2(gv[0], gv[1]) : 0u;
           }
-          tmem_st8(buf + (c0 >> 1), pp);
-          tmem_st8(buf + 64 + (c0 >> 1), dd);
+          tmem_st8(buf + packed_col(c0 >> 4), pp);
+          tmem_st8(buf + 64 + packed_col(c0 >> 4), dd);
           // dS (not transposed) for dQ: [key row][query contiguous]: two 16-byte chunks of this row's 128-byte line
           const int ch = c0 >> 3;
           *reinterpret_cast<uint4*>(blk + (((ch) ^ (row & 7)) << 4)) = make_uint4(dd[0], dd[1], dd[2], dd[3]);
@@ -665,7 +671,7 @@ attention_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_c
         fence_proxy_async_smem();
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(&pds_full[grp]);
+        if (lane == 0) mbar_arrive(&pds_full[n & 1u]);
         c_work += clock64() - t_work;
       }
       // ---- epilogues of the head: group 0 drains dV / dK of the last key tile, group 1 both query halves of dQ ----
