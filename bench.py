@@ -502,10 +502,13 @@ def run_ours(args):
     tkn_buf = (ctypes.c_int * (3 * cap))()
     nrec = lib.ffm_profile_read(ctypes.cast(ms_buf, ctypes.c_void_p), ctypes.cast(tkn_buf, ctypes.c_void_p), cap)
     R = c["rank"]
-    flops = sum(2.0 * tkn_buf[3 * i] * tkn_buf[3 * i + 1] * tkn_buf[3 * i + 2] +
-                2.0 * tkn_buf[3 * i] * R * (tkn_buf[3 * i + 1] + tkn_buf[3 * i + 2]) for i in range(nrec))
+    # records with N < 0 are launches of the adapter-free build (frozen in_proj / out_proj): no low-rank terms
+    flops = sum(2.0 * tkn_buf[3 * i] * tkn_buf[3 * i + 1] * abs(tkn_buf[3 * i + 2]) +
+                (2.0 * tkn_buf[3 * i] * R * (tkn_buf[3 * i + 1] + tkn_buf[3 * i + 2]) if tkn_buf[3 * i + 2] > 0 else 0.0)
+                for i in range(nrec))
     gemm_ms = sum(ms_buf[i] for i in range(nrec))
     shapes = sorted({(tkn_buf[3 * i], tkn_buf[3 * i + 1], tkn_buf[3 * i + 2]) for i in range(nrec)})
+    n_adapted = sum(1 for i in range(nrec) if tkn_buf[3 * i + 2] > 0)
     status_nan = int(tr.model.last_status[1].item()) if tr.model.last_status is not None else 0
 
     parity = aggregation_parity(tr, agg, dist, world, rank, dev) if world > 1 else None
@@ -532,13 +535,16 @@ def run_ours(args):
             traffic = None
     achieved = flops / (gemm_ms * 1e-3) / 1e12 if gemm_ms > 0 else 0.0
     roofline = {
-        "kernel": "ffm::svlora_gemm_kernel (fused FairLoRA linear fwd / dX, tcgen05 + TMA)",
+        "kernel": "ffm::svlora_gemm_kernel / pair::svlora_gemm_pair_kernel (fused FairLoRA linear fwd / dX and the frozen "
+                  "attention projections on the same tcgen05 + TMA kernel), FLOP-weighted over every launch of a step",
         "bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
         "traffic": traffic, "traffic_source": "ncu --set full dram__bytes_read+write per launch (profiles/roofline_traffic.json)"
         if traffic else None, "peak_source": peak_src, "launches_timed": nrec,
         "avg_launch_us": 1e3 * gemm_ms / max(nrec, 1),
         "share_of_step": (gemm_ms / prof_steps) / (ms_total / args.steps),
-        "algorithmic_flops_per_launch": f"2*T*K*N + 2*T*r*(K+N), r={R}; (T,K,N) launched: {shapes[:6]}"
+        "launches_adapted": n_adapted,
+        "algorithmic_flops_per_launch": f"2*T*K*N + 2*T*r*(K+N), r={R} (adapted linears; N < 0 marks the adapter-free launches of "
+                                        f"the frozen in_proj / out_proj: 2*T*K*|N|); (T,K,N) launched: {shapes[:6]}"
                                         + (" ..." if len(shapes) > 6 else ""),
     }
     roofline_hbm = None

@@ -355,8 +355,12 @@ __device__ __forceinline__ void st_shared_cluster_f32(uint32_t cluster_addr, flo
   asm volatile("st.shared::cluster.f32 [%0], %1;" ::"r"(cluster_addr), "f"(v) : "memory");
 }
 
+// Arrive on a barrier of another CTA of the cluster (address from mapa).  Default semantics (release at CTA scope), as the
+// CUTLASS cluster barriers use for the same hand-offs: what is handed over lives in the ARRIVING CTA's own shared memory /
+// tensor memory (made visible with fence.proxy.async / tcgen05.fence before the arrive); only the signal crosses CTAs.  The
+// .release.cluster form compiles to MEMBAR.ALL.GPU + ERRBAR per arrive, ~1 k cycles on the per-tile critical chain.
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
 
 __device__ __forceinline__ bool mbar_try_wait_cluster(uint64_t* bar, uint32_t parity) {

@@ -532,18 +532,19 @@ int make_map_bf16(CUtensorMap* out, const void* ptr, uint64_t rows, uint64_t col
 }
 
 
-// Which build runs: the CTA-pair kernel (deeper ring: 6 stages of 29 KB, half the issue overhead per FLOP) wins when a
-// tile has many k-blocks (K >= 2048: 51 us vs 58 us at T=12608, K=3072, N=768); with 12 k-blocks per tile (K = 768) its
-// per-tile hand-offs cost more than they save (72 us vs 61 us), so short contractions stay on the single-CTA kernel.
-// FFM_GEMM_PAIR=0 / 1 forces one build (A/B measurements).
-static bool use_pair_kernel(int K) {
+// Which build runs: the CTA-pair kernel (cta_group::2 MMAs at the ideal issue rate, 0.69x the L2 -> shared-memory operand
+// bytes per FLOP, 6-stage ring) for everything except the QuickGELU dual-store epilogue (c_fc forward), where both builds
+// are bound by the epilogue (76.8 vs 77.9 us).  T = 12608: K=768 N=3072 plain 63.7 -> 56.3 us, dX of c_fc 62.4 -> 56.0 us,
+// K=3072 N=768 59.4 -> 51.4 us.  (Until the cross-CTA arrives stopped compiling to MEMBAR.GPU — see mbar_arrive_cluster —
+// the pair build lost on K = 768: 69.7 us.)  FFM_GEMM_PAIR=0 / 1 forces one build (A/B measurements).
+static bool use_pair_kernel(int act) {
   static int v = -2;
   if (v == -2) {
     const char* e = getenv("FFM_GEMM_PAIR");
     v = (e == nullptr) ? -1 : (e[0] != '0');
   }
   if (v >= 0) return v != 0;
-  return K >= 2048;
+  return act != ACT_QUICKGELU;
 }
 
 // FFM_GEMM_DBG: bottleneck experiments only (1: no MMA, 2: no TMA loads, 4: no TMA stores); results are garbage
@@ -608,7 +609,7 @@ static int launch_single(const GemmOperands& o, const GemmParams& p0, cudaStream
                                                                                          tm_y2, p);
     FFM_CHECK_CUDA(cudaGetLastError());
     count_launch();
-    return gemm_profile_end(&prof, o.T, o.K, o.N, stream);
+    return gemm_profile_end(&prof, o.T, o.K, -o.N, stream);     // N < 0 in the record: launch without the adapter terms
   }
   switch (p.act) {
     case ACT_QUICKGELU:
@@ -641,7 +642,7 @@ static int launch_svlora_gemm(const GemmOperands& o, cudaStream_t stream) {
                              reinterpret_cast<uintptr_t>(o.s_rows) | reinterpret_cast<uintptr_t>(o.h_out) |
                              reinterpret_cast<uintptr_t>(o.z_out) | reinterpret_cast<uintptr_t>(o.aux);
   FFM_CHECK_ARG((align_or & 15u) == 0, "svlora gemm: all device pointers must be 16-byte aligned");
-  if (o.rp == RP && use_pair_kernel(o.K)) return launch_svlora_gemm_pair(o, stream);
+  if (o.rp == RP && use_pair_kernel(o.act)) return launch_svlora_gemm_pair(o, stream);
 
   GemmParams p;
   p.bias = o.bias;

@@ -159,9 +159,9 @@ __device__ __forceinline__ void epi_store_piece(const GemmParams& p, float (&f)[
       pk.y = pack_bf16x2(f[j8 * 8 + 2], f[j8 * 8 + 3]);
       pk.z = pack_bf16x2(f[j8 * 8 + 4], f[j8 * 8 + 5]);
       pk.w = pack_bf16x2(f[j8 * 8 + 6], f[j8 * 8 + 7]);
-      *reinterpret_cast<uint4*>(orow + ((static_cast<uint32_t>(j8) ^ sw) << 4)) = pk;
+      if (!(p.dbg & 256)) *reinterpret_cast<uint4*>(orow + ((static_cast<uint32_t>(j8) ^ sw) << 4)) = pk;
     }
-    fence_proxy_async_smem();
+    if (!(p.dbg & 128)) fence_proxy_async_smem();
     __syncwarp();
     if (lane == 0) {
       const CUtensorMap* tm = (n_pass == 2 && pass == 0) ? tm_y2 : tm_y;

@@ -43,7 +43,8 @@ int ffm_version(void);
  *   ffm_launch_count : number of kernels this library has launched since the last reset (host-side counter).
  *   ffm_profile_*    : when enabled, every launch of the fused SVLoRA GEMM kernel is bracketed by CUDA events on
  *                      its own stream; ffm_profile_read synchronises them and returns per-launch milliseconds and
- *                      (T, K, N) triples (host arrays), then clears the record list.
+ *                      (T, K, N) triples (host arrays), then clears the record list.  N is negated for launches of the
+ *                      adapter-free build (ffm_frozen_linear): their FLOPs are 2*T*K*|N| without the low-rank terms.
  */
 long long ffm_launch_count(int reset);
 int ffm_profile_enable(int enable);
