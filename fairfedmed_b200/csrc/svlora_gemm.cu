@@ -826,6 +826,9 @@ int ffm_frozen_linear(const void* x, const void* w, const float* bias, void* y, 
   p.T = T; p.K = K; p.N = N; p.rp = RP; p.b_prime = 1; p.num_slices = 1; p.row_div = 1; p.act = ACT_NONE; p.has_pre = 0;
   p.m_tiles = p.n_tiles = p.k_blocks = 0;
   p.dbg = gemm_debug_mask();
+  // FFM_FROZEN_PAIR=0 keeps the single-CTA adapter-free build (A/B measurements)
+  static const bool pair_ok = [] { const char* e = getenv("FFM_FROZEN_PAIR"); return e == nullptr || e[0] != '0'; }();
+  if (pair_ok) return launch_svlora_gemm_pair(o, stream);
   return launch_single<RP, false>(o, p, stream);
 }
 

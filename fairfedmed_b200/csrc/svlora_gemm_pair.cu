@@ -70,7 +70,10 @@ constexpr int NUM_THREADS = 384;
 constexpr int EPI_THREADS = 256;
 constexpr int Z_THREADS = 128;
 
-template <int ACT>
+// ADAPT = false: the adapter-free build (frozen projections, ffm_frozen_linear): no Aside / Bside tiles, no H -> Z -> fix-up
+// chain, UMMA N = 192 (accumulator columns [0, 96) from the leader's Wmat rows, [96, 192) from the peer's), the mainloop
+// commits d_full directly.
+template <int ACT, bool ADAPT = true>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
 svlora_gemm_pair_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_w,
                         const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b,
@@ -101,8 +104,10 @@ svlora_gemm_pair_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_c
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tm_x);
     tma_prefetch_desc(&tm_w);
-    tma_prefetch_desc(&tm_a);
-    tma_prefetch_desc(&tm_b);
+    if (ADAPT) {
+      tma_prefetch_desc(&tm_a);
+      tma_prefetch_desc(&tm_b);
+    }
     tma_prefetch_desc(&tm_y);
     if (p.has_pre) tma_prefetch_desc(&tm_y2);
   }
@@ -153,12 +158,14 @@ svlora_gemm_pair_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_c
           if (p.dbg & 2) {
             if (leader) mbar_arrive(&full_bar[stage]);
           } else {
-            if (leader) mbar_arrive_expect_tx(&full_bar[stage], 2 * STAGE_BYTES);
+            if (leader)
+              mbar_arrive_expect_tx(&full_bar[stage], 2 * (ADAPT ? STAGE_BYTES : X_TILE_BYTES + W_TILE_BYTES));
             tma_load_2d_pair(st, &tm_x, &full_bar[stage], kb * BK, m_blk * BM);
             tma_load_2d_pair(st + X_TILE_BYTES, &tm_w, &full_bar[stage], kb * BK,
                              n_blk * BN + static_cast<int>(rank) * HN);
-            tma_load_2d_pair(st + X_TILE_BYTES + W_TILE_BYTES, &tm_a, &full_bar[stage], kb * BK,
-                             static_cast<int>(rank) * HR);
+            if (ADAPT)
+              tma_load_2d_pair(st + X_TILE_BYTES + W_TILE_BYTES, &tm_a, &full_bar[stage], kb * BK,
+                               static_cast<int>(rank) * HR);
           }
         }
         __syncwarp();
@@ -168,7 +175,7 @@ svlora_gemm_pair_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_c
   } else if (warp == 1) {
     // =========================== MMA issuer (leader CTA only; whole warp, one elected lane issues) ==============
     if (leader) {
-      constexpr uint32_t idesc = umma_idesc_bf16(UMMA_M, UMMA_N);
+      constexpr uint32_t idesc = umma_idesc_bf16(UMMA_M, ADAPT ? UMMA_N : BN);
       const uint32_t stages_base = smem_u32(smem + OFF_STAGES);
       uint32_t stage = 0, phase = 0;
       int pend = -1;
@@ -195,14 +202,16 @@ svlora_gemm_pair_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_c
         tc_fence_after();
         // Bside halves of this tile (buffer s was last read by the fix-up UMMA of tile it-2, long complete): loaded from
         // here and from the peer's otherwise idle warp 1, so the k-slice producers never wait on a per-tile event
-        if (elect_one()) {
-          mbar_arrive_expect_tx(&bs_full[s], 2 * BS_LOAD_BYTES);
-          tma_load_2d_pair(smem + OFF_BS + s * BS_TILE_BYTES, &tm_b, &bs_full[s], 0, (tile % p.n_tiles) * BN);
+        if (ADAPT) {
+          if (elect_one()) {
+            mbar_arrive_expect_tx(&bs_full[s], 2 * BS_LOAD_BYTES);
+            tma_load_2d_pair(smem + OFF_BS + s * BS_TILE_BYTES, &tm_b, &bs_full[s], 0, (tile % p.n_tiles) * BN);
+          }
+          __syncwarp();
         }
-        __syncwarp();
         const uint32_t d_tmem = tmem_base + s * ACC_COLS;
         for (int kb = 0; kb < p.k_blocks; ++kb) {
-          if (pend >= 0) {
+          if (ADAPT && pend >= 0) {
             if (__all_sync(0xffffffffu, mbar_test_wait_cluster(&z_full[pend], pend_phase))) {
               fixup(pend, pend_phase);
               pend = -1;
@@ -224,6 +233,11 @@ svlora_gemm_pair_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_c
           __syncwarp();
           if (++stage == STAGES) { stage = 0; phase ^= 1u; }
         }
+        if (!ADAPT) {
+          if (elect_one()) umma_commit_pair(&d_full[s]);        // no fix-up: the accumulator is final
+          __syncwarp();
+          continue;
+        }
         if (elect_one()) umma_commit_pair(&h_full[s]);
         __syncwarp();
         if (pend >= 0) {
@@ -233,11 +247,11 @@ svlora_gemm_pair_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_c
         pend = s;
         pend_phase = aph;
       }
-      if (pend >= 0) {
+      if (ADAPT && pend >= 0) {
         mbar_wait_cluster_uniform(&z_full[pend], pend_phase);
         fixup(pend, pend_phase);
       }
-    } else {
+    } else if (ADAPT) {
       // peer CTA: its half of every tile's Bside (credited to the leader's bs_full barrier)
       int it = 0;
       for (int tile = cluster_id; tile < num_tiles; tile += num_clusters, ++it) {
@@ -278,7 +292,7 @@ svlora_gemm_pair_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_c
         bias_w[pc * EPI_PIECE_COLS + lane] = (p.bias != nullptr && col < p.N) ? __ldg(p.bias + col) : 0.0f;
       }
 
-      if (half == 0) {
+      if (ADAPT && half == 0) {
         // ---- H -> Z ----
         // this row's scaled singular values first: their global-load latency hides behind the wait for H
         const int grow_c = grow < p.T ? grow : (p.T - 1);
@@ -344,7 +358,7 @@ svlora_gemm_pair_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_c
         if (pc + 1 < PIECES)
           epi_load_aux<ACT>(p, aux_nxt, grow, n0 + (2 * (pc + 1) + static_cast<int>(half)) * EPI_PIECE_COLS);
         const int cc = (2 * pc + static_cast<int>(half)) * EPI_PIECE_COLS;   // tile column of this piece
-        const int tcol = cc < HN ? cc : cc + HR;                               // accumulator column (skip the H block)
+        const int tcol = (!ADAPT || cc < HN) ? cc : cc + HR;                   // accumulator column (skip the H block)
         uint32_t v[32];
         const long long q0 = clock64();
         tmem_ld32(acc + tcol, v);
@@ -383,12 +397,18 @@ svlora_gemm_pair_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_c
 
 int launch_svlora_gemm_pair(const GemmOperands& o, cudaStream_t stream) {
   using namespace pair;
+  const bool adapt = o.a_side != nullptr;      // nullptr: adapter-free build (ffm_frozen_linear)
   CUtensorMap tm_x, tm_w, tm_a, tm_b, tm_y, tm_y2;
   int rc;
   if ((rc = make_map_bf16(&tm_x, o.x, o.T, o.K, BM, BK, CU_TENSOR_MAP_SWIZZLE_128B, true))) return rc;
   if ((rc = make_map_bf16(&tm_w, o.wmat, o.N, o.K, HN, BK, CU_TENSOR_MAP_SWIZZLE_128B, true))) return rc;
-  if ((rc = make_map_bf16(&tm_a, o.a_side, RP, o.K, HR, BK, CU_TENSOR_MAP_SWIZZLE_128B, true))) return rc;
-  if ((rc = make_map_bf16(&tm_b, o.b_side, o.N, RP, HN, RP, CU_TENSOR_MAP_SWIZZLE_32B, false))) return rc;
+  if (adapt) {
+    if ((rc = make_map_bf16(&tm_a, o.a_side, RP, o.K, HR, BK, CU_TENSOR_MAP_SWIZZLE_128B, true))) return rc;
+    if ((rc = make_map_bf16(&tm_b, o.b_side, o.N, RP, HN, RP, CU_TENSOR_MAP_SWIZZLE_32B, false))) return rc;
+  } else {
+    tm_a = tm_w;      // never dereferenced by the adapter-free build
+    tm_b = tm_w;
+  }
   if ((rc = make_map_bf16(&tm_y, o.out, o.T, o.N, 32, EPI_PIECE_COLS, CU_TENSOR_MAP_SWIZZLE_64B, false))) return rc;
   const bool has_pre = (o.act == ACT_QUICKGELU && o.out_pre != nullptr);
   if ((rc = make_map_bf16(&tm_y2, has_pre ? o.out_pre : o.out, o.T, o.N, 32, EPI_PIECE_COLS, CU_TENSOR_MAP_SWIZZLE_64B,
@@ -421,6 +441,8 @@ int launch_svlora_gemm_pair(const GemmOperands& o, cudaStream_t stream) {
                                         cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
     FFM_CHECK_CUDA(cudaFuncSetAttribute(svlora_gemm_pair_kernel<ACT_QUICKGELU_GRAD>,
                                         cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    FFM_CHECK_CUDA(cudaFuncSetAttribute(svlora_gemm_pair_kernel<ACT_NONE, false>,
+                                        cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
     attr_dev = dev;
   }
   const int pair_tiles = ((p.m_tiles + 1) / 2) * p.n_tiles;
@@ -429,6 +451,13 @@ int launch_svlora_gemm_pair(const GemmOperands& o, cudaStream_t stream) {
   GemmProfileScope prof;
   if ((rc = gemm_profile_begin(&prof, stream))) return rc;
   const int grid = 2 * clusters;
+  if (!adapt) {
+    svlora_gemm_pair_kernel<ACT_NONE, false><<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(tm_x, tm_w, tm_a, tm_b, tm_y, tm_y2,
+                                                                                         p);
+    FFM_CHECK_CUDA(cudaGetLastError());
+    count_launch();
+    return gemm_profile_end(&prof, o.T, o.K, -o.N, stream);     // N < 0: launch without the adapter terms
+  }
   switch (p.act) {
     case ACT_QUICKGELU:
       svlora_gemm_pair_kernel<ACT_QUICKGELU><<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(tm_x, tm_w, tm_a, tm_b, tm_y,
