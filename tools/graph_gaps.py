@@ -63,3 +63,12 @@ tot = sum(g for g, _, _ in gaps if g > 0)
 print(f"critical stream {main}: sum of gaps {tot:.1f} us over {len(gaps)} hand-offs, median {sorted(g for g, _, _ in gaps)[len(gaps) // 2]:.2f} us")
 for g, x, y in sorted(gaps, reverse=True)[:12]:
     print(f"   {g:7.2f} us  after {x}  before {y}")
+
+agg = collections.defaultdict(lambda: [0, 0.0])
+for s_, e_, st, nm in step:
+    k = nm.split("(")[0].replace("void ", "")[:70]
+    agg[k][0] += 1
+    agg[k][1] += e_ - s_
+print("per-kernel device time inside the replayed step (streams overlap, so the sum exceeds the wall):")
+for k, (n_, t_) in sorted(agg.items(), key=lambda kv: -kv[1][1])[:24]:
+    print(f"  {t_:8.1f} us  x{n_:3d}  avg {t_ / n_:6.1f}  {k}")
