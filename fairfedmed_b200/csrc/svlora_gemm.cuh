@@ -130,7 +130,7 @@ __device__ __forceinline__ void epi_store_piece(const GemmParams& p, float (&f)[
   for (int pass = 0; pass < n_pass; ++pass) {
     uint8_t* ob = stage_w + (unit & 1u) * EPI_PIECE_BYTES;
     // the TMA store that last read this buffer (2 units ago) must have finished reading smem
-    if (lane == 0) tma_store_wait_read<1>();
+    if (lane == 0 && !(p.dbg & 512)) tma_store_wait_read<1>();
     __syncwarp();
     if (ACT == ACT_QUICKGELU) {
       if (n_pass == 2 && pass == 0) {

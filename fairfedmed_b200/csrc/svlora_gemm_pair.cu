@@ -25,6 +25,15 @@
 #include "../../include/ffm_b200.h"
 #include "svlora_gemm.cuh"
 
+// Per-phase cycle accounting of the epilogue (wait for H, H -> Z, wait for the fix-up, D -> OUT pieces), printed by the first
+// cluster when built with -DFFM_GEMM_PAIR_PROF and run with FFM_GEMM_DBG & 64: how the MEMBAR.GPU of the cluster-scope
+// arrives was found.  Compiled out by default (costs ~20 registers).
+#ifdef FFM_GEMM_PAIR_PROF
+#define PAIR_PROF(stmt) stmt
+#else
+#define PAIR_PROF(stmt)
+#endif
+
 namespace ffm {
 namespace pair {
 
@@ -275,7 +284,8 @@ svlora_gemm_pair_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_c
     uint32_t unit = 0;
     constexpr int PIECES = BN / (2 * EPI_PIECE_COLS);
     int it = 0;
-    long long pr_h = 0, pr_z = 0, pr_d = 0, pr_p = 0, pr_ld = 0, pr_st = 0, pr_t0 = clock64();     // FFM_GEMM_DBG & 64: per-phase cycles
+    PAIR_PROF(long long pr_h = 0; long long pr_z = 0; long long pr_d = 0; long long pr_p = 0; long long pr_ld = 0;
+              long long pr_st = 0; const long long pr_t0 = clock64();)
     for (int tile = cluster_id; tile < num_tiles; tile += num_clusters, ++it) {
       const int m_pair = tile / p.n_tiles;
       const int n_blk = tile - m_pair * p.n_tiles;
@@ -299,11 +309,10 @@ svlora_gemm_pair_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_c
         const int sample = ((grow_c / p.row_div) % p.b_prime) / p.num_slices;
         const float4* sr = reinterpret_cast<const float4*>(p.s_rows + static_cast<size_t>(sample) * RP);
         const float4 s0 = __ldg(sr), s1 = __ldg(sr + 1), s2 = __ldg(sr + 2), s3 = __ldg(sr + 3);
-        const long long k0 = clock64();
+        PAIR_PROF(const long long k0 = clock64();)
         mbar_wait(&h_full[s], aph, 600 + s);
         tc_fence_after();
-        const long long k1 = clock64();
-        pr_h += k1 - k0;
+        PAIR_PROF(const long long k1 = clock64(); pr_h += k1 - k0;)
         uint32_t h0[8], h1[8];
         tmem_ld8(acc + HN, h0);            // H columns 0..7  (leader's Aside rows)
         tmem_ld8(acc + BH + HN, h1);       // H columns 8..15 (peer's Aside rows)
@@ -327,7 +336,7 @@ svlora_gemm_pair_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_c
         *reinterpret_cast<uint4*>(zrow + ((1u ^ sw) << 4)) = c1;
         fence_proxy_async_smem();
         mbar_arrive_cluster(mapa_u32(smem_u32(&z_full[s]), 0));       // leader's barrier (local when rank 0)
-        pr_z += clock64() - k1;
+        PAIR_PROF(pr_z += clock64() - k1;)
         // side outputs to HBM after the signal: they are off the tile's critical chain
         if (n_blk == 0 && grow < p.T) {
           if (p.h_out != nullptr) {
@@ -347,11 +356,10 @@ svlora_gemm_pair_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_c
       // ---- D -> OUT ----
       EpiAux aux_cur, aux_nxt;
       epi_load_aux<ACT>(p, aux_nxt, grow, n0 + static_cast<int>(half) * EPI_PIECE_COLS);   // piece 0, before the wait
-      const long long k2 = clock64();
+      PAIR_PROF(const long long k2 = clock64();)
       mbar_wait(&d_full[s], aph, 700 + s);
       tc_fence_after();
-      const long long k3 = clock64();
-      pr_d += k3 - k2;
+      PAIR_PROF(const long long k3 = clock64(); pr_d += k3 - k2;)
 #pragma unroll 1
       for (int pc = 0; pc < PIECES; ++pc) {
         aux_cur = aux_nxt;
@@ -360,11 +368,10 @@ svlora_gemm_pair_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_c
         const int cc = (2 * pc + static_cast<int>(half)) * EPI_PIECE_COLS;   // tile column of this piece
         const int tcol = (!ADAPT || cc < HN) ? cc : cc + HR;                   // accumulator column (skip the H block)
         uint32_t v[32];
-        const long long q0 = clock64();
+        PAIR_PROF(const long long q0 = clock64();)
         tmem_ld32(acc + tcol, v);
         tmem_ld_wait();
-        const long long q1 = clock64();
-        pr_ld += q1 - q0;
+        PAIR_PROF(const long long q1 = clock64(); pr_ld += q1 - q0;)
         if (pc == PIECES - 1) {
           tc_fence_before();
           __syncwarp();
@@ -374,15 +381,17 @@ svlora_gemm_pair_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_c
 #pragma unroll
         for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]) + bias_w[pc * EPI_PIECE_COLS + j];
         epi_store_piece<ACT>(p, f, aux_cur, &tm_y, &tm_y2, stage_w, unit, lane, grow, n0 + cc, m_blk * BM + static_cast<int>(q) * 32);
-        pr_st += clock64() - q1;
+        PAIR_PROF(pr_st += clock64() - q1;)
       }
       __syncwarp();
-      pr_p += clock64() - k3;
+      PAIR_PROF(pr_p += clock64() - k3;)
     }
     if (lane == 0) tma_store_wait_all<0>();
+#ifdef FFM_GEMM_PAIR_PROF
     if ((p.dbg & 64) && blockIdx.x < 2 && lane == 0 && (ew == 0 || ew == 4))
       printf("[gemm pair prof] cta %d ew %u tiles %d total %lld | wait h %lld  z %lld  wait d %lld  pieces %lld (tmem ld %lld, math+store %lld)\n",
              (int)blockIdx.x, ew, it, clock64() - pr_t0, pr_h, pr_z, pr_d, pr_p, pr_ld, pr_st);
+#endif
   }
 
   // teardown: nobody may leave while the peer can still address this CTA's barriers / TMEM
