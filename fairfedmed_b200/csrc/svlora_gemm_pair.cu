@@ -46,7 +46,7 @@ constexpr int BK = 64;
 constexpr int UMMA_K = 16;
 constexpr int UMMA_M = 2 * BM;       // 256
 constexpr int UMMA_N = 2 * BH;       // 208
-constexpr int STAGES = 5;
+constexpr int STAGES = 6;
 constexpr int ACC_COLS = 256;
 constexpr int TMEM_COLS = 512;
 
@@ -54,12 +54,11 @@ constexpr int X_TILE_BYTES = BM * BK * 2;     // 16384
 constexpr int W_TILE_BYTES = HN * BK * 2;     // 12288
 constexpr int A_TILE_BYTES = HR * BK * 2;     //  1024
 constexpr int STAGE_BYTES = X_TILE_BYTES + W_TILE_BYTES + A_TILE_BYTES;   // 29696 = 29 * 1024
-constexpr int MAX_EPW = 3;                           // epilogue warp groups (4 warps each): 2 plain, 3 with an activation
-constexpr int OUT_STAGING_BYTES = 4 * MAX_EPW * 2 * EPI_PIECE_BYTES;   // epilogue warps x 2 buffers x 2 KB
+constexpr int OUT_STAGING_BYTES = 8 * 2 * EPI_PIECE_BYTES;   // 8 epilogue warps x 2 buffers x 2 KB
 constexpr int Z_TILE_BYTES = BM * RP * 2;            //  4096
 constexpr int BS_LOAD_BYTES = HN * RP * 2;           //  3072 (TMA box)
 constexpr int BS_TILE_BYTES = 4096;                  //  104 rows x 32 B = 3328, padded
-constexpr int BIAS_BYTES = 4 * BN * 4;                 //  3072: every epilogue warp's own copy of its columns' bias
+constexpr int BIAS_BYTES = 8 * (BN / 2) * 4;           //  3072
 
 constexpr int OFF_STAGES = 0;
 constexpr int OFF_OUT = OFF_STAGES + STAGES * STAGE_BYTES;
@@ -76,18 +75,15 @@ static_assert(OFF_OUT % 1024 == 0 && OFF_Z % 1024 == 0 && OFF_BS % 1024 == 0, "t
 static_assert(SMEM_BYTES <= 232448, "exceeds 227 KB of shared memory per CTA");
 static_assert(HN % 32 == 0, "a 32-column epilogue slice must not straddle the two accumulator halves");
 
-constexpr int num_threads(int epw) { return 128 + 128 * epw; }
+constexpr int NUM_THREADS = 384;
+constexpr int EPI_THREADS = 256;
 constexpr int Z_THREADS = 128;
 
 // ADAPT = false: the adapter-free build (frozen projections, ffm_frozen_linear): no Aside / Bside tiles, no H -> Z -> fix-up
 // chain, UMMA N = 192 (accumulator columns [0, 96) from the leader's Wmat rows, [96, 192) from the peer's), the mainloop
 // commits d_full directly.
-// EPW = epilogue warp groups of four warps (one warp per TMEM lane quarter): group g converts the 32-column pieces
-// g, g + EPW, ... of the tile.  With an activation in the epilogue (QuickGELU + dual store, x QuickGELU') two groups need
-// longer for a tile than the 12-k-block mainloop of the K = 768 shapes lasts (clock64 phases: 7.8 k cycles of pieces per tile
-// against an 8 k-cycle mainloop, and only two accumulator stages fit TMEM), so those builds run three groups.
-template <int ACT, bool ADAPT = true, int EPW = 2>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(num_threads(EPW), 1)
+template <int ACT, bool ADAPT = true>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
 svlora_gemm_pair_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_w,
                         const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b,
                         const __grid_constant__ CUtensorMap tm_y, const __grid_constant__ CUtensorMap tm_y2,
@@ -133,7 +129,7 @@ svlora_gemm_pair_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_c
       mbar_init(&h_full[i], 1);
       mbar_init(&z_full[i], 2 * Z_THREADS);
       mbar_init(&d_full[i], 1);
-      mbar_init(&tmem_empty[i], 2 * 4 * EPW);
+      mbar_init(&tmem_empty[i], 2 * (EPI_THREADS / 32));
       mbar_init(&bs_full[i], 1);
     }
     fence_mbar_init();
@@ -280,13 +276,13 @@ svlora_gemm_pair_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_c
     // =========================== epilogue (8 independent warps, both CTAs) ===========================
     const uint32_t ew = warp - 4u;
     const uint32_t q = warp & 3u;
-    const uint32_t grp = ew >> 2;                 // piece group of this warp
+    const uint32_t half = ew >> 2;
     const uint32_t row = q * 32u + lane;
     const uint32_t lane_addr = (q * 32u) << 16;
     uint8_t* stage_w = smem + OFF_OUT + ew * (2 * EPI_PIECE_BYTES);
-    float* bias_w = reinterpret_cast<float*>(smem + OFF_BIAS) + ew * (BN / EPW);
+    float* bias_w = reinterpret_cast<float*>(smem + OFF_BIAS) + ew * (BN / 2);
     uint32_t unit = 0;
-    constexpr int PIECES = BN / (EPW * EPI_PIECE_COLS);
+    constexpr int PIECES = BN / (2 * EPI_PIECE_COLS);
     int it = 0;
     PAIR_PROF(long long pr_h = 0; long long pr_z = 0; long long pr_d = 0; long long pr_p = 0; long long pr_ld = 0;
               long long pr_st = 0; const long long pr_t0 = clock64();)
@@ -302,11 +298,11 @@ svlora_gemm_pair_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_c
 
 #pragma unroll
       for (int pc = 0; pc < PIECES; ++pc) {
-        const int col = n0 + (EPW * pc + static_cast<int>(grp)) * EPI_PIECE_COLS + static_cast<int>(lane);
+        const int col = n0 + (2 * pc + static_cast<int>(half)) * EPI_PIECE_COLS + static_cast<int>(lane);
         bias_w[pc * EPI_PIECE_COLS + lane] = (p.bias != nullptr && col < p.N) ? __ldg(p.bias + col) : 0.0f;
       }
 
-      if (ADAPT && grp == 0) {
+      if (ADAPT && half == 0) {
         // ---- H -> Z ----
         // this row's scaled singular values first: their global-load latency hides behind the wait for H
         const int grow_c = grow < p.T ? grow : (p.T - 1);
@@ -359,7 +355,7 @@ svlora_gemm_pair_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_c
 
       // ---- D -> OUT ----
       EpiAux aux_cur, aux_nxt;
-      epi_load_aux<ACT>(p, aux_nxt, grow, n0 + static_cast<int>(grp) * EPI_PIECE_COLS);   // piece 0, before the wait
+      epi_load_aux<ACT>(p, aux_nxt, grow, n0 + static_cast<int>(half) * EPI_PIECE_COLS);   // piece 0, before the wait
       PAIR_PROF(const long long k2 = clock64();)
       mbar_wait(&d_full[s], aph, 700 + s);
       tc_fence_after();
@@ -368,8 +364,8 @@ svlora_gemm_pair_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_c
       for (int pc = 0; pc < PIECES; ++pc) {
         aux_cur = aux_nxt;
         if (pc + 1 < PIECES)
-          epi_load_aux<ACT>(p, aux_nxt, grow, n0 + (EPW * (pc + 1) + static_cast<int>(grp)) * EPI_PIECE_COLS);
-        const int cc = (EPW * pc + static_cast<int>(grp)) * EPI_PIECE_COLS;   // tile column of this piece
+          epi_load_aux<ACT>(p, aux_nxt, grow, n0 + (2 * (pc + 1) + static_cast<int>(half)) * EPI_PIECE_COLS);
+        const int cc = (2 * pc + static_cast<int>(half)) * EPI_PIECE_COLS;   // tile column of this piece
         const int tcol = (!ADAPT || cc < HN) ? cc : cc + HR;                   // accumulator column (skip the H block)
         uint32_t v[32];
         PAIR_PROF(const long long q0 = clock64();)
@@ -450,9 +446,9 @@ int launch_svlora_gemm_pair(const GemmOperands& o, cudaStream_t stream) {
   if (dev != attr_dev) {
     FFM_CHECK_CUDA(cudaFuncSetAttribute(svlora_gemm_pair_kernel<ACT_NONE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                         SMEM_BYTES));
-    FFM_CHECK_CUDA(cudaFuncSetAttribute(svlora_gemm_pair_kernel<ACT_QUICKGELU, true, 3>,
+    FFM_CHECK_CUDA(cudaFuncSetAttribute(svlora_gemm_pair_kernel<ACT_QUICKGELU>,
                                         cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-    FFM_CHECK_CUDA(cudaFuncSetAttribute(svlora_gemm_pair_kernel<ACT_QUICKGELU_GRAD, true, 3>,
+    FFM_CHECK_CUDA(cudaFuncSetAttribute(svlora_gemm_pair_kernel<ACT_QUICKGELU_GRAD>,
                                         cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
     FFM_CHECK_CUDA(cudaFuncSetAttribute(svlora_gemm_pair_kernel<ACT_NONE, false>,
                                         cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
@@ -465,7 +461,7 @@ int launch_svlora_gemm_pair(const GemmOperands& o, cudaStream_t stream) {
   if ((rc = gemm_profile_begin(&prof, stream))) return rc;
   const int grid = 2 * clusters;
   if (!adapt) {
-    svlora_gemm_pair_kernel<ACT_NONE, false><<<grid, num_threads(2), SMEM_BYTES, stream>>>(tm_x, tm_w, tm_a, tm_b, tm_y, tm_y2,
+    svlora_gemm_pair_kernel<ACT_NONE, false><<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(tm_x, tm_w, tm_a, tm_b, tm_y, tm_y2,
                                                                                          p);
     FFM_CHECK_CUDA(cudaGetLastError());
     count_launch();
@@ -473,15 +469,15 @@ int launch_svlora_gemm_pair(const GemmOperands& o, cudaStream_t stream) {
   }
   switch (p.act) {
     case ACT_QUICKGELU:
-      svlora_gemm_pair_kernel<ACT_QUICKGELU, true, 3><<<grid, num_threads(3), SMEM_BYTES, stream>>>(tm_x, tm_w, tm_a, tm_b, tm_y,
+      svlora_gemm_pair_kernel<ACT_QUICKGELU><<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(tm_x, tm_w, tm_a, tm_b, tm_y,
                                                                                         tm_y2, p);
       break;
     case ACT_QUICKGELU_GRAD:
-      svlora_gemm_pair_kernel<ACT_QUICKGELU_GRAD, true, 3><<<grid, num_threads(3), SMEM_BYTES, stream>>>(tm_x, tm_w, tm_a, tm_b,
+      svlora_gemm_pair_kernel<ACT_QUICKGELU_GRAD><<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(tm_x, tm_w, tm_a, tm_b,
                                                                                              tm_y, tm_y2, p);
       break;
     default:
-      svlora_gemm_pair_kernel<ACT_NONE><<<grid, num_threads(2), SMEM_BYTES, stream>>>(tm_x, tm_w, tm_a, tm_b, tm_y, tm_y2,
+      svlora_gemm_pair_kernel<ACT_NONE><<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(tm_x, tm_w, tm_a, tm_b, tm_y, tm_y2,
                                                                                    p);
   }
   FFM_CHECK_CUDA(cudaGetLastError());
