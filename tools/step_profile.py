@@ -4,20 +4,15 @@ import argparse, sys, collections
 from pathlib import Path
 import torch
 sys.path.insert(0, str(Path(__file__).resolve().parent.parent))
+sys.path.insert(0, str(Path(__file__).resolve().parent))
 import bench  # noqa: E402
-import fairfedmed_b200.trainer  # noqa: F401,E402
-from fairfedmed_b200.registry import build_trainer  # noqa: E402
+import step_ablation  # noqa: E402
 
 ap = argparse.ArgumentParser(); ap.add_argument("--steps", type=int, default=3); ap.add_argument("--ot", default="Sinkhorn")
 a = ap.parse_args()
 dev = torch.device("cuda:0")
-cfg = bench.make_cfg(1, bench.BATCH, a.ot)
-tr = build_trainer(cfg); tr.sync_metrics = False; tr.step_auc = False; tr.model.check_nan = False
-tr.batch_idx, tr.num_batches = 0, 10 ** 9
+tr, _c = step_ablation.build("baseline")       # configs[1], batch 64, Sinkhorn head (eager launches are profiled here)
 g = torch.Generator().manual_seed(0)
-with torch.no_grad():
-    for n_, p_ in tr.model.named_parameters():
-        if "lora_A" in n_: p_.copy_((0.02 * torch.randn(p_.shape, generator=g)).to(dev))
 batch = {"img": torch.randint(0, 256, (bench.BATCH, 1, 224, 224), generator=g).float().repeat(1, 3, 1, 1).to(dev),
          "label": (torch.arange(bench.BATCH) % 2).to(dev), "attrs": torch.randint(0, 3, (bench.BATCH, 1), generator=g).to(dev)}
 for _ in range(5): tr.forward_backward(batch)
