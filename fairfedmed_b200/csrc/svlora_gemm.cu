@@ -506,11 +506,27 @@ static PFN_encodeTiled get_encode_fn() {
   return fn;
 }
 
-PFN_encodeTiled tensor_map_encode_fn() { return get_encode_fn(); }   // shared with attention.cu
+// cuTensorMapEncodeTiled is a DRIVER entry point and needs a context bound to the calling thread.  PyTorch's autograd worker
+// threads only select a device; the primary context is bound lazily by the first runtime call that needs it, and a backward
+// node whose first action is encoding a tensor map (ffm_frozen_linear, ffm_attention_bwd) would otherwise fail with
+// CUDA_ERROR_INVALID_CONTEXT when nothing else ran on that thread before it.  Once per thread.
+static void bind_context_to_thread() {
+  static thread_local bool bound = false;
+  if (!bound) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) == cudaSuccess) cudaSetDevice(dev);   // CUDA 12: initialises and binds the primary context;
+    bound = true;                                                 // not a stream operation, legal during graph capture
+  }
+}
+
+PFN_encodeTiled tensor_map_encode_fn() {          // shared with attention.cu
+  bind_context_to_thread();
+  return get_encode_fn();
+}
 
 int make_map_bf16(CUtensorMap* out, const void* ptr, uint64_t rows, uint64_t cols, uint32_t box_rows,
                          uint32_t box_cols, CUtensorMapSwizzle swz, bool promote) {
-  PFN_encodeTiled enc = get_encode_fn();
+  PFN_encodeTiled enc = tensor_map_encode_fn();
   if (enc == nullptr) {
     set_last_error("cuTensorMapEncodeTiled driver entry point not available");
     return FFM_ERR_CUDA;
