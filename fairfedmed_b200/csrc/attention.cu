@@ -275,6 +275,9 @@ attention_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_c
       const int b = u / p.H, h = u - b * p.H;
       for (int t = 0; t < nt; ++t, ++n) {
         mbar_wait(o_full, n & 1u, 200);
+        // the statistics were released on p_full by the softmax warps: acquire that barrier directly (already complete: the
+        // P V contraction that o_full tracks was issued after it) instead of relying on the hand-off through the MMA warp
+        mbar_wait(&p_full[n & 1u], (n >> 1) & 1u, 201);
         tc_fence_after();
         const float2 st2 = stat[(n & 1u) * 128 + row];
         const int qi = t * 128 + row;
@@ -440,7 +443,7 @@ attention_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_c
       mbar_init(&pds_full[i], 8);
       mbar_init(&stage_free[i], 1);
       mbar_init(&dq_full[i], 1);
-      mbar_init(&delta_full[i], 1);
+      mbar_init(&delta_full[i], 32);
       mbar_init(&delta_free[i], 8);
     }
     fence_mbar_init();
@@ -586,8 +589,7 @@ attention_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_c
         del_b[r] = d;
         lse_b[r] = l2;
       }
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&delta_full[it & 1]);
+      mbar_arrive(&delta_full[it & 1]);          // every lane releases its own rows
     }
   } else {
     // ============================== element-wise warps ==============================
