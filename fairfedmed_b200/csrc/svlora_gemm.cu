@@ -563,7 +563,9 @@ static bool use_pair_kernel(int act) {
   return act != ACT_QUICKGELU;
 }
 
-// FFM_GEMM_DBG: bottleneck experiments only (1: no MMA, 2: no TMA loads, 4: no TMA stores); results are garbage
+// FFM_GEMM_DBG: bottleneck experiments only (1: no MMA, 2: no TMA loads, 4: no TMA stores, 64: print the pair build's epilogue
+// phases when compiled with -DFFM_GEMM_PAIR_PROF, 128: no proxy fence, 256: no staging stores, 512: no staging-buffer reuse
+// wait); results are garbage
 int gemm_debug_mask() {
   static int v = -1;
   if (v < 0) {

@@ -22,7 +22,7 @@ struct GemmParams {
   int act;
   int has_pre;                  // ACT_QUICKGELU: also store QuickGELU'(u) through tm_y2
   int m_tiles, n_tiles, k_blocks;
-  int dbg;                      // FFM_GEMM_DBG experiment mask (1: no MMA, 2: no TMA loads, 4: no TMA stores); 0 in production
+  int dbg;                      // FFM_GEMM_DBG experiment mask (see gemm_debug_mask); 0 in production
 };
 
 int gemm_debug_mask();

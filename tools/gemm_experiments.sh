@@ -1,6 +1,7 @@
 #!/bin/bash
 # Bottleneck experiments for the fused SVLoRA GEMM (run on the B200 box): which of TMA loads / MMA issue / epilogue bounds it.
-# FFM_GEMM_DBG bits: 1 no MMA, 2 no TMA loads, 4 no TMA stores, 8 main MMA with N=192 (no H columns), 16 skeleton epilogue
+# FFM_GEMM_DBG bits: 1 no MMA, 2 no TMA loads, 4 no TMA stores, 128 no proxy fence, 256 no staging stores, 512 no staging-buffer
+# reuse wait (64: epilogue phase print-out of the pair build when compiled with -DFFM_GEMM_PAIR_PROF)
 out=gpurun_out/gemm_experiments.txt
 : > $out
 for pair in ${PAIRS:-0}; do
