@@ -509,7 +509,11 @@ class CustomCLIP(nn.Module):
             # convolution), then min-max scaling + mean/std + bf16 cast + im2col as two fused passes (own backward)
             fast_input = True
             slices = image.float().reshape(-1, self.dim_per_3d_slice, image.shape[2], image.shape[3])
-            y = F.conv2d(slices, self.proj_per_3d_slice.weight / 255.0, self.proj_per_3d_slice.bias, padding=2)
+            pw, pb = self.proj_per_3d_slice.weight, self.proj_per_3d_slice.bias
+            if ops.oct_slice_conv_supported(slices, pw, 2) and pb is not None:
+                y = ops.oct_slice_conv(slices, pw, pb, 1.0 / 255.0)            # own forward + weight-gradient kernels
+            else:
+                y = F.conv2d(slices, pw / 255.0, pb, padding=2)
             patches = ops.oct_minmax_patchify(y, self.pixel_mean.reshape(-1), self.pixel_std.reshape(-1), ve.patch_size)
             feats = ve.forward_patches(patches, attr=attr_dev, batch_first=True)
         elif fast_input:

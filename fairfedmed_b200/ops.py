@@ -678,6 +678,66 @@ def _(image, mean, std, patch, div255):
     return image.new_empty((bp, (h // patch) * (w // patch), c * patch * patch), dtype=torch.bfloat16)
 
 
+@torch.library.custom_op("ffm::oct_slice_conv_fwd", mutates_args=())
+def oct_slice_conv_fwd_op(x: Tensor, w: Tensor, bias: Tensor, in_scale: float) -> Tensor:
+    _need_cuda(x, w, bias)
+    bp, cin, h, wd = x.shape
+    cout = w.shape[0]
+    y = torch.empty((bp, cout, h, wd), device=x.device, dtype=torch.float32)
+    _cabi.call("ffm_oct_slice_conv_fwd", _ptr(x), _ptr(w), _ptr(bias), _ptr(y), bp, cin, cout, h, wd, float(in_scale),
+               _stream())
+    return y
+
+
+@oct_slice_conv_fwd_op.register_fake
+def _(x, w, bias, in_scale):
+    return x.new_empty((x.shape[0], w.shape[0], x.shape[2], x.shape[3]))
+
+
+@torch.library.custom_op("ffm::oct_slice_conv_wgrad", mutates_args=())
+def oct_slice_conv_wgrad_op(x: Tensor, dy: Tensor, cout: int, in_scale: float) -> Tuple[Tensor, Tensor]:
+    _need_cuda(x, dy)
+    bp, cin, h, wd = x.shape
+    dw = torch.empty((cout, cin, 5, 5), device=x.device, dtype=torch.float32)
+    db = torch.empty((cout,), device=x.device, dtype=torch.float32)
+    nbytes = int(_cabi.load().ffm_oct_slice_conv_wgrad_ws_bytes(cin))
+    ws = torch.empty((nbytes // 4,), device=x.device, dtype=torch.float32)
+    _cabi.call("ffm_oct_slice_conv_wgrad", _ptr(x), _ptr(dy), _ptr(dw), _ptr(db), _ptr(ws), nbytes, bp, cin, cout, h, wd,
+               float(in_scale), _stream())
+    return dw, db
+
+
+@oct_slice_conv_wgrad_op.register_fake
+def _(x, dy, cout, in_scale):
+    return x.new_empty((cout, x.shape[1], 5, 5)), x.new_empty((cout,))
+
+
+class _OctSliceConv(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, w, bias, in_scale):
+        ctx.save_for_backward(x)
+        ctx.cfg = (w.shape[0], in_scale)
+        return oct_slice_conv_fwd_op(x, w, bias, in_scale)
+
+    @staticmethod
+    def backward(ctx, dy):
+        (x,) = ctx.saved_tensors
+        cout, in_scale = ctx.cfg
+        dw, db = oct_slice_conv_wgrad_op(x, dy.float().contiguous(), cout, in_scale)
+        return None, dw, db, None
+
+
+def oct_slice_conv_supported(x: Tensor, w: Tensor, padding: int) -> bool:
+    return (x.is_cuda and x.dim() == 4 and w.dim() == 4 and tuple(w.shape[2:]) == (5, 5) and padding == 2 and
+            w.shape[0] <= 4 and w.shape[1] <= 32 and x.shape[3] % 4 == 0 and x.shape[0] <= 65535 and not x.requires_grad)
+
+
+def oct_slice_conv(x: Tensor, w: Tensor, bias: Tensor, in_scale: float = 1.0 / 255.0) -> Tensor:
+    """proj_per_3d_slice(image * in_scale) for the raw slices x f32 [B', Cin, H, W] (trainers/GLP_OT_SVLoRA.py:684): own
+    forward and weight-gradient kernels (the input is data and gets no gradient)."""
+    return _OctSliceConv.apply(x.float().contiguous(), w.float().contiguous(), bias.float().contiguous(), float(in_scale))
+
+
 @torch.library.custom_op("ffm::oct_minmax_patchify", mutates_args=())
 def oct_minmax_patchify_op(y: Tensor, mean: Tensor, std: Tensor, patch: int) -> Tuple[Tensor, Tensor, Tensor]:
     """patches, lo, hi: per-slice min-max scaling + mean/std + bf16 im2col of y f32 [B', C, H, W] (ffm_oct_minmax_patchify)."""

@@ -222,6 +222,20 @@ int ffm_oct_input_bwd(const void* d_patches, const float* y, const float* lo, co
                       float* d_y, void* ws, size_t ws_bytes, int Bp, int C, int H, int W, int patch, ffm_stream_t stream);
 
 /*
+ * OCT slice projection — proj_per_3d_slice = Conv2d(dim_per_3d_slice -> 3, kernel 5, padding 2) on image / 255
+ * (trainers/GLP_OT_SVLoRA.py:587-595, :684); in_scale (1 / 255) is folded into the weights.
+ *   x f32 [Bp, Cin, H, W] (the raw slices), w f32 [Cout, Cin, 5, 5], bias f32 [Cout], y / dy f32 [Bp, Cout, H, W];
+ *   Cin <= 32, Cout <= 4, W a multiple of 4.
+ * ffm_oct_slice_conv_wgrad: dw [Cout, Cin, 5, 5] and dbias [Cout] of the same expression (the input is data and needs no
+ * gradient); deterministic; `ws` of at least ffm_oct_slice_conv_wgrad_ws_bytes(Cin) bytes.
+ */
+size_t ffm_oct_slice_conv_wgrad_ws_bytes(int Cin);
+int ffm_oct_slice_conv_fwd(const float* x, const float* w, const float* bias, float* y, int Bp, int Cin, int Cout, int H,
+                           int W, float in_scale, ffm_stream_t stream);
+int ffm_oct_slice_conv_wgrad(const float* x, const float* dy, float* dw, float* dbias, void* ws, size_t ws_bytes, int Bp,
+                             int Cin, int Cout, int H, int W, float in_scale, ffm_stream_t stream);
+
+/*
  * Merged weight of a plain LoRA projection — LoRALinear.weight(x, attr), trainers/GLP_OT_SVLoRA.py:235-239, consumed by the
  * RN50 attention pool (clip/model.py:88-97):  out[o, i] = W[o, i] + scaling * sum_j A[i, j] * B[j, o]
  *   W, out f32 [out_f, in_f]; A = lora_A.weight f32 [in_f, r]; B = lora_B.weight f32 [r, out_f]; r <= 32.

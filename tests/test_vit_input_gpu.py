@@ -211,3 +211,29 @@ def test_oct_minmax_patchify_forward_and_backward_match_autograd(shape, patch):
     y3 = y.clone().requires_grad_(True)
     (ops.oct_minmax_patchify(y3, mean, std, patch).float() * w_out).sum().backward()
     assert torch.equal(y1.grad, y3.grad)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("shape,cout", [((3, 8, 64, 64), 3), ((4, 8, 224, 224), 3), ((2, 16, 40, 52), 3), ((1, 5, 33, 36), 2)])
+def test_oct_slice_projection_matches_conv2d(shape, cout):
+    """proj_per_3d_slice(image / 255) (trainers/GLP_OT_SVLoRA.py:587-595, :684): own forward and weight-gradient kernels against
+    torch's convolution in fp64 on the same inputs (raw 0..255 slices; the input needs no gradient); ragged tiles included."""
+    from fairfedmed_b200 import ops
+    torch.manual_seed(11)
+    bp, cin, h, w = shape
+    x = torch.randint(0, 256, shape).float().to("cuda:0")
+    wt = (torch.randn(cout, cin, 5, 5) * cin ** -0.5).to("cuda:0").requires_grad_(True)
+    b = torch.randn(cout).to("cuda:0").requires_grad_(True)
+    dy = torch.randn(bp, cout, h, w).to("cuda:0")
+    assert ops.oct_slice_conv_supported(x, wt, 2)
+    y = ops.oct_slice_conv(x, wt, b, 1.0 / 255.0)
+    y.backward(dy)
+    w64, b64 = wt.detach().double().requires_grad_(True), b.detach().double().requires_grad_(True)
+    ref = F.conv2d(x.double() / 255.0, w64, b64, padding=2)
+    ref.backward(dy.double())
+    torch.testing.assert_close(y.detach().double(), ref.detach(), rtol=1e-4, atol=1e-4)
+    torch.testing.assert_close(wt.grad.double(), w64.grad, rtol=2e-4, atol=2e-4 * float(w64.grad.abs().max()))
+    torch.testing.assert_close(b.grad.double(), b64.grad, rtol=2e-4, atol=2e-4 * float(b64.grad.abs().max()))
+    w2, b2 = wt.detach().clone().requires_grad_(True), b.detach().clone().requires_grad_(True)
+    ops.oct_slice_conv(x, w2, b2, 1.0 / 255.0).backward(dy)
+    assert torch.equal(wt.grad, w2.grad) and torch.equal(b.grad, b2.grad)        # deterministic
