@@ -444,6 +444,60 @@ def svlora_mlp(x2d, fc, proj, scaling: float, b_prime: int, num_slices: int, row
 
 
 # =====================================================================================================
+# average pooling of the ResNet trunk on channels-last activations
+# =====================================================================================================
+@torch.library.custom_op("ffm::avgpool_nhwc_fwd", mutates_args=())
+def avgpool_nhwc_fwd_op(x: Tensor, k: int) -> Tensor:
+    _need_cuda(x)
+    b, c, h, w = x.shape
+    y = torch.empty((b, c, h // k, w // k), device=x.device, dtype=torch.float32, memory_format=torch.channels_last)
+    _cabi.call("ffm_avgpool_nhwc_fwd", _ptr(x), _ptr(y), b, h, w, c, int(k), _stream())
+    return y
+
+
+@avgpool_nhwc_fwd_op.register_fake
+def _(x, k):
+    b, c, h, w = x.shape
+    return torch.empty((b, c, h // k, w // k), device=x.device, dtype=torch.float32, memory_format=torch.channels_last)
+
+
+@torch.library.custom_op("ffm::avgpool_nhwc_bwd", mutates_args=())
+def avgpool_nhwc_bwd_op(dy: Tensor, k: int) -> Tensor:
+    _need_cuda(dy)
+    b, c, ho, wo = dy.shape
+    dx = torch.empty((b, c, ho * k, wo * k), device=dy.device, dtype=torch.float32, memory_format=torch.channels_last)
+    _cabi.call("ffm_avgpool_nhwc_bwd", _ptr(dy), _ptr(dx), b, ho * k, wo * k, c, int(k), _stream())
+    return dx
+
+
+@avgpool_nhwc_bwd_op.register_fake
+def _(dy, k):
+    b, c, ho, wo = dy.shape
+    return torch.empty((b, c, ho * k, wo * k), device=dy.device, dtype=torch.float32, memory_format=torch.channels_last)
+
+
+class _AvgPoolNHWC(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, k):
+        ctx.k = k
+        return avgpool_nhwc_fwd_op(x, k)
+
+    @staticmethod
+    def backward(ctx, dy):
+        return avgpool_nhwc_bwd_op(dy.float().contiguous(memory_format=torch.channels_last), ctx.k), None
+
+
+def avgpool_nhwc_supported(x: Tensor, k: int) -> bool:
+    return (x.is_cuda and x.dim() == 4 and x.dtype == torch.float32 and x.shape[1] % 4 == 0 and x.shape[2] % k == 0 and
+            x.shape[3] % k == 0 and x.is_contiguous(memory_format=torch.channels_last))
+
+
+def avgpool_nhwc(x: Tensor, k: int) -> Tensor:
+    """nn.AvgPool2d(k) for channels-last fp32 activations (clip/model.py:30, :42, :108) with its own backward."""
+    return _AvgPoolNHWC.apply(x, int(k))
+
+
+# =====================================================================================================
 # merged weight of a plain LoRA projection (RN50 attention pool)
 # =====================================================================================================
 @torch.library.custom_op("ffm::lora_merged_weight", mutates_args=())

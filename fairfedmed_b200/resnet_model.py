@@ -20,6 +20,7 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
+from . import ops
 from .modules import _AdapterBase, _attr_on
 
 
@@ -49,7 +50,7 @@ class Bottleneck(nn.Module):
         self.bn1 = nn.BatchNorm2d(planes)
         self.conv2 = nn.Conv2d(planes, planes, 3, padding=1, bias=False)
         self.bn2 = nn.BatchNorm2d(planes)
-        self.avgpool = nn.AvgPool2d(stride) if stride > 1 else nn.Identity()
+        self.avgpool = _AvgPool2d(stride) if stride > 1 else nn.Identity()
         self.conv3 = nn.Conv2d(planes, planes * self.expansion, 1, bias=False)
         self.bn3 = nn.BatchNorm2d(planes * self.expansion)
         self.relu = nn.ReLU(inplace=True)
@@ -57,7 +58,7 @@ class Bottleneck(nn.Module):
         self.stride = stride
         if stride > 1 or inplanes != planes * Bottleneck.expansion:
             self.downsample = nn.Sequential(OrderedDict([
-                ("-1", nn.AvgPool2d(stride)),
+                ("-1", _AvgPool2d(stride)),
                 ("0", nn.Conv2d(inplanes, planes * self.expansion, 1, stride=1, bias=False)),
                 ("1", nn.BatchNorm2d(planes * self.expansion)),
             ]))
@@ -74,6 +75,17 @@ class Bottleneck(nn.Module):
         return self.relu(out + identity)
 
 
+class _AvgPool2d(nn.AvgPool2d):
+    """nn.AvgPool2d(stride) (clip/model.py:30, :42, :108): channels-last fp32 activations on CUDA go through the package's own
+    streaming kernels (forward + backward), everything else through the library."""
+
+    def forward(self, x):
+        k = self.kernel_size if isinstance(self.kernel_size, int) else self.kernel_size[0]
+        if ops.avgpool_nhwc_supported(x, k) and self.stride in (k, (k, k), None) and self.padding in (0, (0, 0)):
+            return ops.avgpool_nhwc(x, k)
+        return super().forward(x)
+
+
 class AttentionPool2d(nn.Module):
     """QKV attention over the HW tokens + their mean, every token as a query (clip/model.py:63-118)."""
 
@@ -85,6 +97,11 @@ class AttentionPool2d(nn.Module):
         self.v_proj = nn.Linear(embed_dim, embed_dim)
         self.c_proj = nn.Linear(embed_dim, output_dim or embed_dim)
         self.num_heads, self.embed_dim, self.spacial_dim = num_heads, embed_dim, spacial_dim
+
+    # the four projections and the attention run on the bf16 tensor cores (the reference runs them in fp16 under its
+    # half-precision CLIP, clip/model.py:88-118); fp32 masters / merged weights are cast on the way in.  torch.float32
+    # reproduces the reference's fp32 CPU arithmetic (tests) at the price of SIMT fp32 GEMMs (5.3 ms per RN50 step).
+    compute_dtype = torch.bfloat16
 
     @staticmethod
     def _wb(layer, x, attr):
@@ -99,6 +116,8 @@ class AttentionPool2d(nn.Module):
         x = torch.cat([x.mean(dim=0, keepdim=True), x], dim=0)                         # (HW+1) N C
         x = x + self.positional_embedding[:, None, :].to(x.dtype)
         L = x.shape[0]
+        if x.is_cuda and self.compute_dtype is not None:
+            x = x.to(self.compute_dtype)
         dt = x.dtype
         hd = c // self.num_heads
         proj = []
@@ -126,7 +145,7 @@ class ModifiedResNet_GLP_OT(nn.Module):
         self.bn2 = nn.BatchNorm2d(width // 2)
         self.conv3 = nn.Conv2d(width // 2, width, kernel_size=3, padding=1, bias=False)
         self.bn3 = nn.BatchNorm2d(width)
-        self.avgpool = nn.AvgPool2d(2)
+        self.avgpool = _AvgPool2d(2)
         self.relu = nn.ReLU(inplace=True)
         self._inplanes = width
         self.layer1 = self._make_layer(width, layers[0])

@@ -249,6 +249,13 @@ int ffm_lora_merged_weight_bwd(const float* dWm, const float* A, const float* B,
                                size_t ws_bytes, int out_f, int in_f, int r, float scaling, ffm_stream_t stream);
 
 /*
+ * nn.AvgPool2d(k) of the ResNet trunk (clip/model.py:30, :42, :108) on channels-last fp32 activations:
+ *   x, dx f32 [B, H, W, C] (NHWC memory), y, dy f32 [B, H/k, W/k, C]; H, W multiples of k, C a multiple of 4.
+ */
+int ffm_avgpool_nhwc_fwd(const float* x, float* y, int B, int H, int W, int C, int k, ffm_stream_t stream);
+int ffm_avgpool_nhwc_bwd(const float* dy, float* dx, int B, int H, int W, int C, int k, ffm_stream_t stream);
+
+/*
  * Group mixing of singular values — trainers/GLP_OT_SVLoRA.py:453-467.
  *   attr != NULL: pi[b,g] = lambda (0.7 in the reference) if attr[b]==g else (1-lambda)/(G-1)
  *   attr == NULL: n_samples must be 1 and pi = 1/G

@@ -237,3 +237,24 @@ def test_oct_slice_projection_matches_conv2d(shape, cout):
     w2, b2 = wt.detach().clone().requires_grad_(True), b.detach().clone().requires_grad_(True)
     ops.oct_slice_conv(x, w2, b2, 1.0 / 255.0).backward(dy)
     assert torch.equal(wt.grad, w2.grad) and torch.equal(b.grad, b2.grad)        # deterministic
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("shape,k", [((3, 64, 16, 16), 2), ((2, 256, 56, 56), 2), ((2, 8, 12, 20), 4)])
+def test_avgpool_nhwc_matches_torch(shape, k):
+    """nn.AvgPool2d(k) of the ResNet trunk (clip/model.py:30, :42, :108) on channels-last fp32 activations: forward and backward
+    against torch."""
+    from fairfedmed_b200 import ops
+    torch.manual_seed(2)
+    x = torch.randn(shape, device="cuda:0").contiguous(memory_format=torch.channels_last)
+    assert ops.avgpool_nhwc_supported(x, k)
+    x1 = x.clone().requires_grad_(True)
+    y = ops.avgpool_nhwc(x1, k)
+    dy = torch.randn_like(y)
+    y.backward(dy)
+    x2 = x.clone().requires_grad_(True)
+    ref = F.avg_pool2d(x2, k)
+    ref.backward(dy)
+    torch.testing.assert_close(y, ref, rtol=1e-6, atol=1e-6)
+    torch.testing.assert_close(x1.grad, x2.grad, rtol=1e-6, atol=1e-7)
+    assert y.is_contiguous(memory_format=torch.channels_last) and x1.grad.is_contiguous(memory_format=torch.channels_last)
