@@ -7,45 +7,79 @@
 
 namespace ffm {
 
-// one thread = 4 channels of one OUTPUT pixel
+// 16 bytes of activations = 4 fp32 or 8 bf16 channels, accumulated in fp32
+template <bool BF16>
+struct Vec16 {
+  static constexpr int N = BF16 ? 8 : 4;
+  __device__ static void load(const uint4* p, float (&v)[8]) {
+    const uint4 r = __ldg(p);
+    if (BF16) {
+      const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&r);
+#pragma unroll
+      for (int e = 0; e < 4; ++e) { const float2 f = __bfloat1622float2(h2[e]); v[2 * e] = f.x; v[2 * e + 1] = f.y; }
+    } else {
+      v[0] = __uint_as_float(r.x); v[1] = __uint_as_float(r.y); v[2] = __uint_as_float(r.z); v[3] = __uint_as_float(r.w);
+    }
+  }
+  __device__ static void store(uint4* p, const float (&v)[8]) {
+    uint4 r;
+    if (BF16) {
+      r.x = pack_bf16x2(v[0], v[1]); r.y = pack_bf16x2(v[2], v[3]); r.z = pack_bf16x2(v[4], v[5]); r.w = pack_bf16x2(v[6], v[7]);
+    } else {
+      r.x = __float_as_uint(v[0]); r.y = __float_as_uint(v[1]); r.z = __float_as_uint(v[2]); r.w = __float_as_uint(v[3]);
+    }
+    *p = r;
+  }
+};
+
+// one thread = one 16-byte channel group of one OUTPUT pixel
+template <bool BF16>
 __global__ void __launch_bounds__(256)
-avgpool_nhwc_fwd_kernel(const float4* __restrict__ x, float4* __restrict__ y, int Ho, int Wo, int C4, int W, int k,
+avgpool_nhwc_fwd_kernel(const uint4* __restrict__ x, uint4* __restrict__ y, int Ho, int Wo, int CV, int W, int k,
                         long long n_out) {
   const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (i >= n_out) return;
-  const int c = static_cast<int>(i % C4);
-  long long r = i / C4;
+  const int c = static_cast<int>(i % CV);
+  long long r = i / CV;
   const int wo = static_cast<int>(r % Wo);
   r /= Wo;
   const int ho = static_cast<int>(r % Ho);
   const long long b = r / Ho;
   const long long H = static_cast<long long>(Ho) * k;
-  float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+  float s[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
   for (int di = 0; di < k; ++di)
     for (int dj = 0; dj < k; ++dj) {
-      const float4 v = __ldg(x + ((b * H + static_cast<long long>(ho) * k + di) * W + static_cast<long long>(wo) * k + dj) * C4 + c);
-      s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+      float v[8];
+      Vec16<BF16>::load(x + ((b * H + static_cast<long long>(ho) * k + di) * W + static_cast<long long>(wo) * k + dj) * CV + c, v);
+#pragma unroll
+      for (int e = 0; e < Vec16<BF16>::N; ++e) s[e] += v[e];
     }
   const float inv = 1.0f / static_cast<float>(k * k);
-  y[i] = make_float4(s.x * inv, s.y * inv, s.z * inv, s.w * inv);
+#pragma unroll
+  for (int e = 0; e < 8; ++e) s[e] *= inv;
+  Vec16<BF16>::store(y + i, s);
 }
 
-// one thread = 4 channels of one INPUT pixel: dx = dy[h / k, w / k] / k^2
+// one thread = one 16-byte channel group of one INPUT pixel: dx = dy[h / k, w / k] / k^2
+template <bool BF16>
 __global__ void __launch_bounds__(256)
-avgpool_nhwc_bwd_kernel(const float4* __restrict__ dy, float4* __restrict__ dx, int H, int W, int C4, int k,
+avgpool_nhwc_bwd_kernel(const uint4* __restrict__ dy, uint4* __restrict__ dx, int H, int W, int CV, int k,
                         long long n_in) {
   const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (i >= n_in) return;
-  const int c = static_cast<int>(i % C4);
-  long long r = i / C4;
+  const int c = static_cast<int>(i % CV);
+  long long r = i / CV;
   const int w = static_cast<int>(r % W);
   r /= W;
   const int h = static_cast<int>(r % H);
   const long long b = r / H;
   const int Ho = H / k, Wo = W / k;
-  const float4 v = __ldg(dy + ((b * Ho + h / k) * Wo + w / k) * C4 + c);
+  float v[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  Vec16<BF16>::load(dy + ((b * Ho + h / k) * Wo + w / k) * CV + c, v);
   const float inv = 1.0f / static_cast<float>(k * k);
-  dx[i] = make_float4(v.x * inv, v.y * inv, v.z * inv, v.w * inv);
+#pragma unroll
+  for (int e = 0; e < 8; ++e) v[e] *= inv;
+  Vec16<BF16>::store(dx + i, v);
 }
 
 }  // namespace ffm
@@ -54,29 +88,39 @@ using namespace ffm;
 
 extern "C" {
 
-int ffm_avgpool_nhwc_fwd(const float* x, float* y, int B, int H, int W, int C, int k, cudaStream_t stream) {
+int ffm_avgpool_nhwc_fwd(const void* x, void* y, int B, int H, int W, int C, int k, int elem_bf16, cudaStream_t stream) {
   FFM_CHECK_ARG(x && y, "ffm_avgpool_nhwc_fwd: null pointer argument");
-  FFM_CHECK_ARG(B >= 1 && k >= 1 && H % k == 0 && W % k == 0 && C % 4 == 0 && H >= k && W >= k,
-                "ffm_avgpool_nhwc_fwd: H, W must be multiples of k and C a multiple of 4");
-  const long long n_out = static_cast<long long>(B) * (H / k) * (W / k) * (C / 4);
+  const int per = elem_bf16 ? 8 : 4;
+  FFM_CHECK_ARG(B >= 1 && k >= 1 && H % k == 0 && W % k == 0 && C % per == 0 && H >= k && W >= k,
+                "ffm_avgpool_nhwc_fwd: H, W must be multiples of k and C a multiple of 4 (fp32) / 8 (bf16)");
+  const long long n_out = static_cast<long long>(B) * (H / k) * (W / k) * (C / per);
   const long long blocks = (n_out + 255) / 256;
   FFM_CHECK_ARG(blocks <= 0x7fffffffLL, "ffm_avgpool_nhwc_fwd: too many elements");
-  avgpool_nhwc_fwd_kernel<<<static_cast<unsigned>(blocks), 256, 0, stream>>>(
-      reinterpret_cast<const float4*>(x), reinterpret_cast<float4*>(y), H / k, W / k, C / 4, W, k, n_out);
+  if (elem_bf16)
+    avgpool_nhwc_fwd_kernel<true><<<static_cast<unsigned>(blocks), 256, 0, stream>>>(
+        static_cast<const uint4*>(x), static_cast<uint4*>(y), H / k, W / k, C / per, W, k, n_out);
+  else
+    avgpool_nhwc_fwd_kernel<false><<<static_cast<unsigned>(blocks), 256, 0, stream>>>(
+        static_cast<const uint4*>(x), static_cast<uint4*>(y), H / k, W / k, C / per, W, k, n_out);
   FFM_CHECK_CUDA(cudaGetLastError());
   count_launch();
   return FFM_OK;
 }
 
-int ffm_avgpool_nhwc_bwd(const float* dy, float* dx, int B, int H, int W, int C, int k, cudaStream_t stream) {
+int ffm_avgpool_nhwc_bwd(const void* dy, void* dx, int B, int H, int W, int C, int k, int elem_bf16, cudaStream_t stream) {
   FFM_CHECK_ARG(dy && dx, "ffm_avgpool_nhwc_bwd: null pointer argument");
-  FFM_CHECK_ARG(B >= 1 && k >= 1 && H % k == 0 && W % k == 0 && C % 4 == 0 && H >= k && W >= k,
-                "ffm_avgpool_nhwc_bwd: H, W must be multiples of k and C a multiple of 4");
-  const long long n_in = static_cast<long long>(B) * H * W * (C / 4);
+  const int per = elem_bf16 ? 8 : 4;
+  FFM_CHECK_ARG(B >= 1 && k >= 1 && H % k == 0 && W % k == 0 && C % per == 0 && H >= k && W >= k,
+                "ffm_avgpool_nhwc_bwd: H, W must be multiples of k and C a multiple of 4 (fp32) / 8 (bf16)");
+  const long long n_in = static_cast<long long>(B) * H * W * (C / per);
   const long long blocks = (n_in + 255) / 256;
   FFM_CHECK_ARG(blocks <= 0x7fffffffLL, "ffm_avgpool_nhwc_bwd: too many elements");
-  avgpool_nhwc_bwd_kernel<<<static_cast<unsigned>(blocks), 256, 0, stream>>>(
-      reinterpret_cast<const float4*>(dy), reinterpret_cast<float4*>(dx), H, W, C / 4, k, n_in);
+  if (elem_bf16)
+    avgpool_nhwc_bwd_kernel<true><<<static_cast<unsigned>(blocks), 256, 0, stream>>>(
+        static_cast<const uint4*>(dy), static_cast<uint4*>(dx), H, W, C / per, k, n_in);
+  else
+    avgpool_nhwc_bwd_kernel<false><<<static_cast<unsigned>(blocks), 256, 0, stream>>>(
+        static_cast<const uint4*>(dy), static_cast<uint4*>(dx), H, W, C / per, k, n_in);
   FFM_CHECK_CUDA(cudaGetLastError());
   count_launch();
   return FFM_OK;

@@ -450,30 +450,31 @@ def svlora_mlp(x2d, fc, proj, scaling: float, b_prime: int, num_slices: int, row
 def avgpool_nhwc_fwd_op(x: Tensor, k: int) -> Tensor:
     _need_cuda(x)
     b, c, h, w = x.shape
-    y = torch.empty((b, c, h // k, w // k), device=x.device, dtype=torch.float32, memory_format=torch.channels_last)
-    _cabi.call("ffm_avgpool_nhwc_fwd", _ptr(x), _ptr(y), b, h, w, c, int(k), _stream())
+    y = torch.empty((b, c, h // k, w // k), device=x.device, dtype=x.dtype, memory_format=torch.channels_last)
+    _cabi.call("ffm_avgpool_nhwc_fwd", _ptr(x), _ptr(y), b, h, w, c, int(k), int(x.dtype == torch.bfloat16), _stream())
     return y
 
 
 @avgpool_nhwc_fwd_op.register_fake
 def _(x, k):
     b, c, h, w = x.shape
-    return torch.empty((b, c, h // k, w // k), device=x.device, dtype=torch.float32, memory_format=torch.channels_last)
+    return torch.empty((b, c, h // k, w // k), device=x.device, dtype=x.dtype, memory_format=torch.channels_last)
 
 
 @torch.library.custom_op("ffm::avgpool_nhwc_bwd", mutates_args=())
 def avgpool_nhwc_bwd_op(dy: Tensor, k: int) -> Tensor:
     _need_cuda(dy)
     b, c, ho, wo = dy.shape
-    dx = torch.empty((b, c, ho * k, wo * k), device=dy.device, dtype=torch.float32, memory_format=torch.channels_last)
-    _cabi.call("ffm_avgpool_nhwc_bwd", _ptr(dy), _ptr(dx), b, ho * k, wo * k, c, int(k), _stream())
+    dx = torch.empty((b, c, ho * k, wo * k), device=dy.device, dtype=dy.dtype, memory_format=torch.channels_last)
+    _cabi.call("ffm_avgpool_nhwc_bwd", _ptr(dy), _ptr(dx), b, ho * k, wo * k, c, int(k), int(dy.dtype == torch.bfloat16),
+               _stream())
     return dx
 
 
 @avgpool_nhwc_bwd_op.register_fake
 def _(dy, k):
     b, c, ho, wo = dy.shape
-    return torch.empty((b, c, ho * k, wo * k), device=dy.device, dtype=torch.float32, memory_format=torch.channels_last)
+    return torch.empty((b, c, ho * k, wo * k), device=dy.device, dtype=dy.dtype, memory_format=torch.channels_last)
 
 
 class _AvgPoolNHWC(torch.autograd.Function):
@@ -484,12 +485,13 @@ class _AvgPoolNHWC(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, dy):
-        return avgpool_nhwc_bwd_op(dy.float().contiguous(memory_format=torch.channels_last), ctx.k), None
+        return avgpool_nhwc_bwd_op(dy.contiguous(memory_format=torch.channels_last), ctx.k), None
 
 
 def avgpool_nhwc_supported(x: Tensor, k: int) -> bool:
-    return (x.is_cuda and x.dim() == 4 and x.dtype == torch.float32 and x.shape[1] % 4 == 0 and x.shape[2] % k == 0 and
-            x.shape[3] % k == 0 and x.is_contiguous(memory_format=torch.channels_last))
+    per = 8 if x.dtype == torch.bfloat16 else 4
+    return (x.is_cuda and x.dim() == 4 and x.dtype in (torch.float32, torch.bfloat16) and x.shape[1] % per == 0 and
+            x.shape[2] % k == 0 and x.shape[3] % k == 0 and x.is_contiguous(memory_format=torch.channels_last))
 
 
 def avgpool_nhwc(x: Tensor, k: int) -> Tensor:

@@ -250,10 +250,11 @@ int ffm_lora_merged_weight_bwd(const float* dWm, const float* A, const float* B,
 
 /*
  * nn.AvgPool2d(k) of the ResNet trunk (clip/model.py:30, :42, :108) on channels-last fp32 activations:
- *   x, dx f32 [B, H, W, C] (NHWC memory), y, dy f32 [B, H/k, W/k, C]; H, W multiples of k, C a multiple of 4.
+ *   x, dx [B, H, W, C] (NHWC memory), y, dy [B, H/k, W/k, C], f32 (elem_bf16 = 0) or bf16 (elem_bf16 = 1, fp32
+ *   accumulation); H, W multiples of k, C a multiple of 4 (fp32) / 8 (bf16).
  */
-int ffm_avgpool_nhwc_fwd(const float* x, float* y, int B, int H, int W, int C, int k, ffm_stream_t stream);
-int ffm_avgpool_nhwc_bwd(const float* dy, float* dx, int B, int H, int W, int C, int k, ffm_stream_t stream);
+int ffm_avgpool_nhwc_fwd(const void* x, void* y, int B, int H, int W, int C, int k, int elem_bf16, ffm_stream_t stream);
+int ffm_avgpool_nhwc_bwd(const void* dy, void* dx, int B, int H, int W, int C, int k, int elem_bf16, ffm_stream_t stream);
 
 /*
  * Group mixing of singular values — trainers/GLP_OT_SVLoRA.py:453-467.

@@ -111,6 +111,7 @@ def test_rn50_wiring_is_exact_with_reference_math(monkeypatch):
         m, params, _ = _build(rc, gold, name)
         m.text_encoder.compute_dtype = torch.float32
         m.image_encoder.attnpool.compute_dtype = torch.float32
+        m.image_encoder.trunk_dtype = None
         image, label, attr = recipes.model_batch(rc)
         logits = m(image.to(DEV), attr)
         ref = torch.from_numpy(gold[f"{name}.logits"])

@@ -240,13 +240,14 @@ def test_oct_slice_projection_matches_conv2d(shape, cout):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
 @pytest.mark.parametrize("shape,k", [((3, 64, 16, 16), 2), ((2, 256, 56, 56), 2), ((2, 8, 12, 20), 4)])
-def test_avgpool_nhwc_matches_torch(shape, k):
+def test_avgpool_nhwc_matches_torch(shape, k, dtype):
     """nn.AvgPool2d(k) of the ResNet trunk (clip/model.py:30, :42, :108) on channels-last fp32 activations: forward and backward
     against torch."""
     from fairfedmed_b200 import ops
     torch.manual_seed(2)
-    x = torch.randn(shape, device="cuda:0").contiguous(memory_format=torch.channels_last)
+    x = torch.randn(shape, device="cuda:0").to(dtype).contiguous(memory_format=torch.channels_last)
     assert ops.avgpool_nhwc_supported(x, k)
     x1 = x.clone().requires_grad_(True)
     y = ops.avgpool_nhwc(x1, k)
@@ -255,6 +256,7 @@ def test_avgpool_nhwc_matches_torch(shape, k):
     x2 = x.clone().requires_grad_(True)
     ref = F.avg_pool2d(x2, k)
     ref.backward(dy)
-    torch.testing.assert_close(y, ref, rtol=1e-6, atol=1e-6)
-    torch.testing.assert_close(x1.grad, x2.grad, rtol=1e-6, atol=1e-7)
+    tol = dict(rtol=1e-6, atol=1e-6) if dtype == torch.float32 else dict(rtol=2 ** -7, atol=2 ** -8)
+    torch.testing.assert_close(y, ref, **tol)
+    torch.testing.assert_close(x1.grad, x2.grad, **tol)
     assert y.is_contiguous(memory_format=torch.channels_last) and x1.grad.is_contiguous(memory_format=torch.channels_last)
