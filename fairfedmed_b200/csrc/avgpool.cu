@@ -82,6 +82,21 @@ avgpool_nhwc_bwd_kernel(const uint4* __restrict__ dy, uint4* __restrict__ dx, in
   Vec16<BF16>::store(dx + i, v);
 }
 
+// bf16 -> fp32 widening of a contiguous buffer (the output side of the adapted 1x1 convolutions inside the fp32 ResNet trunk):
+// 8 elements per thread, 16-byte load, two 16-byte stores.  The library's converting copy for this direction is not vectorised
+// (92 us for 51 M elements against 47 us at the HBM roofline).
+__global__ void __launch_bounds__(256)
+widen_bf16_kernel(const uint4* __restrict__ in, float4* __restrict__ out, long long n8) {
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= n8) return;
+  const uint4 r = __ldg(in + i);
+  const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&r);
+  const float2 a = __bfloat1622float2(h2[0]), b = __bfloat1622float2(h2[1]);
+  const float2 c = __bfloat1622float2(h2[2]), d = __bfloat1622float2(h2[3]);
+  out[2 * i] = make_float4(a.x, a.y, b.x, b.y);
+  out[2 * i + 1] = make_float4(c.x, c.y, d.x, d.y);
+}
+
 }  // namespace ffm
 
 using namespace ffm;
@@ -121,6 +136,18 @@ int ffm_avgpool_nhwc_bwd(const void* dy, void* dx, int B, int H, int W, int C, i
   else
     avgpool_nhwc_bwd_kernel<false><<<static_cast<unsigned>(blocks), 256, 0, stream>>>(
         static_cast<const uint4*>(dy), static_cast<uint4*>(dx), H, W, C / per, k, n_in);
+  FFM_CHECK_CUDA(cudaGetLastError());
+  count_launch();
+  return FFM_OK;
+}
+
+int ffm_widen_bf16(const void* in, float* out, int64_t n, cudaStream_t stream) {
+  FFM_CHECK_ARG(in && out, "ffm_widen_bf16: null pointer argument");
+  FFM_CHECK_ARG(n >= 8 && n % 8 == 0, "ffm_widen_bf16: element count must be a positive multiple of 8");
+  const long long n8 = n / 8, blocks = (n8 + 255) / 256;
+  FFM_CHECK_ARG(blocks <= 0x7fffffffLL, "ffm_widen_bf16: too many elements");
+  widen_bf16_kernel<<<static_cast<unsigned>(blocks), 256, 0, stream>>>(static_cast<const uint4*>(in),
+                                                                       reinterpret_cast<float4*>(out), n8);
   FFM_CHECK_CUDA(cudaGetLastError());
   count_launch();
   return FFM_OK;

@@ -159,8 +159,9 @@ class _AdapterBase(nn.Module):
         num_slices = bp // n_samples                                   # OCT slices per sample (:473-475)
         y2d = ops.svlora_linear(x2d, w, w_t, bias, self.lora_A.weight, self.lora_B.weight, s_eff, self.scaling, bp,
                                 num_slices, row_div)
-        y = restore(y2d)
-        return y if y.dtype == x.dtype else y.to(x.dtype)
+        if y2d.dtype != x.dtype:           # on the contiguous [T, N] matrix, before the layout view
+            y2d = ops.widen_bf16(y2d) if x.dtype == torch.float32 else y2d.to(x.dtype)
+        return restore(y2d)
 
 
 class FairLoRALinear(_AdapterBase):

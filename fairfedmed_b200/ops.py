@@ -499,6 +499,36 @@ def avgpool_nhwc(x: Tensor, k: int) -> Tensor:
     return _AvgPoolNHWC.apply(x, int(k))
 
 
+@torch.library.custom_op("ffm::widen_bf16", mutates_args=())
+def widen_bf16_op(x: Tensor) -> Tensor:
+    _need_cuda(x)
+    out = torch.empty(x.shape, device=x.device, dtype=torch.float32)
+    _cabi.call("ffm_widen_bf16", _ptr(x), _ptr(out), x.numel(), _stream())
+    return out
+
+
+@widen_bf16_op.register_fake
+def _(x):
+    return torch.empty(x.shape, device=x.device, dtype=torch.float32)
+
+
+class _WidenBf16(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x):
+        return widen_bf16_op(x)
+
+    @staticmethod
+    def backward(ctx, dy):
+        return dy.to(torch.bfloat16)
+
+
+def widen_bf16(x: Tensor) -> Tensor:
+    """bf16 -> fp32 of a contiguous CUDA tensor (vectorised; differentiable); anything else falls back to Tensor.to."""
+    if x.is_cuda and x.dtype == torch.bfloat16 and x.is_contiguous() and x.numel() >= 8 and x.numel() % 8 == 0:
+        return _WidenBf16.apply(x)
+    return x.to(torch.float32)
+
+
 # =====================================================================================================
 # merged weight of a plain LoRA projection (RN50 attention pool)
 # =====================================================================================================

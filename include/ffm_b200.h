@@ -255,6 +255,9 @@ int ffm_lora_merged_weight_bwd(const float* dWm, const float* A, const float* B,
  */
 int ffm_avgpool_nhwc_fwd(const void* x, void* y, int B, int H, int W, int C, int k, int elem_bf16, ffm_stream_t stream);
 int ffm_avgpool_nhwc_bwd(const void* dy, void* dx, int B, int H, int W, int C, int k, int elem_bf16, ffm_stream_t stream);
+/* out f32 [n] = in bf16 [n] (contiguous, n a multiple of 8): the adapters' bf16 output back into the fp32 ResNet trunk
+ * (the `.to(x.dtype)` at the end of FairLoRALinear.forward, trainers/GLP_OT_SVLoRA.py:479-482). */
+int ffm_widen_bf16(const void* in, float* out, int64_t n, ffm_stream_t stream);
 
 /*
  * Group mixing of singular values — trainers/GLP_OT_SVLoRA.py:453-467.
