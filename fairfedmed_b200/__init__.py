@@ -6,7 +6,7 @@ binding), `ops` (torch custom ops + autograd), and the host-side mirrors of the 
 `modules` (FairLoRALinear & co), `clip_model` (attr-aware CLIP ViT + CustomCLIP), `trainer`
 (TRAINER_REGISTRY entry GLP_OT_SVLoRA), `fed_utils` / `federated` (aggregation, round loop), `metrics`.
 """
-__version__ = "0.1.0"
+__version__ = "0.2.0"
 
 from . import _cabi  # noqa: F401
 

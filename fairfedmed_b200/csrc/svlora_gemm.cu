@@ -726,7 +726,7 @@ extern "C" {
 
 const char* ffm_last_error(void) { return g_last_error; }
 
-int ffm_version(void) { return 101; }
+int ffm_version(void) { return 200; }   // round 2: tcgen05 attention, frozen linear, OCT / RN50 entry points
 
 int ffm_svlora_max_rank(void) { return RP_MAX; }
 
