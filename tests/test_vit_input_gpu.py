@@ -260,3 +260,19 @@ def test_avgpool_nhwc_matches_torch(shape, k, dtype):
     torch.testing.assert_close(y, ref, **tol)
     torch.testing.assert_close(x1.grad, x2.grad, **tol)
     assert y.is_contiguous(memory_format=torch.channels_last) and x1.grad.is_contiguous(memory_format=torch.channels_last)
+
+
+@pytest.mark.gpu
+def test_widen_bf16_is_exact_and_differentiable():
+    """The adapters' bf16 output back into the fp32 ResNet trunk (the `.to(x.dtype)` of trainers/GLP_OT_SVLoRA.py:479-482):
+    bit-exact widening, bf16 gradient on the way back, fallback for shapes the vector kernel does not take."""
+    from fairfedmed_b200 import ops
+    torch.manual_seed(4)
+    x = torch.randn(1000, 256, device="cuda:0").bfloat16().requires_grad_(True)
+    y = ops.widen_bf16(x)
+    assert y.dtype == torch.float32 and torch.equal(y, x.detach().float())
+    g = torch.randn_like(y)
+    y.backward(g)
+    assert x.grad.dtype == torch.bfloat16 and torch.equal(x.grad, g.to(torch.bfloat16))
+    odd = torch.randn(7, 3, device="cuda:0").bfloat16()
+    assert torch.equal(ops.widen_bf16(odd), odd.float())
