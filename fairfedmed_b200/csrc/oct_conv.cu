@@ -5,9 +5,10 @@
 //   forward : one block per 32 x 32 output tile; the input halo tile [Cin][36][36] sits in shared memory, a thread computes
 //             4 horizontally adjacent pixels of all output channels (two 16-byte reads of the input row and five broadcast
 //             reads of the weights per (c, i) for 60 FMAs) — FMA-bound, 15.4 GFLOP at config 3.
-//   wgrad   : the same tiles, persistent blocks; thread k owns weight tap (c, i, j) for every output channel (one more thread
-//             the bias) and walks the tile's pixels with the dy values broadcast from shared memory; per-block partials are
-//             folded in block order by a second kernel (deterministic, no atomics).  The input needs no gradient (it is data).
+//   wgrad   : the same tiles, persistent blocks; a thread owns the five taps (c, i, 0..4) of every output channel and a group of
+//             the tile's rows: one new 16-byte read of its input row and the broadcast dy quads per 60 FMAs; per-(block, row
+//             group) partials are folded in order by a second kernel (deterministic, no atomics).  The input needs no
+//             gradient (it is data).
 // The 1/255 of `image / 255` is folded into the weights on the way into shared memory (in_scale) and into dW on the way out.
 #include "../../include/ffm_b200.h"
 #include "ffm_common.cuh"
@@ -88,18 +89,28 @@ oct_conv_fwd_kernel(const float* __restrict__ x, const float* __restrict__ wgt, 
   }
 }
 
-// partial[block][k][o]: k < Cin * 25 = weight tap (c, i, j), k == Cin * 25 = bias; sums over the tiles this block walks
-__global__ void __launch_bounds__(1024)
+// partial[set][k][o]: k < Cin * 25 = weight tap (c, i, j), k == Cin * 25 = bias; set = (block, row group).
+// A thread owns the five taps (c, i, 0..4) of every output channel — 15 accumulators — and one group of the tile's rows
+// (rows g, g + G, ...): per 4 pixels it reads ONE new 16-byte piece of its input row (sliding 8-value window) and the dy quads
+// (broadcast within the group) for 60 FMAs; `units` = Cin * 5 tap rows + 1 bias unit per group, G groups per block.
+template <int COUT>
+__global__ void __launch_bounds__(256)
 oct_conv_wgrad_kernel(const float* __restrict__ x, const float* __restrict__ dy, float* __restrict__ part, int Bp, int Cin,
-                      int Cout, int H, int W, int tiles_x, int tiles_y) {
+                      int H, int W, int tiles_x, int tiles_y, int G) {
   extern __shared__ __align__(16) float oc_smem[];
   float* x_s = oc_smem;                                   // [Cin][36][40] (+4 per channel)
-  float* dy_s = oc_smem + Cin * OC_CH;                    // [OC_MAX_COUT][32][32], zero beyond Cout / the image
-  const int K = Cin * 25;
-  const int k = threadIdx.x;
-  const int c = k / 25, ij = k - c * 25, i = ij / 5, j = ij - i * 5;
-  const float* xk = x_s + (k < K ? c * OC_CH + i * OC_ROW + j : 0);
-  float acc[OC_MAX_COUT] = {0.f, 0.f, 0.f, 0.f};
+  float* dy_s = oc_smem + Cin * OC_CH;                    // [COUT][32][32], zero beyond the image
+  const int units = Cin * 5 + 1;
+  const int g = threadIdx.x / units, u = threadIdx.x - g * units;
+  const bool active = g < G;
+  const bool is_bias = u == units - 1;
+  const int c = u / 5, i = u - c * 5;
+  const float* xrow = x_s + (is_bias ? 0 : c * OC_CH + i * OC_ROW);
+  float acc[5][COUT];
+#pragma unroll
+  for (int j = 0; j < 5; ++j)
+#pragma unroll
+    for (int o = 0; o < COUT; ++o) acc[j][o] = 0.f;
   const int tiles = tiles_x * tiles_y;
   const long long total = static_cast<long long>(Bp) * tiles;
   for (long long t = blockIdx.x; t < total; t += gridDim.x) {
@@ -108,40 +119,47 @@ oct_conv_wgrad_kernel(const float* __restrict__ x, const float* __restrict__ dy,
     const int h0 = ty_t * OC_TILE, w0 = tx_t * OC_TILE;
     __syncthreads();                                      // the previous tile is consumed
     oc_load_halo(x_s, x + static_cast<size_t>(b) * Cin * H * W, Cin, H, W, h0, w0, threadIdx.x, blockDim.x);
-    for (int e = threadIdx.x; e < OC_MAX_COUT * OC_TILE * OC_TILE; e += blockDim.x) {
+    for (int e = threadIdx.x; e < COUT * OC_TILE * OC_TILE; e += blockDim.x) {
       const int o = e >> 10, r = e & 1023;
       const int h = h0 + (r >> 5), w = w0 + (r & 31);
-      dy_s[e] = (o < Cout && h < H && w < W) ? __ldg(dy + ((static_cast<size_t>(b) * Cout + o) * H + h) * W + w) : 0.f;
+      dy_s[e] = (h < H && w < W) ? __ldg(dy + ((static_cast<size_t>(b) * COUT + o) * H + h) * W + w) : 0.f;
     }
     __syncthreads();
-    if (k <= K) {
-      for (int py = 0; py < OC_TILE; ++py) {
+    if (!active) continue;
+    for (int py = g; py < OC_TILE; py += G) {
+      const float* xr = xrow + py * OC_ROW;
+      float4 lo = is_bias ? make_float4(1.f, 1.f, 1.f, 1.f) : *reinterpret_cast<const float4*>(xr);
 #pragma unroll
-        for (int q = 0; q < OC_TILE / 4; ++q) {
-          float xv[4];
-          if (k < K) {
+      for (int q = 0; q < OC_TILE / 4; ++q) {
+        const float4 hi = is_bias ? make_float4(0.f, 0.f, 0.f, 0.f) : *reinterpret_cast<const float4*>(xr + 4 * q + 4);
+        const float w8[8] = {lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w};
 #pragma unroll
-            for (int e = 0; e < 4; ++e) xv[e] = xk[py * OC_ROW + 4 * q + e];
-          } else {
+        for (int o = 0; o < COUT; ++o) {
+          const float4 d = *reinterpret_cast<const float4*>(dy_s + (o << 10) + py * OC_TILE + 4 * q);
 #pragma unroll
-            for (int e = 0; e < 4; ++e) xv[e] = 1.0f;     // the bias "tap"
-          }
-#pragma unroll
-          for (int o = 0; o < OC_MAX_COUT; ++o) {
-            const float4 d = *reinterpret_cast<const float4*>(dy_s + (o << 10) + py * OC_TILE + 4 * q);
-            acc[o] = fmaf(d.x, xv[0], acc[o]);
-            acc[o] = fmaf(d.y, xv[1], acc[o]);
-            acc[o] = fmaf(d.z, xv[2], acc[o]);
-            acc[o] = fmaf(d.w, xv[3], acc[o]);
+          for (int j = 0; j < 5; ++j) {
+            acc[j][o] = fmaf(d.x, w8[j], acc[j][o]);
+            acc[j][o] = fmaf(d.y, w8[j + 1], acc[j][o]);
+            acc[j][o] = fmaf(d.z, w8[j + 2], acc[j][o]);
+            acc[j][o] = fmaf(d.w, w8[j + 3], acc[j][o]);
           }
         }
+        lo = is_bias ? lo : hi;
       }
     }
   }
-  if (k <= K) {
-    float* dst = part + (static_cast<size_t>(blockIdx.x) * (K + 1) + k) * OC_MAX_COUT;
+  if (active) {
+    const int K = Cin * 25;
+    float* base = part + (static_cast<size_t>(blockIdx.x) * G + g) * (K + 1) * OC_MAX_COUT;
+    if (is_bias) {
 #pragma unroll
-    for (int o = 0; o < OC_MAX_COUT; ++o) dst[o] = acc[o];
+      for (int o = 0; o < OC_MAX_COUT; ++o) base[K * OC_MAX_COUT + o] = o < COUT ? acc[0][o] : 0.f;   // tap j = 0 saw the ones
+    } else {
+#pragma unroll
+      for (int j = 0; j < 5; ++j)
+#pragma unroll
+        for (int o = 0; o < OC_MAX_COUT; ++o) base[(u * 5 + j) * OC_MAX_COUT + o] = o < COUT ? acc[j][o] : 0.f;
+    }
   }
 }
 
@@ -162,6 +180,10 @@ __global__ void oct_conv_wgrad_fold_kernel(const float* __restrict__ part, float
 }
 
 static int oc_wgrad_blocks() { return 2 * num_sms(); }
+static int oc_wgrad_groups(int Cin) {
+  const int g = 256 / (Cin * 5 + 1);
+  return g < 1 ? 1 : (g > 8 ? 8 : g);
+}
 
 }  // namespace ffm
 
@@ -170,7 +192,9 @@ using namespace ffm;
 extern "C" {
 
 size_t ffm_oct_slice_conv_wgrad_ws_bytes(int Cin) {
-  return static_cast<size_t>(oc_wgrad_blocks()) * (static_cast<size_t>(Cin > 0 ? Cin : 0) * 25 + 1) * OC_MAX_COUT * sizeof(float);
+  const int cin = Cin > 0 ? Cin : 1;
+  return static_cast<size_t>(oc_wgrad_blocks()) * oc_wgrad_groups(cin) * (static_cast<size_t>(cin) * 25 + 1) * OC_MAX_COUT *
+         sizeof(float);
 }
 
 int ffm_oct_slice_conv_fwd(const float* x, const float* w, const float* bias, float* y, int Bp, int Cin, int Cout, int H,
@@ -197,22 +221,34 @@ int ffm_oct_slice_conv_wgrad(const float* x, const float* dy, float* dw, float* 
   FFM_CHECK_ARG(x && dy && dw && dbias && ws, "ffm_oct_slice_conv_wgrad: null pointer argument");
   FFM_CHECK_ARG(Bp >= 1 && Cin >= 1 && Cin <= 32 && Cout >= 1 && Cout <= OC_MAX_COUT && H >= 1 && W >= 1,
                 "ffm_oct_slice_conv_wgrad: Cin <= 32, Cout <= 4");
+  static_assert(32 * 5 + 1 <= 256, "one row group of tap units must fit a 256-thread block");
   FFM_CHECK_ARG(ws_bytes >= ffm_oct_slice_conv_wgrad_ws_bytes(Cin), "ffm_oct_slice_conv_wgrad: workspace too small");
   const int tiles_x = (W + OC_TILE - 1) / OC_TILE, tiles_y = (H + OC_TILE - 1) / OC_TILE;
   const long long total = static_cast<long long>(Bp) * tiles_x * tiles_y;
   const int nblocks = static_cast<int>(total < oc_wgrad_blocks() ? total : oc_wgrad_blocks());
-  const int nthreads = ((Cin * 25 + 1) + 31) & ~31;
-  const size_t smem = (static_cast<size_t>(Cin) * OC_CH + OC_MAX_COUT * OC_TILE * OC_TILE) * sizeof(float);
-  static thread_local size_t attr_smem = 0;
-  if (smem > attr_smem) {
-    FFM_CHECK_CUDA(cudaFuncSetAttribute(oct_conv_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-    attr_smem = smem;
-  }
+  const int G = oc_wgrad_groups(Cin);
+  const size_t smem = (static_cast<size_t>(Cin) * OC_CH + static_cast<size_t>(Cout) * OC_TILE * OC_TILE) * sizeof(float);
   float* part = static_cast<float*>(ws);
-  oct_conv_wgrad_kernel<<<nblocks, nthreads, smem, stream>>>(x, dy, part, Bp, Cin, Cout, H, W, tiles_x, tiles_y);
+#define FFM_OC_WGRAD(CO)                                                                                                    \
+  do {                                                                                                                     \
+    static thread_local size_t attr_smem = 0;                                                                              \
+    if (smem > attr_smem) {                                                                                                \
+      FFM_CHECK_CUDA(cudaFuncSetAttribute(oct_conv_wgrad_kernel<CO>, cudaFuncAttributeMaxDynamicSharedMemorySize,           \
+                                          static_cast<int>(smem)));                                                        \
+      attr_smem = smem;                                                                                                    \
+    }                                                                                                                      \
+    oct_conv_wgrad_kernel<CO><<<nblocks, 256, smem, stream>>>(x, dy, part, Bp, Cin, H, W, tiles_x, tiles_y, G);             \
+  } while (0)
+  switch (Cout) {
+    case 1: FFM_OC_WGRAD(1); break;
+    case 2: FFM_OC_WGRAD(2); break;
+    case 3: FFM_OC_WGRAD(3); break;
+    default: FFM_OC_WGRAD(4); break;
+  }
+#undef FFM_OC_WGRAD
   FFM_CHECK_CUDA(cudaGetLastError());
   const int n_out = (Cin * 25 + 1) * Cout;
-  oct_conv_wgrad_fold_kernel<<<(n_out + 127) / 128, 128, 0, stream>>>(part, dw, dbias, nblocks, Cin, Cout, in_scale);
+  oct_conv_wgrad_fold_kernel<<<(n_out + 127) / 128, 128, 0, stream>>>(part, dw, dbias, nblocks * G, Cin, Cout, in_scale);
   FFM_CHECK_CUDA(cudaGetLastError());
   count_launch(2);
   return FFM_OK;
