@@ -499,6 +499,84 @@ def avgpool_nhwc(x: Tensor, k: int) -> Tensor:
     return _AvgPoolNHWC.apply(x, int(k))
 
 
+# =====================================================================================================
+# training-mode BatchNorm (+ ReLU) of the ResNet trunk on channels-last fp32 activations
+# =====================================================================================================
+@torch.library.custom_op("ffm::bn_relu_fwd", mutates_args=("running_mean", "running_var"))
+def bn_relu_fwd_op(x: Tensor, gamma: Tensor, beta: Tensor, running_mean: Tensor, running_var: Tensor, momentum: float,
+                   eps: float, relu: bool) -> Tuple[Tensor, Tensor, Tensor]:
+    _need_cuda(x, gamma, beta, running_mean, running_var)
+    b, c, h, w = x.shape
+    y = torch.empty_like(x, memory_format=torch.channels_last)
+    mean = torch.empty((c,), device=x.device, dtype=torch.float32)
+    rstd = torch.empty((c,), device=x.device, dtype=torch.float32)
+    nbytes = int(_cabi.load().ffm_bn_ws_bytes(c))
+    ws = torch.empty((nbytes // 4,), device=x.device, dtype=torch.float32)
+    _cabi.call("ffm_bn_relu_fwd", _ptr(x), _ptr(gamma), _ptr(beta), _ptr(running_mean), _ptr(running_var), _ptr(y),
+               _ptr(mean), _ptr(rstd), _ptr(ws), nbytes, b * h * w, c, float(momentum), float(eps), int(bool(relu)), _stream())
+    return y, mean, rstd
+
+
+@bn_relu_fwd_op.register_fake
+def _(x, gamma, beta, running_mean, running_var, momentum, eps, relu):
+    c = x.shape[1]
+    return (torch.empty_like(x, memory_format=torch.channels_last), x.new_empty((c,)), x.new_empty((c,)))
+
+
+@torch.library.custom_op("ffm::bn_relu_bwd", mutates_args=())
+def bn_relu_bwd_op(x: Tensor, dy: Tensor, gamma: Tensor, beta: Tensor, mean: Tensor, rstd: Tensor,
+                   relu: bool) -> Tuple[Tensor, Tensor, Tensor]:
+    _need_cuda(x, dy, gamma, beta, mean, rstd)
+    b, c, h, w = x.shape
+    dx = torch.empty_like(x, memory_format=torch.channels_last)
+    dgamma = torch.empty((c,), device=x.device, dtype=torch.float32)
+    dbeta = torch.empty((c,), device=x.device, dtype=torch.float32)
+    nbytes = int(_cabi.load().ffm_bn_ws_bytes(c))
+    ws = torch.empty((nbytes // 4,), device=x.device, dtype=torch.float32)
+    _cabi.call("ffm_bn_relu_bwd", _ptr(x), _ptr(dy), _ptr(gamma), _ptr(beta), _ptr(mean), _ptr(rstd), _ptr(dx), _ptr(dgamma),
+               _ptr(dbeta), _ptr(ws), nbytes, b * h * w, c, int(bool(relu)), _stream())
+    return dx, dgamma, dbeta
+
+
+@bn_relu_bwd_op.register_fake
+def _(x, dy, gamma, beta, mean, rstd, relu):
+    c = x.shape[1]
+    return torch.empty_like(x, memory_format=torch.channels_last), x.new_empty((c,)), x.new_empty((c,))
+
+
+class _BatchNormReLU(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, gamma, beta, running_mean, running_var, momentum, eps, relu):
+        y, mean, rstd = bn_relu_fwd_op(x, gamma, beta, running_mean, running_var, momentum, eps, relu)
+        ctx.save_for_backward(x, gamma, beta, mean, rstd)
+        ctx.relu = relu
+        ctx.mark_non_differentiable(mean, rstd)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, gamma, beta, mean, rstd = ctx.saved_tensors
+        dy = dy.contiguous(memory_format=torch.channels_last)
+        if dy.dtype != torch.float32:
+            dy = dy.float()
+        dx, dgamma, dbeta = bn_relu_bwd_op(x, dy, gamma.detach(), beta.detach(), mean, rstd, ctx.relu)
+        return dx, dgamma, dbeta, None, None, None, None, None
+
+
+def batchnorm_relu_supported(x: Tensor) -> bool:
+    return (x.is_cuda and x.dim() == 4 and x.dtype == torch.float32 and x.shape[1] % 4 == 0 and
+            x.is_contiguous(memory_format=torch.channels_last))
+
+
+def batchnorm_relu(x: Tensor, gamma: Tensor, beta: Tensor, running_mean: Tensor, running_var: Tensor, momentum: float,
+                   eps: float, relu: bool) -> Tensor:
+    """Training-mode nn.BatchNorm2d followed (relu=True) by ReLU on channels-last fp32 activations (clip/model.py:18-58): batch
+    statistics, running-statistics update as torch does, gradients for x / gamma / beta; the ReLU mask is recomputed in the
+    backward, so only x is kept."""
+    return _BatchNormReLU.apply(x, gamma.float().contiguous(), beta.float().contiguous(), running_mean, running_var,
+                                float(momentum), float(eps), bool(relu))
+
+
 @torch.library.custom_op("ffm::widen_bf16", mutates_args=())
 def widen_bf16_op(x: Tensor) -> Tensor:
     _need_cuda(x)

@@ -260,6 +260,22 @@ int ffm_avgpool_nhwc_bwd(const void* dy, void* dx, int B, int H, int W, int C, i
 int ffm_widen_bf16(const void* in, float* out, int64_t n, ffm_stream_t stream);
 
 /*
+ * Training-mode nn.BatchNorm2d (+ the ReLU that follows it) of the ResNet trunk (clip/model.py:18-58) on channels-last fp32
+ * activations viewed as x f32 [R = B*H*W, C]; gamma / beta f32 [C] (trainable in the RN50 recipe).
+ * ffm_bn_relu_fwd: y = [relu](gamma * (x - mean) * rstd + beta) with the batch statistics (biased variance), which are also
+ *   returned (mean_out, rstd_out f32 [C]) for the backward; running_mean / running_var (may both be NULL) are updated as torch
+ *   does (momentum, unbiased variance).  ffm_bn_relu_bwd: dx, dgamma, dbeta (the ReLU mask is recomputed from x).
+ * `ws` of at least ffm_bn_ws_bytes(C) bytes; C a multiple of 4; deterministic.
+ */
+size_t ffm_bn_ws_bytes(int C);
+int ffm_bn_relu_fwd(const float* x, const float* gamma, const float* beta, float* running_mean, float* running_var, float* y,
+                    float* mean_out, float* rstd_out, void* ws, size_t ws_bytes, int64_t R, int C, float momentum, float eps,
+                    int relu, ffm_stream_t stream);
+int ffm_bn_relu_bwd(const float* x, const float* dy, const float* gamma, const float* beta, const float* mean,
+                    const float* rstd, float* dx, float* dgamma, float* dbeta, void* ws, size_t ws_bytes, int64_t R, int C,
+                    int relu, ffm_stream_t stream);
+
+/*
  * Group mixing of singular values — trainers/GLP_OT_SVLoRA.py:453-467.
  *   attr != NULL: pi[b,g] = lambda (0.7 in the reference) if attr[b]==g else (1-lambda)/(G-1)
  *   attr == NULL: n_samples must be 1 and pi = 1/G

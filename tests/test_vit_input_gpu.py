@@ -276,3 +276,36 @@ def test_widen_bf16_is_exact_and_differentiable():
     assert x.grad.dtype == torch.bfloat16 and torch.equal(x.grad, g.to(torch.bfloat16))
     odd = torch.randn(7, 3, device="cuda:0").bfloat16()
     assert torch.equal(ops.widen_bf16(odd), odd.float())
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("relu", [True, False])
+@pytest.mark.parametrize("shape", [(4, 64, 14, 14), (64, 256, 56, 56), (2, 8, 3, 5)])
+def test_batchnorm_relu_matches_torch(shape, relu):
+    """Training-mode nn.BatchNorm2d (+ ReLU) of the ResNet trunk (clip/model.py:18-58) on channels-last fp32 activations: output,
+    running statistics and the gradients of x / gamma / beta against torch in fp64."""
+    from fairfedmed_b200 import ops
+    torch.manual_seed(9)
+    c = shape[1]
+    x = (torch.randn(shape, device="cuda:0") * 2.0 + 0.7).contiguous(memory_format=torch.channels_last)
+    gamma = (torch.rand(c, device="cuda:0") + 0.5).requires_grad_(True)
+    beta = (0.3 * torch.randn(c, device="cuda:0")).requires_grad_(True)
+    rm, rv = torch.zeros(c, device="cuda:0"), torch.ones(c, device="cuda:0")
+    dy = torch.randn(shape, device="cuda:0").contiguous(memory_format=torch.channels_last)
+    x1 = x.clone().requires_grad_(True)
+    y = ops.batchnorm_relu(x1, gamma, beta, rm, rv, 0.1, 1e-5, relu)
+    y.backward(dy)
+    x2 = x.double().requires_grad_(True)
+    g2, b2 = gamma.detach().double().requires_grad_(True), beta.detach().double().requires_grad_(True)
+    rm2, rv2 = torch.zeros(c, device="cuda:0", dtype=torch.float64), torch.ones(c, device="cuda:0", dtype=torch.float64)
+    ref = F.batch_norm(x2, rm2, rv2, g2, b2, True, 0.1, 1e-5)
+    if relu:
+        ref = F.relu(ref)
+    ref.backward(dy.double())
+    torch.testing.assert_close(y.detach().double(), ref.detach(), rtol=1e-4, atol=1e-5)
+    torch.testing.assert_close(rm.double(), rm2, rtol=1e-5, atol=1e-6)
+    torch.testing.assert_close(rv.double(), rv2, rtol=1e-5, atol=1e-6)
+    scale = float(x2.grad.abs().max())
+    torch.testing.assert_close(x1.grad.double(), x2.grad, rtol=1e-3, atol=2e-5 * max(scale, 1.0))
+    torch.testing.assert_close(gamma.grad.double(), g2.grad, rtol=1e-4, atol=1e-4 * float(g2.grad.abs().max()))
+    torch.testing.assert_close(beta.grad.double(), b2.grad, rtol=1e-4, atol=1e-4 * float(b2.grad.abs().max()))
