@@ -58,6 +58,8 @@ SIGNATURES = {
     "ffm_bn_ws_bytes": (_sz, [_i]),
     "ffm_bn_relu_fwd": (_i, [_fp, _fp, _fp, _fp, _fp, _fp, _fp, _fp, _vp, _sz, _i64, _i, _f, _f, _i, _vp]),
     "ffm_bn_relu_bwd": (_i, [_fp, _fp, _fp, _fp, _fp, _fp, _fp, _fp, _fp, _vp, _sz, _i64, _i, _i, _vp]),
+    "ffm_add_relu": (_i, [_fp, _fp, _fp, _i64, _vp]),
+    "ffm_relu_mask": (_i, [_fp, _fp, _fp, _i64, _vp]),
     "ffm_seff": (_i, [_vp, _fp, _fp, _fp, _i, _i, _i, _f, _vp]),
     "ffm_ds": (_i, [_vp, _fp, _fp, _fp, _i, _i, _i, _f, _vp]),
     "ffm_ot_head_workspace_bytes": (_sz, [_i, _i, _i, _i, _i]),

@@ -97,6 +97,24 @@ widen_bf16_kernel(const uint4* __restrict__ in, float4* __restrict__ out, long l
   out[2 * i + 1] = make_float4(c.x, c.y, d.x, d.y);
 }
 
+// y = relu(a + b) (the closing `relu(out + identity)` of a bottleneck, clip/model.py:56-58) and its backward g = dy * [y > 0]
+// (the same tensor is the gradient of both inputs): one pass each instead of add + ReLU / threshold kernels.
+__global__ void __launch_bounds__(256)
+add_relu_kernel(const float4* __restrict__ a, const float4* __restrict__ b, float4* __restrict__ y, long long n4) {
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= n4) return;
+  const float4 u = __ldg(a + i), v = __ldg(b + i);
+  y[i] = make_float4(fmaxf(u.x + v.x, 0.f), fmaxf(u.y + v.y, 0.f), fmaxf(u.z + v.z, 0.f), fmaxf(u.w + v.w, 0.f));
+}
+
+__global__ void __launch_bounds__(256)
+relu_mask_kernel(const float4* __restrict__ dy, const float4* __restrict__ y, float4* __restrict__ g, long long n4) {
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= n4) return;
+  const float4 d = __ldg(dy + i), v = __ldg(y + i);
+  g[i] = make_float4(v.x > 0.f ? d.x : 0.f, v.y > 0.f ? d.y : 0.f, v.z > 0.f ? d.z : 0.f, v.w > 0.f ? d.w : 0.f);
+}
+
 }  // namespace ffm
 
 using namespace ffm;
@@ -136,6 +154,32 @@ int ffm_avgpool_nhwc_bwd(const void* dy, void* dx, int B, int H, int W, int C, i
   else
     avgpool_nhwc_bwd_kernel<false><<<static_cast<unsigned>(blocks), 256, 0, stream>>>(
         static_cast<const uint4*>(dy), static_cast<uint4*>(dx), H, W, C / per, k, n_in);
+  FFM_CHECK_CUDA(cudaGetLastError());
+  count_launch();
+  return FFM_OK;
+}
+
+int ffm_add_relu(const float* a, const float* b, float* y, int64_t n, cudaStream_t stream) {
+  FFM_CHECK_ARG(a && b && y, "ffm_add_relu: null pointer argument");
+  FFM_CHECK_ARG(n >= 4 && n % 4 == 0, "ffm_add_relu: element count must be a positive multiple of 4");
+  const long long n4 = n / 4, blocks = (n4 + 255) / 256;
+  FFM_CHECK_ARG(blocks <= 0x7fffffffLL, "ffm_add_relu: too many elements");
+  add_relu_kernel<<<static_cast<unsigned>(blocks), 256, 0, stream>>>(reinterpret_cast<const float4*>(a),
+                                                                     reinterpret_cast<const float4*>(b),
+                                                                     reinterpret_cast<float4*>(y), n4);
+  FFM_CHECK_CUDA(cudaGetLastError());
+  count_launch();
+  return FFM_OK;
+}
+
+int ffm_relu_mask(const float* dy, const float* y, float* g, int64_t n, cudaStream_t stream) {
+  FFM_CHECK_ARG(dy && y && g, "ffm_relu_mask: null pointer argument");
+  FFM_CHECK_ARG(n >= 4 && n % 4 == 0, "ffm_relu_mask: element count must be a positive multiple of 4");
+  const long long n4 = n / 4, blocks = (n4 + 255) / 256;
+  FFM_CHECK_ARG(blocks <= 0x7fffffffLL, "ffm_relu_mask: too many elements");
+  relu_mask_kernel<<<static_cast<unsigned>(blocks), 256, 0, stream>>>(reinterpret_cast<const float4*>(dy),
+                                                                      reinterpret_cast<const float4*>(y),
+                                                                      reinterpret_cast<float4*>(g), n4);
   FFM_CHECK_CUDA(cudaGetLastError());
   count_launch();
   return FFM_OK;

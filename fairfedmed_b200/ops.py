@@ -577,6 +577,58 @@ def batchnorm_relu(x: Tensor, gamma: Tensor, beta: Tensor, running_mean: Tensor,
                                 float(momentum), float(eps), bool(relu))
 
 
+@torch.library.custom_op("ffm::add_relu", mutates_args=())
+def add_relu_op(a: Tensor, b: Tensor) -> Tensor:
+    _need_cuda(a, b)
+    y = torch.empty_like(a)
+    _cabi.call("ffm_add_relu", _ptr(a), _ptr(b), _ptr(y), a.numel(), _stream())
+    return y
+
+
+@add_relu_op.register_fake
+def _(a, b):
+    return torch.empty_like(a)
+
+
+@torch.library.custom_op("ffm::relu_mask", mutates_args=())
+def relu_mask_op(dy: Tensor, y: Tensor) -> Tensor:
+    _need_cuda(dy, y)
+    g = torch.empty_like(y)
+    _cabi.call("ffm_relu_mask", _ptr(dy), _ptr(y), _ptr(g), y.numel(), _stream())
+    return g
+
+
+@relu_mask_op.register_fake
+def _(dy, y):
+    return torch.empty_like(y)
+
+
+class _AddReLU(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, a, b):
+        y = add_relu_op(a, b)
+        ctx.save_for_backward(y)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        (y,) = ctx.saved_tensors
+        if dy.dtype != torch.float32 or dy.stride() != y.stride():
+            dy = dy.float().contiguous(memory_format=torch.channels_last) if y.dim() == 4 and \
+                y.is_contiguous(memory_format=torch.channels_last) else dy.float().contiguous()
+        g = relu_mask_op(dy, y)
+        return g, g
+
+
+def add_relu(a: Tensor, b: Tensor) -> Tensor:
+    """relu(a + b) for two fp32 CUDA tensors of identical shape and memory layout (clip/model.py:56-58); torch otherwise."""
+    if (a.is_cuda and b.is_cuda and a.dtype == torch.float32 and b.dtype == torch.float32 and a.shape == b.shape and
+            a.stride() == b.stride() and a.numel() >= 4 and a.numel() % 4 == 0 and
+            (a.is_contiguous() or (a.dim() == 4 and a.is_contiguous(memory_format=torch.channels_last)))):
+        return _AddReLU.apply(a, b)
+    return torch.relu(a + b)
+
+
 @torch.library.custom_op("ffm::widen_bf16", mutates_args=())
 def widen_bf16_op(x: Tensor) -> Tensor:
     _need_cuda(x)

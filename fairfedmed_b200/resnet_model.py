@@ -88,7 +88,7 @@ class Bottleneck(nn.Module):
         if self.downsample is not None:
             identity = self.downsample[0](x)
             identity = _bn(self.downsample[2], _conv(self, "downsample", self.downsample[1], identity, None), False)
-        return self.relu(out + identity)
+        return ops.add_relu(out, identity)
 
 
 class _AvgPool2d(nn.AvgPool2d):

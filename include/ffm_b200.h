@@ -258,6 +258,10 @@ int ffm_avgpool_nhwc_bwd(const void* dy, void* dx, int B, int H, int W, int C, i
 /* out f32 [n] = in bf16 [n] (contiguous, n a multiple of 8): the adapters' bf16 output back into the fp32 ResNet trunk
  * (the `.to(x.dtype)` at the end of FairLoRALinear.forward, trainers/GLP_OT_SVLoRA.py:479-482). */
 int ffm_widen_bf16(const void* in, float* out, int64_t n, ffm_stream_t stream);
+/* y = relu(a + b) — the closing `relu(out + identity)` of a bottleneck (clip/model.py:56-58) — and its backward
+ * g = dy * [y > 0] (the gradient of both a and b); f32, same memory layout for all operands, n a multiple of 4. */
+int ffm_add_relu(const float* a, const float* b, float* y, int64_t n, ffm_stream_t stream);
+int ffm_relu_mask(const float* dy, const float* y, float* g, int64_t n, ffm_stream_t stream);
 
 /*
  * Training-mode nn.BatchNorm2d (+ the ReLU that follows it) of the ResNet trunk (clip/model.py:18-58) on channels-last fp32

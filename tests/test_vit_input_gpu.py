@@ -309,3 +309,21 @@ def test_batchnorm_relu_matches_torch(shape, relu):
     torch.testing.assert_close(x1.grad.double(), x2.grad, rtol=1e-3, atol=2e-5 * max(scale, 1.0))
     torch.testing.assert_close(gamma.grad.double(), g2.grad, rtol=1e-4, atol=1e-4 * float(g2.grad.abs().max()))
     torch.testing.assert_close(beta.grad.double(), b2.grad, rtol=1e-4, atol=1e-4 * float(b2.grad.abs().max()))
+
+
+@pytest.mark.gpu
+def test_add_relu_matches_torch():
+    """relu(out + identity) closing a bottleneck (clip/model.py:56-58), channels-last fp32, forward and both gradients."""
+    from fairfedmed_b200 import ops
+    torch.manual_seed(6)
+    a = torch.randn(4, 64, 14, 14, device="cuda:0").contiguous(memory_format=torch.channels_last)
+    b = torch.randn(4, 64, 14, 14, device="cuda:0").contiguous(memory_format=torch.channels_last)
+    a1, b1 = a.clone().requires_grad_(True), b.clone().requires_grad_(True)
+    y = ops.add_relu(a1, b1)
+    dy = torch.randn_like(y)
+    y.backward(dy)
+    a2, b2 = a.clone().requires_grad_(True), b.clone().requires_grad_(True)
+    ref = torch.relu(a2 + b2)
+    ref.backward(dy)
+    assert torch.equal(y, ref) and torch.equal(a1.grad, a2.grad) and torch.equal(b1.grad, b2.grad)
+    assert y.is_contiguous(memory_format=torch.channels_last)
