@@ -217,3 +217,25 @@ def test_adapt_attention_opt_in_adds_adapters_without_touching_reference_keys():
     assert not any(p.requires_grad for n, p in on.named_parameters() if ".attn.in_proj" in n or ".attn.out_proj" in n)
     with pytest.raises(NotImplementedError):
         modules.apply_lora_to_model(build(False), True, rank=4, lora_type="LoRA", adapt_attention=True)
+
+
+def test_resnet_glue_falls_back_to_the_library_off_gpu():
+    """The ResNet trunk's glue ops (BatchNorm + ReLU, average pooling, relu(out + identity)) use the package's kernels only for
+    CUDA tensors in the layouts they were built for; anything else (CPU tensors here) must take the library path and give
+    torch's own results — construction / state-dict handling of the model happens on the CPU."""
+    import torch
+    import torch.nn as nn
+    import torch.nn.functional as F
+    from fairfedmed_b200 import ops, resnet_model as rm
+    torch.manual_seed(0)
+    x = torch.randn(2, 8, 6, 6)
+    bn = nn.BatchNorm2d(8)
+    ref_bn = nn.BatchNorm2d(8)
+    ref_bn.load_state_dict(bn.state_dict())
+    y = rm._bn(bn, x, True)
+    torch.testing.assert_close(y, F.relu(ref_bn(x)))
+    torch.testing.assert_close(bn.running_mean, ref_bn.running_mean)
+    assert int(bn.num_batches_tracked) == 1
+    torch.testing.assert_close(rm._AvgPool2d(2)(x), F.avg_pool2d(x, 2))
+    torch.testing.assert_close(ops.add_relu(x, -0.5 * x), torch.relu(0.5 * x))
+    assert not ops.batchnorm_relu_supported(x) and not ops.avgpool_nhwc_supported(x, 2)
